@@ -1,0 +1,138 @@
+/* scema_hist.h — C ABI of libscema_hist.so: SCEMa's MD-redundancy clustering hot path on B200.
+ *
+ * The reference (UCL-CCS/SCEMa) has no FFI layer for this path; its de-facto boundary is the
+ * header API of namespace MatHistPredict (headers/strain2spline.h), two command lines
+ * (clustering/compare_all_histories.cc, clustering/mpi_comparison_test.cc) and three file
+ * formats. Each entry point below names the reference interface it replaces (file:line relative
+ * to the reference root). scema_b200/host/strain2spline_b200.h re-creates the MatHistPredict
+ * header API on top of this ABI, and INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions: plain pointers and sizes only; every function returns SCEMA_OK or an error code
+ * and never exits the process (the reference does fprintf(stderr)+exit(1) everywhere; the C++
+ * shim maps non-zero codes back to that behaviour). A context is bound to one CUDA device and
+ * one stream; calls on one context are not thread-safe; different contexts are independent.
+ * There is NO CPU fallback: without a CUDA device scema_create fails with SCEMA_ERR_CUDA.
+ */
+#ifndef SCEMA_HIST_H
+#define SCEMA_HIST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCEMA_OK 0
+#define SCEMA_ERR_INVALID 1 /* bad argument; includes a history with < 3 steps (strain2spline.h:142-148) */
+#define SCEMA_ERR_CUDA 2    /* CUDA runtime failure, or no device */
+#define SCEMA_ERR_NOMEM 3   /* host or device allocation failed */
+#define SCEMA_ERR_IO 4      /* file could not be opened (strain2spline.h:117-120, :303-307) */
+#define SCEMA_ERR_STATE 5   /* call order: e.g. compare before any spline matrix exists (strain2spline.h:214-221) */
+#define SCEMA_ERR_MAPPING 6 /* graph reduction: ID >= num_gps or dist == 0 (coarsegrain_dependency_network.py:57,73) */
+
+/* Which kernel evaluates the all-pairs distance (north star: DMMA tensor path, CUDA-core FMA
+ * variant kept for comparison, exact direct-difference kernel as the anchor). All three emit
+ * the bit-identical edge list. */
+#define SCEMA_PAIRS_DMMA 0  /* GEMM-form filter on FP64 mma.sync (DMMA) + exact recompute of survivors */
+#define SCEMA_PAIRS_FMA 1   /* GEMM-form filter on CUDA-core DFMA + exact recompute of survivors */
+#define SCEMA_PAIRS_EXACT 2 /* every pair by direct differences (compare_L2_norm order), no filter */
+
+typedef struct scema_ctx scema_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* device: CUDA ordinal. stream: a cudaStream_t passed as void* (NULL = the library creates its
+ * own non-blocking stream). */
+int scema_create(scema_ctx **out, int device, void *stream);
+void scema_destroy(scema_ctx *ctx);
+const char *scema_last_error(const scema_ctx *ctx); /* "" when the last call succeeded */
+const char *scema_version(void);
+
+/* ---- ingest: replaces Strain6D storage, add_current_strain (strain2spline.h:75-86) and the
+ *      data half of from_file (:112-134) for a whole batch of quadrature points ---------------
+ * steps:   [sum_i L_i][6] doubles, component order xx yy zz xy xz yz (as one line of strain_<ID>).
+ * offsets: HOST array [n+1], offsets[i] = first step of history i (in steps, not doubles).
+ * ids:     HOST array [n] of history IDs (set_ID, :68-72) or NULL for 0..n-1.
+ * steps_on_device != 0: `steps` is a device pointer on the context's device; it is borrowed (not
+ * copied) and must stay valid until the next scema_set_* call or scema_destroy. */
+int scema_set_histories(scema_ctx *ctx, const double *steps, int steps_on_device,
+                        const uint64_t *offsets, const uint32_t *ids, uint64_t n);
+
+/* ---- K1 resample: replaces Strain6D::splinify for every history (strain2spline.h:140-180;
+ *      tk::spline::set_points / operator(), spline.h:284-396). Result: device matrix
+ *      [n][6*spline_points], row layout p*6+c exactly as Strain6D::spline. Bit-exact. ---------- */
+int scema_resample(scema_ctx *ctx, uint32_t spline_points);
+
+/* Already-resampled rows (what Strain6D::get_spline() returns, :214-221), row-major [n][k].
+ * rows_on_device != 0: borrowed device pointer. ids as above. */
+int scema_set_spline(scema_ctx *ctx, const double *rows, int rows_on_device, uint64_t n, uint32_t k,
+                     const uint32_t *ids);
+
+/* Copy the current spline matrix [n][k] to host memory / expose it on the device. */
+int scema_get_spline(scema_ctx *ctx, double *out_host);
+int scema_spline_info(scema_ctx *ctx, uint64_t *n, uint32_t *k, const double **device_rows);
+
+/* ---- K2+K3 compare: replaces compare_histories_with_all_ranks (strain2spline.h:546-614) with
+ *      compare_L2_norm (:469-484) and the strict threshold of choose_most_similar_history
+ *      (:265-274). Produces the UNIQUE pairs a<b (indices into the batch) with
+ *      diff = compare_L2_norm(a,b) < threshold, sorted by (a,b), diff bit-identical to the
+ *      reference. shard/n_shards: this context evaluates only its share of the pair-matrix tiles
+ *      (one context per GPU, shard = rank); shard=0,n_shards=1 is the whole problem. ---------- */
+int scema_compare(scema_ctx *ctx, double threshold, int variant, uint32_t shard, uint32_t n_shards,
+                  uint64_t *n_edges);
+
+/* Edge list of the last scema_compare. Host copies (any pointer may be NULL): index_a/index_b are
+ * batch indices, diff the distance. cap = array capacity in edges. */
+int scema_get_edges(scema_ctx *ctx, uint32_t *index_a, uint32_t *index_b, double *diff, uint64_t cap);
+/* Device views: keys[e] = (a << key_shift) | b sorted ascending, diff[e]. Valid until the next
+ * compare. */
+int scema_edges_device(scema_ctx *ctx, const uint64_t **keys, const double **diff, uint32_t *key_shift,
+                       uint64_t *n_edges);
+/* Per-history number of partners (size of most_similar_histories, strain2spline.h:429). */
+int scema_get_degrees(scema_ctx *ctx, uint32_t *degree_host);
+
+/* One call for a host caller: set_histories + resample + compare. */
+int scema_cluster(scema_ctx *ctx, const double *steps, const uint64_t *offsets, const uint32_t *ids,
+                  uint64_t n, uint32_t spline_points, double threshold, int variant, uint64_t *n_edges);
+
+/* ---- result files: replaces most_similar_histories_to_file (strain2spline.h:301-314) as driven
+ *      by FE_problem.h:1232-1235 ("<dir>/last.%u.similar_hist") and mpi_comparison_test.cc:99-103
+ *      ("__results/ID_%u.txt"). One file per history of the batch (created even when empty), one
+ *      line "<ID> <otherID> <diff>\n" per partner in the reference's single-rank order (partners in
+ *      ascending batch index), diff in default ostream formatting (%g). fname_pattern has one %u. */
+int scema_write_similar_hist(scema_ctx *ctx, const char *fname_pattern);
+
+/* ---- graph reduction: native replacement of clustering/coarsegrain_dependency_network.py:24-94
+ *      (greedy max-degree removal, ties to the node inserted last). mapping_host[num_gps].
+ *      scema_reduce_edges uses the last compare's edges in the order the per-history files of
+ *      scema_write_similar_hist would be globbed if the directory enumerated in batch order.
+ *      scema_reduce_dir reads "<input_folder>/last.*.similar_hist" in readdir order exactly like the
+ *      script's glob and writes out_mapping_csv ("<i> <m_i>\n", :88-90); no context needed. */
+int scema_reduce_edges(scema_ctx *ctx, uint32_t num_gps, uint32_t *mapping_host, uint64_t *iterations,
+                       uint64_t *neighbours_removed);
+/* Same reduction for an explicit G.add_edge(cell1[k], cell2[k]) call sequence (:57); no context needed. */
+int scema_reduce_calls(const uint32_t *cell1, const uint32_t *cell2, uint64_t n_calls, uint32_t num_gps,
+                       uint32_t *mapping_host, uint64_t *iterations, uint64_t *neighbours_removed);
+int scema_reduce_dir(const char *input_folder, const char *out_mapping_csv, uint32_t num_gps,
+                     uint64_t *iterations, uint64_t *files_read, uint64_t *neighbours_removed);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+#define SCEMA_T_RESAMPLE 0 /* K1 kernel(s) */
+#define SCEMA_T_PREP 1     /* norms + filter-layout copy */
+#define SCEMA_T_FILTER 2   /* K2 GEMM-form filter (DMMA or FMA) or the exact all-pairs kernel */
+#define SCEMA_T_EXACT 3    /* exact recompute of survivors + K3 compaction */
+#define SCEMA_T_SORT 4     /* canonical (a,b) ordering */
+#define SCEMA_T_COUNT 8
+/* CUDA-event durations (ms) of the phases of the last resample/compare on this context. */
+int scema_last_timings(scema_ctx *ctx, float ms[SCEMA_T_COUNT]);
+/* Counters of the last compare: [0] pairs evaluated by the filter, [1] survivors recomputed
+ * exactly, [2] edges, [3] passes (>1 when a buffer had to grow), [4] tiles. */
+int scema_last_counters(scema_ctx *ctx, uint64_t counters[8]);
+/* Total kernels launched by this context so far. */
+uint64_t scema_kernel_launches(const scema_ctx *ctx);
+/* Measured FP64 issue rates on the context's device (TFLOP/s): out[0] DFMA, out[1] DMMA m8n8k4. */
+int scema_fp64_peak(scema_ctx *ctx, double out[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCEMA_HIST_H */

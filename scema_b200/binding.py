@@ -1,0 +1,221 @@
+"""ctypes binding of include/scema_hist.h and include/scema_synth.h (one function per entry point)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+PAIRS_DMMA, PAIRS_FMA, PAIRS_EXACT = 0, 1, 2
+T_NAMES = ("resample", "prep", "filter", "exact", "sort")
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+class ScemaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"scema error {code}: {msg}")
+        self.code = code
+
+
+def lib_path():
+    return os.path.join(_HERE, "libscema_hist.so")
+
+
+def lib():
+    """Load libscema_hist.so. Fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, u64, u32, i32, dbl = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_double
+    P = C.POINTER
+    sig = {
+        "scema_create": (i32, [P(vp), i32, vp]),
+        "scema_destroy": (None, [vp]),
+        "scema_last_error": (C.c_char_p, [vp]),
+        "scema_version": (C.c_char_p, []),
+        "scema_set_histories": (i32, [vp, vp, i32, vp, vp, u64]),
+        "scema_resample": (i32, [vp, u32]),
+        "scema_set_spline": (i32, [vp, vp, i32, u64, u32, vp]),
+        "scema_get_spline": (i32, [vp, vp]),
+        "scema_spline_info": (i32, [vp, P(u64), P(u32), P(vp)]),
+        "scema_compare": (i32, [vp, dbl, i32, u32, u32, P(u64)]),
+        "scema_get_edges": (i32, [vp, vp, vp, vp, u64]),
+        "scema_edges_device": (i32, [vp, P(vp), P(vp), P(u32), P(u64)]),
+        "scema_get_degrees": (i32, [vp, vp]),
+        "scema_cluster": (i32, [vp, vp, vp, vp, u64, u32, dbl, i32, P(u64)]),
+        "scema_write_similar_hist": (i32, [vp, C.c_char_p]),
+        "scema_reduce_edges": (i32, [vp, u32, vp, P(u64), P(u64)]),
+        "scema_reduce_calls": (i32, [vp, vp, u64, u32, vp, P(u64), P(u64)]),
+        "scema_reduce_dir": (i32, [C.c_char_p, C.c_char_p, u32, P(u64), P(u64), P(u64)]),
+        "scema_last_timings": (i32, [vp, P(C.c_float)]),
+        "scema_last_counters": (i32, [vp, P(u64)]),
+        "scema_kernel_launches": (u64, [vp]),
+        "scema_fp64_peak": (i32, [vp, P(dbl)]),
+        "scema_synth_offsets": (i32, [u64, u64, u32, u32, u32, vp]),
+        "scema_synth_histories_device": (i32, [u64, u64, u32, dbl, dbl, vp, vp, vp]),
+        "scema_synth_rows_device": (i32, [u64, u64, u32, u32, dbl, dbl, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTED = (
+    "scema_create scema_destroy scema_last_error scema_version scema_set_histories scema_resample "
+    "scema_set_spline scema_get_spline scema_spline_info scema_compare scema_get_edges scema_edges_device "
+    "scema_get_degrees scema_cluster scema_write_similar_hist scema_reduce_edges scema_reduce_calls scema_reduce_dir "
+    "scema_last_timings scema_last_counters scema_kernel_launches scema_fp64_peak scema_synth_offsets "
+    "scema_synth_histories_device scema_synth_rows_device").split()
+
+
+def _ptr(a):
+    """Host numpy array or raw integer (device pointer) -> c_void_p value."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a)
+
+
+def reduce_dir(input_folder, out_mapping_csv, num_gps):
+    """Native coarsegrain_dependency_network.py. -> (iterations, files, neighbours_removed)."""
+    it, nf, nr = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    rc = lib().scema_reduce_dir(os.fsencode(input_folder), os.fsencode(out_mapping_csv), num_gps,
+                                C.byref(it), C.byref(nf), C.byref(nr))
+    if rc:
+        raise ScemaError(rc, "reduce_dir failed")
+    return int(it.value), int(nf.value), int(nr.value)
+
+
+class HistCluster:
+    """One context = one GPU + one stream. Methods map 1:1 onto include/scema_hist.h."""
+
+    def __init__(self, device=0, stream=None):
+        self._L = lib()
+        self._h = C.c_void_p(None)
+        rc = self._L.scema_create(C.byref(self._h), int(device), _ptr(stream) if stream else None)
+        if rc:
+            self._h = None
+            raise ScemaError(rc, "scema_create failed (no CUDA device? there is no CPU fallback)")
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.scema_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise ScemaError(rc, self._L.scema_last_error(self._h).decode())
+
+    # ---- ingest ----
+    def set_histories(self, steps, offsets, ids=None, device_ptr=None):
+        """steps: host ndarray [sumL,6] (or pass device_ptr=int for a device-resident buffer)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)
+        if device_ptr is not None:
+            self._ck(self._L.scema_set_histories(self._h, int(device_ptr), 1, _ptr(offsets), _ptr(ids_a), n))
+        else:
+            steps = np.ascontiguousarray(steps, dtype=np.float64)
+            self._ck(self._L.scema_set_histories(self._h, _ptr(steps), 0, _ptr(offsets), _ptr(ids_a), n))
+
+    def resample(self, spline_points):
+        self._ck(self._L.scema_resample(self._h, int(spline_points)))
+
+    def set_spline(self, rows=None, ids=None, device_ptr=None, n=None, k=None):
+        ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)
+        if device_ptr is not None:
+            self._ck(self._L.scema_set_spline(self._h, int(device_ptr), 1, int(n), int(k), _ptr(ids_a)))
+        else:
+            rows = np.ascontiguousarray(rows, dtype=np.float64)
+            self._ck(self._L.scema_set_spline(self._h, _ptr(rows), 0, rows.shape[0], rows.shape[1], _ptr(ids_a)))
+
+    def spline_info(self):
+        n, k, p = C.c_uint64(0), C.c_uint32(0), C.c_void_p(None)
+        self._ck(self._L.scema_spline_info(self._h, C.byref(n), C.byref(k), C.byref(p)))
+        return int(n.value), int(k.value), p.value
+
+    def get_spline(self):
+        n, k, _ = self.spline_info()
+        out = np.empty((n, k), dtype=np.float64)
+        self._ck(self._L.scema_get_spline(self._h, _ptr(out)))
+        return out
+
+    # ---- compare ----
+    def compare(self, threshold, variant=PAIRS_DMMA, shard=0, n_shards=1):
+        ne = C.c_uint64(0)
+        self._ck(self._L.scema_compare(self._h, float(threshold), int(variant), int(shard), int(n_shards), C.byref(ne)))
+        self.n_edges = int(ne.value)
+        return self.n_edges
+
+    def get_edges(self):
+        m = self.n_edges
+        a = np.empty(m, dtype=np.uint32)
+        b = np.empty(m, dtype=np.uint32)
+        d = np.empty(m, dtype=np.float64)
+        self._ck(self._L.scema_get_edges(self._h, _ptr(a), _ptr(b), _ptr(d), m))
+        return a, b, d
+
+    def edges_device(self):
+        keys, diff, sh, ne = C.c_void_p(None), C.c_void_p(None), C.c_uint32(0), C.c_uint64(0)
+        self._ck(self._L.scema_edges_device(self._h, C.byref(keys), C.byref(diff), C.byref(sh), C.byref(ne)))
+        return keys.value, diff.value, int(sh.value), int(ne.value)
+
+    def get_degrees(self, n):
+        out = np.empty(n, dtype=np.uint32)
+        self._ck(self._L.scema_get_degrees(self._h, _ptr(out)))
+        return out
+
+    def cluster(self, steps, offsets, ids, spline_points, threshold, variant=PAIRS_DMMA):
+        steps = np.ascontiguousarray(steps, dtype=np.float64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)
+        ne = C.c_uint64(0)
+        self._ck(self._L.scema_cluster(self._h, _ptr(steps), _ptr(offsets), _ptr(ids_a), len(offsets) - 1,
+                                       int(spline_points), float(threshold), int(variant), C.byref(ne)))
+        self.n_edges = int(ne.value)
+        return self.n_edges
+
+    # ---- outputs ----
+    def write_similar_hist(self, pattern):
+        self._ck(self._L.scema_write_similar_hist(self._h, os.fsencode(pattern)))
+
+    def reduce_edges(self, num_gps):
+        mapping = np.empty(num_gps, dtype=np.uint32)
+        it, nr = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self._L.scema_reduce_edges(self._h, int(num_gps), _ptr(mapping), C.byref(it), C.byref(nr)))
+        return mapping, int(it.value), int(nr.value)
+
+    # ---- instrumentation ----
+    def timings(self):
+        ms = (C.c_float * 8)()
+        self._ck(self._L.scema_last_timings(self._h, ms))
+        return {T_NAMES[i]: float(ms[i]) for i in range(len(T_NAMES))}
+
+    def counters(self):
+        c = (C.c_uint64 * 8)()
+        self._ck(self._L.scema_last_counters(self._h, c))
+        return {"pairs": int(c[0]), "survivors": int(c[1]), "edges": int(c[2]), "passes": int(c[3]), "tiles": int(c[4])}
+
+    def kernel_launches(self):
+        return int(self._L.scema_kernel_launches(self._h))
+
+    def fp64_peak(self):
+        out = (C.c_double * 2)()
+        self._ck(self._L.scema_fp64_peak(self._h, out))
+        return {"dfma_tflops": float(out[0]), "dmma_tflops": float(out[1])}

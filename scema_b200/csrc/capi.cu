@@ -1,0 +1,309 @@
+// C ABI of libscema_hist.so (include/scema_hist.h). Thin host glue: context, ingest, result access.
+#include "common.cuh"
+#include <new>
+#include <algorithm>
+
+using namespace scema;
+
+extern "C" {
+
+const char *scema_version(void) { return "scema-b200-histcluster 0.1 (sm_100a)"; }
+
+int scema_create(scema_ctx **out, int device, void *stream)
+{
+    if (!out) return SCEMA_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return SCEMA_ERR_CUDA;  // no CPU fallback by design
+    }
+    scema_ctx *c = new (std::nothrow) scema_ctx();
+    if (!c) return SCEMA_ERR_NOMEM;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return SCEMA_ERR_CUDA; }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { delete c; return SCEMA_ERR_CUDA; }
+    c->sm_count = p.multiProcessorCount;
+    c->smem_optin = p.sharedMemPerBlockOptin;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SCEMA_ERR_CUDA; }
+        c->own_stream = true;
+    }
+    for (int i = 0; i < 2 * SCEMA_T_COUNT; i++)
+        if (cudaEventCreate(&c->ev[i]) != cudaSuccess) { delete c; return SCEMA_ERR_CUDA; }
+    *out = c;
+    return SCEMA_OK;
+}
+
+void scema_destroy(scema_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->steps_own.release(); c->d_offsets.release(); c->d_tables.release(); c->d_table_index.release();
+    c->zscratch.release(); c->spline_own.release(); c->d_filter.release(); c->d_halfnorm.release();
+    c->d_blockmax.release(); c->d_panel_start.release(); c->d_cand.release(); c->d_counters.release();
+    for (int b = 0; b < 2; b++) { c->d_edge_key[b].release(); c->d_edge_val[b].release(); }
+    c->d_sort_tmp.release();
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    for (int i = 0; i < 2 * SCEMA_T_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *scema_last_error(const scema_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+static int enter(scema_ctx *c)
+{
+    if (!c) return SCEMA_ERR_INVALID;
+    c->err.clear();
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, SCEMA_ERR_CUDA, "cudaSetDevice failed");
+    return SCEMA_OK;
+}
+
+static void set_ids(scema_ctx *c, const uint32_t *ids, uint64_t n)
+{
+    c->ids.resize(n);
+    if (ids) std::copy(ids, ids + n, c->ids.begin());
+    else for (uint64_t i = 0; i < n; i++) c->ids[i] = (uint32_t)i;
+}
+
+int scema_set_histories(scema_ctx *c, const double *steps, int steps_on_device, const uint64_t *offsets,
+                        const uint32_t *ids, uint64_t n)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    if (n && (!offsets || !steps)) return fail(c, SCEMA_ERR_INVALID, "set_histories: null pointer");
+    if (n >= (1ull << 32)) return fail(c, SCEMA_ERR_INVALID, "set_histories: more than 2^32-1 histories");
+    c->have_histories = false;
+    c->have_spline = false;
+    c->have_edges = false;
+    c->n = n;
+    if (offsets) c->h_offsets.assign(offsets, offsets + n + 1);
+    else c->h_offsets.assign(1, 0);
+    uint32_t mx = 0, mn = 0xffffffffu;
+    for (uint64_t i = 0; i < n; i++) {
+        if (offsets[i + 1] < offsets[i]) return fail(c, SCEMA_ERR_INVALID, "set_histories: offsets not monotone");
+        uint64_t L = offsets[i + 1] - offsets[i];
+        if (L > 0x7fffffffull / 64) return fail(c, SCEMA_ERR_INVALID, "set_histories: history too long");
+        mx = std::max<uint32_t>(mx, (uint32_t)L);
+        mn = std::min<uint32_t>(mn, (uint32_t)L);
+    }
+    c->max_len = mx;
+    c->min_len = n ? mn : 0;
+    c->total_steps = n ? offsets[n] : 0;  // offsets index `steps` absolutely
+    set_ids(c, ids, n);
+    SCEMA_CUDA(c, c->d_offsets.reserve((n + 1) * sizeof(uint64_t)));
+    SCEMA_CUDA(c, cudaMemcpyAsync(c->d_offsets.p, c->h_offsets.data(), (n + 1) * sizeof(uint64_t),
+                                  cudaMemcpyHostToDevice, c->stream));
+    if (steps_on_device) {
+        c->d_steps = steps;
+    } else {
+        const uint64_t last = n ? offsets[n] : 0;
+        SCEMA_CUDA(c, c->steps_own.reserve(std::max<uint64_t>(last, 1) * 6 * sizeof(double)));
+        if (last)
+            SCEMA_CUDA(c, cudaMemcpyAsync(c->steps_own.p, steps, last * 6 * sizeof(double), cudaMemcpyHostToDevice,
+                                          c->stream));
+        c->d_steps = c->steps_own.as<double>();
+    }
+    SCEMA_CUDA(c, cudaStreamSynchronize(c->stream));  // h_offsets / caller buffers may be pageable
+    c->have_histories = true;
+    return SCEMA_OK;
+}
+
+int scema_resample(scema_ctx *c, uint32_t spline_points)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    c->ev_used[SCEMA_T_RESAMPLE] = false;
+    return resample_run(c, spline_points);
+}
+
+int scema_set_spline(scema_ctx *c, const double *rows, int rows_on_device, uint64_t n, uint32_t k, const uint32_t *ids)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    if (n && k && !rows) return fail(c, SCEMA_ERR_INVALID, "set_spline: null pointer");
+    if (n >= (1ull << 32)) return fail(c, SCEMA_ERR_INVALID, "set_spline: more than 2^32-1 histories");
+    c->have_histories = false;
+    c->have_edges = false;
+    c->n = n;
+    c->K = k;
+    set_ids(c, ids, n);
+    if (rows_on_device) {
+        c->d_spline = rows;
+    } else {
+        SCEMA_CUDA(c, c->spline_own.reserve(std::max<uint64_t>(n * k, 1) * sizeof(double)));
+        if (n * k != 0)
+            SCEMA_CUDA(c, cudaMemcpyAsync(c->spline_own.p, rows, n * k * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        SCEMA_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->d_spline = c->spline_own.as<double>();
+    }
+    c->spline_version++;
+    c->have_spline = true;
+    return SCEMA_OK;
+}
+
+int scema_get_spline(scema_ctx *c, double *out_host)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    if (!c->have_spline) return fail(c, SCEMA_ERR_STATE, "Spline is not up to date.");
+    if (c->n * c->K == 0) return SCEMA_OK;
+    if (!out_host) return fail(c, SCEMA_ERR_INVALID, "get_spline: null pointer");
+    SCEMA_CUDA(c, cudaMemcpyAsync(out_host, c->d_spline, c->n * c->K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SCEMA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SCEMA_OK;
+}
+
+int scema_spline_info(scema_ctx *c, uint64_t *n, uint32_t *k, const double **device_rows)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    if (!c->have_spline) return fail(c, SCEMA_ERR_STATE, "Spline is not up to date.");
+    if (n) *n = c->n;
+    if (k) *k = c->K;
+    if (device_rows) *device_rows = c->d_spline;
+    return SCEMA_OK;
+}
+
+int scema_compare(scema_ctx *c, double threshold, int variant, uint32_t shard, uint32_t n_shards, uint64_t *n_edges)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    rc = compare_run(c, threshold, variant, shard, n_shards);
+    if (rc) { c->have_edges = false; return rc; }
+    if (n_edges) *n_edges = c->n_edges;
+    return SCEMA_OK;
+}
+
+int scema_get_edges(scema_ctx *c, uint32_t *ia, uint32_t *ib, double *diff, uint64_t cap)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    if (!c->have_edges) return fail(c, SCEMA_ERR_STATE, "get_edges: no compare result");
+    const uint64_t m = std::min<uint64_t>(cap, c->n_edges);
+    if (m == 0) return SCEMA_OK;
+    if (diff) SCEMA_CUDA(c, cudaMemcpyAsync(diff, c->d_edge_val[c->edge_cur].p, m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<uint64_t> keys;
+    if (ia || ib) {
+        keys.resize(m);
+        SCEMA_CUDA(c, cudaMemcpyAsync(keys.data(), c->d_edge_key[c->edge_cur].p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    SCEMA_CUDA(c, cudaStreamSynchronize(c->stream));
+    const uint64_t mask = (1ull << c->key_shift) - 1;
+    for (uint64_t e = 0; e < keys.size(); e++) {
+        if (ia) ia[e] = (uint32_t)(keys[e] >> c->key_shift);
+        if (ib) ib[e] = (uint32_t)(keys[e] & mask);
+    }
+    return SCEMA_OK;
+}
+
+int scema_edges_device(scema_ctx *c, const uint64_t **keys, const double **diff, uint32_t *key_shift, uint64_t *n_edges)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    if (!c->have_edges) return fail(c, SCEMA_ERR_STATE, "edges_device: no compare result");
+    if (keys) *keys = c->d_edge_key[c->edge_cur].as<uint64_t>();
+    if (diff) *diff = c->d_edge_val[c->edge_cur].as<double>();
+    if (key_shift) *key_shift = c->key_shift;
+    if (n_edges) *n_edges = c->n_edges;
+    return SCEMA_OK;
+}
+
+int scema_get_degrees(scema_ctx *c, uint32_t *degree_host)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    if (!c->have_edges) return fail(c, SCEMA_ERR_STATE, "get_degrees: no compare result");
+    std::vector<uint32_t> a(c->n_edges), b(c->n_edges);
+    rc = scema_get_edges(c, a.data(), b.data(), nullptr, c->n_edges);
+    if (rc) return rc;
+    std::fill(degree_host, degree_host + c->n, 0u);
+    for (uint64_t e = 0; e < c->n_edges; e++) { degree_host[a[e]]++; degree_host[b[e]]++; }
+    return SCEMA_OK;
+}
+
+int scema_cluster(scema_ctx *c, const double *steps, const uint64_t *offsets, const uint32_t *ids, uint64_t n,
+                  uint32_t spline_points, double threshold, int variant, uint64_t *n_edges)
+{
+    int rc = scema_set_histories(c, steps, 0, offsets, ids, n);
+    if (rc) return rc;
+    rc = scema_resample(c, spline_points);
+    if (rc) return rc;
+    return scema_compare(c, threshold, variant, 0, 1, n_edges);
+}
+
+int scema_write_similar_hist(scema_ctx *c, const char *fname_pattern)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    if (!c->have_edges) return fail(c, SCEMA_ERR_STATE, "write_similar_hist: no compare result");
+    if (!fname_pattern) return fail(c, SCEMA_ERR_INVALID, "write_similar_hist: null pattern");
+    return write_similar_hist(c, fname_pattern);
+}
+
+int scema_reduce_edges(scema_ctx *c, uint32_t num_gps, uint32_t *mapping_host, uint64_t *iterations,
+                       uint64_t *neighbours_removed)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    if (!c->have_edges) return fail(c, SCEMA_ERR_STATE, "reduce_edges: no compare result");
+    const uint64_t m = c->n_edges;
+    std::vector<uint32_t> a(m), b(m);
+    std::vector<double> d(m);
+    rc = scema_get_edges(c, a.data(), b.data(), d.data(), m);
+    if (rc) return rc;
+    // add_edge call sequence of the per-history files read in batch order: history k lists its
+    // partners in ascending batch index (smaller ones first), see host_io.cc
+    std::vector<uint64_t> start(c->n + 2, 0);
+    for (uint64_t e = 0; e < m; e++) { start[a[e] + 1]++; start[b[e] + 1]++; }
+    for (uint64_t i = 0; i < c->n; i++) start[i + 1] += start[i];
+    std::vector<uint64_t> fill(start.begin(), start.begin() + c->n);
+    std::vector<uint32_t> eu(2 * m), ev(2 * m);
+    for (uint64_t e = 0; e < m; e++) {
+        if (d[e] == 0.0) return fail(c, SCEMA_ERR_MAPPING, "reduce: dist == 0 (the script raises ZeroDivisionError)");
+        uint64_t q = fill[b[e]]++; eu[q] = c->ids[b[e]]; ev[q] = c->ids[a[e]];
+    }
+    for (uint64_t e = 0; e < m; e++) { uint64_t q = fill[a[e]]++; eu[q] = c->ids[a[e]]; ev[q] = c->ids[b[e]]; }
+    rc = reduce_graph_calls(eu.data(), ev.data(), 2 * m, num_gps, mapping_host, iterations, neighbours_removed);
+    if (rc) return fail(c, rc, "reduce: history ID >= num_gps (the script raises IndexError)");
+    return SCEMA_OK;
+}
+
+int scema_last_timings(scema_ctx *c, float ms[SCEMA_T_COUNT])
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    SCEMA_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int w = 0; w < SCEMA_T_COUNT; w++) {
+        ms[w] = 0.f;
+        if (c->ev_used[w]) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, c->ev[2 * w], c->ev[2 * w + 1]) == cudaSuccess) ms[w] = t;
+            else cudaGetLastError();
+        }
+    }
+    return SCEMA_OK;
+}
+
+int scema_last_counters(scema_ctx *c, uint64_t counters[8])
+{
+    if (!c) return SCEMA_ERR_INVALID;
+    for (int i = 0; i < 8; i++) counters[i] = c->counters[i];
+    return SCEMA_OK;
+}
+
+uint64_t scema_kernel_launches(const scema_ctx *c) { return c ? c->launches : 0; }
+
+int scema_fp64_peak(scema_ctx *c, double out[2])
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    return fp64_peak_run(c, out);
+}
+
+}  // extern "C"

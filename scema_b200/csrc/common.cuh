@@ -1,0 +1,138 @@
+// Internal declarations shared by the translation units of libscema_hist.so.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../../include/scema_hist.h"
+
+namespace scema {
+
+constexpr int TILE = 128;         // rows per pair-matrix tile side (K2)
+constexpr int PANEL_ROWBLOCKS = 16;  // row blocks per scheduling panel (L2 reuse of the B tiles)
+
+// Growable device buffer.
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need)
+    {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        size_t want = need + need / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        bytes = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// Layout of the filter copy F of the spline matrix S (see DESIGN.md "K2 data layout"):
+// F[chunk][row_padded][kc] with K zero-padded to n_chunks*kc, rows zero-padded to a multiple of
+// TILE. kc % 8 == 4 makes the DMMA fragment loads (lane -> row g, column t) bank-conflict free
+// when a TILE x kc block lands densely in shared memory.
+struct FilterLayout {
+    uint32_t K = 0, kc = 0, n_chunks = 0;
+    uint64_t n = 0, n_pad = 0, n_blocks = 0;
+};
+
+struct SplineTable {  // per distinct history length L: factorised tridiagonal system + sample map
+    uint64_t offset;  // in doubles, into tables buffer
+};
+
+}  // namespace scema
+
+struct scema_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    uint64_t launches = 0;
+
+    // ---- raw histories
+    uint64_t n = 0;              // histories in the batch
+    uint64_t total_steps = 0;
+    uint32_t max_len = 0, min_len = 0;
+    const double *d_steps = nullptr;  // borrowed or = steps_own
+    scema::DevBuf steps_own, d_offsets;
+    std::vector<uint64_t> h_offsets;
+    std::vector<uint32_t> ids;
+    bool have_histories = false;
+
+    // ---- K1 tables: one per (L) for the current P
+    uint32_t table_P = 0;
+    std::map<uint32_t, uint64_t> table_off;  // L -> offset (doubles) in d_tables
+    scema::DevBuf d_tables, d_table_index;   // d_table_index: int64 [max_len+1] -> offset or -1
+    uint64_t tables_used = 0;                // doubles
+    uint32_t table_index_len = 0;
+    scema::DevBuf zscratch;
+
+    // ---- spline matrix S [n][K]
+    uint32_t K = 0;
+    const double *d_spline = nullptr;  // borrowed or = spline_own
+    scema::DevBuf spline_own;
+    bool have_spline = false;
+
+    // ---- K2 filter copy
+    scema::FilterLayout fl;
+    scema::DevBuf d_filter, d_halfnorm, d_blockmax, d_panel_start;
+    uint64_t filter_for_spline_version = 0, spline_version = 0;
+    int filter_variant = -1;
+
+    // ---- candidate queue + edges
+    scema::DevBuf d_cand, d_counters;  // counters: [0] candidates, [1] edges, [2] flags
+    scema::DevBuf d_edge_key[2], d_edge_val[2], d_sort_tmp;
+    uint64_t cand_cap = 0, edge_cap = 0;
+    int edge_cur = 0;            // which of the double buffers holds the sorted result
+    uint64_t n_edges = 0;
+    uint32_t key_shift = 0;
+    bool have_edges = false;
+    uint64_t *h_counters = nullptr;  // pinned, 8 entries
+
+    // ---- instrumentation
+    cudaEvent_t ev[2 * SCEMA_T_COUNT] = {};
+    bool ev_used[SCEMA_T_COUNT] = {};
+    uint64_t counters[8] = {};
+};
+
+namespace scema {
+
+#define SCEMA_CUDA(ctx, call)                                                                   \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                   \
+            return e__ == cudaErrorMemoryAllocation ? SCEMA_ERR_NOMEM : SCEMA_ERR_CUDA;         \
+        }                                                                                       \
+    } while (0)
+
+inline int fail(scema_ctx *ctx, int code, const std::string &msg)
+{
+    ctx->err = msg;
+    return code;
+}
+
+inline void t_begin(scema_ctx *c, int which) { cudaEventRecord(c->ev[2 * which], c->stream); c->ev_used[which] = true; }
+inline void t_end(scema_ctx *c, int which) { cudaEventRecord(c->ev[2 * which + 1], c->stream); }
+
+// resample.cu
+int resample_run(scema_ctx *ctx, uint32_t P);
+// pairs.cu
+int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards);
+int fp64_peak_run(scema_ctx *ctx, double out[2]);
+// host_io.cc
+int write_similar_hist(scema_ctx *ctx, const char *pattern);
+int reduce_graph_calls(const uint32_t *eu, const uint32_t *ev, uint64_t n_calls, uint32_t num_gps,
+                       uint32_t *mapping, uint64_t *iterations, uint64_t *neighbours_removed);
+
+}  // namespace scema

@@ -1,0 +1,188 @@
+// Host-side ends of the path: the per-history similarity files and the native graph reduction.
+//
+//  * write_similar_hist: Strain6D::most_similar_histories_to_file (reference
+//    headers/strain2spline.h:301-314) for every history of the batch, as FE_problem.h:1232-1235 and
+//    clustering/mpi_comparison_test.cc:99-103 call it.
+//  * reduce_graph_calls / scema_reduce_dir: clustering/coarsegrain_dependency_network.py:24-94 —
+//    greedy removal of the maximum-degree node with its neighbours; ties go to the node that
+//    entered the networkx node dict last (stable sort + [-1], :20-21). The script re-sorts all
+//    nodes every iteration (O(V^2 log V)); here a lazy max-heap keyed by (degree, insertion
+//    position) gives O(E log E) with the identical choice sequence.
+#include "common.cuh"
+#include <algorithm>
+#include <dirent.h>
+#include <queue>
+#include <string>
+#include <sys/types.h>
+#include <unordered_map>
+
+namespace scema {
+
+int write_similar_hist(scema_ctx *c, const char *pattern)
+{
+    const uint64_t m = c->n_edges, n = c->n;
+    std::vector<uint32_t> a(m), b(m);
+    std::vector<double> d(m);
+    int rc = scema_get_edges(c, a.data(), b.data(), d.data(), m);
+    if (rc) return rc;
+    // history k lists partners in ascending batch index: those below k first (edges (i,k), which
+    // are ascending in i for fixed k because the list is sorted by (a,b)), then those above k.
+    // This is the order in which the single-rank loop strain2spline.h:603-611 appends them.
+    std::vector<uint64_t> start(n + 2, 0);
+    for (uint64_t e = 0; e < m; e++) { start[a[e] + 1]++; start[b[e] + 1]++; }
+    for (uint64_t i = 0; i < n; i++) start[i + 1] += start[i];
+    std::vector<uint64_t> fill(start.begin(), start.begin() + n);
+    std::vector<uint32_t> other(2 * m);
+    std::vector<double> dist(2 * m);
+    for (uint64_t e = 0; e < m; e++) { uint64_t q = fill[b[e]]++; other[q] = a[e]; dist[q] = d[e]; }
+    for (uint64_t e = 0; e < m; e++) { uint64_t q = fill[a[e]]++; other[q] = b[e]; dist[q] = d[e]; }
+    char name[4096];
+    std::string buf;
+    char line[96];
+    for (uint64_t k = 0; k < n; k++) {
+        snprintf(name, sizeof name, pattern, c->ids[k]);
+        FILE *f = fopen(name, "w");
+        if (!f) return fail(c, SCEMA_ERR_IO, std::string("Could not open ") + name + " for writing.");
+        buf.clear();
+        for (uint64_t q = start[k]; q < start[k + 1]; q++) {
+            // default ostream formatting of a double == %g (6 significant digits)
+            int len = snprintf(line, sizeof line, "%u %u %g\n", c->ids[k], c->ids[other[q]], dist[q]);
+            buf.append(line, len);
+        }
+        if (!buf.empty() && fwrite(buf.data(), 1, buf.size(), f) != buf.size()) {
+            fclose(f);
+            return fail(c, SCEMA_ERR_IO, std::string("short write to ") + name);
+        }
+        fclose(f);
+    }
+    return SCEMA_OK;
+}
+
+// add_edge(eu[k], ev[k]) call sequence -> mapping. Returns 0, or SCEMA_ERR_MAPPING if an ID is
+// >= num_gps (the script's IndexError).
+int reduce_graph_calls(const uint32_t *eu, const uint32_t *ev, uint64_t n_calls, uint32_t num_gps, uint32_t *mapping,
+                       uint64_t *iterations, uint64_t *neighbours_removed)
+{
+    for (uint32_t i = 0; i < num_gps; i++) mapping[i] = i;
+    // node dict order = first appearance, cell1 before cell2
+    std::vector<int64_t> pos(num_gps, -1);
+    std::vector<uint32_t> order;
+    for (uint64_t e = 0; e < n_calls; e++) {
+        if (eu[e] >= num_gps || ev[e] >= num_gps) return SCEMA_ERR_MAPPING;
+        if (pos[eu[e]] < 0) { pos[eu[e]] = (int64_t)order.size(); order.push_back(eu[e]); }
+        if (pos[ev[e]] < 0) { pos[ev[e]] = (int64_t)order.size(); order.push_back(ev[e]); }
+    }
+    // deduplicated adjacency (both directions)
+    std::vector<uint64_t> arcs;
+    arcs.reserve(2 * n_calls);
+    for (uint64_t e = 0; e < n_calls; e++) {
+        arcs.push_back(((uint64_t)eu[e] << 32) | ev[e]);
+        arcs.push_back(((uint64_t)ev[e] << 32) | eu[e]);
+    }
+    std::sort(arcs.begin(), arcs.end());
+    arcs.erase(std::unique(arcs.begin(), arcs.end()), arcs.end());
+    std::vector<uint64_t> start((size_t)num_gps + 1, 0);
+    for (uint64_t x : arcs) start[(x >> 32) + 1]++;
+    for (uint32_t i = 0; i < num_gps; i++) start[i + 1] += start[i];
+    std::vector<int64_t> deg(num_gps, 0);
+    for (uint32_t i = 0; i < num_gps; i++) {
+        deg[i] = (int64_t)(start[i + 1] - start[i]);
+        for (uint64_t q = start[i]; q < start[i + 1]; q++)
+            if ((uint32_t)arcs[q] == i) deg[i]++;  // a self loop counts twice in networkx
+    }
+    std::vector<uint8_t> alive(num_gps, 0);
+    typedef std::pair<int64_t, int64_t> Key;  // (degree, insertion position): max = script's choice
+    std::priority_queue<std::pair<Key, uint32_t>> heap;
+    for (uint32_t v : order) { alive[v] = 1; heap.push({{deg[v], pos[v]}, v}); }
+    uint64_t remaining = order.size(), iters = 0, removed = 0;
+    std::vector<uint32_t> batch;
+    while (remaining > 0) {
+        uint32_t best;
+        while (true) {
+            auto top = heap.top();
+            heap.pop();
+            best = top.second;
+            if (alive[best] && top.first.first == deg[best]) break;
+        }
+        mapping[best] = best;
+        batch.clear();
+        batch.push_back(best);
+        for (uint64_t q = start[best]; q < start[best + 1]; q++) {
+            uint32_t w = (uint32_t)arcs[q];
+            if (!alive[w]) continue;
+            mapping[w] = best;
+            removed++;
+            if (w != best) batch.push_back(w);
+        }
+        for (uint32_t rnode : batch) alive[rnode] = 0;
+        for (uint32_t rnode : batch)
+            for (uint64_t q = start[rnode]; q < start[rnode + 1]; q++) {
+                uint32_t w = (uint32_t)arcs[q];
+                if (alive[w]) { deg[w]--; heap.push({{deg[w], pos[w]}, w}); }
+            }
+        remaining -= batch.size();
+        iters++;
+    }
+    if (iterations) *iterations = iters;
+    if (neighbours_removed) *neighbours_removed = removed;
+    return SCEMA_OK;
+}
+
+}  // namespace scema
+
+extern "C" int scema_reduce_calls(const uint32_t *cell1, const uint32_t *cell2, uint64_t n_calls, uint32_t num_gps,
+                                  uint32_t *mapping_host, uint64_t *iterations, uint64_t *neighbours_removed)
+{
+    if ((n_calls && (!cell1 || !cell2)) || (num_gps && !mapping_host)) return SCEMA_ERR_INVALID;
+    return scema::reduce_graph_calls(cell1, cell2, n_calls, num_gps, mapping_host, iterations, neighbours_removed);
+}
+
+extern "C" int scema_reduce_dir(const char *input_folder, const char *out_mapping_csv, uint32_t num_gps,
+                                uint64_t *iterations, uint64_t *files_read, uint64_t *neighbours_removed)
+{
+    if (!input_folder || !out_mapping_csv) return SCEMA_ERR_INVALID;
+    DIR *dirp = opendir(input_folder);
+    if (!dirp) return SCEMA_ERR_IO;
+    // glob(input_folder + "/last.*.similar_hist") (coarsegrain_dependency_network.py:48): directory
+    // order, no sorting; fnmatch '*' may match the empty string and dots.
+    std::vector<std::string> names;
+    const std::string pre = "last.", suf = ".similar_hist";
+    while (struct dirent *dp = readdir(dirp)) {
+        std::string nm = dp->d_name;
+        if (nm.size() >= pre.size() + suf.size() && nm.compare(0, pre.size(), pre) == 0 &&
+            nm.compare(nm.size() - suf.size(), suf.size(), suf) == 0)
+            names.push_back(nm);
+    }
+    closedir(dirp);
+    std::vector<uint32_t> eu, ev;
+    for (const std::string &nm : names) {
+        std::string path = std::string(input_folder) + "/" + nm;
+        FILE *f = fopen(path.c_str(), "r");
+        if (!f) return SCEMA_ERR_IO;
+        char line[512];
+        while (fgets(line, sizeof line, f)) {
+            long long c1, c2;
+            double dist;
+            char extra;
+            // `cell1, cell2, dist = line.split()` needs exactly three tokens (:53)
+            if (sscanf(line, "%lld %lld %lf %c", &c1, &c2, &dist, &extra) != 3) { fclose(f); return SCEMA_ERR_INVALID; }
+            if (dist == 0.0) { fclose(f); return SCEMA_ERR_MAPPING; }  // 1.0/dist raises (:57)
+            if (c1 < 0 || c2 < 0 || c1 >= (long long)num_gps || c2 >= (long long)num_gps) { fclose(f); return SCEMA_ERR_MAPPING; }
+            eu.push_back((uint32_t)c1);
+            ev.push_back((uint32_t)c2);
+        }
+        fclose(f);
+    }
+    std::vector<uint32_t> mapping(num_gps);
+    uint64_t it = 0, nr = 0;
+    int rc = scema::reduce_graph_calls(eu.data(), ev.data(), eu.size(), num_gps, mapping.data(), &it, &nr);
+    if (rc) return rc;
+    FILE *o = fopen(out_mapping_csv, "w");
+    if (!o) return SCEMA_ERR_IO;
+    for (uint32_t i = 0; i < num_gps; i++) fprintf(o, "%u %u\n", i, mapping[i]);
+    fclose(o);
+    if (iterations) *iterations = it;
+    if (files_read) *files_read = names.size();
+    if (neighbours_removed) *neighbours_removed = nr;
+    return SCEMA_OK;
+}

@@ -1,0 +1,769 @@
+// K2 + K3 — all-pairs L2 distance between resampled histories, thresholded, compacted (sm_100a).
+//
+// Replaces the double loop of compare_histories_with_all_ranks (reference
+// headers/strain2spline.h:603-611, and the MPI ring :571-599) that calls compare_L2_norm
+// (:469-484) and choose_most_similar_history (:265-274, strict `diff < threshold`).
+//
+// Design (DESIGN.md "K2"):
+//  * k_filter<..>: GEMM-form filter. For a 128x128 tile of the pair matrix it evaluates
+//        acc = a.b - (|a|^2 + |b|^2)/2  ( = -d^2/2 )
+//    as an FP64 dense contraction — DMMA (mma.sync m8n8k4 f64, the only FP64 tensor shape sm_100a
+//    has in SASS) or, for comparison, CUDA-core DFMA register tiles — over operand tiles staged
+//    into shared memory by the TMA engine (cp.async.bulk + mbarrier, double buffered), and
+//    rejects every pair that PROVABLY fails the threshold: -2*acc > T_tile, where T_tile is
+//    thr^2 widened by a rigorous rounding-error band that scales with the row norms.
+//    Everything else (true edges plus a guard band around the threshold) is a survivor.
+//  * Survivors go through a warp-aggregated atomic append into a candidate queue (K3 pattern).
+//  * k_exact_queue recomputes every survivor by direct differences in the reference's exact
+//    operation order (sequential k, separate multiply and add, IEEE sqrt) and appends the edges
+//    (key = a<<shift|b, diff) with warp-aggregated atomics. Every emitted distance therefore
+//    carries the reference's bits and the edge SET is identical to the reference's.
+//  * k_exact_all is the filter-free anchor (SCEMA_PAIRS_EXACT) and the fallback when survivors
+//    are too dense for a queue.
+//  * The edge list is put in canonical (a,b) order with a radix sort on the packed key.
+#include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cmath>
+#include <algorithm>
+
+namespace scema {
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers (mbarrier + 1-D bulk tensor-memory-accelerator copies)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// global -> shared bulk copy executed by the TMA engine (SASS: UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact pair distance: compare_L2_norm, strain2spline.h:476-483, operation for operation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double exact_l2(const double *__restrict__ a, const double *__restrict__ b, uint32_t K)
+{
+    double sum = 0.0;
+#pragma unroll 4
+    for (uint32_t k = 0; k < K; k++) {
+        double diff = __dsub_rn(__ldg(a + k), __ldg(b + k));
+        sum = __dadd_rn(sum, __dmul_rn(diff, diff));
+    }
+    return __dsqrt_rn(sum);
+}
+
+// K3: warp-aggregated append. All 32 lanes must call. Returns nothing; drops (but still counts)
+// entries beyond cap so the host can detect overflow and retry with a larger buffer.
+__device__ __forceinline__ void warp_append_edge(bool keep, uint64_t key, double val, unsigned long long *counter,
+                                                 uint64_t cap, uint64_t *keys, double *vals)
+{
+    unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m == 0) return;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (keep) {
+        uint64_t pos = base + __popc(m & ((1u << lane) - 1));
+        if (pos < cap) { keys[pos] = key; vals[pos] = val; }
+    }
+}
+__device__ __forceinline__ void warp_append_cand(bool keep, uint64_t packed, unsigned long long *counter, uint64_t cap,
+                                                 uint64_t *queue)
+{
+    unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m == 0) return;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (keep) {
+        uint64_t pos = base + __popc(m & ((1u << lane) - 1));
+        if (pos < cap) queue[pos] = packed;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep: S[n][K] -> F[chunk][n_pad][ks] (zero padded), HN[n_pad] = -|row|^2/2, BM[block] = max |row|^2
+// one warp per row
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prep(const double *__restrict__ S, uint64_t n, uint32_t K, uint64_t n_pad,
+                                              uint32_t kc, uint32_t ks, uint32_t n_chunks, double *__restrict__ F,
+                                              double *__restrict__ HN, unsigned long long *__restrict__ BM)
+{
+    const uint64_t row = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    double nrm = 0.0;
+    const uint32_t kp = kc * n_chunks;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        double *dst = F + ((uint64_t)c * n_pad + row) * ks;
+        for (uint32_t q = lane; q < ks; q += 32) {
+            uint32_t k = c * kc + q;
+            double v = 0.0;
+            if (q < kc && k < K && row < n) v = S[row * K + k];
+            dst[q] = v;
+            nrm = fma(v, v, nrm);
+        }
+    }
+    (void)kp;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    if (lane == 0) {
+        HN[row] = row < n ? -0.5 * nrm : -INFINITY;
+        if (row < n) atomicMax(BM + row / TILE, (unsigned long long)__double_as_longlong(nrm));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// filter kernel
+// ------------------------------------------------------------------------------------------------
+struct FilterArgs {
+    const double *F;           // [n_chunks][n_pad][KS]
+    const double *HN;          // [n_pad]
+    const double *BM;          // [n_blocks]
+    const uint64_t *panel_start;  // [n_panels+1] prefix of strip groups
+    unsigned long long *work_counter;
+    unsigned long long *cand_count;
+    uint64_t *cand;
+    uint64_t cand_cap;
+    uint64_t n, n_pad;
+    uint32_t n_blocks, n_panels, n_chunks, strip_len;
+    uint64_t n_groups_local;
+    uint32_t shard, n_shards;
+    double T0, cband;
+};
+
+template <int KC, int KS, bool MULTI>
+struct FilterSmem {
+    static constexpr int A_BUFS = MULTI ? 2 : 1;
+    static constexpr size_t tile_doubles = (size_t)TILE * KS;
+    static constexpr size_t bytes = (A_BUFS + 2) * tile_doubles * 8 + (TILE + 2 * TILE) * 8 + 64;
+};
+
+template <int KC, int KS, bool MULTI, bool DMMA>
+__global__ void __launch_bounds__(256, 1) k_filter(const FilterArgs a)
+{
+    using SM = FilterSmem<KC, KS, MULTI>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *As = reinterpret_cast<double *>(smem_raw);
+    double *Bs = As + SM::A_BUFS * SM::tile_doubles;
+    double *hA = Bs + 2 * SM::tile_doubles;
+    double *hB = hA + TILE;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(hB + 2 * TILE);
+    __shared__ unsigned long long s_item;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr uint32_t TILE_BYTES = (uint32_t)(SM::tile_doubles * 8);
+    constexpr uint32_t HN_BYTES = TILE * 8;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t uses0 = 0, uses1 = 0;
+
+    // thread -> accumulator mapping
+    // DMMA: 8 warps as 2 (rows) x 4 (cols); warp tile 64 x 32 = 8 x 4 m8n8 fragments.
+    //       fragment element e of (mi,ni): row = mi*8 + (lane>>2), col = ni*8 + 2*(lane&3) + e
+    // FMA : 16 x 16 threads, each 8 x 8 pairs: row = ty + 16*mi, col = tx + 16*ni
+    const int g = lane >> 2, t4 = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int ty = tid >> 4, tx = tid & 15;
+
+    while (true) {
+        __syncthreads();  // s_item and all smem buffers are free again
+        if (tid == 0) s_item = atomicAdd(a.work_counter, 1ull);
+        __syncthreads();
+        const uint64_t item = s_item;
+        if (item >= a.n_groups_local * PANEL_ROWBLOCKS) break;
+        const uint64_t grp = (item / PANEL_ROWBLOCKS) * a.n_shards + a.shard;
+        const uint32_t r = (uint32_t)(item % PANEL_ROWBLOCKS);
+        // binary search: panel with panel_start[p] <= grp < panel_start[p+1]
+        uint32_t lo = 0, hi = a.n_panels;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (a.panel_start[mid] <= grp) lo = mid; else hi = mid;
+        }
+        const uint32_t panel = lo;
+        const uint32_t strip = (uint32_t)(grp - a.panel_start[panel]);
+        const uint32_t I = panel * PANEL_ROWBLOCKS + r;
+        if (I >= a.n_blocks) continue;
+        uint32_t J0 = panel * PANEL_ROWBLOCKS + strip * a.strip_len;
+        uint32_t J1 = J0 + a.strip_len;
+        if (J1 > a.n_blocks) J1 = a.n_blocks;
+        if (J0 < I) J0 = I;
+        if (J0 >= J1) continue;
+        const uint32_t n_tiles = J1 - J0;
+        const uint32_t n_steps = n_tiles * a.n_chunks;
+        const double bmI = a.BM[I];
+
+        auto issue = [&](uint32_t q) {
+            const uint32_t st = q & 1;
+            const uint32_t jt = q / a.n_chunks, c = q - jt * a.n_chunks;
+            const uint32_t J = J0 + jt;
+            uint32_t bytes = TILE_BYTES;
+            if (c == 0) bytes += HN_BYTES;
+            if (MULTI) bytes += TILE_BYTES;
+            if (q == 0) bytes += HN_BYTES + (MULTI ? 0u : TILE_BYTES);
+            mbar_expect_tx(&bars[st], bytes);
+            tma_bulk_g2s(Bs + st * SM::tile_doubles, a.F + ((uint64_t)c * a.n_pad + (uint64_t)J * TILE) * KS, TILE_BYTES,
+                         &bars[st]);
+            if (c == 0) tma_bulk_g2s(hB + st * TILE, a.HN + (uint64_t)J * TILE, HN_BYTES, &bars[st]);
+            if (MULTI)
+                tma_bulk_g2s(As + st * SM::tile_doubles, a.F + ((uint64_t)c * a.n_pad + (uint64_t)I * TILE) * KS,
+                             TILE_BYTES, &bars[st]);
+            if (q == 0) {
+                tma_bulk_g2s(hA, a.HN + (uint64_t)I * TILE, HN_BYTES, &bars[st]);
+                if (!MULTI) tma_bulk_g2s(As, a.F + (uint64_t)I * TILE * KS, TILE_BYTES, &bars[st]);
+            }
+        };
+
+        if (tid == 0) issue(0);
+
+        double acc[8][4][2];  // DMMA: [mi][ni][e]; FMA: [mi][ni*2+e] viewed as 8x8
+
+        for (uint32_t q = 0; q < n_steps; q++) {
+            const uint32_t st = q & 1;
+            const uint32_t jt = q / a.n_chunks, c = q - jt * a.n_chunks;
+            if (q + 1 < n_steps && tid == 0) issue(q + 1);
+            if (st == 0) { mbar_wait(&bars[0], uses0 & 1); uses0++; }
+            else         { mbar_wait(&bars[1], uses1 & 1); uses1++; }
+
+            const double *Ab = MULTI ? As + st * SM::tile_doubles : As;
+            const double *Bb = Bs + st * SM::tile_doubles;
+
+            if (c == 0) {
+                // acc starts at -(|a|^2+|b|^2)/2 so that after the contraction acc = -d^2/2
+                const double *hb = hB + st * TILE;
+                if (DMMA) {
+#pragma unroll
+                    for (int mi = 0; mi < 8; mi++) {
+                        const double ha = hA[wm * 64 + mi * 8 + g];
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++) {
+                            acc[mi][ni][0] = ha + hb[wn * 32 + ni * 8 + 2 * t4];
+                            acc[mi][ni][1] = ha + hb[wn * 32 + ni * 8 + 2 * t4 + 1];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int mi = 0; mi < 8; mi++) {
+                        const double ha = hA[ty + 16 * mi];
+#pragma unroll
+                        for (int ni = 0; ni < 8; ni++) acc[mi][ni >> 1][ni & 1] = ha + hb[tx + 16 * ni];
+                    }
+                }
+            }
+
+            if (DMMA) {
+                const double *ap = Ab + (wm * 64 + g) * KS + t4;
+                const double *bp = Bb + (wn * 32 + g) * KS + t4;
+#pragma unroll
+                for (int ks = 0; ks < KC / 4; ks++) {
+                    double af[8], bf[4];
+#pragma unroll
+                    for (int mi = 0; mi < 8; mi++) af[mi] = ap[mi * 8 * KS + ks * 4];
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) bf[ni] = bp[ni * 8 * KS + ks * 4];
+#pragma unroll
+                    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+                }
+            } else {
+                const double *ap = Ab + ty * KS;
+                const double *bp = Bb + tx * KS;
+#pragma unroll 4
+                for (int k = 0; k < KC; k++) {
+                    double af[8], bf[8];
+#pragma unroll
+                    for (int mi = 0; mi < 8; mi++) af[mi] = ap[mi * 16 * KS + k];
+#pragma unroll
+                    for (int ni = 0; ni < 8; ni++) bf[ni] = bp[ni * 16 * KS + k];
+#pragma unroll
+                    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 8; ni++)
+                            acc[mi][ni >> 1][ni & 1] = fma(af[mi], bf[ni], acc[mi][ni >> 1][ni & 1]);
+                }
+            }
+
+            if (c == a.n_chunks - 1) {
+                // ---- epilogue: provable rejection, survivors to the queue
+                const uint32_t J = J0 + jt;
+                const double T = (a.T0 + a.cband * (bmI + a.BM[J])) * (1.0 + 1e-15);
+                const double negHalfT = -0.5 * T;
+                bool any = false;
+#pragma unroll
+                for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) {
+                        any |= !(acc[mi][ni][0] < negHalfT);
+                        any |= !(acc[mi][ni][1] < negHalfT);
+                    }
+                if (__any_sync(0xffffffffu, any)) {
+                    const uint64_t rbase = (uint64_t)I * TILE, cbase = (uint64_t)J * TILE;
+#pragma unroll
+                    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                            for (int e = 0; e < 2; e++) {
+                                uint64_t row, col;
+                                if (DMMA) {
+                                    row = rbase + wm * 64 + mi * 8 + g;
+                                    col = cbase + wn * 32 + ni * 8 + 2 * t4 + e;
+                                } else {
+                                    row = rbase + ty + 16 * mi;
+                                    col = cbase + tx + 16 * (ni * 2 + e);
+                                }
+                                const bool keep = !(acc[mi][ni][e] < negHalfT) && row < col && col < a.n;
+                                warp_append_cand(keep, (row << 32) | col, a.cand_count, a.cand_cap, a.cand);
+                            }
+                }
+            }
+            __syncthreads();  // stage st may be refilled by the issue of the next iteration
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact recompute of the survivors + K3 compaction of the edges
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_exact_queue(const double *__restrict__ S, uint32_t K, const uint64_t *__restrict__ cand,
+                                                     const unsigned long long *__restrict__ cand_count, uint64_t cand_cap,
+                                                     double thr, uint32_t key_shift, unsigned long long *edge_count,
+                                                     uint64_t edge_cap, uint64_t *__restrict__ keys, double *__restrict__ vals)
+{
+    uint64_t n_c = *cand_count;
+    if (n_c > cand_cap) n_c = cand_cap;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (n_c + stride - 1) / stride;
+    for (uint64_t rd = 0; rd < rounds; rd++) {
+        const uint64_t idx = rd * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool keep = false;
+        uint64_t key = 0;
+        double d = 0.0;
+        if (idx < n_c) {
+            const uint64_t pk = cand[idx];
+            const uint64_t i = pk >> 32, j = pk & 0xffffffffull;
+            d = exact_l2(S + i * K, S + j * K, K);
+            keep = d < thr;  // strict, strain2spline.h:272
+            key = (i << key_shift) | j;
+        }
+        warp_append_edge(keep, key, d, edge_count, edge_cap, keys, vals);
+    }
+}
+
+// Filter-free all-pairs kernel: 64x64 pair tiles, 4x4 pairs per thread, K streamed through shared
+// memory in chunks while the per-pair sums keep the reference's sequential-k order.
+constexpr int XT = 64, XKC = 32;
+__global__ void __launch_bounds__(256) k_exact_all(const double *__restrict__ S, uint64_t n, uint32_t K, double thr,
+                                                   uint32_t key_shift, uint32_t shard, uint32_t n_shards,
+                                                   unsigned long long *edge_count, uint64_t edge_cap,
+                                                   uint64_t *__restrict__ keys, double *__restrict__ vals)
+{
+    const uint32_t I = blockIdx.y, J = blockIdx.x;
+    if (J < I) return;
+    if (((uint64_t)I + J) % n_shards != shard) return;
+    __shared__ double As[XT][XKC + 1], Bs[XT][XKC + 1];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double sum[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) sum[p][q] = 0.0;
+    const uint64_t r0 = (uint64_t)I * XT, c0 = (uint64_t)J * XT;
+    for (uint32_t k0 = 0; k0 < K; k0 += XKC) {
+        const uint32_t kn = K - k0 < (uint32_t)XKC ? K - k0 : (uint32_t)XKC;
+        __syncthreads();
+        for (int e = tid; e < XT * XKC; e += 256) {
+            const int rr = e / XKC, kk = e - rr * XKC;
+            double va = 0.0, vb = 0.0;
+            if ((uint32_t)kk < kn) {
+                if (r0 + rr < n) va = S[(r0 + rr) * K + k0 + kk];
+                if (c0 + rr < n) vb = S[(c0 + rr) * K + k0 + kk];
+            }
+            As[rr][kk] = va;
+            Bs[rr][kk] = vb;
+        }
+        __syncthreads();
+        for (uint32_t kk = 0; kk < kn; kk++) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) av[p] = As[ty + 16 * p][kk];
+#pragma unroll
+            for (int q = 0; q < 4; q++) bv[q] = Bs[tx + 16 * q][kk];
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double diff = __dsub_rn(av[p], bv[q]);
+                    sum[p][q] = __dadd_rn(sum[p][q], __dmul_rn(diff, diff));
+                }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint64_t row = r0 + ty + 16 * p, col = c0 + tx + 16 * q;
+            const double d = __dsqrt_rn(sum[p][q]);
+            const bool keep = row < col && col < n && d < thr;
+            warp_append_edge(keep, (row << key_shift) | col, d, edge_count, edge_cap, keys, vals);
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static void choose_chunks(uint32_t K, uint32_t *kc, uint32_t *n_chunks)
+{
+    static const uint32_t single[] = {12, 20, 28, 36, 44, 52, 60};
+    for (uint32_t s : single)
+        if (K <= s) { *kc = s; *n_chunks = 1; return; }
+    static const uint32_t multi[] = {44, 52};
+    uint32_t best_kc = 52, best_n = (K + 51) / 52;
+    uint64_t best_pad = (uint64_t)best_kc * best_n;
+    for (uint32_t m : multi) {
+        uint32_t nn = (K + m - 1) / m;
+        if ((uint64_t)m * nn < best_pad) { best_pad = (uint64_t)m * nn; best_kc = m; best_n = nn; }
+    }
+    *kc = best_kc; *n_chunks = best_n;
+}
+
+template <int KC, bool MULTI, bool DMMA>
+static int launch_filter_t(scema_ctx *ctx, const FilterArgs &fa)
+{
+    constexpr int KS = DMMA ? KC : KC + 1;
+    auto kern = k_filter<KC, KS, MULTI, DMMA>;
+    const size_t smem = FilterSmem<KC, KS, MULTI>::bytes;
+    if (smem > ctx->smem_optin) return fail(ctx, SCEMA_ERR_CUDA, "filter kernel shared memory exceeds device limit");
+    SCEMA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint64_t items = fa.n_groups_local * PANEL_ROWBLOCKS;
+    unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count, std::max<uint64_t>(items, 1));
+    kern<<<grid, 256, smem, ctx->stream>>>(fa);
+    ctx->launches++;
+    SCEMA_CUDA(ctx, cudaGetLastError());
+    return SCEMA_OK;
+}
+
+template <bool DMMA>
+static int launch_filter(scema_ctx *ctx, const FilterArgs &fa, uint32_t kc, bool multi)
+{
+    if (!multi) {
+        switch (kc) {
+        case 12: return launch_filter_t<12, false, DMMA>(ctx, fa);
+        case 20: return launch_filter_t<20, false, DMMA>(ctx, fa);
+        case 28: return launch_filter_t<28, false, DMMA>(ctx, fa);
+        case 36: return launch_filter_t<36, false, DMMA>(ctx, fa);
+        case 44: return launch_filter_t<44, false, DMMA>(ctx, fa);
+        case 52: return launch_filter_t<52, false, DMMA>(ctx, fa);
+        case 60: return launch_filter_t<60, false, DMMA>(ctx, fa);
+        }
+    } else {
+        switch (kc) {
+        case 44: return launch_filter_t<44, true, DMMA>(ctx, fa);
+        case 52: return launch_filter_t<52, true, DMMA>(ctx, fa);
+        }
+    }
+    return fail(ctx, SCEMA_ERR_INVALID, "no filter kernel instantiation for this chunk size");
+}
+
+static uint32_t bits_for(uint64_t n)
+{
+    uint32_t b = 1;
+    while (b < 32 && (1ull << b) < n) b++;
+    return b;
+}
+
+static int prepare_filter(scema_ctx *ctx, int variant)
+{
+    FilterLayout &fl = ctx->fl;
+    if (ctx->filter_for_spline_version == ctx->spline_version && ctx->filter_variant == variant && fl.n == ctx->n &&
+        fl.K == ctx->K)
+        return SCEMA_OK;
+    fl.K = ctx->K;
+    fl.n = ctx->n;
+    choose_chunks(fl.K, &fl.kc, &fl.n_chunks);
+    fl.n_blocks = (fl.n + TILE - 1) / TILE;
+    fl.n_pad = fl.n_blocks * TILE;
+    const uint32_t ks = variant == SCEMA_PAIRS_DMMA ? fl.kc : fl.kc + 1;
+    SCEMA_CUDA(ctx, ctx->d_filter.reserve((size_t)fl.n_chunks * fl.n_pad * ks * sizeof(double)));
+    SCEMA_CUDA(ctx, ctx->d_halfnorm.reserve(fl.n_pad * sizeof(double)));
+    SCEMA_CUDA(ctx, ctx->d_blockmax.reserve(fl.n_blocks * sizeof(double)));
+    SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_blockmax.p, 0, fl.n_blocks * sizeof(double), ctx->stream));
+    k_prep<<<(unsigned)((fl.n_pad + 7) / 8), 256, 0, ctx->stream>>>(ctx->d_spline, fl.n, fl.K, fl.n_pad, fl.kc, ks,
+                                                                     fl.n_chunks, ctx->d_filter.as<double>(),
+                                                                     ctx->d_halfnorm.as<double>(),
+                                                                     ctx->d_blockmax.as<unsigned long long>());
+    ctx->launches++;
+    SCEMA_CUDA(ctx, cudaGetLastError());
+    ctx->filter_for_spline_version = ctx->spline_version;
+    ctx->filter_variant = variant;
+    return SCEMA_OK;
+}
+
+static int ensure_edge_buffers(scema_ctx *ctx, uint64_t cap)
+{
+    if (cap <= ctx->edge_cap) return SCEMA_OK;
+    for (int b = 0; b < 2; b++) {
+        SCEMA_CUDA(ctx, ctx->d_edge_key[b].reserve(cap * sizeof(uint64_t)));
+        SCEMA_CUDA(ctx, ctx->d_edge_val[b].reserve(cap * sizeof(double)));
+    }
+    ctx->edge_cap = cap;
+    return SCEMA_OK;
+}
+
+int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards)
+{
+    if (!ctx->have_spline) return fail(ctx, SCEMA_ERR_STATE, "Spline is not up to date.");
+    if (n_shards == 0 || shard >= n_shards) return fail(ctx, SCEMA_ERR_INVALID, "compare: bad shard");
+    if (variant < 0 || variant > 2) return fail(ctx, SCEMA_ERR_INVALID, "compare: bad variant");
+    if (ctx->n >= (1ull << 32)) return fail(ctx, SCEMA_ERR_INVALID, "compare: more than 2^32-1 histories");
+    for (int i = 0; i < 8; i++) ctx->counters[i] = 0;
+    for (int w = SCEMA_T_PREP; w <= SCEMA_T_SORT; w++) ctx->ev_used[w] = false;
+    ctx->n_edges = 0;
+    ctx->have_edges = true;
+    ctx->edge_cur = 0;
+    ctx->key_shift = bits_for(ctx->n);
+    const uint64_t n = ctx->n;
+    const uint32_t K = ctx->K;
+    // diff >= 0 or NaN, so nothing passes a non-positive or NaN threshold
+    if (n < 2 || !(thr > 0.0)) return SCEMA_OK;
+
+    SCEMA_CUDA(ctx, ctx->d_counters.reserve(8 * sizeof(uint64_t)));
+    if (!ctx->h_counters) SCEMA_CUDA(ctx, cudaMallocHost(&ctx->h_counters, 8 * sizeof(uint64_t)));
+    int rc = ensure_edge_buffers(ctx, std::max<uint64_t>(1ull << 20, 16 * n));
+    if (rc) return rc;
+    unsigned long long *d_cnt = ctx->d_counters.as<unsigned long long>();
+
+    size_t free_b = 0, total_b = 0;
+    uint64_t passes = 0;
+    while (true) {
+        passes++;
+        if (passes > 8) return fail(ctx, SCEMA_ERR_NOMEM, "compare: buffers kept overflowing");
+        SCEMA_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 8 * sizeof(uint64_t), ctx->stream));
+        if (variant == SCEMA_PAIRS_EXACT) {
+            const uint32_t nbx = (uint32_t)((n + XT - 1) / XT);
+            if (nbx > 65535) return fail(ctx, SCEMA_ERR_INVALID, "exact all-pairs variant supports n <= 4194240");
+            t_begin(ctx, SCEMA_T_FILTER);
+            k_exact_all<<<dim3(nbx, nbx), 256, 0, ctx->stream>>>(ctx->d_spline, n, K, thr, ctx->key_shift, shard, n_shards,
+                                                                 d_cnt + 1, ctx->edge_cap, ctx->d_edge_key[0].as<uint64_t>(),
+                                                                 ctx->d_edge_val[0].as<double>());
+            ctx->launches++;
+            t_end(ctx, SCEMA_T_FILTER);
+            SCEMA_CUDA(ctx, cudaGetLastError());
+            ctx->counters[4] = (uint64_t)nbx * (nbx + 1) / 2;
+        } else {
+            t_begin(ctx, SCEMA_T_PREP);
+            rc = prepare_filter(ctx, variant);
+            if (rc) return rc;
+            const FilterLayout &fl = ctx->fl;
+            // scheduling tables: panels of PANEL_ROWBLOCKS row blocks, column strips of strip_len tiles
+            const uint64_t nb = fl.n_blocks;
+            const uint64_t tiles = nb * (nb + 1) / 2;
+            uint32_t strip_len = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(4, tiles / ((uint64_t)ctx->sm_count * 8)));
+            const uint32_t n_panels = (uint32_t)((nb + PANEL_ROWBLOCKS - 1) / PANEL_ROWBLOCKS);
+            std::vector<uint64_t> ps(n_panels + 1, 0);
+            for (uint32_t p = 0; p < n_panels; p++) {
+                uint64_t cols = nb - (uint64_t)p * PANEL_ROWBLOCKS;
+                ps[p + 1] = ps[p] + (cols + strip_len - 1) / strip_len;
+            }
+            const uint64_t groups = ps[n_panels];
+            SCEMA_CUDA(ctx, ctx->d_panel_start.reserve(ps.size() * sizeof(uint64_t)));
+            SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_panel_start.p, ps.data(), ps.size() * sizeof(uint64_t),
+                                            cudaMemcpyHostToDevice, ctx->stream));
+            SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // ps is a stack-lifetime host buffer
+            if (ctx->cand_cap == 0) ctx->cand_cap = std::max<uint64_t>(1ull << 20, 32 * n);
+            SCEMA_CUDA(ctx, ctx->d_cand.reserve(ctx->cand_cap * sizeof(uint64_t)));
+            t_end(ctx, SCEMA_T_PREP);
+
+            FilterArgs fa;
+            fa.F = ctx->d_filter.as<double>();
+            fa.HN = ctx->d_halfnorm.as<double>();
+            fa.BM = ctx->d_blockmax.as<double>();
+            fa.panel_start = ctx->d_panel_start.as<uint64_t>();
+            fa.work_counter = d_cnt + 3;
+            fa.cand_count = d_cnt + 0;
+            fa.cand = ctx->d_cand.as<uint64_t>();
+            fa.cand_cap = ctx->cand_cap;
+            fa.n = n;
+            fa.n_pad = fl.n_pad;
+            fa.n_blocks = (uint32_t)nb;
+            fa.n_panels = n_panels;
+            fa.n_chunks = fl.n_chunks;
+            fa.strip_len = strip_len;
+            fa.n_groups_local = groups > shard ? (groups - shard + n_shards - 1) / n_shards : 0;
+            fa.shard = shard;
+            fa.n_shards = n_shards;
+            const double eps = 1.1102230246251565e-16;  // 2^-53
+            fa.T0 = thr * thr * (1.0 + (2.0 * K + 16.0) * eps) * (1.0 + 4.0 * eps);
+            fa.cband = (4.0 * K + 64.0) * eps;
+            ctx->counters[4] = tiles;
+
+            t_begin(ctx, SCEMA_T_FILTER);
+            rc = variant == SCEMA_PAIRS_DMMA ? launch_filter<true>(ctx, fa, fl.kc, fl.n_chunks > 1)
+                                             : launch_filter<false>(ctx, fa, fl.kc, fl.n_chunks > 1);
+            if (rc) return rc;
+            t_end(ctx, SCEMA_T_FILTER);
+
+            t_begin(ctx, SCEMA_T_EXACT);
+            k_exact_queue<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->d_spline, K, ctx->d_cand.as<uint64_t>(), d_cnt + 0,
+                                                                      ctx->cand_cap, thr, ctx->key_shift, d_cnt + 1,
+                                                                      ctx->edge_cap, ctx->d_edge_key[0].as<uint64_t>(),
+                                                                      ctx->d_edge_val[0].as<double>());
+            ctx->launches++;
+            t_end(ctx, SCEMA_T_EXACT);
+            SCEMA_CUDA(ctx, cudaGetLastError());
+        }
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, d_cnt, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const uint64_t n_cand = ctx->h_counters[0], n_edge = ctx->h_counters[1];
+        ctx->counters[1] = n_cand;
+        ctx->counters[2] = n_edge;
+        ctx->counters[3] = passes;
+        if (variant != SCEMA_PAIRS_EXACT && n_cand > ctx->cand_cap) {
+            SCEMA_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+            const uint64_t want = n_cand + n_cand / 4;
+            if (want * sizeof(uint64_t) > (free_b + ctx->d_cand.bytes) / 2) {
+                variant = SCEMA_PAIRS_EXACT;  // survivors too dense for a queue: filter-free kernel
+            } else {
+                ctx->cand_cap = want;
+            }
+            continue;
+        }
+        if (n_edge > ctx->edge_cap) {
+            rc = ensure_edge_buffers(ctx, n_edge + n_edge / 8);
+            if (rc) return rc;
+            continue;
+        }
+        ctx->n_edges = n_edge;
+        break;
+    }
+    if (n_shards == 1) ctx->counters[0] = n * (n - 1) / 2;
+
+    // canonical order: ascending (a,b) == ascending packed key
+    if (ctx->n_edges > 1) {
+        t_begin(ctx, SCEMA_T_SORT);
+        cub::DoubleBuffer<uint64_t> dk(ctx->d_edge_key[0].as<uint64_t>(), ctx->d_edge_key[1].as<uint64_t>());
+        cub::DoubleBuffer<double> dv(ctx->d_edge_val[0].as<double>(), ctx->d_edge_val[1].as<double>());
+        size_t tmp = 0;
+        const int end_bit = (int)std::min<uint32_t>(64, 2 * ctx->key_shift);
+        SCEMA_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int64_t)ctx->n_edges, 0, end_bit, ctx->stream));
+        SCEMA_CUDA(ctx, ctx->d_sort_tmp.reserve(tmp));
+        SCEMA_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp.p, tmp, dk, dv, (int64_t)ctx->n_edges, 0, end_bit,
+                                                        ctx->stream));
+        ctx->launches += 2 * ((end_bit + 7) / 8) + 1;
+        ctx->edge_cur = dk.selector;
+        t_end(ctx, SCEMA_T_SORT);
+        SCEMA_CUDA(ctx, cudaGetLastError());
+    }
+    return SCEMA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 issue-rate probes (roofline denominators; MEASURED_PEAKS.json has no FP64 figure)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_peak_dfma(double *out, double a, double b, int iters)
+{
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = threadIdx.x * 1e-9 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += acc[i];
+    if (s == 123.456) out[0] = s;
+}
+__global__ void __launch_bounds__(256) k_peak_dmma(double *out, double av, double bv, int iters)
+{
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) c[i][0] = c[i][1] = 0.0;
+    const double a = av + threadIdx.x * 1e-12, b = bv;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) dmma_m8n8k4(c[i][0], c[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
+
+int fp64_peak_run(scema_ctx *ctx, double out[2])
+{
+    SCEMA_CUDA(ctx, ctx->d_counters.reserve(8 * sizeof(uint64_t)));
+    double *d = ctx->d_counters.as<double>();
+    const int iters = 2048, blocks = ctx->sm_count * 8;
+    cudaEvent_t e0, e1;
+    SCEMA_CUDA(ctx, cudaEventCreate(&e0));
+    SCEMA_CUDA(ctx, cudaEventCreate(&e1));
+    for (int which = 0; which < 2; which++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 6; rep++) {
+            SCEMA_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+            if (which == 0) k_peak_dfma<<<blocks, 256, 0, ctx->stream>>>(d, 1.0000001, 1e-9, iters);
+            else k_peak_dmma<<<blocks, 256, 0, ctx->stream>>>(d, 1.0, 1e-9, iters);
+            ctx->launches++;
+            SCEMA_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+            SCEMA_CUDA(ctx, cudaEventSynchronize(e1));
+            float ms;
+            SCEMA_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+            if (rep >= 2 && ms < best) best = ms;
+        }
+        const double threads = (double)blocks * 256;
+        const double flops = which == 0 ? threads * iters * 16 * 2.0 : threads / 32 * iters * 16 * (8 * 8 * 4 * 2.0);
+        out[which] = flops / (best * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return SCEMA_OK;
+}
+
+}  // namespace scema

@@ -1,0 +1,83 @@
+"""numpy twin of scema_b200/csrc/synth.cu (include/scema_synth.h): identical bits on the host.
+
+Every arithmetic step is a separately rounded IEEE double operation in the same order as the
+device code, and the counter-based hash is pure uint64 arithmetic, so the host array equals the
+device array bit-for-bit (tests/test_gpu_parity.py::test_synth_matches_numpy).
+"""
+import numpy as np
+
+_M1 = np.uint64(0xBF58476D1CE4E5B9)
+_M2 = np.uint64(0x94D049BB133111EB)
+_G = np.uint64(0x9E3779B97F4A7C15)
+_U = 1.1102230246251565e-16  # 2^-53
+
+
+def _mix64(z):
+    z = (z ^ (z >> np.uint64(30))) * _M1
+    z = (z ^ (z >> np.uint64(27))) * _M2
+    return z ^ (z >> np.uint64(31))
+
+
+def hash4(seed, a, b, stream):
+    with np.errstate(over="ignore"):
+        a = np.asarray(a, dtype=np.uint64)
+        b = np.asarray(b, dtype=np.uint64)
+        z = _mix64(np.uint64(seed) + _G * (a + np.uint64(1)))
+        z = _mix64(z + b)
+        return _mix64(z + np.uint64(stream))
+
+
+def u01(x):
+    return (x >> np.uint64(11)).astype(np.float64) * _U
+
+
+def offsets(seed, n, cluster_size, len_min, len_max):
+    q = np.arange(n, dtype=np.uint64) // np.uint64(cluster_size)
+    lens = np.uint64(len_min) + hash4(seed, q, 0, 7) % np.uint64(len_max - len_min + 1)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    return off
+
+
+def _value(seed, i, q, c, t, amp, pert):
+    A = amp * (2.0 * u01(hash4(seed, q, c, 1)) - 1.0)
+    beta = u01(hash4(seed, q, c, 2)) - 0.5
+    delta = pert * (2.0 * u01(hash4(seed, i, c, 3)) - 1.0)
+    centre = A * (t + beta * (t * t))
+    return centre + delta * t
+
+
+def histories(seed, n, cluster_size, amp, pert, off):
+    """-> steps [off[n], 6] float64 for the given offsets."""
+    off = np.asarray(off, dtype=np.uint64)
+    lens = (off[1:] - off[:-1]).astype(np.int64)
+    total = int(off[-1])
+    i = np.repeat(np.arange(n, dtype=np.uint64), lens)
+    s = np.arange(total, dtype=np.int64) - np.repeat(off[:-1].astype(np.int64), lens)
+    Lm1 = np.repeat(lens - 1, lens).astype(np.float64)
+    t = s.astype(np.float64) / Lm1
+    q = i // np.uint64(cluster_size)
+    out = np.empty((total, 6), dtype=np.float64)
+    for c in range(6):
+        out[:, c] = _value(seed, i, q, c, t, amp, pert)
+    return out
+
+
+def rows(seed, n, cluster_size, spline_points, amp, pert):
+    """-> already-resampled rows [n, 6*P] in the reference's p*6+c order."""
+    P = spline_points
+    i = np.arange(n, dtype=np.uint64)[:, None]
+    q = i // np.uint64(cluster_size)
+    t = (np.arange(P, dtype=np.float64) / float(P - 1))[None, :]
+    out = np.empty((n, P, 6), dtype=np.float64)
+    for c in range(6):
+        out[:, :, c] = _value(seed, i, q, c, t, amp, pert)
+    return out.reshape(n, 6 * P)
+
+
+def default_pert(threshold, spline_points):
+    """Perturbation amplitude that puts the median intra-cluster distance near the threshold,
+    so about half of a cluster's pairs become edges (mean degree ~ cluster_size/2)."""
+    P = spline_points
+    s2 = sum((p / (P - 1.0)) ** 2 for p in range(P))
+    return float(threshold) * 0.5 / (s2 ** 0.5)

@@ -1,0 +1,145 @@
+// FP64 issue-rate microbenchmark for B200 (sm_100a): the roofline denominators that
+// MEASURED_PEAKS.json does not carry ("FP64_peak must be measured on the box").
+//   - DFMA: register-resident independent FMA chains (vector FP64 pipe)
+//   - DMMA: mma.sync.aligned.{m8n8k4,m16n8k4,m16n8k8,m16n8k16}.f64 (FP64 tensor path)
+//   - dependent-chain latencies of DADD/DMUL/DFMA/DDIV (they bound the K1 tridiagonal sweeps)
+// Prints one JSON object. Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { fprintf(stderr, "%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e)); exit(2); } } while (0)
+
+constexpr int ITERS = 4096;
+
+__global__ void __launch_bounds__(256) k_dfma(double *out, double a, double b)
+{
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = threadIdx.x * 1e-9 + i;
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += acc[i];
+    if (s == 123.456) out[0] = s;
+}
+
+template <int SHAPE>  // 0: m8n8k4, 1: m16n8k4, 2: m16n8k8, 3: m16n8k16
+__global__ void __launch_bounds__(256) k_dmma(double *out, double av, double bv)
+{
+    constexpr int NACC = 8;  // independent accumulator tiles per warp
+    double c[NACC][4];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.0; }
+    double a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = av + threadIdx.x * 1e-12 + i;
+#pragma unroll
+    for (int i = 0; i < 4; i++) b[i] = bv + i;
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < NACC; i++) {
+            if (SHAPE == 0) {
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a[0]), "d"(b[0]));
+            } else if (SHAPE == 1) {
+                asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                             : "+d"(c[i][0]), "+d"(c[i][1]), "+d"(c[i][2]), "+d"(c[i][3])
+                             : "d"(a[0]), "d"(a[1]), "d"(b[0]));
+            } else if (SHAPE == 2) {
+                asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+d"(c[i][0]), "+d"(c[i][1]), "+d"(c[i][2]), "+d"(c[i][3])
+                             : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+            } else {
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, {%0,%1,%2,%3};"
+                             : "+d"(c[i][0]), "+d"(c[i][1]), "+d"(c[i][2]), "+d"(c[i][3])
+                             : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
+                               "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    if (s == 123.456) out[0] = s;
+}
+
+// one warp, one thread active: dependent chain latency in cycles per op
+template <int OP>
+__global__ void k_lat(double *out, long long *cyc, double a, double b)
+{
+    double x = a;
+    long long t0 = clock64();
+#pragma unroll 16
+    for (int it = 0; it < 4096; it++) {
+        if (OP == 0) x = __dadd_rn(x, b);
+        else if (OP == 1) x = __dmul_rn(x, b);
+        else if (OP == 2) x = fma(x, b, a);
+        else x = b / x + a;  // IEEE division + add
+    }
+    long long t1 = clock64();
+    out[1] = x;
+    cyc[OP] = t1 - t0;
+}
+
+static float time_kernel(void (*launch)(), int reps)
+{
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    launch(); launch();
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < reps; r++) {
+        CK(cudaEventRecord(e0));
+        launch();
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    return best;
+}
+
+static double *g_out;
+static int g_blocks;
+static void l_dfma() { k_dfma<<<g_blocks, 256>>>(g_out, 1.0000001, 1e-9); }
+static void l_dmma0() { k_dmma<0><<<g_blocks, 256>>>(g_out, 1.0, 1e-9); }
+static void l_dmma1() { k_dmma<1><<<g_blocks, 256>>>(g_out, 1.0, 1e-9); }
+static void l_dmma2() { k_dmma<2><<<g_blocks, 256>>>(g_out, 1.0, 1e-9); }
+static void l_dmma3() { k_dmma<3><<<g_blocks, 256>>>(g_out, 1.0, 1e-9); }
+
+int main()
+{
+    cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+    int sms = p.multiProcessorCount;
+    g_blocks = sms * 8;  // 8 CTAs x 256 threads = full occupancy
+    CK(cudaMalloc(&g_out, 64));
+    long long *cyc; CK(cudaMalloc(&cyc, 64));
+    double threads = (double)g_blocks * 256, warps = threads / 32;
+    float t;
+    printf("{\"gpu\": \"%s\", \"sms\": %d", p.name, sms);
+    t = time_kernel(l_dfma, 5);
+    printf(", \"dfma_tflops\": %.3f", threads * ITERS * 16 * 2 / (t * 1e-3) / 1e12);
+    const double fl[4] = {8 * 8 * 4 * 2.0, 16 * 8 * 4 * 2.0, 16 * 8 * 8 * 2.0, 16 * 8 * 16 * 2.0};
+    void (*ls[4])() = {l_dmma0, l_dmma1, l_dmma2, l_dmma3};
+    const char *nm[4] = {"dmma_m8n8k4_tflops", "dmma_m16n8k4_tflops", "dmma_m16n8k8_tflops", "dmma_m16n8k16_tflops"};
+    for (int s = 0; s < 4; s++) {
+        t = time_kernel(ls[s], 5);
+        printf(", \"%s\": %.3f", nm[s], warps * ITERS * 8 * fl[s] / (t * 1e-3) / 1e12);
+    }
+    k_lat<0><<<1, 1>>>(g_out, cyc, 1.0, 1e-9);
+    k_lat<1><<<1, 1>>>(g_out, cyc, 1.0, 1.0000001);
+    k_lat<2><<<1, 1>>>(g_out, cyc, 1.0, 0.999);
+    k_lat<3><<<1, 1>>>(g_out, cyc, 1.0, 0.999);
+    CK(cudaDeviceSynchronize());
+    long long h[4]; CK(cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost));
+    printf(", \"lat_cycles\": {\"dadd\": %.2f, \"dmul\": %.2f, \"dfma\": %.2f, \"ddiv_plus_dadd\": %.2f}",
+           h[0] / 4096.0, h[1] / 4096.0, h[2] / 4096.0, h[3] / 4096.0);
+    int clk; CK(cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0));
+    printf(", \"sm_clock_khz_max\": %d}\n", clk);
+    return 0;
+}
