@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — history pair comparisons / second of the MD-redundancy clustering hot path.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over the synthetic batch: K1 ragged spline resample of every
+history -> (N>1: one NCCL all-gather of the resampled rows) -> K2 all-pairs GEMM-form filter (DMMA)
++ exact recompute of the survivors -> K3 edge compaction -> canonical sort (-> N>1: all-gather of
+the edge counts). Workload (BASELINE.json configs[3], the one the 1/2/4/8 scaling is quoted on; it
+fits one GPU): 1M histories x 6 components x 10 spline points, all-pairs = 5.0e11 unordered pairs,
+tile-sharded over the ranks (strong scaling: total work fixed). `value` = pairs / second over the
+whole job with the raw histories resident in HBM; `e2e` = the same through the C ABI with HOST
+buffers (pinned host -> device copy of the histories and device -> host read of the edge list
+inside the timed region).
+
+The reference arm (--impl reference) times the reference's own CPU code (oracle/_ref, the
+unmodified header compiled with -O2 and OpenMP over rows) on a bounded sample of the same
+workload, on all host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+THR = 1e-6
+AMP = 5e-3
+CLUSTER = 16
+SEED = 4
+WORKLOADS = {
+    # name: n, spline points, raw history length range
+    "c2": dict(n=16384, P=10, lmin=8, lmax=64, desc="BASELINE configs[1]: 16k histories x 6 x 10"),
+    "c3": dict(n=200000, P=10, lmin=6, lmax=200, desc="BASELINE configs[2]: 200k ragged histories (6..200 steps)"),
+    "c4": dict(n=1000000, P=10, lmin=8, lmax=64, desc="BASELINE configs[3]: 1M histories x 6 x 10 spline points"),
+    "c5": dict(n=4000000, P=50, lmin=8, lmax=64, desc="BASELINE configs[4]: 4M histories x 6 x 50 spline points"),
+}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v == "Active":
+                    reasons.add(nm)
+        busy = [x for x in sm if x > 300] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rows(wl, m, timed):
+    """First m histories of the workload, generated with the numpy twin and resampled by the
+    reference's own splinify. -> (rows, lib, kind, splinify_seconds)."""
+    from scema_b200 import synth
+    from oracle.pyoracle import Oracle, Reference, have_reference
+    if have_reference():
+        lib, kind = Reference(), "reference"
+    else:
+        lib, kind = Oracle(), "port"
+    off = synth.offsets(SEED, m, CLUSTER, wl["lmin"], wl["lmax"])
+    steps = synth.histories(SEED, m, CLUSTER, AMP, synth.default_pert(THR, wl["P"]), off)
+    t0 = time.perf_counter()
+    rows = lib.splinify_batch(steps, off, wl["P"])
+    return rows, lib, kind, time.perf_counter() - t0
+
+
+def cpu_pairs_step(lib, rows, r0, r1):
+    t0 = time.perf_counter()
+    edges, pairs = lib.all_pairs(rows, THR, r0, r1, 0, count_only=True)
+    return pairs, time.perf_counter() - t0, edges
+
+
+def run_reference(args, wl, wl_name):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return  # the CPU reference runs once, on rank 0
+    m = min(wl["n"], 65536)
+    rows, lib, kind, t_spl = cpu_reference_rows(wl, m, True)
+    cores = lib.max_threads()
+    # calibrate the per-step sample: whole run ~ 100 s at most
+    pairs, dt, _ = cpu_pairs_step(lib, rows, 0, 64)
+    rate = pairs / dt
+    budget = max(1.0, min(8.0, 100.0 / (args.steps + args.warmup)))
+    rows_per_step = int(max(16, min(m // 2, rate * budget / m)))
+    cursor = 0
+
+    def one():
+        nonlocal cursor
+        if cursor + rows_per_step >= m // 2:
+            cursor = 0
+        r = cpu_pairs_step(lib, rows, cursor, cursor + rows_per_step)
+        cursor += rows_per_step
+        return r
+
+    for _ in range(args.warmup):
+        one()
+    tot_p, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        p, t, _ = one()
+        tot_p += p
+        tot_t += t
+    value = tot_p / tot_t
+    sample = (f"first {m} of {wl['n']} histories (numpy twin of the generator, resampled by the reference's "
+              f"splinify: {m / t_spl:.0f} histories/s); each step = rows [r, r+{rows_per_step}) against all later "
+              f"rows = {tot_p // args.steps} pairs; compare_L2_norm + strict threshold, OpenMP over rows")
+    line = {
+        "impl": "reference", "metric": "history pair comparisons/sec", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{wl_name}: {wl['desc']}", "threshold": THR, "spline_points": wl["P"]},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, wl, wl_name):
+    import torch
+    import torch.distributed as dist
+    import scema_b200
+    from scema_b200 import synth
+    from scema_b200.distributed import ShardedCluster, shard_bounds
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, P = wl["n"], wl["P"]
+    K = 6 * P
+    variant = {"dmma": 0, "fma": 1, "exact": 2}[args.variant]
+    pert = synth.default_pert(THR, P)
+    b, e = shard_bounds(n, world)[rank]
+    n_local = e - b
+
+    stream = torch.cuda.current_stream()
+    hc = scema_b200.HistCluster(local_rank, stream.cuda_stream)
+    off = synth.device_offsets(SEED, n_local, CLUSTER, wl["lmin"], wl["lmax"], first=b)
+    d_steps = synth.device_histories(SEED, n_local, CLUSTER, AMP, pert, off, first=b, device=dev)
+    steps_bytes = d_steps.numel() * 8
+    h_steps = torch.empty(d_steps.shape, dtype=torch.float64, pin_memory=True)
+    h_steps.copy_(d_steps)
+    torch.cuda.synchronize()
+    h_steps_np = h_steps.numpy()
+    sc = ShardedCluster(hc) if world > 1 else None
+    total_pairs = n * (n - 1) // 2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    acc = {"filter": 0.0, "resample": 0.0, "exact": 0.0, "sort": 0.0, "prep": 0.0, "steps": 0, "edges": 0,
+           "survivors": 0}
+
+    def step_resident(record):
+        if world > 1:
+            ne, counts, offs, _ = sc.run(n, P, THR, variant)
+            tot = sum(counts)
+        else:
+            hc.resample(P)
+            t_res = hc.timings()["resample"] if record else 0.0
+            ne = hc.compare(THR, variant)
+            tot = ne
+        if record:
+            t = hc.timings()
+            for k in ("filter", "exact", "sort", "prep"):
+                acc[k] += t[k]
+            acc["resample"] += t["resample"] if world > 1 else t_res
+            acc["steps"] += 1
+            acc["edges"] = tot
+            acc["survivors"] = hc.counters()["survivors"]
+        return tot
+
+    def step_e2e():
+        hc.set_histories(h_steps_np, off)            # pinned host -> device inside the timed region
+        if world > 1:
+            ne, counts, offs, _ = sc.run(n, P, THR, variant)
+        else:
+            hc.resample(P)
+            ne = hc.compare(THR, variant)
+        hc.get_edges()                               # device -> host read of the result
+        return ne
+
+    # ---- device-resident timing: the raw histories are handed over once (borrowed device pointer)
+    hc.set_histories(None, off, device_ptr=d_steps.data_ptr())
+    for _ in range(args.warmup):
+        step_resident(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = hc.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_resident(True)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = hc.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = total_pairs * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end timing (host buffers)
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    ev0.record(stream)
+    ne_local = 0
+    for _ in range(e2e_steps):
+        ne_local = step_e2e()
+    ev1.record(stream)
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = total_pairs * e2e_steps / (ms_e2e * 1e-3)
+    h2d = steps_bytes + off.nbytes
+    d2h = ne_local * 16
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (K2 filter): algorithmic 2*K flops per unordered pair
+        pairs_this_rank = total_pairs / world
+        filt_ms = acc["filter"] / max(acc["steps"], 1)
+        achieved = pairs_this_rank * 2 * K / (filt_ms * 1e-3) / 1e12 if filt_ms > 0 else None
+        peaks = hc.fp64_peak()
+        peak = peaks["dmma_tflops"] if variant == 0 else peaks["dfma_tflops"]
+        traffic = None
+        tfile = os.path.join(ROOT, "profiles", "filter_traffic.json")
+        if os.path.exists(tfile):
+            try:
+                traffic = json.load(open(tfile)).get(wl_name)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                    "kernel": "k_filter (K2 GEMM-form filter, %s)" % args.variant,
+                    "peak_source": "measured live on this GPU: FP64 %s issue-rate probe (scema_fp64_peak); "
+                                   "MEASURED_PEAKS.json has no FP64 figure" % ("DMMA m8n8k4" if variant == 0 else "DFMA"),
+                    "launch_ms": filt_ms,
+                    "other_kernels_ms": {k: acc[k] / max(acc["steps"], 1) for k in ("resample", "prep", "exact", "sort")}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            m = min(n, 65536)
+            rows, lib, kind, t_spl = cpu_reference_rows(wl, m, True)
+            pairs, dt, _ = cpu_pairs_step(lib, rows, 0, 64)
+            rps = int(max(64, min(m // 2, (pairs / dt) * 12.0 / m)))
+            pairs, dt, _ = cpu_pairs_step(lib, rows, 0, rps)
+            cpu = {"value": pairs / dt, "unit": "pairs/s", "cores": lib.max_threads(), "kind": kind,
+                   "sample": f"first {m} of {n} histories; rows [0,{rps}) x all later rows = {pairs} pairs in {dt:.1f} s; "
+                             f"reference splinify {m / t_spl:.0f} histories/s"}
+        line = {
+            "metric": "history pair comparisons/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{wl_name}: {wl['desc']}", "histories": n, "spline_points": P, "threshold": THR,
+                       "raw_steps_per_history": [wl["lmin"], wl["lmax"]], "cluster_size": CLUSTER, "variant": args.variant,
+                       "parallelism": f"tile-shard x{world}", "l2": "inputs (raw histories + spline matrix) larger than L2",
+                       "edges": acc["edges"], "survivors_last_rank0": acc["survivors"]},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    hc.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", default="dmma", choices=["dmma", "fma", "exact"])
+    ap.add_argument("--histories", type=int, default=0, help="override the workload's history count")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = dict(WORKLOADS[args.workload])
+    if args.histories:
+        wl["n"] = args.histories
+    if args.impl == "reference":
+        run_reference(args, wl, args.workload)
+    else:
+        run_ours(args, wl, args.workload)
+
+
+if __name__ == "__main__":
+    main()

@@ -19,14 +19,16 @@
 extern "C" {
 #endif
 
-/* Host: offsets[n+1] (in steps) for cluster-wise lengths uniform in [len_min, len_max]. */
-int scema_synth_offsets(uint64_t seed, uint64_t n, uint32_t cluster_size, uint32_t len_min, uint32_t len_max,
-                        uint64_t *offsets_host);
+/* All functions generate histories first .. first+n-1 of the infinite synthetic population, so a
+ * rank can generate just its own shard. Offsets are relative to the shard (offsets[0] == 0).
+ * Host: offsets[n+1] (in steps) for cluster-wise lengths uniform in [len_min, len_max]. */
+int scema_synth_offsets(uint64_t seed, uint64_t first, uint64_t n, uint32_t cluster_size, uint32_t len_min,
+                        uint32_t len_max, uint64_t *offsets_host);
 /* Device: fill d_steps [offsets[n]][6] given device offsets. stream: cudaStream_t as void*. */
-int scema_synth_histories_device(uint64_t seed, uint64_t n, uint32_t cluster_size, double amp, double pert,
+int scema_synth_histories_device(uint64_t seed, uint64_t first, uint64_t n, uint32_t cluster_size, double amp, double pert,
                                  const uint64_t *d_offsets, double *d_steps, void *stream);
 /* Device: already-resampled rows d_rows [n][6*spline_points] in the reference's p*6+c order. */
-int scema_synth_rows_device(uint64_t seed, uint64_t n, uint32_t cluster_size, uint32_t spline_points, double amp,
+int scema_synth_rows_device(uint64_t seed, uint64_t first, uint64_t n, uint32_t cluster_size, uint32_t spline_points, double amp,
                             double pert, double *d_rows, void *stream);
 
 #ifdef __cplusplus

@@ -56,9 +56,9 @@ def lib():
         "scema_last_counters": (i32, [vp, P(u64)]),
         "scema_kernel_launches": (u64, [vp]),
         "scema_fp64_peak": (i32, [vp, P(dbl)]),
-        "scema_synth_offsets": (i32, [u64, u64, u32, u32, u32, vp]),
-        "scema_synth_histories_device": (i32, [u64, u64, u32, dbl, dbl, vp, vp, vp]),
-        "scema_synth_rows_device": (i32, [u64, u64, u32, u32, dbl, dbl, vp, vp]),
+        "scema_synth_offsets": (i32, [u64, u64, u64, u32, u32, u32, vp]),
+        "scema_synth_histories_device": (i32, [u64, u64, u64, u32, dbl, dbl, vp, vp, vp]),
+        "scema_synth_rows_device": (i32, [u64, u64, u64, u32, u32, dbl, dbl, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -44,7 +44,7 @@ void scema_destroy(scema_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->steps_own.release(); c->d_offsets.release(); c->d_tables.release(); c->d_table_index.release();
-    c->zscratch.release(); c->spline_own.release(); c->d_filter.release(); c->d_halfnorm.release();
+    c->zscratch.release(); c->d_order.release(); c->spline_own.release(); c->d_filter.release(); c->d_halfnorm.release();
     c->d_blockmax.release(); c->d_panel_start.release(); c->d_cand.release(); c->d_counters.release();
     for (int b = 0; b < 2; b++) { c->d_edge_key[b].release(); c->d_edge_val[b].release(); }
     c->d_sort_tmp.release();
@@ -64,11 +64,11 @@ static int enter(scema_ctx *c)
     return SCEMA_OK;
 }
 
-static void set_ids(scema_ctx *c, const uint32_t *ids, uint64_t n)
+static void set_ids(std::vector<uint32_t> &dst, const uint32_t *ids, uint64_t n)
 {
-    c->ids.resize(n);
-    if (ids) std::copy(ids, ids + n, c->ids.begin());
-    else for (uint64_t i = 0; i < n; i++) c->ids[i] = (uint32_t)i;
+    dst.resize(n);
+    if (ids) std::copy(ids, ids + n, dst.begin());
+    else for (uint64_t i = 0; i < n; i++) dst[i] = (uint32_t)i;
 }
 
 int scema_set_histories(scema_ctx *c, const double *steps, int steps_on_device, const uint64_t *offsets,
@@ -79,9 +79,9 @@ int scema_set_histories(scema_ctx *c, const double *steps, int steps_on_device, 
     if (n && (!offsets || !steps)) return fail(c, SCEMA_ERR_INVALID, "set_histories: null pointer");
     if (n >= (1ull << 32)) return fail(c, SCEMA_ERR_INVALID, "set_histories: more than 2^32-1 histories");
     c->have_histories = false;
-    c->have_spline = false;
+    c->have_spline = false;  // as add_current_strain: up_to_date = false (strain2spline.h:77)
     c->have_edges = false;
-    c->n = n;
+    c->hn = n;
     if (offsets) c->h_offsets.assign(offsets, offsets + n + 1);
     else c->h_offsets.assign(1, 0);
     uint32_t mx = 0, mn = 0xffffffffu;
@@ -95,7 +95,7 @@ int scema_set_histories(scema_ctx *c, const double *steps, int steps_on_device, 
     c->max_len = mx;
     c->min_len = n ? mn : 0;
     c->total_steps = n ? offsets[n] : 0;  // offsets index `steps` absolutely
-    set_ids(c, ids, n);
+    set_ids(c->hist_ids, ids, n);
     SCEMA_CUDA(c, c->d_offsets.reserve((n + 1) * sizeof(uint64_t)));
     SCEMA_CUDA(c, cudaMemcpyAsync(c->d_offsets.p, c->h_offsets.data(), (n + 1) * sizeof(uint64_t),
                                   cudaMemcpyHostToDevice, c->stream));
@@ -111,6 +111,7 @@ int scema_set_histories(scema_ctx *c, const double *steps, int steps_on_device, 
     }
     SCEMA_CUDA(c, cudaStreamSynchronize(c->stream));  // h_offsets / caller buffers may be pageable
     c->have_histories = true;
+    c->histories_version++;
     return SCEMA_OK;
 }
 
@@ -128,11 +129,11 @@ int scema_set_spline(scema_ctx *c, const double *rows, int rows_on_device, uint6
     if (rc) return rc;
     if (n && k && !rows) return fail(c, SCEMA_ERR_INVALID, "set_spline: null pointer");
     if (n >= (1ull << 32)) return fail(c, SCEMA_ERR_INVALID, "set_spline: more than 2^32-1 histories");
-    c->have_histories = false;
+    c->have_spline = false;
     c->have_edges = false;
     c->n = n;
     c->K = k;
-    set_ids(c, ids, n);
+    set_ids(c->ids, ids, n);
     if (rows_on_device) {
         c->d_spline = rows;
     } else {

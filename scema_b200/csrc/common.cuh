@@ -60,13 +60,13 @@ struct scema_ctx {
     uint64_t launches = 0;
 
     // ---- raw histories
-    uint64_t n = 0;              // histories in the batch
+    uint64_t hn = 0;             // raw histories in the batch
     uint64_t total_steps = 0;
     uint32_t max_len = 0, min_len = 0;
     const double *d_steps = nullptr;  // borrowed or = steps_own
     scema::DevBuf steps_own, d_offsets;
     std::vector<uint64_t> h_offsets;
-    std::vector<uint32_t> ids;
+    std::vector<uint32_t> hist_ids;
     bool have_histories = false;
 
     // ---- K1 tables: one per (L) for the current P
@@ -75,10 +75,13 @@ struct scema_ctx {
     scema::DevBuf d_tables, d_table_index;   // d_table_index: int64 [max_len+1] -> offset or -1
     uint64_t tables_used = 0;                // doubles
     uint32_t table_index_len = 0;
-    scema::DevBuf zscratch;
+    scema::DevBuf zscratch, d_order;
+    uint64_t histories_version = 0, order_version = ~0ull;
 
-    // ---- spline matrix S [n][K]
+    // ---- spline matrix S [n][K] (n == hn after a resample; set_spline may install any n)
+    uint64_t n = 0;
     uint32_t K = 0;
+    std::vector<uint32_t> ids;
     const double *d_spline = nullptr;  // borrowed or = spline_own
     scema::DevBuf spline_own;
     bool have_spline = false;

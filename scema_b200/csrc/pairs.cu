@@ -722,17 +722,18 @@ __global__ void __launch_bounds__(256) k_peak_dfma(double *out, double a, double
 }
 __global__ void __launch_bounds__(256) k_peak_dmma(double *out, double av, double bv, int iters)
 {
-    double c[16][2];
+    constexpr int NACC = 8;  // independent accumulator fragments per warp
+    double c[NACC][2];
 #pragma unroll
-    for (int i = 0; i < 16; i++) c[i][0] = c[i][1] = 0.0;
+    for (int i = 0; i < NACC; i++) c[i][0] = c[i][1] = 0.0;
     const double a = av + threadIdx.x * 1e-12, b = bv;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) dmma_m8n8k4(c[i][0], c[i][1], a, b);
+        for (int i = 0; i < NACC; i++) dmma_m8n8k4(c[i][0], c[i][1], a, b);
     }
     double s = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) s += c[i][0] + c[i][1];
+    for (int i = 0; i < NACC; i++) s += c[i][0] + c[i][1];
     if (s == 123.456) out[0] = s;
 }
 
@@ -740,13 +741,13 @@ int fp64_peak_run(scema_ctx *ctx, double out[2])
 {
     SCEMA_CUDA(ctx, ctx->d_counters.reserve(8 * sizeof(uint64_t)));
     double *d = ctx->d_counters.as<double>();
-    const int iters = 2048, blocks = ctx->sm_count * 8;
+    const int iters = 8192, blocks = ctx->sm_count * 8;
     cudaEvent_t e0, e1;
     SCEMA_CUDA(ctx, cudaEventCreate(&e0));
     SCEMA_CUDA(ctx, cudaEventCreate(&e1));
     for (int which = 0; which < 2; which++) {
         float best = 1e30f;
-        for (int rep = 0; rep < 6; rep++) {
+        for (int rep = 0; rep < 7; rep++) {
             SCEMA_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
             if (which == 0) k_peak_dfma<<<blocks, 256, 0, ctx->stream>>>(d, 1.0000001, 1e-9, iters);
             else k_peak_dmma<<<blocks, 256, 0, ctx->stream>>>(d, 1.0, 1e-9, iters);
@@ -758,7 +759,7 @@ int fp64_peak_run(scema_ctx *ctx, double out[2])
             if (rep >= 2 && ms < best) best = ms;
         }
         const double threads = (double)blocks * 256;
-        const double flops = which == 0 ? threads * iters * 16 * 2.0 : threads / 32 * iters * 16 * (8 * 8 * 4 * 2.0);
+        const double flops = which == 0 ? threads * iters * 16 * 2.0 : threads / 32 * iters * 8 * (8 * 8 * 4 * 2.0);
         out[which] = flops / (best * 1e-3) / 1e12;
     }
     cudaEventDestroy(e0);

@@ -14,16 +14,25 @@
 //  * The tridiagonal matrix depends only on the history length L (knots are i/(L-1)), so its
 //    preconditioned LU factors are tabulated once per distinct L (k_build_tables), together with
 //    the sample -> interval map for the current spline_points.
-//  * k_resample: one warp per group of five histories; lane = (history-in-group, component)
-//    runs the two sequential sweeps of its own chain (30 of 32 lanes busy), z/b live in a
-//    per-warp shared-memory slab laid out [step][lane] (conflict-free); the whole warp then
-//    evaluates the 5*6*P samples and stores them coalesced in the reference's p*6+c order.
+//  * k_resample_staged: one warp per group of five histories. The TMA engine copies each
+//    history's contiguous [L][6] block into the warp's shared-memory slab (cp.async.bulk +
+//    mbarrier: coalesced, no register staging); lane = (history-in-group, component) then runs
+//    the two sequential sweeps of its own chain out of shared memory (30 of 32 lanes busy),
+//    overwriting y by z and b in place; finally the whole warp evaluates the 5*6*P samples and
+//    stores them in the reference's p*6+c order (one contiguous 48*P-byte row per history).
+//  * Histories are processed in length classes (one launch each) so the slab, and with it the
+//    number of resident warps per SM, is sized for the class and not for the longest history.
+//  * k_resample_global: fallback for histories longer than a slab (L > 800).
 #include "common.cuh"
+#include <algorithm>
 
 namespace scema {
 
-// table for one L: x[L] hd[L] sd[L] lo[L] up[L] di[L] ht[P] idx[P]
-__host__ __device__ inline uint64_t table_doubles(uint32_t L, uint32_t P) { return 6ull * L + 2ull * P; }
+// table for one L, every array padded to an even length Lp (so each starts 16-byte aligned and the
+// five arrays the sweeps need are one contiguous block for a bulk copy):
+//   x[Lp] | hd[Lp] sd[Lp] lo[Lp] up[Lp] di[Lp] | ht[Pp] idx[Pp]
+__host__ __device__ inline uint32_t pad2(uint32_t v) { return v + (v & 1u); }
+__host__ __device__ inline uint64_t table_doubles(uint32_t L, uint32_t P) { return 6ull * pad2(L) + 2ull * pad2(P); }
 
 __global__ void k_build_tables(const uint32_t *__restrict__ lens, const uint64_t *__restrict__ offs,
                                uint32_t n_tables, uint32_t P, double *__restrict__ tables)
@@ -32,8 +41,10 @@ __global__ void k_build_tables(const uint32_t *__restrict__ lens, const uint64_t
     if (ti >= n_tables) return;
     const uint32_t L = lens[ti];
     const int n = (int)L;
-    double *x = tables + offs[ti], *hd = x + L, *sd = hd + L, *lo = sd + L, *up = lo + L, *di = up + L,
-           *ht = di + L, *ix = ht + P;
+    const uint32_t Lp = pad2(L);
+    double *x = tables + offs[ti], *hd = x + Lp, *sd = hd + Lp, *lo = sd + Lp, *up = lo + Lp, *di = up + Lp,
+           *ht = di + Lp, *ix = ht + pad2(P);
+    if (Lp != L) x[L] = hd[L] = sd[L] = lo[L] = up[L] = di[L] = 0.0;
     const double third = 1.0 / 3.0, twothird = 2.0 / 3.0;  // spline.h:303-305
     for (int i = 0; i < n; i++) x[i] = __ddiv_rn((double)i, (double)(L - 1));  // strain2spline.h:157
     for (int i = 0; i < n; i++) hd[i] = i < n - 1 ? __dsub_rn(x[i + 1], x[i]) : 0.0;
@@ -72,43 +83,197 @@ __global__ void k_build_tables(const uint32_t *__restrict__ lens, const uint64_t
 
 constexpr int GROUP = 5;  // histories per warp (5*6 = 30 chain lanes)
 
-template <bool SMEM_Z>
-__global__ void __launch_bounds__(32) k_resample(const double *__restrict__ steps,
-                                                 const uint64_t *__restrict__ offsets,
-                                                 const int64_t *__restrict__ table_index,
-                                                 const double *__restrict__ tables, uint32_t P, uint64_t n,
-                                                 double *__restrict__ out, double *__restrict__ zglobal)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- staged kernel: each history's [L][6] block is brought into the warp's shared-memory slab by
+// one 1-D bulk copy of the TMA engine (cp.async.bulk, completion on an mbarrier); the sweeps run out
+// of shared memory and overwrite y_i by z_i and then b_i in place. History hh of the group starts at
+// a slab offset == 6*hh (mod 16 doubles), which makes the lock-step accesses of the 30 chain lanes
+// (stride 6 doubles per step) shared-memory bank-conflict free.
+__global__ void __launch_bounds__(32) k_resample_staged(const double *__restrict__ steps,
+                                                        const uint64_t *__restrict__ offsets,
+                                                        const uint32_t *__restrict__ order, uint64_t first, uint64_t count,
+                                                        const int64_t *__restrict__ table_index,
+                                                        const double *__restrict__ tables, uint32_t P,
+                                                        double *__restrict__ out, uint32_t cap)
 {
-    extern __shared__ double zs[];  // [Lmax][32] when SMEM_Z
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *tslot = reinterpret_cast<double *>(smem_raw + 16);  // hd sd lo up di of one length
+    double *slab = tslot + 5 * (size_t)pad2(cap);
     const int lane = threadIdx.x;
     const uint32_t K = 6 * P;
     const double third = 1.0 / 3.0;
-    const uint64_t n_groups = (n + GROUP - 1) / GROUP;
+    const uint64_t n_groups = (count + GROUP - 1) / GROUP;
+    int slot_len = -1;  // length whose factor table currently sits in tslot
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t phase = 0;
 
     for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int hh = lane / 6, c = lane - hh * 6;
-        const uint64_t h = grp * GROUP + hh;
-        const bool chain = lane < GROUP * 6 && h < n;
-        uint64_t off = 0;
-        int L = 0;
-        const double *tab = tables;
-        if (chain) {
-            off = offsets[h];
-            L = (int)(offsets[h + 1] - off);
-            tab = tables + table_index[L];
+        const uint64_t q0 = first + grp * GROUP;
+        const uint32_t n_here = (uint32_t)((count - grp * GROUP) < (uint64_t)GROUP ? (count - grp * GROUP) : (uint64_t)GROUP);
+        // group geometry, computed redundantly by every lane
+        uint64_t h_idx[GROUP], h_off[GROUP];
+        int h_len[GROUP];
+        uint32_t h_base[GROUP];
+        uint32_t total_bytes = 0, next = 0;
+#pragma unroll
+        for (int j = 0; j < GROUP; j++) {
+            h_idx[j] = 0; h_off[j] = 0; h_len[j] = 0; h_base[j] = 0;
+            if ((uint32_t)j < n_here) {
+                h_idx[j] = order ? (uint64_t)order[q0 + j] : q0 + j;
+                h_off[j] = offsets[h_idx[j]];
+                h_len[j] = (int)(offsets[h_idx[j] + 1] - h_off[j]);
+                uint32_t want = (6u * j) & 15u;
+                next += (want + 16u - (next & 15u)) & 15u;
+                h_base[j] = next;
+                next += 6u * h_len[j];
+                total_bytes += 48u * h_len[j];
+            }
         }
-        const double *y = steps + off * 6 + c;
-        const double *hd = tab + L, *sd = hd + L, *lo = sd + L, *up = lo + L, *di = up + L;
-        double *zg = SMEM_Z ? nullptr : zglobal + off * 6 + c;
+        // the group is sorted by length, so one table usually serves all five histories; it stays in
+        // the slot across groups until the length changes
+        const bool load_table = h_len[0] != slot_len;
+        const uint32_t table_bytes = 5u * pad2((uint32_t)h_len[0]) * 8u;
+        if (load_table) { total_bytes += table_bytes; slot_len = h_len[0]; }
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(total_bytes) : "memory");
+        __syncwarp();
+        if (lane == GROUP && load_table)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(tslot)),
+                         "l"(tables + table_index[h_len[0]] + pad2((uint32_t)h_len[0])), "r"(table_bytes), "r"(smem_u32(bar))
+                         : "memory");
+#pragma unroll
+        for (int j = 0; j < GROUP; j++)
+            if (lane == j && (uint32_t)j < n_here)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(slab + h_base[j])),
+                             "l"(steps + h_off[j] * 6), "r"(48u * h_len[j]), "r"(smem_u32(bar))
+                             : "memory");
+        {
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile(
+                    "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                    : "=r"(ok)
+                    : "r"(smem_u32(bar)), "r"(phase)
+                    : "memory");
+            phase ^= 1;
+        }
 
-#define ZAT(i) (SMEM_Z ? zs[(i) * 32 + lane] : zg[(size_t)(i) * 6])
-
+        const int hh = lane / 6, c = lane - hh * 6;
+        int L = 0;
+        uint32_t base = 0;
+#pragma unroll
+        for (int j = 0; j < GROUP; j++)
+            if (j == hh) { L = h_len[j]; base = h_base[j]; }
+        const bool chain = lane < GROUP * 6 && (uint32_t)hh < n_here;
         if (chain) {
+            // factor table: the shared-memory slot when this history has the slot's length, else global
+            const uint32_t Lp = pad2((uint32_t)L);
+            const double *hd = L == slot_len ? tslot : tables + table_index[L] + Lp;
+            const double *sd = hd + Lp, *lo = sd + Lp, *up = lo + Lp, *di = up + Lp;
+            double *ys = slab + base + c;
             // ---- forward substitution fused with the right-hand side (spline.h:306, :228-233)
+            double y1 = ys[0], y2 = ys[6];
+            double s_prev = __ddiv_rn(__dsub_rn(y2, y1), hd[0]);
+            double z_prev = __dsub_rn(__dmul_rn(0.0, sd[0]), 0.0);  // row 0: rhs = 0, empty sum
+            ys[0] = z_prev;
+            y1 = y2;
+#pragma unroll 4
+            for (int i = 1; i < L - 1; i++) {
+                y2 = ys[(i + 1) * 6];
+                double s_cur = __ddiv_rn(__dsub_rn(y2, y1), hd[i]);
+                double r = __dmul_rn(__dsub_rn(s_cur, s_prev), sd[i]);
+                double sum = __dadd_rn(0.0, __dmul_rn(lo[i], z_prev));
+                z_prev = __dsub_rn(r, sum);
+                ys[i * 6] = z_prev;
+                s_prev = s_cur;
+                y1 = y2;
+            }
+            {
+                double r = __dmul_rn(0.0, sd[L - 1]);  // row L-1: rhs = 0
+                double sum = __dadd_rn(0.0, __dmul_rn(lo[L - 1], z_prev));
+                z_prev = __dsub_rn(r, sum);
+            }
+            // ---- back substitution (spline.h:243-248); b overwrites z
+            double b_next = __ddiv_rn(__dsub_rn(z_prev, 0.0), di[L - 1]);
+            ys[(L - 1) * 6] = b_next;
+#pragma unroll 4
+            for (int i = L - 2; i >= 0; i--) {
+                double sum = __dadd_rn(0.0, __dmul_rn(up[i], b_next));
+                b_next = __ddiv_rn(__dsub_rn(ys[i * 6], sum), di[i]);
+                ys[i * 6] = b_next;
+            }
+        }
+        __syncwarp();
+
+        // ---- evaluation at the P sample points, all 32 lanes (spline.h:345-349, :393)
+        for (uint32_t o = lane; o < n_here * K; o += 32) {
+            const uint32_t eh = o / K, k = o - eh * K, p = k / 6, ec = k - p * 6;
+            uint64_t eidx = 0, eoff = 0;
+            int eL = 0;
+            uint32_t ebase = 0;
+#pragma unroll
+            for (int j = 0; j < GROUP; j++)
+                if ((uint32_t)j == eh) { eidx = h_idx[j]; eoff = h_off[j]; eL = h_len[j]; ebase = h_base[j]; }
+            const double *etab = tables + table_index[eL];
+            const double *ehd = etab + pad2((uint32_t)eL), *eht = etab + 6 * (size_t)pad2((uint32_t)eL), *eix = eht + pad2(P);
+            const int idx = (int)__ldg(eix + p);
+            const double hstep = __ldg(eht + p), hdv = __ldg(ehd + idx);
+            const double *ey = steps + eoff * 6 + ec;
+            const double ya = __ldg(ey + (size_t)idx * 6), yb = __ldg(ey + (size_t)(idx + 1) * 6);
+            const double b0 = slab[ebase + idx * 6 + ec], b1 = slab[ebase + (idx + 1) * 6 + ec];
+            const double a_i = __ddiv_rn(__dmul_rn(third, __dsub_rn(b1, b0)), hdv);
+            const double c_i = __dsub_rn(__ddiv_rn(__dsub_rn(yb, ya), hdv),
+                                         __dmul_rn(__dmul_rn(third, __dadd_rn(__dmul_rn(2.0, b0), b1)), hdv));
+            double v = __dadd_rn(__dmul_rn(a_i, hstep), b0);
+            v = __dadd_rn(__dmul_rn(v, hstep), c_i);
+            v = __dadd_rn(__dmul_rn(v, hstep), ya);
+            out[eidx * K + k] = v;
+        }
+        // the slab was written through the generic proxy; order that before the next bulk copy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+    }
+}
+
+// ---- fallback for histories too long for a shared-memory slab: the sweeps read y from global
+// memory and keep z/b in a global scratch buffer of the input's shape.
+__global__ void __launch_bounds__(32) k_resample_global(const double *__restrict__ steps,
+                                                        const uint64_t *__restrict__ offsets,
+                                                        const uint32_t *__restrict__ order, uint64_t first, uint64_t count,
+                                                        const int64_t *__restrict__ table_index,
+                                                        const double *__restrict__ tables, uint32_t P,
+                                                        double *__restrict__ out, double *__restrict__ zglobal)
+{
+    const int lane = threadIdx.x;
+    const uint32_t K = 6 * P;
+    const double third = 1.0 / 3.0;
+    const uint64_t n_groups = (count + GROUP - 1) / GROUP;
+    for (uint64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const uint64_t q0 = first + grp * GROUP;
+        const uint32_t n_here = (uint32_t)((count - grp * GROUP) < (uint64_t)GROUP ? (count - grp * GROUP) : (uint64_t)GROUP);
+        const int hh = lane / 6, c = lane - hh * 6;
+        const bool chain = lane < GROUP * 6 && (uint32_t)hh < n_here;
+        if (chain) {
+            const uint64_t h = order ? (uint64_t)order[q0 + hh] : q0 + hh;
+            const uint64_t off = offsets[h];
+            const int L = (int)(offsets[h + 1] - off);
+            const double *tab = tables + table_index[L];
+            const double *y = steps + off * 6 + c;
+            const uint32_t Lp = pad2((uint32_t)L);
+            const double *hd = tab + Lp, *sd = hd + Lp, *lo = sd + Lp, *up = lo + Lp, *di = up + Lp;
+            double *zg = zglobal + off * 6 + c;
             double y1 = __ldg(y), y2 = __ldg(y + 6);
             double s_prev = __ddiv_rn(__dsub_rn(y2, y1), __ldg(hd));
-            double z_prev = __dsub_rn(__dmul_rn(0.0, __ldg(sd)), 0.0);  // row 0: rhs = 0, empty sum
-            ZAT(0) = z_prev;
+            double z_prev = __dsub_rn(__dmul_rn(0.0, __ldg(sd)), 0.0);
+            zg[0] = z_prev;
             y1 = y2;
 #pragma unroll 4
             for (int i = 1; i < L - 1; i++) {
@@ -117,55 +282,48 @@ __global__ void __launch_bounds__(32) k_resample(const double *__restrict__ step
                 double r = __dmul_rn(__dsub_rn(s_cur, s_prev), __ldg(sd + i));
                 double sum = __dadd_rn(0.0, __dmul_rn(__ldg(lo + i), z_prev));
                 z_prev = __dsub_rn(r, sum);
-                ZAT(i) = z_prev;
+                zg[(size_t)i * 6] = z_prev;
                 s_prev = s_cur;
                 y1 = y2;
             }
             {
-                double r = __dmul_rn(0.0, __ldg(sd + L - 1));  // row L-1: rhs = 0
+                double r = __dmul_rn(0.0, __ldg(sd + L - 1));
                 double sum = __dadd_rn(0.0, __dmul_rn(__ldg(lo + L - 1), z_prev));
                 z_prev = __dsub_rn(r, sum);
             }
-            // ---- back substitution (spline.h:243-248); b overwrites z
             double b_next = __ddiv_rn(__dsub_rn(z_prev, 0.0), __ldg(di + L - 1));
-            ZAT(L - 1) = b_next;
+            zg[(size_t)(L - 1) * 6] = b_next;
 #pragma unroll 4
             for (int i = L - 2; i >= 0; i--) {
                 double sum = __dadd_rn(0.0, __dmul_rn(__ldg(up + i), b_next));
-                b_next = __ddiv_rn(__dsub_rn(ZAT(i), sum), __ldg(di + i));
-                ZAT(i) = b_next;
+                b_next = __ddiv_rn(__dsub_rn(zg[(size_t)i * 6], sum), __ldg(di + i));
+                zg[(size_t)i * 6] = b_next;
             }
         }
-        if (!SMEM_Z) __threadfence_block();
+        __threadfence_block();
         __syncwarp();
-
-        // ---- evaluation at the P sample points, all 32 lanes (spline.h:345-349, :393)
-        const uint64_t h0 = grp * GROUP;
-        const uint32_t n_here = (uint32_t)((n - h0) < (uint64_t)GROUP ? (n - h0) : (uint64_t)GROUP);
         for (uint32_t o = lane; o < n_here * K; o += 32) {
             const uint32_t eh = o / K, k = o - eh * K, p = k / 6, ec = k - p * 6;
-            const uint64_t eoff = offsets[h0 + eh];
-            const int eL = (int)(offsets[h0 + eh + 1] - eoff);
+            const uint64_t eidx = order ? (uint64_t)order[q0 + eh] : q0 + eh;
+            const uint64_t eoff = offsets[eidx];
+            const int eL = (int)(offsets[eidx + 1] - eoff);
             const double *etab = tables + table_index[eL];
-            const double *ehd = etab + eL, *eht = etab + 6 * (size_t)eL, *eix = eht + P;
+            const double *ehd = etab + pad2((uint32_t)eL), *eht = etab + 6 * (size_t)pad2((uint32_t)eL), *eix = eht + pad2(P);
             const int idx = (int)__ldg(eix + p);
             const double hstep = __ldg(eht + p), hdv = __ldg(ehd + idx);
             const double *ey = steps + eoff * 6 + ec;
             const double ya = __ldg(ey + (size_t)idx * 6), yb = __ldg(ey + (size_t)(idx + 1) * 6);
-            const int cl = eh * 6 + ec;
-            double b0, b1;
-            if (SMEM_Z) { b0 = zs[idx * 32 + cl]; b1 = zs[(idx + 1) * 32 + cl]; }
-            else { const double *g = zglobal + eoff * 6 + ec; b0 = g[(size_t)idx * 6]; b1 = g[(size_t)(idx + 1) * 6]; }
+            const double *g = zglobal + eoff * 6 + ec;
+            const double b0 = g[(size_t)idx * 6], b1 = g[(size_t)(idx + 1) * 6];
             const double a_i = __ddiv_rn(__dmul_rn(third, __dsub_rn(b1, b0)), hdv);
             const double c_i = __dsub_rn(__ddiv_rn(__dsub_rn(yb, ya), hdv),
                                          __dmul_rn(__dmul_rn(third, __dadd_rn(__dmul_rn(2.0, b0), b1)), hdv));
             double v = __dadd_rn(__dmul_rn(a_i, hstep), b0);
             v = __dadd_rn(__dmul_rn(v, hstep), c_i);
             v = __dadd_rn(__dmul_rn(v, hstep), ya);
-            out[h0 * K + o] = v;
+            out[eidx * K + k] = v;
         }
         __syncwarp();
-#undef ZAT
     }
 }
 
@@ -173,7 +331,7 @@ static int ensure_tables(scema_ctx *ctx, uint32_t P)
 {
     // distinct lengths of the current batch
     std::vector<uint8_t> present((size_t)ctx->max_len + 1, 0);
-    for (uint64_t i = 0; i < ctx->n; i++) present[ctx->h_offsets[i + 1] - ctx->h_offsets[i]] = 1;
+    for (uint64_t i = 0; i < ctx->hn; i++) present[ctx->h_offsets[i + 1] - ctx->h_offsets[i]] = 1;
     if (ctx->table_P != P) { ctx->table_off.clear(); ctx->tables_used = 0; ctx->table_P = P; }
     std::vector<uint32_t> new_lens;
     std::vector<uint64_t> new_offs;
@@ -232,45 +390,76 @@ int resample_run(scema_ctx *ctx, uint32_t P)
 {
     if (!ctx->have_histories) return fail(ctx, SCEMA_ERR_STATE, "resample: no histories set");
     if (P == 0) return fail(ctx, SCEMA_ERR_INVALID, "resample: spline_points must be >= 1");
-    if (ctx->n && ctx->min_len < 3)
+    if (ctx->hn && ctx->min_len < 3)
         return fail(ctx, SCEMA_ERR_INVALID,
                     "Not enough strain steps added. Need at least 3 points for splinify().");
     const uint32_t K = 6 * P;
-    SCEMA_CUDA(ctx, ctx->spline_own.reserve((size_t)(ctx->n ? ctx->n : 1) * K * sizeof(double)));
+    SCEMA_CUDA(ctx, ctx->spline_own.reserve((size_t)(ctx->hn ? ctx->hn : 1) * K * sizeof(double)));
     ctx->d_spline = ctx->spline_own.as<double>();
+    ctx->n = ctx->hn;
+    ctx->ids = ctx->hist_ids;
     ctx->K = K;
     ctx->spline_version++;
     ctx->have_spline = true;
     ctx->have_edges = false;
-    if (ctx->n == 0) return SCEMA_OK;
+    if (ctx->hn == 0) return SCEMA_OK;
 
     int rc = ensure_tables(ctx, P);
     if (rc) return rc;
 
-    const uint64_t n_groups = (ctx->n + GROUP - 1) / GROUP;
-    const size_t slab = (size_t)ctx->max_len * 32 * sizeof(double);
-    t_begin(ctx, SCEMA_T_RESAMPLE);
-    if (slab <= ctx->smem_optin) {
-        int per_sm = (int)(ctx->smem_optin / (slab + 1024));
-        if (per_sm > 32) per_sm = 32;
-        if (per_sm < 1) per_sm = 1;
-        uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
-        if (grid > n_groups) grid = n_groups;
-        SCEMA_CUDA(ctx, cudaFuncSetAttribute(k_resample<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)slab));
-        k_resample<true><<<(unsigned)grid, 32, slab, ctx->stream>>>(
-            ctx->d_steps, ctx->d_offsets.as<uint64_t>(), ctx->d_table_index.as<int64_t>(),
-            ctx->d_tables.as<double>(), P, ctx->n, ctx->spline_own.as<double>(), nullptr);
-    } else {
-        // very long histories: z/b sweep buffers in global memory (same [step][6] shape as the input)
-        SCEMA_CUDA(ctx, ctx->zscratch.reserve((size_t)ctx->total_steps * 6 * sizeof(double)));
-        uint64_t grid = (uint64_t)ctx->sm_count * 32;
-        if (grid > n_groups) grid = n_groups;
-        k_resample<false><<<(unsigned)grid, 32, 0, ctx->stream>>>(
-            ctx->d_steps, ctx->d_offsets.as<uint64_t>(), ctx->d_table_index.as<int64_t>(),
-            ctx->d_tables.as<double>(), P, ctx->n, ctx->spline_own.as<double>(), ctx->zscratch.as<double>());
+    // Length classes: every class gets its own launch with a slab sized for the class, so short
+    // histories are not starved of resident warps by the longest one. Inside a class the work order
+    // is sorted by exact length (stable counting sort), so the five histories of a warp group almost
+    // always share one factor table and neighbours in memory stay neighbours in the work order.
+    static const uint32_t caps[] = {16, 32, 48, 64, 96, 128, 192, 256, 384, 512, 800};
+    constexpr int NCLS = sizeof(caps) / sizeof(caps[0]) + 1;  // last class: global-scratch fallback
+    auto cls_of = [&](uint64_t L) { int k = 0; while (k < NCLS - 1 && L > caps[k]) k++; return k; };
+    uint64_t cls_count[NCLS] = {};
+    for (uint64_t i = 0; i < ctx->hn; i++) cls_count[cls_of(ctx->h_offsets[i + 1] - ctx->h_offsets[i])]++;
+    uint64_t cls_first[NCLS + 1] = {};
+    for (int k = 0; k < NCLS; k++) cls_first[k + 1] = cls_first[k] + cls_count[k];
+    const uint32_t *d_order = nullptr;
+    if (ctx->min_len != ctx->max_len) {
+        if (ctx->order_version != ctx->histories_version) {
+            std::vector<uint64_t> len_first((size_t)ctx->max_len + 2, 0);
+            for (uint64_t i = 0; i < ctx->hn; i++) len_first[ctx->h_offsets[i + 1] - ctx->h_offsets[i] + 1]++;
+            for (uint32_t L = 0; L <= ctx->max_len; L++) len_first[L + 1] += len_first[L];
+            std::vector<uint32_t> order(ctx->hn);
+            for (uint64_t i = 0; i < ctx->hn; i++) order[len_first[ctx->h_offsets[i + 1] - ctx->h_offsets[i]]++] = (uint32_t)i;
+            SCEMA_CUDA(ctx, ctx->d_order.reserve(ctx->hn * sizeof(uint32_t)));
+            SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_order.p, order.data(), ctx->hn * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                            ctx->stream));
+            SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->order_version = ctx->histories_version;
+        }
+        d_order = ctx->d_order.as<uint32_t>();
     }
-    ctx->launches++;
+    if (cls_count[NCLS - 1]) SCEMA_CUDA(ctx, ctx->zscratch.reserve((size_t)ctx->total_steps * 6 * sizeof(double)));
+    auto smem_for = [&](uint32_t cap) { return (size_t)16 + 5 * (size_t)pad2(cap) * 8 + ((size_t)GROUP * 6 * cap + 64) * sizeof(double); };
+
+    t_begin(ctx, SCEMA_T_RESAMPLE);
+    for (int k = 0; k < NCLS; k++) {
+        if (!cls_count[k]) continue;
+        const uint64_t n_groups = (cls_count[k] + GROUP - 1) / GROUP;
+        if (k < NCLS - 1) {
+            const size_t slab = smem_for(caps[k]);
+            int per_sm = (int)(ctx->smem_optin / (slab + 1024));
+            per_sm = per_sm > 32 ? 32 : (per_sm < 1 ? 1 : per_sm);
+            uint64_t grid = std::min<uint64_t>((uint64_t)ctx->sm_count * per_sm, n_groups);
+            SCEMA_CUDA(ctx, cudaFuncSetAttribute(k_resample_staged, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem_for(caps[NCLS - 2])));
+            k_resample_staged<<<(unsigned)grid, 32, slab, ctx->stream>>>(
+                ctx->d_steps, ctx->d_offsets.as<uint64_t>(), d_order, cls_first[k], cls_count[k],
+                ctx->d_table_index.as<int64_t>(), ctx->d_tables.as<double>(), P, ctx->spline_own.as<double>(), caps[k]);
+        } else {
+            uint64_t grid = std::min<uint64_t>((uint64_t)ctx->sm_count * 32, n_groups);
+            k_resample_global<<<(unsigned)grid, 32, 0, ctx->stream>>>(
+                ctx->d_steps, ctx->d_offsets.as<uint64_t>(), d_order, cls_first[k], cls_count[k],
+                ctx->d_table_index.as<int64_t>(), ctx->d_tables.as<double>(), P, ctx->spline_own.as<double>(),
+                ctx->zscratch.as<double>());
+        }
+        ctx->launches++;
+    }
     t_end(ctx, SCEMA_T_RESAMPLE);
     SCEMA_CUDA(ctx, cudaGetLastError());
     return SCEMA_OK;

@@ -35,15 +35,16 @@ __device__ inline double synth_value(uint64_t seed, uint64_t i, uint64_t q, int 
     return __dadd_rn(centre, __dmul_rn(delta, t));
 }
 
-__global__ void k_synth_hist(uint64_t seed, uint64_t n, uint32_t cs, double amp, double pert,
+__global__ void k_synth_hist(uint64_t seed, uint64_t first, uint64_t n, uint32_t cs, double amp, double pert,
                              const uint64_t *__restrict__ offsets, double *__restrict__ steps)
 {
     // one warp per history, lanes stride the steps
-    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= n) return;
+    const uint64_t li = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (li >= n) return;
     const int lane = threadIdx.x & 31;
-    const uint64_t off = offsets[i];
-    const uint32_t L = (uint32_t)(offsets[i + 1] - off);
+    const uint64_t off = offsets[li];
+    const uint32_t L = (uint32_t)(offsets[li + 1] - off);
+    const uint64_t i = first + li;
     const uint64_t q = i / cs;
     for (uint32_t e = lane; e < L * 6; e += 32) {
         const uint32_t s = e / 6;
@@ -53,14 +54,14 @@ __global__ void k_synth_hist(uint64_t seed, uint64_t n, uint32_t cs, double amp,
     }
 }
 
-__global__ void k_synth_rows(uint64_t seed, uint64_t n, uint32_t cs, uint32_t P, double amp, double pert,
+__global__ void k_synth_rows(uint64_t seed, uint64_t first, uint64_t n, uint32_t cs, uint32_t P, double amp, double pert,
                              double *__restrict__ rows)
 {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t K = 6 * P;
     if (idx >= n * K) return;
-    const uint64_t i = idx / K;
-    const uint32_t k = (uint32_t)(idx - i * K), p = k / 6;
+    const uint64_t li = idx / K, i = first + li;
+    const uint32_t k = (uint32_t)(idx - li * K), p = k / 6;
     const int c = (int)(k - p * 6);
     const double t = __ddiv_rn((double)p, (double)(P - 1));
     rows[idx] = synth_value(seed, i, i / cs, c, t, amp, pert);
@@ -70,33 +71,33 @@ __global__ void k_synth_rows(uint64_t seed, uint64_t n, uint32_t cs, uint32_t P,
 
 extern "C" {
 
-int scema_synth_offsets(uint64_t seed, uint64_t n, uint32_t cluster_size, uint32_t len_min, uint32_t len_max,
-                        uint64_t *offsets_host)
+int scema_synth_offsets(uint64_t seed, uint64_t first, uint64_t n, uint32_t cluster_size, uint32_t len_min,
+                        uint32_t len_max, uint64_t *offsets_host)
 {
     if (!offsets_host || cluster_size == 0 || len_min < 2 || len_max < len_min) return SCEMA_ERR_INVALID;
     offsets_host[0] = 0;
-    for (uint64_t i = 0; i < n; i++) offsets_host[i + 1] = offsets_host[i] + cluster_len(seed, i / cluster_size, len_min, len_max);
+    for (uint64_t i = 0; i < n; i++) offsets_host[i + 1] = offsets_host[i] + cluster_len(seed, (first + i) / cluster_size, len_min, len_max);
     return SCEMA_OK;
 }
 
-int scema_synth_histories_device(uint64_t seed, uint64_t n, uint32_t cluster_size, double amp, double pert,
+int scema_synth_histories_device(uint64_t seed, uint64_t first, uint64_t n, uint32_t cluster_size, double amp, double pert,
                                  const uint64_t *d_offsets, double *d_steps, void *stream)
 {
     if (cluster_size == 0) return SCEMA_ERR_INVALID;
     if (n == 0) return SCEMA_OK;
     const uint64_t blocks = (n * 32 + 255) / 256;
-    k_synth_hist<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(seed, n, cluster_size, amp, pert, d_offsets, d_steps);
+    k_synth_hist<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(seed, first, n, cluster_size, amp, pert, d_offsets, d_steps);
     return cudaGetLastError() == cudaSuccess ? SCEMA_OK : SCEMA_ERR_CUDA;
 }
 
-int scema_synth_rows_device(uint64_t seed, uint64_t n, uint32_t cluster_size, uint32_t spline_points, double amp,
+int scema_synth_rows_device(uint64_t seed, uint64_t first, uint64_t n, uint32_t cluster_size, uint32_t spline_points, double amp,
                             double pert, double *d_rows, void *stream)
 {
     if (cluster_size == 0 || spline_points < 2) return SCEMA_ERR_INVALID;
     if (n == 0) return SCEMA_OK;
     const uint64_t total = n * 6 * spline_points;
-    k_synth_rows<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, n, cluster_size, spline_points,
-                                                                                   amp, pert, d_rows);
+    k_synth_rows<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, first, n, cluster_size,
+                                                                                   spline_points, amp, pert, d_rows);
     return cudaGetLastError() == cudaSuccess ? SCEMA_OK : SCEMA_ERR_CUDA;
 }
 

@@ -31,8 +31,8 @@ def u01(x):
     return (x >> np.uint64(11)).astype(np.float64) * _U
 
 
-def offsets(seed, n, cluster_size, len_min, len_max):
-    q = np.arange(n, dtype=np.uint64) // np.uint64(cluster_size)
+def offsets(seed, n, cluster_size, len_min, len_max, first=0):
+    q = (np.arange(n, dtype=np.uint64) + np.uint64(first)) // np.uint64(cluster_size)
     lens = np.uint64(len_min) + hash4(seed, q, 0, 7) % np.uint64(len_max - len_min + 1)
     off = np.zeros(n + 1, dtype=np.uint64)
     np.cumsum(lens, out=off[1:])
@@ -47,12 +47,12 @@ def _value(seed, i, q, c, t, amp, pert):
     return centre + delta * t
 
 
-def histories(seed, n, cluster_size, amp, pert, off):
-    """-> steps [off[n], 6] float64 for the given offsets."""
+def histories(seed, n, cluster_size, amp, pert, off, first=0):
+    """-> steps [off[n], 6] float64 for the given (shard-relative) offsets."""
     off = np.asarray(off, dtype=np.uint64)
     lens = (off[1:] - off[:-1]).astype(np.int64)
     total = int(off[-1])
-    i = np.repeat(np.arange(n, dtype=np.uint64), lens)
+    i = np.repeat(np.arange(n, dtype=np.uint64) + np.uint64(first), lens)
     s = np.arange(total, dtype=np.int64) - np.repeat(off[:-1].astype(np.int64), lens)
     Lm1 = np.repeat(lens - 1, lens).astype(np.float64)
     t = s.astype(np.float64) / Lm1
@@ -63,10 +63,10 @@ def histories(seed, n, cluster_size, amp, pert, off):
     return out
 
 
-def rows(seed, n, cluster_size, spline_points, amp, pert):
+def rows(seed, n, cluster_size, spline_points, amp, pert, first=0):
     """-> already-resampled rows [n, 6*P] in the reference's p*6+c order."""
     P = spline_points
-    i = np.arange(n, dtype=np.uint64)[:, None]
+    i = (np.arange(n, dtype=np.uint64) + np.uint64(first))[:, None]
     q = i // np.uint64(cluster_size)
     t = (np.arange(P, dtype=np.float64) / float(P - 1))[None, :]
     out = np.empty((n, P, 6), dtype=np.float64)
@@ -81,3 +81,39 @@ def default_pert(threshold, spline_points):
     P = spline_points
     s2 = sum((p / (P - 1.0)) ** 2 for p in range(P))
     return float(threshold) * 0.5 / (s2 ** 0.5)
+
+
+# ---- device-side generation through the C ABI (include/scema_synth.h) into torch tensors --------
+def device_offsets(seed, n, cluster_size, len_min, len_max, first=0):
+    from . import binding
+    off = np.empty(n + 1, dtype=np.uint64)
+    rc = binding.lib().scema_synth_offsets(seed, first, n, cluster_size, len_min, len_max, off.ctypes.data)
+    if rc:
+        raise binding.ScemaError(rc, "synth_offsets")
+    return off
+
+
+def device_histories(seed, n, cluster_size, amp, pert, off, first=0, device="cuda"):
+    """-> torch float64 tensor [off[n], 6] generated on the device (bit-identical to histories())."""
+    import torch
+    from . import binding
+    d_off = torch.from_numpy(off.astype(np.int64)).to(device)
+    steps = torch.empty((int(off[-1]), 6), dtype=torch.float64, device=device)
+    rc = binding.lib().scema_synth_histories_device(seed, first, n, cluster_size, amp, pert, d_off.data_ptr(),
+                                                    steps.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    if rc:
+        raise binding.ScemaError(rc, "synth_histories_device")
+    torch.cuda.current_stream().synchronize()
+    return steps
+
+
+def device_rows(seed, n, cluster_size, spline_points, amp, pert, first=0, device="cuda"):
+    import torch
+    from . import binding
+    rows_t = torch.empty((n, 6 * spline_points), dtype=torch.float64, device=device)
+    rc = binding.lib().scema_synth_rows_device(seed, first, n, cluster_size, spline_points, amp, pert,
+                                               rows_t.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    if rc:
+        raise binding.ScemaError(rc, "synth_rows_device")
+    torch.cuda.current_stream().synchronize()
+    return rows_t
