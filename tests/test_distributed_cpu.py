@@ -1,0 +1,72 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size-2/3 gloo process groups exercise the
+row all-gather (uneven shares), the edge-count all-gather and the shard arithmetic. The kernels
+themselves never run on the CPU."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from scema_b200.distributed import gather_counts, gather_rows, shard_bounds
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, k, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full_ref = torch.arange(n * k, dtype=torch.float64).reshape(n, k) * 0.5
+        b, e = shard_bounds(n, world)[rank]
+        full = gather_rows(full_ref[b:e].clone(), n, world)
+        assert torch.equal(full, full_ref)
+        counts, offs = gather_counts(10 * rank + 3, torch.device("cpu"))
+        assert counts == [10 * r + 3 for r in range(world)]
+        assert offs == [sum(counts[:r]) for r in range(world)]
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, n, k, tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n, k, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def test_shard_bounds():
+    for n in (0, 1, 7, 1000, 1000003):
+        for w in (1, 2, 3, 8):
+            b = shard_bounds(n, w)
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [e - s for s, e in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_gather_even_world2(tmp_path):
+    _run(2, 64, 6, tmp_path)
+
+
+def test_gather_uneven_world3(tmp_path):
+    _run(3, 101, 12, tmp_path)
+
+
+def test_tile_shards_partition_the_groups():
+    """Every strip group of the K2 schedule belongs to exactly one shard (same arithmetic as
+    compare_run in pairs.cu: group g -> shard g % n_shards)."""
+    for groups in (1, 5, 97, 1000):
+        for w in (1, 2, 3, 8):
+            owned = []
+            for s in range(w):
+                local = (groups - s + w - 1) // w if groups > s else 0
+                owned += [lg * w + s for lg in range(local)]
+            assert sorted(owned) == list(range(groups))
