@@ -2,7 +2,7 @@
 // line clustering/compare_all_histories.cc:31-87 (same argv and stdout format).
 //
 // The reference source is stale against its own header (it does not compile: SURVEY.md §8c); this
-// follows its evident intent, which oracle/Makefile's streamed patch also realises: print
+// follows its evident intent (the test-side build of the reference patches it the same way): print
 // "Reading: '<f>'" / "Ignoring: '<f>'" per directory entry, then "<A> vs <B>:<L2>" for every pair
 // i <= j in batch order (self pairs included), then the three wall-clock lines in whole seconds.
 // <A>/<B> are the bare directory entry names. Every distance is computed on the GPU by the exact
