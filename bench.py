@@ -202,8 +202,12 @@ def run_ours(args, wl, wl_name):
     b, e = shard_bounds(n, world)[rank]
     n_local = e - b
 
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream carries everything: the library's kernels, the NCCL
+    # collectives and the timing events
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     hc = scema_b200.HistCluster(local_rank, stream.cuda_stream)
+    assert hc.stream_ptr() == stream.cuda_stream
     off = synth.device_offsets(SEED, n_local, CLUSTER, wl["lmin"], wl["lmax"], first=b)
     d_steps = synth.device_histories(SEED, n_local, CLUSTER, AMP, pert, off, first=b, device=dev)
     steps_bytes = d_steps.numel() * 8

@@ -46,6 +46,11 @@ int scema_create(scema_ctx **out, int device, void *stream);
 void scema_destroy(scema_ctx *ctx);
 const char *scema_last_error(const scema_ctx *ctx); /* "" when the last call succeeded */
 const char *scema_version(void);
+/* The cudaStream_t (as void*) every call of this context is ordered on: the caller's stream given
+ * to scema_create, or the library's own non-blocking stream. Work that produces borrowed device
+ * inputs or consumes device outputs (e.g. an NCCL all-gather of the spline rows) must be ordered
+ * against this stream. */
+int scema_stream(scema_ctx *ctx, void **stream);
 
 /* ---- ingest: replaces Strain6D storage, add_current_strain (strain2spline.h:75-86) and the
  *      data half of from_file (:112-134) for a whole batch of quadrature points ---------------

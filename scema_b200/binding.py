@@ -38,6 +38,7 @@ def lib():
         "scema_destroy": (None, [vp]),
         "scema_last_error": (C.c_char_p, [vp]),
         "scema_version": (C.c_char_p, []),
+        "scema_stream": (i32, [vp, P(vp)]),
         "scema_set_histories": (i32, [vp, vp, i32, vp, vp, u64]),
         "scema_resample": (i32, [vp, u32]),
         "scema_set_spline": (i32, [vp, vp, i32, u64, u32, vp]),
@@ -69,7 +70,7 @@ def lib():
 
 
 EXPORTED = (
-    "scema_create scema_destroy scema_last_error scema_version scema_set_histories scema_resample "
+    "scema_create scema_destroy scema_last_error scema_version scema_stream scema_set_histories scema_resample "
     "scema_set_spline scema_get_spline scema_spline_info scema_compare scema_get_edges scema_edges_device "
     "scema_get_degrees scema_cluster scema_write_similar_hist scema_reduce_edges scema_reduce_calls scema_reduce_dir "
     "scema_last_timings scema_last_counters scema_kernel_launches scema_fp64_peak scema_synth_offsets "
@@ -121,6 +122,12 @@ class HistCluster:
     def _ck(self, rc):
         if rc:
             raise ScemaError(rc, self._L.scema_last_error(self._h).decode())
+
+    def stream_ptr(self):
+        """cudaStream_t (int) all work of this context is ordered on."""
+        p = C.c_void_p(None)
+        self._ck(self._L.scema_stream(self._h, C.byref(p)))
+        return int(p.value or 0)
 
     # ---- ingest ----
     def set_histories(self, steps, offsets, ids=None, device_ptr=None):

@@ -56,6 +56,13 @@ void scema_destroy(scema_ctx *c)
 
 const char *scema_last_error(const scema_ctx *c) { return c ? c->err.c_str() : "null context"; }
 
+int scema_stream(scema_ctx *c, void **stream)
+{
+    if (!c || !stream) return SCEMA_ERR_INVALID;
+    *stream = (void *)c->stream;
+    return SCEMA_OK;
+}
+
 static int enter(scema_ctx *c)
 {
     if (!c) return SCEMA_ERR_INVALID;

@@ -69,15 +69,25 @@ class ShardedCluster:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
+    def stream(self):
+        """The context's CUDA stream as a torch stream: the collectives and every torch op of run()
+        are issued on it, so they are ordered with the library's kernels (the library may run on
+        its own non-blocking stream, which does not synchronise with torch's default stream)."""
+        ptr = self.hc.stream_ptr()
+        if ptr == 0:
+            return torch.cuda.default_stream()
+        return torch.cuda.ExternalStream(ptr)
+
     def run(self, n, spline_points, threshold, variant=0):
         """The local share of the histories must already be set on self.hc (set_histories).
         -> (local_edge_count, counts, offsets, full_rows tensor)."""
         hc = self.hc
-        hc.resample(spline_points)
-        n_local, K, ptr = hc.spline_info()
-        local = torch.as_tensor(CudaView(ptr, (n_local, K)), device="cuda")
-        full = gather_rows(local, n, self.world, self.group)
-        hc.set_spline(device_ptr=full.data_ptr(), n=n, k=K)
-        ne = hc.compare(threshold, variant, shard=self.rank, n_shards=self.world)
-        counts, offs = gather_counts(ne, full.device, self.group)
+        with torch.cuda.stream(self.stream()):
+            hc.resample(spline_points)
+            n_local, K, ptr = hc.spline_info()
+            local = torch.as_tensor(CudaView(ptr, (n_local, K)), device="cuda")
+            full = gather_rows(local, n, self.world, self.group)
+            hc.set_spline(device_ptr=full.data_ptr(), n=n, k=K)
+            ne = hc.compare(threshold, variant, shard=self.rank, n_shards=self.world)
+            counts, offs = gather_counts(ne, full.device, self.group)
         return ne, counts, offs, full

@@ -68,6 +68,51 @@ __global__ void __launch_bounds__(256) k_dmma(double *out, double av, double bv)
     if (s == 123.456) out[0] = s;
 }
 
+
+// Do the FP64 tensor path (DMMA) and the vector FP64 pipe (DFMA) share execution resources? MODE 0:
+// odd warps issue DMMA, even warps DFMA; MODE 1: every warp interleaves ND DMMAs with NF DFMAs per
+// iteration (compile-time counts, fully unrolled). Independent pipes would give dmma + dfma.
+template <int MODE, int ND, int NF>
+__global__ void __launch_bounds__(256) k_mixed(double *out, double a, double b)
+{
+    double c[ND > 0 ? ND : 1][2], acc[NF > 0 ? NF : 1];
+#pragma unroll
+    for (int i = 0; i < ND; i++) c[i][0] = c[i][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NF; i++) acc[i] = threadIdx.x * 1e-9 + i;
+    const bool tensor_warp = MODE == 1 || ((threadIdx.x >> 5) & 1);
+    const bool vector_warp = MODE == 1 || !((threadIdx.x >> 5) & 1);
+    if (MODE == 1) {
+        for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+            for (int i = 0; i < (ND > NF ? ND : NF); i++) {
+                if (i < ND)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+                if (i < NF) acc[i] = fma(acc[i], a, b);
+            }
+        }
+    } else if (tensor_warp) {
+        for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+            for (int i = 0; i < ND; i++)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+        }
+    } else if (vector_warp) {
+        for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+            for (int i = 0; i < NF; i++) acc[i] = fma(acc[i], a, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ND; i++) s += c[i][0] + c[i][1];
+#pragma unroll
+    for (int i = 0; i < NF; i++) s += acc[i];
+    if (s == 123.456) out[0] = s;
+}
+
 // one warp, one thread active: dependent chain latency in cycles per op
 template <int OP>
 __global__ void k_lat(double *out, long long *cyc, double a, double b)
@@ -111,6 +156,7 @@ static void l_dmma0() { k_dmma<0><<<g_blocks, 256>>>(g_out, 1.0, 1e-9); }
 static void l_dmma1() { k_dmma<1><<<g_blocks, 256>>>(g_out, 1.0, 1e-9); }
 static void l_dmma2() { k_dmma<2><<<g_blocks, 256>>>(g_out, 1.0, 1e-9); }
 static void l_dmma3() { k_dmma<3><<<g_blocks, 256>>>(g_out, 1.0, 1e-9); }
+template <int MODE, int ND, int NF> static void l_mix() { k_mixed<MODE, ND, NF><<<g_blocks, 256>>>(g_out, 1.0000001, 1e-9); }
 
 int main()
 {
@@ -130,6 +176,26 @@ int main()
     for (int s = 0; s < 4; s++) {
         t = time_kernel(ls[s], 5);
         printf(", \"%s\": %.3f", nm[s], warps * ITERS * 8 * fl[s] / (t * 1e-3) / 1e12);
+    }
+
+    // mixed issue: flops of both kinds over the common time
+    {
+        struct Cfg { int mode, nd, nf; void (*fn)(); };
+        const Cfg cfg[] = {
+            {0, 8, 0, l_mix<0, 8, 0>}, {0, 0, 16, l_mix<0, 0, 16>}, {0, 8, 16, l_mix<0, 8, 16>}, {0, 8, 4, l_mix<0, 8, 4>},
+            {1, 8, 0, l_mix<1, 8, 0>}, {1, 0, 16, l_mix<1, 0, 16>}, {1, 8, 16, l_mix<1, 8, 16>}, {1, 8, 8, l_mix<1, 8, 8>},
+            {1, 8, 4, l_mix<1, 8, 4>}, {1, 8, 2, l_mix<1, 8, 2>}, {1, 8, 1, l_mix<1, 8, 1>}, {1, 4, 16, l_mix<1, 4, 16>},
+        };
+        printf(", \"mixed\": [");
+        for (unsigned q = 0; q < sizeof(cfg) / sizeof(cfg[0]); q++) {
+            t = time_kernel(cfg[q].fn, 5);
+            const double wt = cfg[q].mode == 0 ? warps / 2 : warps, tt = cfg[q].mode == 0 ? threads / 2 : threads;
+            const double f_t = wt * ITERS * cfg[q].nd * 512.0, f_v = tt * ITERS * cfg[q].nf * 2.0;
+            printf("%s{\"mode\": \"%s\", \"dmma_per_iter\": %d, \"dfma_per_iter\": %d, \"ms\": %.3f, \"dmma_tflops\": %.2f, \"dfma_tflops\": %.2f, \"sum\": %.2f}",
+                   q ? ", " : "", cfg[q].mode == 0 ? "split_warps" : "interleaved", cfg[q].nd, cfg[q].nf, t,
+                   f_t / (t * 1e-3) / 1e12, f_v / (t * 1e-3) / 1e12, (f_t + f_v) / (t * 1e-3) / 1e12);
+        }
+        printf("]");
     }
     k_lat<0><<<1, 1>>>(g_out, cyc, 1.0, 1e-9);
     k_lat<1><<<1, 1>>>(g_out, cyc, 1.0, 1.0000001);

@@ -22,7 +22,9 @@ def main():
     b, e = shard_bounds(n, world)[rank]
     off = synth.offsets(6, e - b, 16, 5, 70, first=b)
     steps = synth.histories(6, e - b, 16, 5e-3, synth.default_pert(thr, P), off, first=b)
-    hc = scema_b200.HistCluster(local, torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    hc = scema_b200.HistCluster(local, stream.cuda_stream)
     hc.set_histories(steps, off)
     sc = ShardedCluster(hc)
     for variant in (0, 1):
