@@ -57,6 +57,19 @@ def lib():
         "scema_last_counters": (i32, [vp, P(u64)]),
         "scema_kernel_launches": (u64, [vp]),
         "scema_fp64_peak": (i32, [vp, P(dbl)]),
+        "scema_ingest_last_error": (C.c_char_p, []),
+        "scema_batch_read_dir": (i32, [C.c_char_p, u32, P(vp)]),
+        "scema_batch_read_files": (i32, [P(C.c_char_p), vp, u64, u32, P(vp)]),
+        "scema_batch_from_lhistory": (i32, [P(C.c_char_p), u64, C.c_char_p, P(vp)]),
+        "scema_batch_count": (u64, [vp]),
+        "scema_batch_total_steps": (u64, [vp]),
+        "scema_batch_steps": (vp, [vp]),
+        "scema_batch_offsets": (vp, [vp]),
+        "scema_batch_ids": (vp, [vp]),
+        "scema_batch_name": (C.c_char_p, [vp, u64]),
+        "scema_batch_write_strain_files": (i32, [vp, C.c_char_p]),
+        "scema_set_histories_from_batch": (i32, [vp, vp]),
+        "scema_batch_free": (None, [vp]),
         "scema_synth_offsets": (i32, [u64, u64, u64, u32, u32, u32, vp]),
         "scema_synth_histories_device": (i32, [u64, u64, u64, u32, dbl, dbl, vp, vp, vp]),
         "scema_synth_rows_device": (i32, [u64, u64, u64, u32, u32, dbl, dbl, vp, vp]),
@@ -74,7 +87,10 @@ EXPORTED = (
     "scema_set_spline scema_get_spline scema_spline_info scema_compare scema_get_edges scema_edges_device "
     "scema_get_degrees scema_cluster scema_write_similar_hist scema_reduce_edges scema_reduce_calls scema_reduce_dir "
     "scema_last_timings scema_last_counters scema_kernel_launches scema_fp64_peak scema_synth_offsets "
-    "scema_synth_histories_device scema_synth_rows_device").split()
+    "scema_synth_histories_device scema_synth_rows_device scema_ingest_last_error scema_batch_read_dir "
+    "scema_batch_read_files scema_batch_from_lhistory scema_batch_count scema_batch_total_steps scema_batch_steps "
+    "scema_batch_offsets scema_batch_ids scema_batch_name scema_batch_write_strain_files "
+    "scema_set_histories_from_batch scema_batch_free").split()
 
 
 def _ptr(a):
@@ -94,6 +110,79 @@ def reduce_dir(input_folder, out_mapping_csv, num_gps):
     if rc:
         raise ScemaError(rc, "reduce_dir failed")
     return int(it.value), int(nf.value), int(nr.value)
+
+
+class Batch:
+    """Host-side ragged batch of strain histories read from files (include/scema_ingest.h)."""
+
+    def __init__(self, handle):
+        self._L = lib()
+        self._h = handle
+
+    @staticmethod
+    def _take(rc, h):
+        if rc:
+            raise ScemaError(rc, lib().scema_ingest_last_error().decode())
+        return Batch(h)
+
+    @classmethod
+    def read_dir(cls, strain_directory, n_threads=0):
+        h = C.c_void_p(None)
+        return cls._take(lib().scema_batch_read_dir(os.fsencode(strain_directory), int(n_threads), C.byref(h)), h)
+
+    @classmethod
+    def read_files(cls, paths, ids=None, n_threads=0):
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)
+        h = C.c_void_p(None)
+        return cls._take(lib().scema_batch_read_files(arr, _ptr(ids_a), len(paths), int(n_threads), C.byref(h)), h)
+
+    @classmethod
+    def from_lhistory(cls, csv_paths, column_prefix="strain"):
+        arr = (C.c_char_p * len(csv_paths))(*[os.fsencode(p) for p in csv_paths])
+        h = C.c_void_p(None)
+        return cls._take(lib().scema_batch_from_lhistory(arr, len(csv_paths), column_prefix.encode(), C.byref(h)), h)
+
+    def __len__(self):
+        return int(self._L.scema_batch_count(self._h))
+
+    @property
+    def offsets(self):
+        n = len(self)
+        return np.ctypeslib.as_array(C.cast(self._L.scema_batch_offsets(self._h), C.POINTER(C.c_uint64)), (n + 1,)).copy()
+
+    @property
+    def ids(self):
+        n = len(self)
+        if n == 0:
+            return np.zeros(0, dtype=np.uint32)
+        return np.ctypeslib.as_array(C.cast(self._L.scema_batch_ids(self._h), C.POINTER(C.c_uint32)), (n,)).copy()
+
+    @property
+    def steps(self):
+        t = int(self._L.scema_batch_total_steps(self._h))
+        if t == 0:
+            return np.zeros((0, 6))
+        return np.ctypeslib.as_array(C.cast(self._L.scema_batch_steps(self._h), C.POINTER(C.c_double)), (t, 6)).copy()
+
+    def name(self, i):
+        return self._L.scema_batch_name(self._h, int(i)).decode()
+
+    def write_strain_files(self, out_directory):
+        rc = self._L.scema_batch_write_strain_files(self._h, os.fsencode(out_directory))
+        if rc:
+            raise ScemaError(rc, self._L.scema_ingest_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.scema_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class HistCluster:
@@ -140,6 +229,9 @@ class HistCluster:
         else:
             steps = np.ascontiguousarray(steps, dtype=np.float64)
             self._ck(self._L.scema_set_histories(self._h, _ptr(steps), 0, _ptr(offsets), _ptr(ids_a), n))
+
+    def set_histories_from_batch(self, batch):
+        self._ck(self._L.scema_set_histories_from_batch(self._h, batch._h))
 
     def resample(self, spline_points):
         self._ck(self._L.scema_resample(self._h, int(spline_points)))

@@ -369,6 +369,226 @@ __global__ void __launch_bounds__(256, 1) k_filter(const FilterArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// filter kernel, warp-specialised (K2 v2, DMMA only)
+//
+// Same tiles, same arithmetic and same rejection rule as k_filter<.., DMMA=true>, different
+// choreography: warp 8 is a producer (one lane: work queue, threshold per tile, TMA bulk copies),
+// warps 0-7 are consumers. Stages are handed over with full/empty mbarriers instead of CTA-wide
+// barriers, so a warp that finishes a tile starts the next one without waiting for the slowest warp
+// and the two warps of a scheduler partition drift apart: one warp's epilogue and accumulator
+// set-up overlap the other's DMMAs. The epilogue compares in the integer pipe (DMMA and every other
+// FP64 instruction share one pipe — tools/fp64_peak.cu: DMMA + DFMA never exceeds 36.8 TFLOP/s): for
+// a negative bound the test acc < bound is implied by hi32(acc) > hi32(bound) as unsigned integers,
+// and pairs that only differ in the low word (2^-20 relative) simply stay survivors.
+// ------------------------------------------------------------------------------------------------
+struct StageMeta {
+    uint32_t I, J, flags, lo_bound, span, pad0, pad1, pad2;
+};
+constexpr uint32_t META_FIRST = 1u, META_LAST = 2u, META_DONE = 4u;
+
+template <int KC, bool MULTI>
+struct WsSmem {
+    static constexpr size_t tile_bytes = (size_t)TILE * KC * 8;
+    static constexpr size_t stage_bytes = (MULTI ? 2 : 1) * tile_bytes + 2 * TILE * 8;  // [A] B hA hB
+    static constexpr size_t fixed_bytes = (MULTI ? 0 : tile_bytes) + 1024;
+    static constexpr size_t budget = 227 * 1024;
+    static constexpr int raw_stages = (int)((budget - fixed_bytes) / stage_bytes);
+    static constexpr int NST = raw_stages >= 4 ? 4 : (raw_stages >= 2 ? 2 : 1);  // power of two
+    static constexpr size_t bytes = fixed_bytes + NST * stage_bytes;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Register budget: 12 warps = 2 consumer warpgroups + 1 producer warpgroup (only its first warp
+// works). Every scheduler partition hosts 2 consumer warps and 1 producer-group warp and owns 16384
+// registers, so the kernel is compiled for 168 registers/thread and re-balanced at run time with
+// setmaxnreg: producer group down to 40, consumers up to 232 (32*(2*232+40) = 16128).
+template <int KC, bool MULTI>
+__global__ void __launch_bounds__(384, 1) k_filter_ws(const FilterArgs a)
+{
+    using SM = WsSmem<KC, MULTI>;
+    constexpr int NST = SM::NST;
+    static_assert(NST >= 2, "need at least two stages");
+    constexpr int KS = KC;
+    constexpr uint32_t TILE_BYTES = (uint32_t)SM::tile_bytes;
+    constexpr uint32_t HN_BYTES = TILE * 8;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [resident A (non-MULTI)] | stage 0 | stage 1 | ... | meta[NST] | full[NST] | empty[NST]
+    double *As = reinterpret_cast<double *>(smem_raw);
+    unsigned char *stage0 = smem_raw + (MULTI ? 0 : SM::tile_bytes);
+    StageMeta *metas = reinterpret_cast<StageMeta *>(stage0 + NST * SM::stage_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(metas + NST);
+    uint64_t *empty = full + NST;
+    auto stageA = [&](int st) { return reinterpret_cast<double *>(stage0 + st * SM::stage_bytes); };
+    auto stageB = [&](int st) { return reinterpret_cast<double *>(stage0 + st * SM::stage_bytes + (MULTI ? SM::tile_bytes : 0)); };
+    auto stageHA = [&](int st) { return stageB(st) + (size_t)TILE * KS; };
+    auto stageHB = [&](int st) { return stageHA(st) + TILE; };
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= 8) {
+        // ------------------------------------------------------------------ producer (one lane)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp != 8 || lane != 0) return;
+        uint32_t t = 0, ephase = (1u << NST) - 1u;  // a fresh barrier passes a parity-1 wait
+        const uint64_t total = a.n_groups_local * PANEL_ROWBLOCKS;
+        while (true) {
+            const uint64_t item = atomicAdd(a.work_counter, 1ull);
+            if (item >= total) break;
+            const uint64_t grp = (item / PANEL_ROWBLOCKS) * a.n_shards + a.shard;
+            const uint32_t r = (uint32_t)(item % PANEL_ROWBLOCKS);
+            uint32_t lo = 0, hi = a.n_panels;
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (a.panel_start[mid] <= grp) lo = mid; else hi = mid;
+            }
+            const uint32_t panel = lo;
+            const uint32_t strip = (uint32_t)(grp - a.panel_start[panel]);
+            const uint32_t I = panel * PANEL_ROWBLOCKS + r;
+            if (I >= a.n_blocks) continue;
+            uint32_t J0 = panel * PANEL_ROWBLOCKS + strip * a.strip_len;
+            uint32_t J1 = J0 + a.strip_len;
+            if (J1 > a.n_blocks) J1 = a.n_blocks;
+            if (J0 < I) J0 = I;
+            if (J0 >= J1) continue;
+            const double bmI = a.BM[I];
+            for (uint32_t J = J0; J < J1; J++) {
+                // rejection bound of the tile, as an unsigned range test on the high word
+                const double T = (a.T0 + a.cband * (bmI + a.BM[J])) * (1.0 + 1e-15);
+                const double negHalfT = -0.5 * T;
+                uint32_t lo_bound = 0, span = 0;
+                {
+                    const uint32_t h = (uint32_t)__double2hiint(negHalfT);
+                    if (negHalfT <= 0.0 && h >= 0x80000000u && h < 0xFFF00000u) {  // negative (or -0), finite
+                        lo_bound = h + 1u;
+                        span = 0xFFF00000u - lo_bound;
+                    }
+                }
+                for (uint32_t c = 0; c < a.n_chunks; c++, t++) {
+                    const int st = (int)(t & (NST - 1));
+                    mbar_wait(&empty[st], (ephase >> st) & 1u);
+                    ephase ^= 1u << st;
+                    const bool new_A = !MULTI && J == J0 && c == 0;
+                    if (new_A)  // every earlier tile must have released the resident A tile
+                        for (int o = 0; o < NST; o++)
+                            if (o != st) mbar_wait(&empty[o], (ephase >> o) & 1u);  // peek, phase not consumed
+                    StageMeta m;
+                    m.I = I; m.J = J;
+                    m.flags = (c == 0 ? META_FIRST : 0u) | (c == a.n_chunks - 1 ? META_LAST : 0u);
+                    m.lo_bound = lo_bound; m.span = span; m.pad0 = m.pad1 = m.pad2 = 0;
+                    metas[st] = m;
+                    uint32_t bytes = TILE_BYTES + (c == 0 ? 2 * HN_BYTES : 0u);
+                    if (MULTI || new_A) bytes += TILE_BYTES;
+                    mbar_expect_tx(&full[st], bytes);
+                    tma_bulk_g2s(stageB(st), a.F + ((uint64_t)c * a.n_pad + (uint64_t)J * TILE) * KS, TILE_BYTES, &full[st]);
+                    if (c == 0) {
+                        tma_bulk_g2s(stageHA(st), a.HN + (uint64_t)I * TILE, HN_BYTES, &full[st]);
+                        tma_bulk_g2s(stageHB(st), a.HN + (uint64_t)J * TILE, HN_BYTES, &full[st]);
+                    }
+                    if (MULTI)
+                        tma_bulk_g2s(stageA(st), a.F + ((uint64_t)c * a.n_pad + (uint64_t)I * TILE) * KS, TILE_BYTES, &full[st]);
+                    else if (new_A)
+                        tma_bulk_g2s(As, a.F + (uint64_t)I * TILE * KS, TILE_BYTES, &full[st]);
+                }
+            }
+        }
+        const int st = (int)(t & (NST - 1));
+        mbar_wait(&empty[st], (ephase >> st) & 1u);
+        StageMeta m = {};
+        m.flags = META_DONE;
+        metas[st] = m;
+        mbar_arrive(&full[st]);
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers (8 warps)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // 2 (rows) x 4 (cols) warps; warp tile 64 x 32 = 8 x 4 m8n8 fragments;
+    // fragment element e of (mi,ni): row = mi*8 + (lane>>2), col = ni*8 + 2*(lane&3) + e
+    const int g = lane >> 2, t4 = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    double acc[8][4][2];
+    uint32_t t = 0, fphase = 0;
+    while (true) {
+        const int st = (int)(t & (NST - 1));
+        mbar_wait(&full[st], (fphase >> st) & 1u);
+        fphase ^= 1u << st;
+        t++;
+        const StageMeta m = metas[st];
+        if (m.flags & META_DONE) break;
+        const double *Ab = MULTI ? stageA(st) : As;
+        const double *Bb = stageB(st);
+        if (m.flags & META_FIRST) {
+            // acc starts at -(|a|^2+|b|^2)/2 so that after the contraction acc = -d^2/2
+            const double *ha = stageHA(st), *hb = stageHB(st);
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++) {
+                const double hav = ha[wm * 64 + mi * 8 + g];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) {
+                    acc[mi][ni][0] = hav + hb[wn * 32 + ni * 8 + 2 * t4];
+                    acc[mi][ni][1] = hav + hb[wn * 32 + ni * 8 + 2 * t4 + 1];
+                }
+            }
+        }
+        {
+            const double *ap = Ab + (wm * 64 + g) * KS + t4;
+            const double *bp = Bb + (wn * 32 + g) * KS + t4;
+#pragma unroll
+            for (int ks = 0; ks < KC / 4; ks++) {
+                double af[8], bf[4];
+#pragma unroll
+                for (int mi = 0; mi < 8; mi++) af[mi] = ap[mi * 8 * KS + ks * 4];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) bf[ni] = bp[ni * 8 * KS + ks * 4];
+#pragma unroll
+                for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+            }
+        }
+        // this warp is done with the stage's shared memory (and, at the last tile of an item, with A)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+
+        if (m.flags & META_LAST) {
+            // ---- epilogue: provable rejection (integer range test), survivors to the queue
+            bool any = false;
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) {
+                    any |= ((uint32_t)__double2hiint(acc[mi][ni][0]) - m.lo_bound) >= m.span;
+                    any |= ((uint32_t)__double2hiint(acc[mi][ni][1]) - m.lo_bound) >= m.span;
+                }
+            if (__any_sync(0xffffffffu, any)) {
+                const uint64_t rbase = (uint64_t)m.I * TILE, cbase = (uint64_t)m.J * TILE;
+#pragma unroll
+                for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const uint64_t row = rbase + wm * 64 + mi * 8 + g;
+                            const uint64_t col = cbase + wn * 32 + ni * 8 + 2 * t4 + e;
+                            const bool keep = (((uint32_t)__double2hiint(acc[mi][ni][e]) - m.lo_bound) >= m.span) &&
+                                              row < col && col < a.n;
+                            warp_append_cand(keep, (row << 32) | col, a.cand_count, a.cand_cap, a.cand);
+                        }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // exact recompute of the survivors + K3 compaction of the edges
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_exact_queue(const double *__restrict__ S, uint32_t K, const uint64_t *__restrict__ cand,
@@ -487,6 +707,42 @@ static int launch_filter_t(scema_ctx *ctx, const FilterArgs &fa)
     ctx->launches++;
     SCEMA_CUDA(ctx, cudaGetLastError());
     return SCEMA_OK;
+}
+
+template <int KC, bool MULTI>
+static int launch_filter_ws_t(scema_ctx *ctx, const FilterArgs &fa)
+{
+    auto kern = k_filter_ws<KC, MULTI>;
+    const size_t smem = WsSmem<KC, MULTI>::bytes;
+    if (smem > ctx->smem_optin) return fail(ctx, SCEMA_ERR_CUDA, "filter kernel shared memory exceeds device limit");
+    SCEMA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint64_t items = fa.n_groups_local * PANEL_ROWBLOCKS;
+    unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count, std::max<uint64_t>(items, 1));
+    kern<<<grid, 384, smem, ctx->stream>>>(fa);
+    ctx->launches++;
+    SCEMA_CUDA(ctx, cudaGetLastError());
+    return SCEMA_OK;
+}
+
+static int launch_filter_ws(scema_ctx *ctx, const FilterArgs &fa, uint32_t kc, bool multi)
+{
+    if (!multi) {
+        switch (kc) {
+        case 12: return launch_filter_ws_t<12, false>(ctx, fa);
+        case 20: return launch_filter_ws_t<20, false>(ctx, fa);
+        case 28: return launch_filter_ws_t<28, false>(ctx, fa);
+        case 36: return launch_filter_ws_t<36, false>(ctx, fa);
+        case 44: return launch_filter_ws_t<44, false>(ctx, fa);
+        case 52: return launch_filter_ws_t<52, false>(ctx, fa);
+        case 60: return launch_filter_ws_t<60, false>(ctx, fa);
+        }
+    } else {
+        switch (kc) {
+        case 44: return launch_filter_ws_t<44, true>(ctx, fa);
+        case 52: return launch_filter_ws_t<52, true>(ctx, fa);
+        }
+    }
+    return fail(ctx, SCEMA_ERR_INVALID, "no filter kernel instantiation for this chunk size");
 }
 
 template <bool DMMA>
@@ -644,7 +900,11 @@ int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_
             ctx->counters[4] = tiles;
 
             t_begin(ctx, SCEMA_T_FILTER);
-            rc = variant == SCEMA_PAIRS_DMMA ? launch_filter<true>(ctx, fa, fl.kc, fl.n_chunks > 1)
+            // SCEMA_K2=v1 selects the barrier-synchronised DMMA kernel (kept for A/B measurements)
+            static const char *k2_env = getenv("SCEMA_K2");
+            const bool ws = !(k2_env && strcmp(k2_env, "v1") == 0);
+            rc = variant == SCEMA_PAIRS_DMMA ? (ws ? launch_filter_ws(ctx, fa, fl.kc, fl.n_chunks > 1)
+                                                   : launch_filter<true>(ctx, fa, fl.kc, fl.n_chunks > 1))
                                              : launch_filter<false>(ctx, fa, fl.kc, fl.n_chunks > 1);
             if (rc) return rc;
             t_end(ctx, SCEMA_T_FILTER);

@@ -30,9 +30,13 @@ namespace scema {
 
 // table for one L, every array padded to an even length Lp (so each starts 16-byte aligned and the
 // five arrays the sweeps need are one contiguous block for a bulk copy):
-//   x[Lp] | hd[Lp] sd[Lp] lo[Lp] up[Lp] di[Lp] | ht[Pp] idx[Pp]
+//   x[Lp] | hd[Lp] sd[Lp] lo[Lp] up[Lp] di[Lp] | ht[Pp] idx[Pp] | FW[Lp][4] | BW[Lp][4]
+// FW[i] = {1/hd_i, hd_i, sd_i, lo_i} and BW[i] = {up_i, di_i, 1/di_i, 0} are what one forward / one
+// backward step of k_resample_stream needs, packed so that each step is two 16-byte loads; the
+// correctly rounded reciprocals feed the exact division div_tab() below.
 __host__ __device__ inline uint32_t pad2(uint32_t v) { return v + (v & 1u); }
-__host__ __device__ inline uint64_t table_doubles(uint32_t L, uint32_t P) { return 6ull * pad2(L) + 2ull * pad2(P); }
+__host__ __device__ inline uint64_t table_fw_offset(uint32_t L, uint32_t P) { return 6ull * pad2(L) + 2ull * pad2(P); }
+__host__ __device__ inline uint64_t table_doubles(uint32_t L, uint32_t P) { return table_fw_offset(L, P) + 8ull * pad2(L); }
 
 __global__ void k_build_tables(const uint32_t *__restrict__ lens, const uint64_t *__restrict__ offs,
                                uint32_t n_tables, uint32_t P, double *__restrict__ tables)
@@ -78,6 +82,18 @@ __global__ void k_build_tables(const uint32_t *__restrict__ lens, const uint64_t
         if (idx > n - 2) idx = n - 2;      // t <= x[n-1] always, so this never binds
         ht[p] = __dsub_rn(t, x[idx]);
         ix[p] = (double)idx;
+    }
+    double *fw = tables + offs[ti] + table_fw_offset(L, P), *bw = fw + 4ull * Lp;
+    for (uint32_t i = 0; i < Lp; i++) {
+        const bool in = i < L;
+        fw[4 * i + 0] = in && i < L - 1 ? __ddiv_rn(1.0, hd[i]) : 0.0;
+        fw[4 * i + 1] = in ? hd[i] : 0.0;
+        fw[4 * i + 2] = in ? sd[i] : 0.0;
+        fw[4 * i + 3] = in ? lo[i] : 0.0;
+        bw[4 * i + 0] = in ? up[i] : 0.0;
+        bw[4 * i + 1] = in ? di[i] : 1.0;
+        bw[4 * i + 2] = in ? __ddiv_rn(1.0, di[i]) : 1.0;
+        bw[4 * i + 3] = 0.0;
     }
 }
 
@@ -240,6 +256,175 @@ __global__ void __launch_bounds__(32) k_resample_staged(const double *__restrict
         // the slab was written through the generic proxy; order that before the next bulk copy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
+    }
+}
+
+
+// ---- streamed kernel (K1 v4). One warp per group of five histories, lane = (history, component)
+// chain as above, but nothing is staged in shared memory, so the number of resident chains is not
+// capped by the slab size: y is read straight from global memory through an 8-deep register ring
+// (each 48-byte step of a history is one sector pair, every line is used by 2.7 consecutive
+// steps), z goes to a warp-private scratch column block zs[i][32] (coalesced 256-byte rows that
+// are re-read by the same warp ~L steps later, i.e. out of L2), and the samples are evaluated
+// inside the backward sweep at the moment b_idx and b_idx+1 exist, so b is never stored.
+//
+// div_tab(a, b, rb) == __ddiv_rn(a, b) for a table divisor b with rb = RN(1/b): two
+// Newton-style FMA corrections of q = a*rb. After the first, q is a faithful rounding of a/b;
+// Markstein's theorem then makes q + (a - b*q)*rb round to RN(a/b). Guarded to numerators whose
+// exponent keeps every intermediate normal; zeros, subnormals, huge values, inf and NaN take the
+// IEEE division. 5 dependent FP64 ops (~40 cycles) instead of ~110 for the division sequence.
+// Checked against the true quotient for 6e8 (a,b) pairs by tests/test_fastdiv.py.
+__device__ __forceinline__ double div_tab(double a, double b, double rb)
+{
+    const uint32_t e = ((uint32_t)__double2hiint(a) >> 20) & 0x7ffu;
+    if (e - 128u < 1792u) {
+        double q = __dmul_rn(a, rb);
+        double r = __fma_rn(-b, q, a);
+        q = __fma_rn(r, rb, q);
+        r = __fma_rn(-b, q, a);
+        return __fma_rn(r, rb, q);
+    }
+    return __ddiv_rn(a, b);
+}
+
+constexpr int RS_WARPS = 4;  // warps per CTA (independent of each other)
+constexpr int RING = 8;      // register prefetch depth of the y / z streams
+
+__global__ void __launch_bounds__(32 * RS_WARPS) k_resample_stream(const double *__restrict__ steps,
+                                                                  const uint64_t *__restrict__ offsets,
+                                                                  const uint32_t *__restrict__ order, uint64_t first,
+                                                                  uint64_t count, const int64_t *__restrict__ table_index,
+                                                                  const double *__restrict__ tables, uint32_t P,
+                                                                  double *__restrict__ out, double *__restrict__ zscratch,
+                                                                  uint32_t cap)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t wid = (uint64_t)blockIdx.x * RS_WARPS + (threadIdx.x >> 5);
+    const uint64_t n_warps = (uint64_t)gridDim.x * RS_WARPS;
+    double *__restrict__ zs = zscratch + wid * cap * 32 + lane;
+    const uint32_t K = 6 * P, Pp = pad2(P);
+    const double third = 1.0 / 3.0;
+    const uint64_t n_groups = (count + GROUP - 1) / GROUP;
+    const int hh = lane / 6, c = lane - hh * 6;
+
+    for (uint64_t grp = wid; grp < n_groups; grp += n_warps) {
+        const uint64_t left = count - grp * GROUP;
+        if (lane >= GROUP * 6 || (uint64_t)hh >= left) continue;  // no warp-level primitive below
+        const uint64_t q = first + grp * GROUP + hh;
+        const uint64_t h = order ? (uint64_t)order[q] : q;
+        const uint64_t off = offsets[h];
+        const int L = (int)(offsets[h + 1] - off);
+        const uint32_t Lp = pad2((uint32_t)L);
+        const double *tab = tables + table_index[L];
+        const double *ht = tab + 6ull * Lp, *ix = ht + Pp;
+        const double2 *FW = reinterpret_cast<const double2 *>(ht + 2ull * Pp);
+        const double2 *BW = FW + 2ull * Lp;
+        const double *y = steps + off * 6 + c;
+
+        // whole history -> L2 now (one bulk prefetch per history); the sweeps then find their lines there
+        if (c == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(steps + off * 6), "r"(48u * (uint32_t)L) : "memory");
+
+        // ---- forward substitution fused with the right-hand side (spline.h:306, :228-233).
+        // Software pipeline: the slope s_{i+1} = (y_{i+2} - y_{i+1}) / hd_{i+1} and the factor-table
+        // entry of step i+1 are produced while the z chain of step i runs; y comes through an
+        // 8-deep register ring (slot k holds y_{m} with m == k+1 mod 8).
+        double yr[RING];
+#pragma unroll
+        for (int u = 0; u < RING; u++) yr[u] = 1 + u < L ? __ldg(y + (size_t)(1 + u) * 6) : 0.0;  // y_1 .. y_8
+        double s_prev, s_cur, z_prev, y_hi;  // y_hi = y_{i+1} at the top of step i
+        double2 f1n;                          // {sd, lo} of the coming step
+        {
+            const double y0 = __ldg(y);
+            const double2 f0 = __ldg(FW), f1 = __ldg(FW + 1), g0 = __ldg(FW + 2);
+            f1n = __ldg(FW + 3);
+            const double ya1 = yr[0], ya2 = yr[1];
+            yr[0] = 1 + RING < L ? __ldg(y + (size_t)(1 + RING) * 6) : 0.0;  // y_9
+            yr[1] = 2 + RING < L ? __ldg(y + (size_t)(2 + RING) * 6) : 0.0;  // y_10
+            s_prev = div_tab(__dsub_rn(ya1, y0), f0.y, f0.x);           // s_0
+            s_cur = div_tab(__dsub_rn(ya2, ya1), g0.y, g0.x);           // s_1 (L >= 3, so y_2 exists)
+            z_prev = __dsub_rn(__dmul_rn(0.0, f1.x), 0.0);              // row 0: rhs = 0, empty sum
+            __stcg(zs, z_prev);
+            y_hi = ya2;
+        }
+        for (int i0 = 1; i0 < L - 1; i0 += RING) {
+#pragma unroll
+            for (int u = 0; u < RING; u++) {
+                const int i = i0 + u;
+                if (i < L - 1) {
+                    // prefetch for step i+1: table entry and y_{i+2} (slot (u+2) mod 8), refill the slot with y_{i+2+8}
+                    const int slot = (u + 2) & (RING - 1);
+                    const double y_nx = yr[slot];
+                    yr[slot] = i + 2 + RING < L ? __ldg(y + (size_t)(i + 2 + RING) * 6) : 0.0;
+                    const double2 g0 = __ldg(FW + 2 * (i + 1));  // i+1 <= L-1 < Lp: always inside the table
+                    const double2 f1 = f1n;
+                    f1n = __ldg(FW + 2 * (i + 1) + 1);
+                    // z chain of step i
+                    const double r = __dmul_rn(__dsub_rn(s_cur, s_prev), f1.x);
+                    const double sum = __dadd_rn(0.0, __dmul_rn(f1.y, z_prev));
+                    z_prev = __dsub_rn(r, sum);
+                    __stcg(zs + (size_t)i * 32, z_prev);
+                    // slope of step i+1 (unused garbage when i+1 == L-1: hd = 0 there, never consumed)
+                    s_prev = s_cur;
+                    if (i + 1 < L - 1) s_cur = div_tab(__dsub_rn(y_nx, y_hi), g0.y, g0.x);
+                    y_hi = y_nx;
+                }
+            }
+        }
+        {
+            const double2 f1 = f1n;  // {sd, lo} of row L-1, fetched by step L-2
+            const double r = __dmul_rn(0.0, f1.x);  // row L-1: rhs = 0
+            const double sum = __dadd_rn(0.0, __dmul_rn(f1.y, z_prev));
+            z_prev = __dsub_rn(r, sum);
+        }
+
+        // ---- back substitution (spline.h:243-248) with the samples evaluated on the way
+        // (spline.h:345-349, :393): sample p lives in interval ix[p], non-increasing as p falls
+        double b_next;
+        {
+            const double2 w1 = __ldg(BW + 2 * (L - 1) + 1), w0 = __ldg(BW + 2 * (L - 1));
+            b_next = div_tab(__dsub_rn(z_prev, 0.0), w0.y, w1.x);
+        }
+        double zr[RING];
+#pragma unroll
+        for (int u = 0; u < RING; u++) zr[u] = L - 2 - u >= 0 ? __ldcg(zs + (size_t)(L - 2 - u) * 32) : 0.0;
+        int p = (int)P - 1;
+        int nxt = (int)__ldg(ix + p);
+        double ya = __ldg(y + (size_t)nxt * 6), yb = __ldg(y + (size_t)(nxt + 1) * 6);
+        double *orow = out + h * K + c;
+        double2 w0n = __ldg(BW + 2 * (L - 2)), w1n = __ldg(BW + 2 * (L - 2) + 1);  // table entry of the coming step
+        for (int i0 = L - 2; i0 >= 0; i0 -= RING) {
+#pragma unroll
+            for (int u = 0; u < RING; u++) {
+                const int i = i0 - u;
+                if (i >= 0) {
+                    const double zi = zr[u];
+                    zr[u] = i - RING >= 0 ? __ldcg(zs + (size_t)(i - RING) * 32) : 0.0;
+                    const double2 w0 = w0n, w1 = w1n;
+                    if (i > 0) { w0n = __ldg(BW + 2 * (i - 1)); w1n = __ldg(BW + 2 * (i - 1) + 1); }
+                    const double sum = __dadd_rn(0.0, __dmul_rn(w0.x, b_next));
+                    const double b_i = div_tab(__dsub_rn(zi, sum), w0.y, w1.x);
+                    if (i == nxt) {
+                        const double2 f0 = __ldg(FW + 2 * i);
+                        const double hdv = f0.y;
+                        const double a_i = div_tab(__dmul_rn(third, __dsub_rn(b_next, b_i)), hdv, f0.x);
+                        const double c_i = __dsub_rn(div_tab(__dsub_rn(yb, ya), hdv, f0.x),
+                                                     __dmul_rn(__dmul_rn(third, __dadd_rn(__dmul_rn(2.0, b_i), b_next)), hdv));
+                        do {
+                            const double hstep = __ldg(ht + p);
+                            double v = __dadd_rn(__dmul_rn(a_i, hstep), b_i);
+                            v = __dadd_rn(__dmul_rn(v, hstep), c_i);
+                            v = __dadd_rn(__dmul_rn(v, hstep), ya);
+                            orow[(size_t)p * 6] = v;
+                            p--;
+                            nxt = p >= 0 ? (int)__ldg(ix + p) : -1;
+                        } while (nxt == i);
+                        if (nxt >= 0) { ya = __ldg(y + (size_t)nxt * 6); yb = __ldg(y + (size_t)(nxt + 1) * 6); }
+                    }
+                    b_next = b_i;
+                }
+            }
+        }
     }
 }
 
@@ -407,16 +592,22 @@ int resample_run(scema_ctx *ctx, uint32_t P)
     int rc = ensure_tables(ctx, P);
     if (rc) return rc;
 
-    // Length classes: every class gets its own launch with a slab sized for the class, so short
-    // histories are not starved of resident warps by the longest one. Inside a class the work order
-    // is sorted by exact length (stable counting sort), so the five histories of a warp group almost
-    // always share one factor table and neighbours in memory stay neighbours in the work order.
-    static const uint32_t caps[] = {16, 32, 48, 64, 96, 128, 192, 256, 384, 512, 800};
-    constexpr int NCLS = sizeof(caps) / sizeof(caps[0]) + 1;  // last class: global-scratch fallback
+    // Length classes: every class gets its own launch, with the warp-private z scratch (and, for
+    // the staged variant, the shared-memory slab) sized for the class. Inside a class the work
+    // order is sorted by exact length (stable counting sort), so the five histories of a warp
+    // group almost always share one factor table and every warp of a launch gets a similar mix.
+    // SCEMA_K1=staged selects the shared-memory-slab kernel (kept for A/B measurements).
+    static const char *k1_env = getenv("SCEMA_K1");
+    const bool staged = k1_env && strcmp(k1_env, "staged") == 0;
+    static const uint32_t caps_staged[] = {16, 32, 48, 64, 96, 128, 192, 256, 384, 512, 800};
+    static const uint32_t caps_stream[] = {64, 256, 2048, 16384, 131072};
+    const uint32_t *caps = staged ? caps_staged : caps_stream;
+    const int NCLS = (int)(staged ? sizeof(caps_staged) / sizeof(uint32_t) : sizeof(caps_stream) / sizeof(uint32_t)) + 1;
+    constexpr int MAXCLS = 12;  // last class: global-scratch fallback
     auto cls_of = [&](uint64_t L) { int k = 0; while (k < NCLS - 1 && L > caps[k]) k++; return k; };
-    uint64_t cls_count[NCLS] = {};
+    uint64_t cls_count[MAXCLS] = {};
     for (uint64_t i = 0; i < ctx->hn; i++) cls_count[cls_of(ctx->h_offsets[i + 1] - ctx->h_offsets[i])]++;
-    uint64_t cls_first[NCLS + 1] = {};
+    uint64_t cls_first[MAXCLS + 1] = {};
     for (int k = 0; k < NCLS; k++) cls_first[k + 1] = cls_first[k] + cls_count[k];
     const uint32_t *d_order = nullptr;
     if (ctx->min_len != ctx->max_len) {
@@ -434,14 +625,37 @@ int resample_run(scema_ctx *ctx, uint32_t P)
         }
         d_order = ctx->d_order.as<uint32_t>();
     }
-    if (cls_count[NCLS - 1]) SCEMA_CUDA(ctx, ctx->zscratch.reserve((size_t)ctx->total_steps * 6 * sizeof(double)));
     auto smem_for = [&](uint32_t cap) { return (size_t)16 + 5 * (size_t)pad2(cap) * 8 + ((size_t)GROUP * 6 * cap + 64) * sizeof(double); };
+    // streamed kernel: resident warps per SM and the scratch they need (one [cap][32] block per warp)
+    static const char *wps_env = getenv("SCEMA_K1_WPS");
+    const int wps = wps_env && atoi(wps_env) > 0 ? atoi(wps_env) : 16;
+    const uint64_t scratch_budget = 1ull << 30;
+    uint64_t stream_warps[MAXCLS] = {};
+    uint64_t scratch_need = 0;
+    if (cls_count[NCLS - 1]) scratch_need = (uint64_t)ctx->total_steps * 6 * sizeof(double);
+    if (!staged)
+        for (int k = 0; k < NCLS - 1; k++) {
+            if (!cls_count[k]) continue;
+            const uint32_t cap = std::min<uint32_t>(caps[k], ctx->max_len);
+            uint64_t w = std::min<uint64_t>((uint64_t)ctx->sm_count * wps, (cls_count[k] + GROUP - 1) / GROUP);
+            w = std::min<uint64_t>(w, std::max<uint64_t>(RS_WARPS, scratch_budget / ((uint64_t)cap * 256)));
+            w = (w + RS_WARPS - 1) / RS_WARPS * RS_WARPS;
+            stream_warps[k] = w;
+            scratch_need = std::max<uint64_t>(scratch_need, w * cap * 256);
+        }
+    if (scratch_need) SCEMA_CUDA(ctx, ctx->zscratch.reserve(scratch_need));
 
     t_begin(ctx, SCEMA_T_RESAMPLE);
     for (int k = 0; k < NCLS; k++) {
         if (!cls_count[k]) continue;
         const uint64_t n_groups = (cls_count[k] + GROUP - 1) / GROUP;
-        if (k < NCLS - 1) {
+        if (k < NCLS - 1 && !staged) {
+            const uint32_t cap = std::min<uint32_t>(caps[k], ctx->max_len);
+            k_resample_stream<<<(unsigned)(stream_warps[k] / RS_WARPS), 32 * RS_WARPS, 0, ctx->stream>>>(
+                ctx->d_steps, ctx->d_offsets.as<uint64_t>(), d_order, cls_first[k], cls_count[k],
+                ctx->d_table_index.as<int64_t>(), ctx->d_tables.as<double>(), P, ctx->spline_own.as<double>(),
+                ctx->zscratch.as<double>(), cap);
+        } else if (k < NCLS - 1) {
             const size_t slab = smem_for(caps[k]);
             int per_sm = (int)(ctx->smem_optin / (slab + 1024));
             per_sm = per_sm > 32 ? 32 : (per_sm < 1 ? 1 : per_sm);

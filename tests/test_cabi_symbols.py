@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = set()
-    for h in ("scema_hist.h", "scema_synth.h"):
+    for h in ("scema_hist.h", "scema_synth.h", "scema_ingest.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names |= set(re.findall(r"\b(scema_[a-z0-9_]+)\s*\(", src))

@@ -94,14 +94,39 @@ def test_k1_long_and_equal_lengths(hc, oracle):
         hc.set_histories(steps, off)
         hc.resample(10)
         assert same_bits(hc.get_spline(), oracle.splinify_batch(steps, off, 10)), L
-    # lengths on both sides of every slab class incl. the global-memory fallback (> 800 steps)
-    lens = np.array([3, 16, 17, 64, 65, 128, 129, 256, 257, 512, 513, 800, 801, 1500, 2500, 5, 5, 5, 801, 4, 4, 7],
-                    dtype=np.uint64)
+    # lengths on both sides of every length class of the streamed kernel (64, 256, 2048, 16384,
+    # 131072) incl. the global-scratch fallback beyond the last one, and of the staged kernel's slabs
+    lens = np.array([3, 16, 17, 64, 65, 128, 129, 256, 257, 512, 513, 800, 801, 1500, 2048, 2049, 2500, 5, 5, 5, 801,
+                     4, 4, 7, 16384, 16385, 131072, 131073], dtype=np.uint64)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
     steps = np.random.default_rng(9).standard_normal((int(off[-1]), 6)) * 1e-2
     hc.set_histories(steps, off)
     hc.resample(10)
     assert same_bits(hc.get_spline(), oracle.splinify_batch(steps, off, 10))
+
+
+def test_k1_special_magnitudes(hc, oracle):
+    """Numerators outside the range where the reciprocal-based exact division applies (zeros,
+    subnormals, 1e+-300, inf, NaN) must take the IEEE division and still match bit for bit."""
+    n, L = 64, 37
+    off = (np.arange(n + 1, dtype=np.uint64) * L)
+    rng = np.random.default_rng(5)
+    steps = rng.standard_normal((n * L, 6)) * 1e-3
+    scale = np.array([1e-300, 1e-310, 5e-324, 1e300, 1e-280, 1e290, 2.0 ** -895, 2.0 ** 897])
+    for q in range(8):
+        steps[q * L:(q + 1) * L] *= scale[q]
+    steps[8 * L + 3, 1] = np.inf
+    steps[9 * L + 5, 2] = np.nan
+    steps[10 * L:(11 * L), 0] = 0.0
+    steps[11 * L:(12 * L), 3] = -0.0
+    steps[12 * L + 7, 4] = 5e-324
+    steps[13 * L:(14 * L), 5] = 1.7976931348623157e308
+    hc.set_histories(steps, off)
+    for P in (10, 50):  # P > L puts several samples into one interval
+        hc.resample(P)
+        with np.errstate(all="ignore"):
+            want = oracle.splinify_batch(steps, off, P)
+        assert same_bits(hc.get_spline(), want), P
 
 
 def test_k1_too_short_history_is_an_error(hc):
