@@ -226,14 +226,20 @@ def run_ours(args, wl, wl_name):
     acc = {"filter": 0.0, "resample": 0.0, "exact": 0.0, "sort": 0.0, "prep": 0.0, "steps": 0, "edges": 0,
            "survivors": 0}
 
+    streamed = {"edges": 0, "chunks": 0}
+
+    def sink(a, b, d):
+        streamed["edges"] += len(a)
+        streamed["chunks"] += 1
+
     def step_resident(record):
         if world > 1:
-            ne, counts, offs, _ = sc.run(n, P, THR, variant)
+            ne, counts, offs, _ = sc.run(n, P, THR, variant, sink=sink if args.stream else None)
             tot = sum(counts)
         else:
             hc.resample(P)
             t_res = hc.timings()["resample"] if record else 0.0
-            ne = hc.compare(THR, variant)
+            ne = hc.compare_stream(THR, sink, variant) if args.stream else hc.compare(THR, variant)
             tot = ne
         if record:
             t = hc.timings()
@@ -248,11 +254,13 @@ def run_ours(args, wl, wl_name):
     def step_e2e():
         hc.set_histories(h_steps_np, off)            # pinned host -> device inside the timed region
         if world > 1:
-            ne, counts, offs, _ = sc.run(n, P, THR, variant)
+            ne, counts, offs, _ = sc.run(n, P, THR, variant, sink=sink if args.stream else None)
         else:
             hc.resample(P)
-            ne = hc.compare(THR, variant)
-        hc.get_edges()                               # device -> host read of the result
+            # streamed: every chunk of edges lands in host memory through the sink
+            ne = hc.compare_stream(THR, sink, variant) if args.stream else hc.compare(THR, variant)
+        if not args.stream:
+            hc.get_edges()                           # device -> host read of the result
         return ne
 
     # ---- device-resident timing: the raw histories are handed over once (borrowed device pointer)
@@ -304,13 +312,16 @@ def run_ours(args, wl, wl_name):
         pairs_this_rank = total_pairs / world
         filt_ms = acc["filter"] / max(acc["steps"], 1)
         achieved = pairs_this_rank * 2 * K / (filt_ms * 1e-3) / 1e12 if filt_ms > 0 else None
-        peaks = hc.fp64_peak()
-        peak = peaks["dmma_tflops"] if variant == 0 else peaks["dfma_tflops"]
+        # issue-rate probe, taken twice (the first call also warms the clocks back up after the host-side
+        # bookkeeping above); the better of the two is the denominator
+        peaks = [hc.fp64_peak() for _ in range(2)]
+        key = "dmma_tflops" if variant == 0 else "dfma_tflops"
+        peak = max(p[key] for p in peaks)
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "filter_traffic.json")
         if os.path.exists(tfile):
             try:
-                traffic = json.load(open(tfile)).get(wl_name)
+                traffic = json.load(open(tfile)).get(f"{wl_name}:{n}")
             except Exception:
                 traffic = None
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -362,9 +373,13 @@ def main():
     ap.add_argument("--variant", default="dmma", choices=["dmma", "fma", "exact"])
     ap.add_argument("--histories", type=int, default=0, help="override the workload's history count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stream", type=int, default=-1,
+                    help="1: edges leave the device chunk by chunk through scema_compare_stream (default for c5), 0: one-shot compare")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = dict(WORKLOADS[args.workload])
+    if args.stream < 0:
+        args.stream = 1 if args.workload == "c5" else 0
     if args.histories:
         wl["n"] = args.histories
     if args.impl == "reference":

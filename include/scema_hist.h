@@ -72,6 +72,25 @@ int scema_resample(scema_ctx *ctx, uint32_t spline_points);
 int scema_set_spline(scema_ctx *ctx, const double *rows, int rows_on_device, uint64_t n, uint32_t k,
                      const uint32_t *ids);
 
+/* ---- device-resident incremental history store: the in-process caller's pattern. Every timestep
+ *      FEProblem::update_strain_quadrature_point_history appends one sample per quadrature point
+ *      (FE_problem.h:1091-1103 -> Strain6D::add_current_strain, strain2spline.h:75-86), then
+ *      spline_building re-fits EVERY point (FE_problem.h:1167-1191) and spline_comparison compares
+ *      only the points flagged for an MD update (FE_problem.h:1202-1229). The store keeps all
+ *      histories on the device (time-major [step][n][6]), so a timestep costs one 48*n-byte copy
+ *      instead of re-sending every history.
+ *        scema_store_reset   n points with their IDs (NULL = 0..n-1), room for capacity_steps (grows)
+ *        scema_store_append  one sample for every point: strain[n][6], xx yy zz xy xz yz
+ *        scema_store_resample  splinify(spline_points) of all n points -> current spline matrix [n][6P]
+ *        scema_select_rows   keep only the given rows of the current spline matrix (the flagged
+ *                            points), IDs carried along; the following compare / get_edges /
+ *                            write_similar_hist work on that subset. */
+int scema_store_reset(scema_ctx *ctx, uint64_t n, const uint32_t *ids, uint32_t capacity_steps);
+int scema_store_append(scema_ctx *ctx, const double *strain, int strain_on_device);
+int scema_store_info(scema_ctx *ctx, uint64_t *n, uint32_t *n_steps, const double **device_steps);
+int scema_store_resample(scema_ctx *ctx, uint32_t spline_points);
+int scema_select_rows(scema_ctx *ctx, const uint32_t *rows, uint64_t m);
+
 /* Copy the current spline matrix [n][k] to host memory / expose it on the device. */
 int scema_get_spline(scema_ctx *ctx, double *out_host);
 int scema_spline_info(scema_ctx *ctx, uint64_t *n, uint32_t *k, const double **device_rows);
@@ -84,6 +103,19 @@ int scema_spline_info(scema_ctx *ctx, uint64_t *n, uint32_t *k, const double **d
  *      (one context per GPU, shard = rank); shard=0,n_shards=1 is the whole problem. ---------- */
 int scema_compare(scema_ctx *ctx, double threshold, int variant, uint32_t shard, uint32_t n_shards,
                   uint64_t *n_edges);
+
+/* Streaming form of scema_compare for edge lists that should not be held on the device (or in one
+ * host array) as a whole — BASELINE config 5, "sparse thresholded edge streaming". The pair matrix
+ * is evaluated in chunks of panels_per_chunk panels (one panel = 2048 rows; 0 = default 64); each
+ * chunk's edges, sorted by (a,b), are handed to `sink` from pinned host memory while the GPU works
+ * on the next chunk. Index a of consecutive chunks is disjoint and increasing, so the calls
+ * concatenate to exactly the list scema_compare would produce. The arrays are only valid during the
+ * call; a non-zero return value of the sink aborts with SCEMA_ERR_STATE. Nothing is retained:
+ * scema_get_edges / scema_write_similar_hist need a plain scema_compare. */
+typedef int (*scema_edge_sink)(void *user, const uint32_t *index_a, const uint32_t *index_b, const double *diff,
+                               uint64_t n_edges);
+int scema_compare_stream(scema_ctx *ctx, double threshold, int variant, uint32_t shard, uint32_t n_shards,
+                         uint32_t panels_per_chunk, scema_edge_sink sink, void *user, uint64_t *n_edges_total);
 
 /* Edge list of the last scema_compare. Host copies (any pointer may be NULL): index_a/index_b are
  * batch indices, diff the distance. cap = array capacity in edges. */

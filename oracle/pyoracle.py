@@ -165,6 +165,15 @@ class Reference(_PairsMixin):
         self.lib.ref_pipeline.restype = None
         self.lib.ref_pipeline.argtypes = [_f64p, _u64p, _u32p, C.c_uint64, C.c_uint32, C.c_double,
                                           C.c_char_p, C.c_void_p]
+        self.lib.ref_from_file.restype = C.c_uint64
+        self.lib.ref_from_file.argtypes = [C.c_char_p, _f64p, C.c_uint64]
+
+    def from_file(self, path, cap_steps=1 << 16):
+        """Strain6D::from_file on one file -> [L, 6] array of the steps it stored."""
+        buf = np.empty((cap_steps, 6), dtype=np.float64)
+        n = int(self.lib.ref_from_file(os.fsencode(path), buf, cap_steps))
+        assert n <= cap_steps
+        return buf[:n].copy()
 
     def pipeline(self, steps, offsets, ids, P, thr, pattern=None, want_spline=False):
         steps = np.ascontiguousarray(steps, dtype=np.float64).reshape(-1, 6)

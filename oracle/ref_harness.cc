@@ -15,6 +15,7 @@
 //   compare_L2_norm(double*,...)   strain2spline.h:469-484
 //   compare_histories_with_all_ranks  strain2spline.h:546-614 (single rank via mpi_shim)
 //   most_similar_histories_to_file strain2spline.h:301-314
+//   Strain6D::from_file            strain2spline.h:112-134
 #include <limits>
 #include <iostream>
 #include <sstream>
@@ -24,7 +25,16 @@
 #include <algorithm>
 #include <stdint.h>
 #include <mpi.h>            // oracle/mpi_shim/mpi.h
+#include <fstream>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+// ref_from_file() below needs to read back what Strain6D::from_file stored; the six input vectors
+// are private and have no accessor, so the header is compiled with `private` spelled `public`
+// (every standard header it uses is already included above; the reference source is untouched).
+#define private public
 #include "strain2spline.h"  // the reference header, unmodified
+#undef private
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -159,6 +169,21 @@ void ref_pipeline(const double *steps, const uint64_t *offsets, const uint32_t *
         }
     }
     for (uint64_t i = 0; i < N; i++) delete hist[i];
+}
+
+// Strain6D::from_file (strain2spline.h:112-134) on one file; the parsed steps come back as
+// [L][6] (xx yy zz xy xz yz). Returns the number of steps read (may exceed cap_steps; then only
+// the first cap_steps were copied).
+uint64_t ref_from_file(const char *path, double *out, uint64_t cap_steps)
+{
+    Strain6D h;
+    h.from_file(path);
+    const uint64_t L = h.in_XX.size();
+    for (uint64_t n = 0; n < L && n < cap_steps; n++) {
+        out[6 * n + 0] = h.in_XX[n]; out[6 * n + 1] = h.in_YY[n]; out[6 * n + 2] = h.in_ZZ[n];
+        out[6 * n + 3] = h.in_XY[n]; out[6 * n + 4] = h.in_XZ[n]; out[6 * n + 5] = h.in_YZ[n];
+    }
+    return L;
 }
 
 // Default-ostream formatting of a double, as every reference writer uses it

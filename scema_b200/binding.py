@@ -41,10 +41,16 @@ def lib():
         "scema_stream": (i32, [vp, P(vp)]),
         "scema_set_histories": (i32, [vp, vp, i32, vp, vp, u64]),
         "scema_resample": (i32, [vp, u32]),
+        "scema_store_reset": (i32, [vp, u64, vp, u32]),
+        "scema_store_append": (i32, [vp, vp, i32]),
+        "scema_store_info": (i32, [vp, P(u64), P(u32), P(vp)]),
+        "scema_store_resample": (i32, [vp, u32]),
+        "scema_select_rows": (i32, [vp, vp, u64]),
         "scema_set_spline": (i32, [vp, vp, i32, u64, u32, vp]),
         "scema_get_spline": (i32, [vp, vp]),
         "scema_spline_info": (i32, [vp, P(u64), P(u32), P(vp)]),
         "scema_compare": (i32, [vp, dbl, i32, u32, u32, P(u64)]),
+        "scema_compare_stream": (i32, [vp, dbl, i32, u32, u32, u32, vp, vp, P(u64)]),
         "scema_get_edges": (i32, [vp, vp, vp, vp, u64]),
         "scema_edges_device": (i32, [vp, P(vp), P(vp), P(u32), P(u64)]),
         "scema_get_degrees": (i32, [vp, vp]),
@@ -84,7 +90,8 @@ def lib():
 
 EXPORTED = (
     "scema_create scema_destroy scema_last_error scema_version scema_stream scema_set_histories scema_resample "
-    "scema_set_spline scema_get_spline scema_spline_info scema_compare scema_get_edges scema_edges_device "
+    "scema_store_reset scema_store_append scema_store_info scema_store_resample scema_select_rows "
+    "scema_set_spline scema_get_spline scema_spline_info scema_compare scema_compare_stream scema_get_edges scema_edges_device "
     "scema_get_degrees scema_cluster scema_write_similar_hist scema_reduce_edges scema_reduce_calls scema_reduce_dir "
     "scema_last_timings scema_last_counters scema_kernel_launches scema_fp64_peak scema_synth_offsets "
     "scema_synth_histories_device scema_synth_rows_device scema_ingest_last_error scema_batch_read_dir "
@@ -233,6 +240,31 @@ class HistCluster:
     def set_histories_from_batch(self, batch):
         self._ck(self._L.scema_set_histories_from_batch(self._h, batch._h))
 
+    # ---- incremental store ----
+    def store_reset(self, n, ids=None, capacity_steps=64):
+        ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)
+        self._ck(self._L.scema_store_reset(self._h, int(n), _ptr(ids_a), int(capacity_steps)))
+
+    def store_append(self, strain=None, device_ptr=None):
+        """strain: host ndarray [n,6] (or device_ptr=int)."""
+        if device_ptr is not None:
+            self._ck(self._L.scema_store_append(self._h, int(device_ptr), 1))
+        else:
+            strain = np.ascontiguousarray(strain, dtype=np.float64)
+            self._ck(self._L.scema_store_append(self._h, _ptr(strain), 0))
+
+    def store_info(self):
+        n, st, p = C.c_uint64(0), C.c_uint32(0), C.c_void_p(None)
+        self._ck(self._L.scema_store_info(self._h, C.byref(n), C.byref(st), C.byref(p)))
+        return int(n.value), int(st.value), p.value
+
+    def store_resample(self, spline_points):
+        self._ck(self._L.scema_store_resample(self._h, int(spline_points)))
+
+    def select_rows(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        self._ck(self._L.scema_select_rows(self._h, _ptr(rows), len(rows)))
+
     def resample(self, spline_points):
         self._ck(self._L.scema_resample(self._h, int(spline_points)))
 
@@ -261,6 +293,33 @@ class HistCluster:
         self._ck(self._L.scema_compare(self._h, float(threshold), int(variant), int(shard), int(n_shards), C.byref(ne)))
         self.n_edges = int(ne.value)
         return self.n_edges
+
+    def compare_stream(self, threshold, sink, variant=PAIRS_DMMA, shard=0, n_shards=1, panels_per_chunk=0):
+        """Chunked compare; sink(a, b, d) is called with numpy copies of every chunk's sorted edges.
+        -> total number of edges."""
+        SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_double),
+                           C.c_uint64)
+        err = []
+
+        def tramp(_user, pa, pb, pd, m):
+            try:
+                m = int(m)
+                sink(np.ctypeslib.as_array(pa, (m,)).copy(), np.ctypeslib.as_array(pb, (m,)).copy(),
+                     np.ctypeslib.as_array(pd, (m,)).copy())
+                return 0
+            except Exception as e:  # noqa: BLE001 - reported after the C call returns
+                err.append(e)
+                return 1
+
+        cb = SINK(tramp)
+        tot = C.c_uint64(0)
+        rc = self._L.scema_compare_stream(self._h, float(threshold), int(variant), int(shard), int(n_shards),
+                                          int(panels_per_chunk), C.cast(cb, C.c_void_p), None, C.byref(tot))
+        if err:
+            raise err[0]
+        self._ck(rc)
+        self.n_edges = 0
+        return int(tot.value)
 
     def get_edges(self):
         m = self.n_edges

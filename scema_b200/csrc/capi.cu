@@ -44,11 +44,16 @@ void scema_destroy(scema_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->steps_own.release(); c->d_offsets.release(); c->d_tables.release(); c->d_table_index.release();
-    c->zscratch.release(); c->d_order.release(); c->spline_own.release(); c->d_filter.release(); c->d_halfnorm.release();
+    c->zscratch.release(); c->d_order.release(); c->spline_own.release(); c->spline_sel.release(); c->d_select.release(); c->d_store.release(); c->d_filter.release(); c->d_halfnorm.release();
     c->d_blockmax.release(); c->d_panel_start.release(); c->d_cand.release(); c->d_counters.release();
     for (int b = 0; b < 2; b++) { c->d_edge_key[b].release(); c->d_edge_val[b].release(); }
     c->d_sort_tmp.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    for (int k = 0; k < 2; k++) {
+        if (c->h_stage_key[k]) cudaFreeHost(c->h_stage_key[k]);
+        if (c->h_stage_val[k]) cudaFreeHost(c->h_stage_val[k]);
+        if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
+    }
     for (int i = 0; i < 2 * SCEMA_T_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -130,6 +135,45 @@ int scema_resample(scema_ctx *c, uint32_t spline_points)
     return resample_run(c, spline_points);
 }
 
+int scema_store_reset(scema_ctx *c, uint64_t n, const uint32_t *ids, uint32_t capacity_steps)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    return store_reset(c, n, ids, capacity_steps);
+}
+
+int scema_store_append(scema_ctx *c, const double *strain, int strain_on_device)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    return store_append(c, strain, strain_on_device);
+}
+
+int scema_store_info(scema_ctx *c, uint64_t *n, uint32_t *n_steps, const double **device_steps)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    if (!c->have_store) return fail(c, SCEMA_ERR_STATE, "store_info: no store (call scema_store_reset)");
+    if (n) *n = c->store_n;
+    if (n_steps) *n_steps = c->store_steps;
+    if (device_steps) *device_steps = c->d_store.as<double>();
+    return SCEMA_OK;
+}
+
+int scema_store_resample(scema_ctx *c, uint32_t spline_points)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    return store_resample(c, spline_points);
+}
+
+int scema_select_rows(scema_ctx *c, const uint32_t *rows, uint64_t m)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    return select_rows(c, rows, m);
+}
+
 int scema_set_spline(scema_ctx *c, const double *rows, int rows_on_device, uint64_t n, uint32_t k, const uint32_t *ids)
 {
     int rc = enter(c);
@@ -186,6 +230,18 @@ int scema_compare(scema_ctx *c, double threshold, int variant, uint32_t shard, u
     if (rc) { c->have_edges = false; return rc; }
     if (n_edges) *n_edges = c->n_edges;
     return SCEMA_OK;
+}
+
+int scema_compare_stream(scema_ctx *c, double threshold, int variant, uint32_t shard, uint32_t n_shards,
+                         uint32_t panels_per_chunk, scema_edge_sink sink, void *user, uint64_t *n_edges_total)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    for (int k = 0; k < 2; k++)
+        if (!c->stage_ev[k]) SCEMA_CUDA(c, cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming));
+    rc = compare_stream_run(c, threshold, variant, shard, n_shards, panels_per_chunk, sink, user, n_edges_total);
+    c->have_edges = false;
+    return rc;
 }
 
 int scema_get_edges(scema_ctx *c, uint32_t *ia, uint32_t *ib, double *diff, uint64_t cap)
@@ -288,10 +344,10 @@ int scema_last_timings(scema_ctx *c, float ms[SCEMA_T_COUNT])
     if (rc) return rc;
     SCEMA_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int w = 0; w < SCEMA_T_COUNT; w++) {
-        ms[w] = 0.f;
+        ms[w] = c->acc_ms[w];
         if (c->ev_used[w]) {
             float t = 0.f;
-            if (cudaEventElapsedTime(&t, c->ev[2 * w], c->ev[2 * w + 1]) == cudaSuccess) ms[w] = t;
+            if (cudaEventElapsedTime(&t, c->ev[2 * w], c->ev[2 * w + 1]) == cudaSuccess) ms[w] += t;
             else cudaGetLastError();
         }
     }

@@ -85,6 +85,14 @@ struct scema_ctx {
     const double *d_spline = nullptr;  // borrowed or = spline_own
     scema::DevBuf spline_own;
     bool have_spline = false;
+    scema::DevBuf spline_sel, d_select;  // scema_select_rows: compacted subset of the rows
+
+    // ---- incremental history store, time-major [step][store_n][6]
+    scema::DevBuf d_store;
+    uint64_t store_n = 0;
+    uint32_t store_steps = 0, store_cap = 0;
+    std::vector<uint32_t> store_ids;
+    bool have_store = false;
 
     // ---- K2 filter copy
     scema::FilterLayout fl;
@@ -101,10 +109,16 @@ struct scema_ctx {
     uint32_t key_shift = 0;
     bool have_edges = false;
     uint64_t *h_counters = nullptr;  // pinned, 8 entries
+    // streaming compare: pinned double-buffered staging of one chunk of edges
+    uint64_t *h_stage_key[2] = {nullptr, nullptr};
+    double *h_stage_val[2] = {nullptr, nullptr};
+    uint64_t stage_cap[2] = {0, 0};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 
     // ---- instrumentation
     cudaEvent_t ev[2 * SCEMA_T_COUNT] = {};
     bool ev_used[SCEMA_T_COUNT] = {};
+    float acc_ms[SCEMA_T_COUNT] = {};  // phases already folded in by earlier chunks of a streamed compare
     uint64_t counters[8] = {};
 };
 
@@ -130,8 +144,14 @@ inline void t_end(scema_ctx *c, int which) { cudaEventRecord(c->ev[2 * which + 1
 
 // resample.cu
 int resample_run(scema_ctx *ctx, uint32_t P);
+int store_reset(scema_ctx *ctx, uint64_t n, const uint32_t *ids, uint32_t capacity_steps);
+int store_append(scema_ctx *ctx, const double *strain, int on_device);
+int store_resample(scema_ctx *ctx, uint32_t P);
+int select_rows(scema_ctx *ctx, const uint32_t *rows, uint64_t m);
 // pairs.cu
 int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards);
+int compare_stream_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards, uint32_t panels_per_chunk,
+                       scema_edge_sink sink, void *user, uint64_t *n_total);
 int fp64_peak_run(scema_ctx *ctx, double out[2]);
 // host_io.cc
 int write_similar_hist(scema_ctx *ctx, const char *pattern);

@@ -25,6 +25,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cmath>
 #include <algorithm>
+#include <functional>
 
 namespace scema {
 
@@ -167,7 +168,8 @@ struct FilterArgs {
     uint64_t cand_cap;
     uint64_t n, n_pad;
     uint32_t n_blocks, n_panels, n_chunks, strip_len;
-    uint64_t n_groups_local;
+    uint64_t n_groups_local;  // strip groups of this launch owned by this shard ...
+    uint64_t lg_first;        // ... starting at this shard-local group index (group = local * n_shards + shard)
     uint32_t shard, n_shards;
     double T0, cband;
 };
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(256, 1) k_filter(const FilterArgs a)
         __syncthreads();
         const uint64_t item = s_item;
         if (item >= a.n_groups_local * PANEL_ROWBLOCKS) break;
-        const uint64_t grp = (item / PANEL_ROWBLOCKS) * a.n_shards + a.shard;
+        const uint64_t grp = (a.lg_first + item / PANEL_ROWBLOCKS) * a.n_shards + a.shard;
         const uint32_t r = (uint32_t)(item % PANEL_ROWBLOCKS);
         // binary search: panel with panel_start[p] <= grp < panel_start[p+1]
         uint32_t lo = 0, hi = a.n_panels;
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(384, 1) k_filter_ws(const FilterArgs a)
         while (true) {
             const uint64_t item = atomicAdd(a.work_counter, 1ull);
             if (item >= total) break;
-            const uint64_t grp = (item / PANEL_ROWBLOCKS) * a.n_shards + a.shard;
+            const uint64_t grp = (a.lg_first + item / PANEL_ROWBLOCKS) * a.n_shards + a.shard;
             const uint32_t r = (uint32_t)(item % PANEL_ROWBLOCKS);
             uint32_t lo = 0, hi = a.n_panels;
             while (hi - lo > 1) {
@@ -620,11 +622,11 @@ __global__ void __launch_bounds__(256) k_exact_queue(const double *__restrict__ 
 // memory in chunks while the per-pair sums keep the reference's sequential-k order.
 constexpr int XT = 64, XKC = 32;
 __global__ void __launch_bounds__(256) k_exact_all(const double *__restrict__ S, uint64_t n, uint32_t K, double thr,
-                                                   uint32_t key_shift, uint32_t shard, uint32_t n_shards,
+                                                   uint32_t key_shift, uint32_t shard, uint32_t n_shards, uint32_t I_first,
                                                    unsigned long long *edge_count, uint64_t edge_cap,
                                                    uint64_t *__restrict__ keys, double *__restrict__ vals)
 {
-    const uint32_t I = blockIdx.y, J = blockIdx.x;
+    const uint32_t I = I_first + blockIdx.y, J = blockIdx.x;
     if (J < I) return;
     if (((uint64_t)I + J) % n_shards != shard) return;
     __shared__ double As[XT][XKC + 1], Bs[XT][XKC + 1];
@@ -812,70 +814,71 @@ static int ensure_edge_buffers(scema_ctx *ctx, uint64_t cap)
     return SCEMA_OK;
 }
 
-int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards)
+// Schedule of one compare: panels of PANEL_ROWBLOCKS row blocks, column strips of strip_len tiles.
+struct Schedule {
+    uint64_t nb = 0, tiles = 0, groups = 0;
+    uint32_t strip_len = 0, n_panels = 0;
+    std::vector<uint64_t> ps;  // [n_panels+1] prefix of strip groups per panel
+};
+
+static void make_schedule(const scema_ctx *ctx, uint64_t n, Schedule &sc)
 {
-    if (!ctx->have_spline) return fail(ctx, SCEMA_ERR_STATE, "Spline is not up to date.");
-    if (n_shards == 0 || shard >= n_shards) return fail(ctx, SCEMA_ERR_INVALID, "compare: bad shard");
-    if (variant < 0 || variant > 2) return fail(ctx, SCEMA_ERR_INVALID, "compare: bad variant");
-    if (ctx->n >= (1ull << 32)) return fail(ctx, SCEMA_ERR_INVALID, "compare: more than 2^32-1 histories");
-    for (int i = 0; i < 8; i++) ctx->counters[i] = 0;
-    for (int w = SCEMA_T_PREP; w <= SCEMA_T_SORT; w++) ctx->ev_used[w] = false;
-    ctx->n_edges = 0;
-    ctx->have_edges = true;
-    ctx->edge_cur = 0;
-    ctx->key_shift = bits_for(ctx->n);
+    sc.nb = (n + TILE - 1) / TILE;
+    sc.tiles = sc.nb * (sc.nb + 1) / 2;
+    sc.strip_len = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(4, sc.tiles / ((uint64_t)ctx->sm_count * 8)));
+    sc.n_panels = (uint32_t)((sc.nb + PANEL_ROWBLOCKS - 1) / PANEL_ROWBLOCKS);
+    sc.ps.assign(sc.n_panels + 1, 0);
+    for (uint32_t p = 0; p < sc.n_panels; p++) {
+        uint64_t cols = sc.nb - (uint64_t)p * PANEL_ROWBLOCKS;
+        sc.ps[p + 1] = sc.ps[p] + (cols + sc.strip_len - 1) / sc.strip_len;
+    }
+    sc.groups = sc.ps[sc.n_panels];
+}
+
+// shard-local index of the first group >= g owned by `shard`
+static uint64_t local_index(uint64_t g, uint32_t shard, uint32_t n_shards)
+{
+    return g > shard ? (g - shard + n_shards - 1) / n_shards : 0;
+}
+
+// Evaluate the pairs of panels [p0, p1) that belong to this shard: filter + exact recompute (or the
+// filter-free kernel), retried with larger buffers on overflow, then the canonical (a,b) sort.
+// Leaves the edges in d_edge_key/val[ctx->edge_cur], their number in ctx->n_edges. *variant may be
+// switched to SCEMA_PAIRS_EXACT when the survivors are too dense for a queue.
+// `overlap` (optional) is host work to do while the GPU runs the first pass: it is called once, after
+// the kernels are queued and before the host blocks on the counter read-back.
+static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t shard, uint32_t n_shards, const Schedule &sc,
+                          uint32_t p0, uint32_t p1, const std::function<int()> &overlap = nullptr)
+{
     const uint64_t n = ctx->n;
     const uint32_t K = ctx->K;
-    // diff >= 0 or NaN, so nothing passes a non-positive or NaN threshold
-    if (n < 2 || !(thr > 0.0)) return SCEMA_OK;
-
-    SCEMA_CUDA(ctx, ctx->d_counters.reserve(8 * sizeof(uint64_t)));
-    if (!ctx->h_counters) SCEMA_CUDA(ctx, cudaMallocHost(&ctx->h_counters, 8 * sizeof(uint64_t)));
-    int rc = ensure_edge_buffers(ctx, std::max<uint64_t>(1ull << 20, 16 * n));
-    if (rc) return rc;
     unsigned long long *d_cnt = ctx->d_counters.as<unsigned long long>();
-
     size_t free_b = 0, total_b = 0;
     uint64_t passes = 0;
+    int rc;
+    ctx->n_edges = 0;
+    ctx->edge_cur = 0;
     while (true) {
         passes++;
         if (passes > 8) return fail(ctx, SCEMA_ERR_NOMEM, "compare: buffers kept overflowing");
         SCEMA_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 8 * sizeof(uint64_t), ctx->stream));
-        if (variant == SCEMA_PAIRS_EXACT) {
+        if (*variant == SCEMA_PAIRS_EXACT) {
             const uint32_t nbx = (uint32_t)((n + XT - 1) / XT);
             if (nbx > 65535) return fail(ctx, SCEMA_ERR_INVALID, "exact all-pairs variant supports n <= 4194240");
+            const uint32_t per_panel = PANEL_ROWBLOCKS * (TILE / XT);
+            const uint32_t i_first = p0 * per_panel;
+            const uint32_t i_end = std::min<uint64_t>((uint64_t)p1 * per_panel, nbx);
             t_begin(ctx, SCEMA_T_FILTER);
-            k_exact_all<<<dim3(nbx, nbx), 256, 0, ctx->stream>>>(ctx->d_spline, n, K, thr, ctx->key_shift, shard, n_shards,
-                                                                 d_cnt + 1, ctx->edge_cap, ctx->d_edge_key[0].as<uint64_t>(),
-                                                                 ctx->d_edge_val[0].as<double>());
+            if (i_end > i_first)
+                k_exact_all<<<dim3(nbx, i_end - i_first), 256, 0, ctx->stream>>>(
+                    ctx->d_spline, n, K, thr, ctx->key_shift, shard, n_shards, i_first, d_cnt + 1, ctx->edge_cap,
+                    ctx->d_edge_key[0].as<uint64_t>(), ctx->d_edge_val[0].as<double>());
             ctx->launches++;
             t_end(ctx, SCEMA_T_FILTER);
             SCEMA_CUDA(ctx, cudaGetLastError());
-            ctx->counters[4] = (uint64_t)nbx * (nbx + 1) / 2;
         } else {
-            t_begin(ctx, SCEMA_T_PREP);
-            rc = prepare_filter(ctx, variant);
-            if (rc) return rc;
             const FilterLayout &fl = ctx->fl;
-            // scheduling tables: panels of PANEL_ROWBLOCKS row blocks, column strips of strip_len tiles
-            const uint64_t nb = fl.n_blocks;
-            const uint64_t tiles = nb * (nb + 1) / 2;
-            uint32_t strip_len = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(4, tiles / ((uint64_t)ctx->sm_count * 8)));
-            const uint32_t n_panels = (uint32_t)((nb + PANEL_ROWBLOCKS - 1) / PANEL_ROWBLOCKS);
-            std::vector<uint64_t> ps(n_panels + 1, 0);
-            for (uint32_t p = 0; p < n_panels; p++) {
-                uint64_t cols = nb - (uint64_t)p * PANEL_ROWBLOCKS;
-                ps[p + 1] = ps[p] + (cols + strip_len - 1) / strip_len;
-            }
-            const uint64_t groups = ps[n_panels];
-            SCEMA_CUDA(ctx, ctx->d_panel_start.reserve(ps.size() * sizeof(uint64_t)));
-            SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_panel_start.p, ps.data(), ps.size() * sizeof(uint64_t),
-                                            cudaMemcpyHostToDevice, ctx->stream));
-            SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // ps is a stack-lifetime host buffer
-            if (ctx->cand_cap == 0) ctx->cand_cap = std::max<uint64_t>(1ull << 20, 32 * n);
             SCEMA_CUDA(ctx, ctx->d_cand.reserve(ctx->cand_cap * sizeof(uint64_t)));
-            t_end(ctx, SCEMA_T_PREP);
-
             FilterArgs fa;
             fa.F = ctx->d_filter.as<double>();
             fa.HN = ctx->d_halfnorm.as<double>();
@@ -887,25 +890,25 @@ int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_
             fa.cand_cap = ctx->cand_cap;
             fa.n = n;
             fa.n_pad = fl.n_pad;
-            fa.n_blocks = (uint32_t)nb;
-            fa.n_panels = n_panels;
+            fa.n_blocks = (uint32_t)sc.nb;
+            fa.n_panels = sc.n_panels;
             fa.n_chunks = fl.n_chunks;
-            fa.strip_len = strip_len;
-            fa.n_groups_local = groups > shard ? (groups - shard + n_shards - 1) / n_shards : 0;
+            fa.strip_len = sc.strip_len;
+            fa.lg_first = local_index(sc.ps[p0], shard, n_shards);
+            fa.n_groups_local = local_index(sc.ps[p1], shard, n_shards) - fa.lg_first;
             fa.shard = shard;
             fa.n_shards = n_shards;
             const double eps = 1.1102230246251565e-16;  // 2^-53
             fa.T0 = thr * thr * (1.0 + (2.0 * K + 16.0) * eps) * (1.0 + 4.0 * eps);
             fa.cband = (4.0 * K + 64.0) * eps;
-            ctx->counters[4] = tiles;
 
             t_begin(ctx, SCEMA_T_FILTER);
             // SCEMA_K2=v1 selects the barrier-synchronised DMMA kernel (kept for A/B measurements)
             static const char *k2_env = getenv("SCEMA_K2");
             const bool ws = !(k2_env && strcmp(k2_env, "v1") == 0);
-            rc = variant == SCEMA_PAIRS_DMMA ? (ws ? launch_filter_ws(ctx, fa, fl.kc, fl.n_chunks > 1)
-                                                   : launch_filter<true>(ctx, fa, fl.kc, fl.n_chunks > 1))
-                                             : launch_filter<false>(ctx, fa, fl.kc, fl.n_chunks > 1);
+            rc = *variant == SCEMA_PAIRS_DMMA ? (ws ? launch_filter_ws(ctx, fa, fl.kc, fl.n_chunks > 1)
+                                                    : launch_filter<true>(ctx, fa, fl.kc, fl.n_chunks > 1))
+                                              : launch_filter<false>(ctx, fa, fl.kc, fl.n_chunks > 1);
             if (rc) return rc;
             t_end(ctx, SCEMA_T_FILTER);
 
@@ -919,16 +922,17 @@ int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_
             SCEMA_CUDA(ctx, cudaGetLastError());
         }
         SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, d_cnt, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (overlap && passes == 1) {
+            rc = overlap();
+            if (rc) return rc;
+        }
         SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         const uint64_t n_cand = ctx->h_counters[0], n_edge = ctx->h_counters[1];
-        ctx->counters[1] = n_cand;
-        ctx->counters[2] = n_edge;
-        ctx->counters[3] = passes;
-        if (variant != SCEMA_PAIRS_EXACT && n_cand > ctx->cand_cap) {
+        if (*variant != SCEMA_PAIRS_EXACT && n_cand > ctx->cand_cap) {
             SCEMA_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
             const uint64_t want = n_cand + n_cand / 4;
             if (want * sizeof(uint64_t) > (free_b + ctx->d_cand.bytes) / 2) {
-                variant = SCEMA_PAIRS_EXACT;  // survivors too dense for a queue: filter-free kernel
+                *variant = SCEMA_PAIRS_EXACT;  // survivors too dense for a queue: filter-free kernel
             } else {
                 ctx->cand_cap = want;
             }
@@ -939,11 +943,11 @@ int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_
             if (rc) return rc;
             continue;
         }
+        ctx->counters[1] += n_cand;
+        ctx->counters[3] += passes;
         ctx->n_edges = n_edge;
         break;
     }
-    if (n_shards == 1) ctx->counters[0] = n * (n - 1) / 2;
-
     // canonical order: ascending (a,b) == ascending packed key
     if (ctx->n_edges > 1) {
         t_begin(ctx, SCEMA_T_SORT);
@@ -960,6 +964,139 @@ int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_
         t_end(ctx, SCEMA_T_SORT);
         SCEMA_CUDA(ctx, cudaGetLastError());
     }
+    return SCEMA_OK;
+}
+
+// Common front end: argument checks, buffers, filter copy and schedule. Returns 1 when there is
+// nothing to compare (result: no edges).
+static int compare_begin(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards, Schedule &sc)
+{
+    if (!ctx->have_spline) return fail(ctx, SCEMA_ERR_STATE, "Spline is not up to date.");
+    if (n_shards == 0 || shard >= n_shards) return fail(ctx, SCEMA_ERR_INVALID, "compare: bad shard");
+    if (variant < 0 || variant > 2) return fail(ctx, SCEMA_ERR_INVALID, "compare: bad variant");
+    if (ctx->n >= (1ull << 32)) return fail(ctx, SCEMA_ERR_INVALID, "compare: more than 2^32-1 histories");
+    for (int i = 0; i < 8; i++) ctx->counters[i] = 0;
+    for (int w = SCEMA_T_PREP; w <= SCEMA_T_SORT; w++) { ctx->ev_used[w] = false; ctx->acc_ms[w] = 0.f; }
+    ctx->n_edges = 0;
+    ctx->have_edges = true;
+    ctx->edge_cur = 0;
+    ctx->key_shift = bits_for(ctx->n);
+    const uint64_t n = ctx->n;
+    // diff >= 0 or NaN, so nothing passes a non-positive or NaN threshold
+    if (n < 2 || !(thr > 0.0)) return -1;
+
+    SCEMA_CUDA(ctx, ctx->d_counters.reserve(8 * sizeof(uint64_t)));
+    if (!ctx->h_counters) SCEMA_CUDA(ctx, cudaMallocHost(&ctx->h_counters, 8 * sizeof(uint64_t)));
+    int rc = ensure_edge_buffers(ctx, std::max<uint64_t>(1ull << 20, 16 * n));
+    if (rc) return rc;
+    make_schedule(ctx, n, sc);
+    ctx->counters[4] = sc.tiles;
+    if (variant != SCEMA_PAIRS_EXACT) {
+        t_begin(ctx, SCEMA_T_PREP);
+        rc = prepare_filter(ctx, variant);
+        if (rc) return rc;
+        SCEMA_CUDA(ctx, ctx->d_panel_start.reserve(sc.ps.size() * sizeof(uint64_t)));
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_panel_start.p, sc.ps.data(), sc.ps.size() * sizeof(uint64_t),
+                                        cudaMemcpyHostToDevice, ctx->stream));
+        SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // sc.ps may not outlive the copy otherwise
+        if (ctx->cand_cap == 0) ctx->cand_cap = std::max<uint64_t>(1ull << 20, 32 * n);
+        t_end(ctx, SCEMA_T_PREP);
+    }
+    return SCEMA_OK;
+}
+
+int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards)
+{
+    Schedule sc;
+    int rc = compare_begin(ctx, thr, variant, shard, n_shards, sc);
+    if (rc < 0) return SCEMA_OK;
+    if (rc) return rc;
+    rc = compare_panels(ctx, thr, &variant, shard, n_shards, sc, 0, sc.n_panels);
+    if (rc) return rc;
+    ctx->counters[2] = ctx->n_edges;
+    if (n_shards == 1) ctx->counters[0] = ctx->n * (ctx->n - 1) / 2;
+    return SCEMA_OK;
+}
+
+// Streaming compare: the panels are evaluated in chunks of panels_per_chunk; each chunk's sorted
+// edges are copied to pinned host memory and handed to `sink` while the GPU already works on the
+// next chunk. Rows (index a) of consecutive chunks are disjoint and increasing, so the concatenation
+// of the chunks is the same (a,b)-sorted list scema_compare produces — without ever holding more
+// than one chunk of edges on the device.
+int compare_stream_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards, uint32_t panels_per_chunk,
+                       scema_edge_sink sink, void *user, uint64_t *n_total)
+{
+    Schedule sc;
+    if (n_total) *n_total = 0;
+    int rc = compare_begin(ctx, thr, variant, shard, n_shards, sc);
+    if (rc < 0) { ctx->have_edges = false; return SCEMA_OK; }
+    if (rc) return rc;
+    if (panels_per_chunk == 0) panels_per_chunk = 64;
+    struct Staged { uint64_t m = 0; bool pending = false; };
+    Staged st[2];
+    std::vector<uint32_t> ha, hb;
+    const uint64_t mask = (1ull << ctx->key_shift) - 1;
+    uint64_t total = 0;
+    auto deliver = [&](int slot) -> int {
+        if (!st[slot].pending) return SCEMA_OK;
+        st[slot].pending = false;
+        SCEMA_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[slot]));
+        const uint64_t m = st[slot].m;
+        const uint64_t *keys = ctx->h_stage_key[slot];
+        ha.resize(m); hb.resize(m);
+        for (uint64_t e = 0; e < m; e++) { ha[e] = (uint32_t)(keys[e] >> ctx->key_shift); hb[e] = (uint32_t)(keys[e] & mask); }
+        total += m;
+        if (m && sink && sink(user, ha.data(), hb.data(), ctx->h_stage_val[slot], m) != 0)
+            return fail(ctx, SCEMA_ERR_STATE, "compare_stream: sink asked to stop");
+        return SCEMA_OK;
+    };
+    uint32_t chunk = 0;
+    for (uint32_t p0 = 0; p0 < sc.n_panels; p0 += panels_per_chunk, chunk++) {
+        const uint32_t p1 = std::min<uint32_t>(sc.n_panels, p0 + panels_per_chunk);
+        const int slot = (int)(chunk & 1);
+        // the previous chunk's edges are unpacked and consumed on the host while this one computes:
+        // compare_panels blocks the host only at its counter read-back, after its kernels are queued
+        rc = compare_panels(ctx, thr, &variant, shard, n_shards, sc, p0, p1, [&]() { return deliver(slot ^ 1); });
+        if (rc) return rc;
+        const uint64_t m = ctx->n_edges;
+        if (m > ctx->stage_cap[slot]) {
+            if (ctx->h_stage_key[slot]) { cudaFreeHost(ctx->h_stage_key[slot]); cudaFreeHost(ctx->h_stage_val[slot]); }
+            ctx->h_stage_key[slot] = nullptr; ctx->h_stage_val[slot] = nullptr; ctx->stage_cap[slot] = 0;
+            const uint64_t cap = m + m / 4 + 1024;
+            SCEMA_CUDA(ctx, cudaMallocHost(&ctx->h_stage_key[slot], cap * sizeof(uint64_t)));
+            SCEMA_CUDA(ctx, cudaMallocHost(&ctx->h_stage_val[slot], cap * sizeof(double)));
+            ctx->stage_cap[slot] = cap;
+        }
+        if (m) {
+            SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage_key[slot], ctx->d_edge_key[ctx->edge_cur].p, m * sizeof(uint64_t),
+                                            cudaMemcpyDeviceToHost, ctx->stream));
+            SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage_val[slot], ctx->d_edge_val[ctx->edge_cur].p, m * sizeof(double),
+                                            cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        SCEMA_CUDA(ctx, cudaEventRecord(ctx->stage_ev[slot], ctx->stream));
+        st[slot].m = m;
+        st[slot].pending = true;
+        // fold this chunk's phase timings in before the events are re-recorded by the next chunk
+        if (p1 < sc.n_panels) {
+            SCEMA_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[slot]));
+            for (int w = SCEMA_T_FILTER; w <= SCEMA_T_SORT; w++)
+                if (ctx->ev_used[w]) {
+                    float t = 0.f;
+                    if (cudaEventElapsedTime(&t, ctx->ev[2 * w], ctx->ev[2 * w + 1]) == cudaSuccess) ctx->acc_ms[w] += t;
+                    else cudaGetLastError();
+                    ctx->ev_used[w] = false;
+                }
+        }
+    }
+    for (int k = 0; k < 2; k++) {
+        rc = deliver((int)((chunk + k) & 1));  // older of the two first
+        if (rc) return rc;
+    }
+    ctx->counters[2] = total;
+    if (n_shards == 1) ctx->counters[0] = ctx->n * (ctx->n - 1) / 2;
+    ctx->have_edges = false;  // the edges went to the sink; nothing is retained on the device
+    ctx->n_edges = 0;
+    if (n_total) *n_total = total;
     return SCEMA_OK;
 }
 

@@ -288,7 +288,89 @@ __device__ __forceinline__ double div_tab(double a, double b, double rb)
 }
 
 constexpr int RS_WARPS = 4;  // warps per CTA (independent of each other)
-constexpr int RING = 8;      // register prefetch depth of the y / z streams
+constexpr int RING = 8;      // steps per unrolled block
+constexpr int DEPTH = 16;    // slots of the per-lane shared-memory prefetch rings (y and z)
+constexpr size_t RS_SMEM = (size_t)RS_WARPS * DEPTH * 32 * sizeof(double);
+
+// The two long-latency streams of a chain — y on the way up, z on the way down — are prefetched
+// DEPTH-2 steps ahead with 8-byte cp.async copies into a per-lane shared-memory ring (one commit
+// group per step, cp.async.wait_group DEPTH-2 before the slot is read). They deliberately do NOT
+// go through registers: a warp has six scoreboards, and with eight register-ring loads in flight
+// the compiler had to put the short-latency factor-table loads on the same scoreboards as the
+// DRAM-latency ring loads, so every step waited a full memory round trip
+// (profiles/r01_ncu_resample_v6_c3.txt: ~1600 cycles per step). cp.async completion is counted
+// per group instead, which leaves the scoreboards to the table loads.
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// table entries of the coming step, loaded into the ping-pong variable they are consumed from
+__device__ __forceinline__ void ld_tab(double2 &d, const double2 *p)
+{
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(d.x), "=d"(d.y) : "l"(p));
+}
+
+// One forward step i = i0 + U (spline.h:306, :228-233). On entry: s_cur = s_i, s_prev = s_{i-1},
+// z_prev = z_{i-1}, y_hi = y_{i+1}, E1 = {sd_i, lo_i}, E0 = {1/hd_{i+1}, hd_{i+1}}. Loads the same
+// two entries for step i+1 into N1/N0, takes y_{i+2} from ring slot (i+2)%DEPTH and starts the copy
+// of y_{i+1+DEPTH} into the slot read one step earlier.
+#define K1_FWD_STEP(U, E1, E0, N1, N0)                                                              \
+    if (i0 + (U) < L - 1) {                                                                         \
+        const int i = i0 + (U);                                                                     \
+        ld_tab(N1, FWb + 2 * ((U) + 1) + 1);                                                        \
+        ld_tab(N0, FWb + 2 * ((U) + 2));                                                            \
+        cp_async_wait<DEPTH - 2>();                                                                 \
+        const double y_nx = ry[((i + 2) & (DEPTH - 1)) * 32];                                       \
+        if (i + 1 + DEPTH < L) cp_async8(ry + ((i + 1) & (DEPTH - 1)) * 32, yb + (size_t)((U) + 1 + DEPTH) * ys); \
+        cp_async_commit();                                                                          \
+        const double r = __dmul_rn(__dsub_rn(s_cur, s_prev), E1.x);                                 \
+        const double sum = __dadd_rn(0.0, __dmul_rn(E1.y, z_prev));                                 \
+        z_prev = __dsub_rn(r, sum);                                                                 \
+        __stcg(zb + (size_t)(U) * 32, z_prev);                                                      \
+        s_prev = s_cur;                                                                             \
+        if (i + 1 < L - 1) s_cur = div_tab(__dsub_rn(y_nx, y_hi), E0.y, E0.x);                      \
+        y_hi = y_nx;                                                                                \
+    }
+
+// One backward step i = i0 - U (spline.h:243-248) plus the samples of interval i (spline.h:345-349,
+// :393). On entry: b_next = b_{i+1}, W0 = {up_i, di_i}, W1 = {1/di_i, -}. Loads the entries of step
+// i-1 into V0/V1, takes z_i from ring slot i%DEPTH and starts the copy of z_{i+1-DEPTH} into the
+// slot read one step earlier.
+#define K1_BWD_STEP(U, W0, W1, V0, V1)                                                              \
+    if (i0 - (U) >= 0) {                                                                            \
+        const int i = i0 - (U);                                                                     \
+        ld_tab(V0, BWb - 2 * ((U) + 1));                                                            \
+        ld_tab(V1, BWb - 2 * ((U) + 1) + 1);                                                        \
+        cp_async_wait<DEPTH - 2>();                                                                 \
+        const double zi = rz[(i & (DEPTH - 1)) * 32];                                               \
+        if (i + 1 - DEPTH >= 0) cp_async8(rz + ((i + 1) & (DEPTH - 1)) * 32, zb - (size_t)((U) - 1 + DEPTH) * 32); \
+        cp_async_commit();                                                                          \
+        const double sum = __dadd_rn(0.0, __dmul_rn(W0.x, b_next));                                 \
+        const double b_i = div_tab(__dsub_rn(zi, sum), W0.y, W1.x);                                 \
+        if (i == nxt) {                                                                             \
+            const double2 f0 = __ldg(FW + 2 * i);                                                   \
+            const double hdv = f0.y;                                                                \
+            const double a_i = div_tab(__dmul_rn(third, __dsub_rn(b_next, b_i)), hdv, f0.x);        \
+            const double c_i =                                                                      \
+                __dsub_rn(div_tab(__dsub_rn(y_b, y_a), hdv, f0.x),                                  \
+                          __dmul_rn(__dmul_rn(third, __dadd_rn(__dmul_rn(2.0, b_i), b_next)), hdv)); \
+            do {                                                                                    \
+                const double hstep = __ldg(ht + p);                                                 \
+                double v = __dadd_rn(__dmul_rn(a_i, hstep), b_i);                                   \
+                v = __dadd_rn(__dmul_rn(v, hstep), c_i);                                            \
+                v = __dadd_rn(__dmul_rn(v, hstep), y_a);                                            \
+                orow[(size_t)p * 6] = v;                                                            \
+                p--;                                                                                \
+                nxt = p >= 0 ? (int)__ldg(ix + p) : -1;                                             \
+            } while (nxt == i);                                                                     \
+            if (nxt >= 0) { y_a = __ldg(y + (size_t)nxt * ys); y_b = __ldg(y + (size_t)(nxt + 1) * ys); } \
+        }                                                                                           \
+        b_next = b_i;                                                                               \
+    }
 
 __global__ void __launch_bounds__(32 * RS_WARPS) k_resample_stream(const double *__restrict__ steps,
                                                                   const uint64_t *__restrict__ offsets,
@@ -296,9 +378,18 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resample_stream(const double 
                                                                   uint64_t count, const int64_t *__restrict__ table_index,
                                                                   const double *__restrict__ tables, uint32_t P,
                                                                   double *__restrict__ out, double *__restrict__ zscratch,
-                                                                  uint32_t cap)
+                                                                  uint32_t cap, uint64_t ys, uint32_t uniform_L)
 {
+    // ys = distance (in doubles) between consecutive steps of one history: 6 for the ragged batch
+    // ([L][6] blocks, history h starts at offsets[h]), n*6 for the time-major history store
+    // ([step][n][6], history h starts at h, every history uniform_L steps long).
+    extern __shared__ __align__(16) double rings[];
     const int lane = threadIdx.x & 31;
+    // this lane's ring, ry[slot * 32]: y on the way up, then (all y copies have landed by then) z on
+    // the way down. Keeping it to 4 KB per warp leaves most of the SM's 256 KB to L1, where the factor
+    // tables live.
+    double *ry = rings + (size_t)(threadIdx.x >> 5) * (DEPTH * 32) + lane;
+    double *rz = ry;
     const uint64_t wid = (uint64_t)blockIdx.x * RS_WARPS + (threadIdx.x >> 5);
     const uint64_t n_warps = (uint64_t)gridDim.x * RS_WARPS;
     double *__restrict__ zs = zscratch + wid * cap * 32 + lane;
@@ -312,8 +403,8 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resample_stream(const double 
         if (lane >= GROUP * 6 || (uint64_t)hh >= left) continue;  // no warp-level primitive below
         const uint64_t q = first + grp * GROUP + hh;
         const uint64_t h = order ? (uint64_t)order[q] : q;
-        const uint64_t off = offsets[h];
-        const int L = (int)(offsets[h + 1] - off);
+        const uint64_t off = uniform_L ? h : offsets[h];
+        const int L = uniform_L ? (int)uniform_L : (int)(offsets[h + 1] - off);
         const uint32_t Lp = pad2((uint32_t)L);
         const double *tab = tables + table_index[L];
         const double *ht = tab + 6ull * Lp, *ix = ht + Pp;
@@ -321,112 +412,89 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_resample_stream(const double 
         const double2 *BW = FW + 2ull * Lp;
         const double *y = steps + off * 6 + c;
 
-        // whole history -> L2 now (one bulk prefetch per history); the sweeps then find their lines there
-        if (c == 0)
+        // whole history -> L2 now (one bulk prefetch per history); the ring copies then hit L2
+        if (c == 0 && !uniform_L)
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(steps + off * 6), "r"(48u * (uint32_t)L) : "memory");
 
-        // ---- forward substitution fused with the right-hand side (spline.h:306, :228-233).
-        // Software pipeline: the slope s_{i+1} = (y_{i+2} - y_{i+1}) / hd_{i+1} and the factor-table
-        // entry of step i+1 are produced while the z chain of step i runs; y comes through an
-        // 8-deep register ring (slot k holds y_{m} with m == k+1 mod 8).
-        double yr[RING];
+        // ---- forward substitution fused with the right-hand side. Software pipeline: the slope
+        // s_{i+1} and the table entries of step i+1 are produced while the z chain of step i runs.
+        // Table reads one entry past the end of FW / before the start of BW stay inside this
+        // table's own allocation and their values are never consumed.
 #pragma unroll
-        for (int u = 0; u < RING; u++) yr[u] = 1 + u < L ? __ldg(y + (size_t)(1 + u) * 6) : 0.0;  // y_1 .. y_8
-        double s_prev, s_cur, z_prev, y_hi;  // y_hi = y_{i+1} at the top of step i
-        double2 f1n;                          // {sd, lo} of the coming step
+        for (int m = 3; m <= DEPTH + 1; m++) {  // y_3 .. y_{DEPTH+1}: DEPTH-1 groups
+            if (m < L) cp_async8(ry + (m & (DEPTH - 1)) * 32, y + (size_t)m * ys);
+            cp_async_commit();
+        }
+        double s_prev, s_cur, z_prev, y_hi;
+        double2 a1, a0, b1, b0;  // ping-pong: {sd, lo} of the coming step and {1/hd, hd} of the one after
         {
-            const double y0 = __ldg(y);
-            const double2 f0 = __ldg(FW), f1 = __ldg(FW + 1), g0 = __ldg(FW + 2);
-            f1n = __ldg(FW + 3);
-            const double ya1 = yr[0], ya2 = yr[1];
-            yr[0] = 1 + RING < L ? __ldg(y + (size_t)(1 + RING) * 6) : 0.0;  // y_9
-            yr[1] = 2 + RING < L ? __ldg(y + (size_t)(2 + RING) * 6) : 0.0;  // y_10
-            s_prev = div_tab(__dsub_rn(ya1, y0), f0.y, f0.x);           // s_0
-            s_cur = div_tab(__dsub_rn(ya2, ya1), g0.y, g0.x);           // s_1 (L >= 3, so y_2 exists)
-            z_prev = __dsub_rn(__dmul_rn(0.0, f1.x), 0.0);              // row 0: rhs = 0, empty sum
+            const double y_0 = __ldg(y), y_1 = __ldg(y + ys), y_2 = __ldg(y + 2 * ys);  // L >= 3
+            const double2 f00 = __ldg(FW), f01 = __ldg(FW + 1), f10 = __ldg(FW + 2);
+            ld_tab(a1, FW + 3);  // {sd_1, lo_1}
+            ld_tab(a0, FW + 4);  // {1/hd_2, hd_2}
+            s_prev = div_tab(__dsub_rn(y_1, y_0), f00.y, f00.x);  // s_0
+            s_cur = div_tab(__dsub_rn(y_2, y_1), f10.y, f10.x);   // s_1
+            z_prev = __dsub_rn(__dmul_rn(0.0, f01.x), 0.0);       // row 0: rhs = 0, empty sum
             __stcg(zs, z_prev);
-            y_hi = ya2;
+            y_hi = y_2;
         }
         for (int i0 = 1; i0 < L - 1; i0 += RING) {
-#pragma unroll
-            for (int u = 0; u < RING; u++) {
-                const int i = i0 + u;
-                if (i < L - 1) {
-                    // prefetch for step i+1: table entry and y_{i+2} (slot (u+2) mod 8), refill the slot with y_{i+2+8}
-                    const int slot = (u + 2) & (RING - 1);
-                    const double y_nx = yr[slot];
-                    yr[slot] = i + 2 + RING < L ? __ldg(y + (size_t)(i + 2 + RING) * 6) : 0.0;
-                    const double2 g0 = __ldg(FW + 2 * (i + 1));  // i+1 <= L-1 < Lp: always inside the table
-                    const double2 f1 = f1n;
-                    f1n = __ldg(FW + 2 * (i + 1) + 1);
-                    // z chain of step i
-                    const double r = __dmul_rn(__dsub_rn(s_cur, s_prev), f1.x);
-                    const double sum = __dadd_rn(0.0, __dmul_rn(f1.y, z_prev));
-                    z_prev = __dsub_rn(r, sum);
-                    __stcg(zs + (size_t)i * 32, z_prev);
-                    // slope of step i+1 (unused garbage when i+1 == L-1: hd = 0 there, never consumed)
-                    s_prev = s_cur;
-                    if (i + 1 < L - 1) s_cur = div_tab(__dsub_rn(y_nx, y_hi), g0.y, g0.x);
-                    y_hi = y_nx;
-                }
-            }
+            const double2 *FWb = FW + 2 * i0;
+            const double *yb = y + (size_t)i0 * ys;
+            double *zb = zs + (size_t)i0 * 32;
+            K1_FWD_STEP(0, a1, a0, b1, b0)
+            K1_FWD_STEP(1, b1, b0, a1, a0)
+            K1_FWD_STEP(2, a1, a0, b1, b0)
+            K1_FWD_STEP(3, b1, b0, a1, a0)
+            K1_FWD_STEP(4, a1, a0, b1, b0)
+            K1_FWD_STEP(5, b1, b0, a1, a0)
+            K1_FWD_STEP(6, a1, a0, b1, b0)
+            K1_FWD_STEP(7, b1, b0, a1, a0)
         }
         {
-            const double2 f1 = f1n;  // {sd, lo} of row L-1, fetched by step L-2
-            const double r = __dmul_rn(0.0, f1.x);  // row L-1: rhs = 0
+            const double2 f1 = __ldg(FW + 2 * (L - 1) + 1);  // {sd, lo} of row L-1
+            const double r = __dmul_rn(0.0, f1.x);           // rhs = 0
             const double sum = __dadd_rn(0.0, __dmul_rn(f1.y, z_prev));
             z_prev = __dsub_rn(r, sum);
         }
 
-        // ---- back substitution (spline.h:243-248) with the samples evaluated on the way
-        // (spline.h:345-349, :393): sample p lives in interval ix[p], non-increasing as p falls
+        // ---- back substitution with the samples evaluated on the way: sample p lives in interval
+        // ix[p], non-increasing as p falls, so b is never stored
+        cp_async_wait<0>();  // the ring changes hands: no y copy may still be in flight
+#pragma unroll
+        for (int u = 0; u < DEPTH - 1; u++) {  // z_{L-2} .. z_{L-DEPTH}: DEPTH-1 groups
+            const int m = L - 2 - u;
+            if (m >= 0) cp_async8(rz + (m & (DEPTH - 1)) * 32, zs + (size_t)m * 32);
+            cp_async_commit();
+        }
         double b_next;
         {
-            const double2 w1 = __ldg(BW + 2 * (L - 1) + 1), w0 = __ldg(BW + 2 * (L - 1));
+            const double2 w0 = __ldg(BW + 2 * (L - 1)), w1 = __ldg(BW + 2 * (L - 1) + 1);
             b_next = div_tab(__dsub_rn(z_prev, 0.0), w0.y, w1.x);
         }
-        double zr[RING];
-#pragma unroll
-        for (int u = 0; u < RING; u++) zr[u] = L - 2 - u >= 0 ? __ldcg(zs + (size_t)(L - 2 - u) * 32) : 0.0;
         int p = (int)P - 1;
         int nxt = (int)__ldg(ix + p);
-        double ya = __ldg(y + (size_t)nxt * 6), yb = __ldg(y + (size_t)(nxt + 1) * 6);
+        double y_a = __ldg(y + (size_t)nxt * ys), y_b = __ldg(y + (size_t)(nxt + 1) * ys);
         double *orow = out + h * K + c;
-        double2 w0n = __ldg(BW + 2 * (L - 2)), w1n = __ldg(BW + 2 * (L - 2) + 1);  // table entry of the coming step
+        ld_tab(a0, BW + 2 * (L - 2));      // {up, di} of step L-2
+        ld_tab(a1, BW + 2 * (L - 2) + 1);  // {1/di, -}
         for (int i0 = L - 2; i0 >= 0; i0 -= RING) {
-#pragma unroll
-            for (int u = 0; u < RING; u++) {
-                const int i = i0 - u;
-                if (i >= 0) {
-                    const double zi = zr[u];
-                    zr[u] = i - RING >= 0 ? __ldcg(zs + (size_t)(i - RING) * 32) : 0.0;
-                    const double2 w0 = w0n, w1 = w1n;
-                    if (i > 0) { w0n = __ldg(BW + 2 * (i - 1)); w1n = __ldg(BW + 2 * (i - 1) + 1); }
-                    const double sum = __dadd_rn(0.0, __dmul_rn(w0.x, b_next));
-                    const double b_i = div_tab(__dsub_rn(zi, sum), w0.y, w1.x);
-                    if (i == nxt) {
-                        const double2 f0 = __ldg(FW + 2 * i);
-                        const double hdv = f0.y;
-                        const double a_i = div_tab(__dmul_rn(third, __dsub_rn(b_next, b_i)), hdv, f0.x);
-                        const double c_i = __dsub_rn(div_tab(__dsub_rn(yb, ya), hdv, f0.x),
-                                                     __dmul_rn(__dmul_rn(third, __dadd_rn(__dmul_rn(2.0, b_i), b_next)), hdv));
-                        do {
-                            const double hstep = __ldg(ht + p);
-                            double v = __dadd_rn(__dmul_rn(a_i, hstep), b_i);
-                            v = __dadd_rn(__dmul_rn(v, hstep), c_i);
-                            v = __dadd_rn(__dmul_rn(v, hstep), ya);
-                            orow[(size_t)p * 6] = v;
-                            p--;
-                            nxt = p >= 0 ? (int)__ldg(ix + p) : -1;
-                        } while (nxt == i);
-                        if (nxt >= 0) { ya = __ldg(y + (size_t)nxt * 6); yb = __ldg(y + (size_t)(nxt + 1) * 6); }
-                    }
-                    b_next = b_i;
-                }
-            }
+            const double2 *BWb = BW + 2 * i0;
+            const double *zb = zs + (size_t)i0 * 32;
+            K1_BWD_STEP(0, a0, a1, b0, b1)
+            K1_BWD_STEP(1, b0, b1, a0, a1)
+            K1_BWD_STEP(2, a0, a1, b0, b1)
+            K1_BWD_STEP(3, b0, b1, a0, a1)
+            K1_BWD_STEP(4, a0, a1, b0, b1)
+            K1_BWD_STEP(5, b0, b1, a0, a1)
+            K1_BWD_STEP(6, a0, a1, b0, b1)
+            K1_BWD_STEP(7, b0, b1, a0, a1)
         }
+        cp_async_wait<0>();  // nothing of this group may land in the rings after the next group starts
     }
 }
+#undef K1_FWD_STEP
+#undef K1_BWD_STEP
 
 // ---- fallback for histories too long for a shared-memory slab: the sweeps read y from global
 // memory and keep z/b in a global scratch buffer of the input's shape.
@@ -512,22 +580,29 @@ __global__ void __launch_bounds__(32) k_resample_global(const double *__restrict
     }
 }
 
+static int ensure_tables_present(scema_ctx *ctx, uint32_t P, const std::vector<uint8_t> &present, uint32_t max_len);
+
 static int ensure_tables(scema_ctx *ctx, uint32_t P)
 {
     // distinct lengths of the current batch
     std::vector<uint8_t> present((size_t)ctx->max_len + 1, 0);
     for (uint64_t i = 0; i < ctx->hn; i++) present[ctx->h_offsets[i + 1] - ctx->h_offsets[i]] = 1;
+    return ensure_tables_present(ctx, P, present, ctx->max_len);
+}
+
+static int ensure_tables_present(scema_ctx *ctx, uint32_t P, const std::vector<uint8_t> &present, uint32_t max_len)
+{
     if (ctx->table_P != P) { ctx->table_off.clear(); ctx->tables_used = 0; ctx->table_P = P; }
     std::vector<uint32_t> new_lens;
     std::vector<uint64_t> new_offs;
     uint64_t used = ctx->tables_used;
-    for (uint32_t L = 3; L <= ctx->max_len; L++) {
+    for (uint32_t L = 3; L <= max_len; L++) {
         if (!present[L] || ctx->table_off.count(L)) continue;
         new_lens.push_back(L);
         new_offs.push_back(used);
         used += table_doubles(L, P);
     }
-    bool index_stale = ctx->table_index_len < ctx->max_len + 1;
+    bool index_stale = ctx->table_index_len < max_len + 1;
     if (new_lens.empty() && !index_stale) return SCEMA_OK;
 
     if (used * sizeof(double) > ctx->d_tables.bytes) {
@@ -560,14 +635,15 @@ static int ensure_tables(scema_ctx *ctx, uint32_t P)
         ctx->tables_used = used;
     }
     // L -> offset index
-    std::vector<int64_t> index((size_t)ctx->max_len + 1, -1);
+    const uint32_t index_len = std::max<uint32_t>(max_len + 1, ctx->table_index_len);
+    std::vector<int64_t> index((size_t)index_len, -1);
     for (auto &kv : ctx->table_off)
-        if (kv.first <= ctx->max_len) index[kv.first] = (int64_t)kv.second;
+        if (kv.first < index_len) index[kv.first] = (int64_t)kv.second;
     SCEMA_CUDA(ctx, ctx->d_table_index.reserve(index.size() * sizeof(int64_t)));
     SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_table_index.p, index.data(), index.size() * sizeof(int64_t),
                                     cudaMemcpyHostToDevice, ctx->stream));
     SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->table_index_len = ctx->max_len + 1;
+    ctx->table_index_len = index_len;
     return SCEMA_OK;
 }
 
@@ -628,7 +704,7 @@ int resample_run(scema_ctx *ctx, uint32_t P)
     auto smem_for = [&](uint32_t cap) { return (size_t)16 + 5 * (size_t)pad2(cap) * 8 + ((size_t)GROUP * 6 * cap + 64) * sizeof(double); };
     // streamed kernel: resident warps per SM and the scratch they need (one [cap][32] block per warp)
     static const char *wps_env = getenv("SCEMA_K1_WPS");
-    const int wps = wps_env && atoi(wps_env) > 0 ? atoi(wps_env) : 16;
+    const int wps = wps_env && atoi(wps_env) > 0 ? atoi(wps_env) : 24;
     const uint64_t scratch_budget = 1ull << 30;
     uint64_t stream_warps[MAXCLS] = {};
     uint64_t scratch_need = 0;
@@ -651,10 +727,10 @@ int resample_run(scema_ctx *ctx, uint32_t P)
         const uint64_t n_groups = (cls_count[k] + GROUP - 1) / GROUP;
         if (k < NCLS - 1 && !staged) {
             const uint32_t cap = std::min<uint32_t>(caps[k], ctx->max_len);
-            k_resample_stream<<<(unsigned)(stream_warps[k] / RS_WARPS), 32 * RS_WARPS, 0, ctx->stream>>>(
+            k_resample_stream<<<(unsigned)(stream_warps[k] / RS_WARPS), 32 * RS_WARPS, RS_SMEM, ctx->stream>>>(
                 ctx->d_steps, ctx->d_offsets.as<uint64_t>(), d_order, cls_first[k], cls_count[k],
                 ctx->d_table_index.as<int64_t>(), ctx->d_tables.as<double>(), P, ctx->spline_own.as<double>(),
-                ctx->zscratch.as<double>(), cap);
+                ctx->zscratch.as<double>(), cap, 6, 0);
         } else if (k < NCLS - 1) {
             const size_t slab = smem_for(caps[k]);
             int per_sm = (int)(ctx->smem_optin / (slab + 1024));
@@ -676,6 +752,137 @@ int resample_run(scema_ctx *ctx, uint32_t P)
     }
     t_end(ctx, SCEMA_T_RESAMPLE);
     SCEMA_CUDA(ctx, cudaGetLastError());
+    return SCEMA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident incremental history store: the in-process caller appends one
+// strain sample per quadrature point per timestep (FEProblem::update_strain_quadrature_point_history,
+// reference headers/FE_problem.h:1091-1103 -> Strain6D::add_current_strain, strain2spline.h:75-86)
+// and re-fits every spline each step (spline_building, FE_problem.h:1167-1191). The store keeps the
+// histories on the device in time-major order [step][n][6]: an append is one contiguous 48*n-byte
+// copy, all histories have the same length (one factor table, no sorting), and in K1 the 30 chain
+// lanes of a warp read 240 contiguous bytes per step.
+// ------------------------------------------------------------------------------------------------
+int store_reset(scema_ctx *ctx, uint64_t n, const uint32_t *ids, uint32_t capacity_steps)
+{
+    if (n >= (1ull << 32)) return fail(ctx, SCEMA_ERR_INVALID, "store_reset: more than 2^32-1 histories");
+    ctx->store_n = n;
+    ctx->store_steps = 0;
+    ctx->store_cap = std::max<uint32_t>(capacity_steps, 8);
+    ctx->store_ids.resize(n);
+    for (uint64_t i = 0; i < n; i++) ctx->store_ids[i] = ids ? ids[i] : (uint32_t)i;
+    SCEMA_CUDA(ctx, ctx->d_store.reserve(std::max<uint64_t>(n, 1) * 6 * sizeof(double) * ctx->store_cap));
+    ctx->have_store = true;
+    return SCEMA_OK;
+}
+
+int store_append(scema_ctx *ctx, const double *strain, int on_device)
+{
+    if (!ctx->have_store) return fail(ctx, SCEMA_ERR_STATE, "store_append: no store (call scema_store_reset)");
+    if (ctx->store_n && !strain) return fail(ctx, SCEMA_ERR_INVALID, "store_append: null pointer");
+    const size_t row = (size_t)ctx->store_n * 6 * sizeof(double);
+    if (ctx->store_steps == ctx->store_cap) {  // grow: the filled prefix is contiguous
+        scema::DevBuf nb;
+        const uint32_t cap = ctx->store_cap * 2;
+        SCEMA_CUDA(ctx, nb.reserve(std::max<size_t>(row, 48) * cap));
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(nb.p, ctx->d_store.p, row * ctx->store_steps, cudaMemcpyDeviceToDevice, ctx->stream));
+        SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->d_store.release();
+        ctx->d_store = nb;
+        ctx->store_cap = cap;
+    }
+    if (row)
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(static_cast<char *>(ctx->d_store.p) + row * ctx->store_steps, strain, row,
+                                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    if (!on_device) SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller's buffer may be pageable / reused
+    ctx->store_steps++;
+    return SCEMA_OK;
+}
+
+int store_resample(scema_ctx *ctx, uint32_t P)
+{
+    if (!ctx->have_store) return fail(ctx, SCEMA_ERR_STATE, "store_resample: no store (call scema_store_reset)");
+    if (P == 0) return fail(ctx, SCEMA_ERR_INVALID, "resample: spline_points must be >= 1");
+    const uint32_t L = ctx->store_steps;
+    if (ctx->store_n && L == 0)
+        return fail(ctx, SCEMA_ERR_INVALID,
+                    "Nothing to splinify! No strain data has been read in yet. Please use .from_file() or .add_current_strain() first.");
+    if (ctx->store_n && L < 3)
+        return fail(ctx, SCEMA_ERR_INVALID, "Not enough strain steps added. Need at least 3 points for splinify().");
+    const uint64_t n = ctx->store_n;
+    const uint32_t K = 6 * P;
+    SCEMA_CUDA(ctx, ctx->spline_own.reserve((size_t)(n ? n : 1) * K * sizeof(double)));
+    ctx->d_spline = ctx->spline_own.as<double>();
+    ctx->n = n;
+    ctx->ids = ctx->store_ids;
+    ctx->K = K;
+    ctx->spline_version++;
+    ctx->have_spline = true;
+    ctx->have_edges = false;
+    ctx->ev_used[SCEMA_T_RESAMPLE] = false;
+    if (n == 0) return SCEMA_OK;
+    std::vector<uint8_t> present((size_t)L + 1, 0);
+    present[L] = 1;
+    int rc = ensure_tables_present(ctx, P, present, L);
+    if (rc) return rc;
+    static const char *wps_env = getenv("SCEMA_K1_WPS");
+    const int wps = wps_env && atoi(wps_env) > 0 ? atoi(wps_env) : 24;
+    const uint64_t n_groups = (n + GROUP - 1) / GROUP;
+    uint64_t w = std::min<uint64_t>((uint64_t)ctx->sm_count * wps, n_groups);
+    w = std::min<uint64_t>(w, std::max<uint64_t>(RS_WARPS, (1ull << 30) / ((uint64_t)L * 256)));
+    w = (w + RS_WARPS - 1) / RS_WARPS * RS_WARPS;
+    SCEMA_CUDA(ctx, ctx->zscratch.reserve(w * L * 256));
+    t_begin(ctx, SCEMA_T_RESAMPLE);
+    k_resample_stream<<<(unsigned)(w / RS_WARPS), 32 * RS_WARPS, RS_SMEM, ctx->stream>>>(
+        ctx->d_store.as<double>(), nullptr, nullptr, 0, n, ctx->d_table_index.as<int64_t>(), ctx->d_tables.as<double>(), P,
+        ctx->spline_own.as<double>(), ctx->zscratch.as<double>(), L, n * 6, L);
+    ctx->launches++;
+    t_end(ctx, SCEMA_T_RESAMPLE);
+    SCEMA_CUDA(ctx, cudaGetLastError());
+    return SCEMA_OK;
+}
+
+// Restrict the current spline matrix to a subset of its rows (the flagged quadrature points that
+// spline_comparison collects, FE_problem.h:1202-1224): gather into a compact matrix that becomes the
+// current one, IDs carried along.
+__global__ void k_gather_rows(const double *__restrict__ src, const uint32_t *__restrict__ rows, uint64_t m, uint32_t K,
+                              double *__restrict__ dst)
+{
+    const uint64_t total = m * K;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = e / K, k = e - r * K;
+        dst[e] = src[(uint64_t)rows[r] * K + k];
+    }
+}
+
+int select_rows(scema_ctx *ctx, const uint32_t *rows, uint64_t m)
+{
+    if (!ctx->have_spline) return fail(ctx, SCEMA_ERR_STATE, "Spline is not up to date.");
+    if (m && !rows) return fail(ctx, SCEMA_ERR_INVALID, "select_rows: null pointer");
+    for (uint64_t i = 0; i < m; i++)
+        if (rows[i] >= ctx->n) return fail(ctx, SCEMA_ERR_INVALID, "select_rows: row index out of range");
+    const uint32_t K = ctx->K;
+    SCEMA_CUDA(ctx, ctx->d_select.reserve(std::max<uint64_t>(m, 1) * sizeof(uint32_t)));
+    SCEMA_CUDA(ctx, ctx->spline_sel.reserve(std::max<uint64_t>(m * K, 1) * sizeof(double)));
+    if (m) {
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_select.p, rows, m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (K) {
+            const unsigned grid = (unsigned)std::min<uint64_t>((m * K + 255) / 256, (uint64_t)ctx->sm_count * 16);
+            k_gather_rows<<<grid, 256, 0, ctx->stream>>>(ctx->d_spline, ctx->d_select.as<uint32_t>(), m, K,
+                                                         ctx->spline_sel.as<double>());
+            ctx->launches++;
+            SCEMA_CUDA(ctx, cudaGetLastError());
+        }
+        SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `rows` is the caller's buffer
+    }
+    std::vector<uint32_t> ids(m);
+    for (uint64_t i = 0; i < m; i++) ids[i] = ctx->ids[rows[i]];
+    ctx->ids.swap(ids);
+    ctx->d_spline = ctx->spline_sel.as<double>();
+    ctx->n = m;
+    ctx->spline_version++;
+    ctx->have_edges = false;
     return SCEMA_OK;
 }
 

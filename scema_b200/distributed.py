@@ -78,8 +78,10 @@ class ShardedCluster:
             return torch.cuda.default_stream()
         return torch.cuda.ExternalStream(ptr)
 
-    def run(self, n, spline_points, threshold, variant=0):
+    def run(self, n, spline_points, threshold, variant=0, sink=None):
         """The local share of the histories must already be set on self.hc (set_histories).
+        sink: callable(a, b, d) -> the shard's edges are streamed chunk by chunk
+        (scema_compare_stream) instead of being kept on the device.
         -> (local_edge_count, counts, offsets, full_rows tensor)."""
         hc = self.hc
         with torch.cuda.stream(self.stream()):
@@ -88,6 +90,9 @@ class ShardedCluster:
             local = torch.as_tensor(CudaView(ptr, (n_local, K)), device="cuda")
             full = gather_rows(local, n, self.world, self.group)
             hc.set_spline(device_ptr=full.data_ptr(), n=n, k=K)
-            ne = hc.compare(threshold, variant, shard=self.rank, n_shards=self.world)
+            if sink is not None:
+                ne = hc.compare_stream(threshold, sink, variant, shard=self.rank, n_shards=self.world)
+            else:
+                ne = hc.compare(threshold, variant, shard=self.rank, n_shards=self.world)
             counts, offs = gather_counts(ne, full.device, self.group)
         return ne, counts, offs, full

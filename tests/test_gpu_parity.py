@@ -129,6 +129,45 @@ def test_k1_special_magnitudes(hc, oracle):
         assert same_bits(hc.get_spline(), want), P
 
 
+def test_history_store_matches_batch_path(hc, oracle):
+    """In-process pattern (FE_problem.h:1091-1103, :1167-1229): append one sample per point per
+    timestep to the device-resident store, re-fit all points, compare the flagged subset."""
+    n, P = 1237, 10
+    ids = (np.arange(n, dtype=np.uint32) * 3 + 7)
+    rng = np.random.default_rng(21)
+    base = rng.standard_normal((n // 8 + 1, 6)) * 1e-3
+    grow = np.repeat(base, 8, axis=0)[:n] * (1.0 + 2e-5 * rng.standard_normal((n, 1)))
+    hc.store_reset(n, ids, capacity_steps=4)  # forces the store to grow several times
+    with pytest.raises(scema_b200.ScemaError):
+        hc.store_resample(P)  # no samples yet (strain2spline.h:142-148)
+    hist = []
+    for t in range(1, 41):
+        sample = grow * t + 1e-9 * rng.standard_normal((n, 6))
+        hist.append(sample)
+        hc.store_append(sample)
+        if t == 2:
+            with pytest.raises(scema_b200.ScemaError) as e:
+                hc.store_resample(P)
+            assert "at least 3 points" in str(e.value)
+        if t in (3, 4, 17, 40):
+            hc.store_resample(P)
+            steps = np.stack(hist, axis=1).reshape(n * t, 6)  # history-major [n][t][6]
+            off = np.arange(n + 1, dtype=np.uint64) * t
+            want = oracle.splinify_batch(steps, off, P)
+            assert same_bits(hc.get_spline(), want), t
+    assert hc.store_info()[:2] == (n, 40)
+    # compare only the flagged points, as spline_comparison does
+    flagged = np.sort(rng.choice(n, size=700, replace=False)).astype(np.uint32)
+    thr = 2e-6
+    hc.select_rows(flagged)
+    ne = hc.compare(thr)
+    got = hc.get_edges()
+    wi, wj, wd, _ = oracle.all_pairs(np.ascontiguousarray(want[flagged]), thr)
+    assert ne == len(wi) and ne > 50 and edges_equal(got, (wi, wj, wd))
+    mapping, _, _ = hc.reduce_edges(int(ids.max()) + 1)  # IDs of the subset are carried along
+    assert set(np.nonzero(mapping != np.arange(len(mapping)))[0]) <= set(ids[flagged].tolist())
+
+
 def test_k1_too_short_history_is_an_error(hc):
     off = np.array([0, 5, 7, 12], dtype=np.uint64)  # middle history has 2 steps
     hc.set_histories(np.zeros((12, 6)), off)
@@ -226,6 +265,39 @@ def test_k2_huge_threshold_all_pairs(hc, oracle):
     hc.set_spline(rows)
     assert hc.compare(float("inf")) == 700 * 699 // 2
     assert edges_equal(hc.get_edges(), want)
+
+
+@pytest.mark.parametrize("vname,variant", [("dmma", 0), ("fma", 1), ("exact", 2)])
+def test_compare_stream_concatenates_to_compare(hc, vname, variant):
+    """Edge streaming (config 5's mode): chunks of panels, delivered through the sink, concatenate
+    to exactly the sorted list of the one-shot compare; also per shard."""
+    n = 9000  # 5 panels of 2048 rows
+    rows = synth.rows(12, n, 16, 10, 5e-3, synth.default_pert(THR, 10))
+    hc.set_spline(rows)
+    ne = hc.compare(THR, variant)
+    want = hc.get_edges()
+    assert ne > 1000
+    for ppc in (1, 2, 64):
+        chunks = []
+        tot = hc.compare_stream(THR, lambda a, b, d: chunks.append((a, b, d)), variant, panels_per_chunk=ppc)
+        got = tuple(np.concatenate([c[k] for c in chunks]) for k in range(3))
+        assert tot == ne and edges_equal(got, want), ppc
+        if ppc == 1:
+            assert len(chunks) >= 4
+            assert all(chunks[i][0].max() < chunks[i + 1][0].min() for i in range(len(chunks) - 1))
+    parts = []
+    for shard in range(3):
+        hc.compare_stream(THR, lambda a, b, d: parts.append((a, b, d)), variant, shard=shard, n_shards=3, panels_per_chunk=2)
+    a = np.concatenate([c[0] for c in parts]); b = np.concatenate([c[1] for c in parts]); d = np.concatenate([c[2] for c in parts])
+    o = np.lexsort((b, a))
+    assert edges_equal((a[o], b[o], d[o]), want)
+    with pytest.raises(scema_b200.ScemaError):
+        hc.get_edges()  # nothing is retained after a streamed compare
+
+    def bad_sink(a, b, d):
+        raise RuntimeError("stop")
+    with pytest.raises(RuntimeError):
+        hc.compare_stream(THR, bad_sink, variant, panels_per_chunk=1)
 
 
 def test_config2_full_oracle(hc, oracle):

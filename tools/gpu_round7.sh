@@ -1,0 +1,25 @@
+#!/bin/bash
+# GPU session 7: full parity suite (new CLI ingest path), K1 shared ring, traffic capture of the K2 filter at c4.
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -12 > gpurun_out/pytest_gpu.txt
+tail -12 gpurun_out/pytest_gpu.txt
+show() { python - "$1" "$2" <<'PY'
+import json,sys
+try:
+    d=json.load(open(sys.argv[1]))
+    r=d["roofline"]
+    print("%-28s resample_ms=%.4f filter_ms=%.3f TF=%.2f frac=%.3f value=%.4g e2e=%.4g edges=%d" % (sys.argv[2], r["other_kernels_ms"]["resample"], r["launch_ms"], r["achieved"], r["frac"], d["value"], d["e2e"]["value"], d["config"]["edges"]))
+except Exception as e:
+    print(sys.argv[2], "FAILED", e)
+PY
+}
+for cfg in "stream 16" "stream 24"; do
+  set -- $cfg
+  SCEMA_K1=$1 SCEMA_K1_WPS=$2 timeout 300 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c3_$1_$2.json 2> gpurun_out/bench_c3_$1_$2.err
+  show gpurun_out/bench_c3_$1_$2.json "c3 k1=$1 wps=$2"
+done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_filter_ws -s 3 -c 1 -o gpurun_out/prof_filter_ws_c4 \
+    python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_filter_ws_c4.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_resample_stream -s 6 -c 2 -o gpurun_out/prof_resample_v8 \
+    python bench.py --workload c3 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_resample_v8.log 2>&1
+ls gpurun_out | wc -l
