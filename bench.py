@@ -173,7 +173,7 @@ def run_reference(args, wl, wl_name):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -319,7 +319,7 @@ def run_ours(args, wl, wl_name):
         peak = max(p[key] for p in peaks)
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "filter_traffic.json")
-        if os.path.exists(tfile):
+        if world == 1 and os.path.exists(tfile):
             try:
                 traffic = json.load(open(tfile)).get(f"{wl_name}:{n}")
             except Exception:
@@ -356,14 +356,34 @@ def run_ours(args, wl, wl_name):
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     hc.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Libraries (NCCL's version banner, for one) write to file descriptor 1. The contract is ONE JSON
+    line on stdout, so everything else is sent to stderr and only emit() reaches the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

@@ -40,7 +40,7 @@ struct DevBuf {
 // TILE. kc % 8 == 4 makes the DMMA fragment loads (lane -> row g, column t) bank-conflict free
 // when a TILE x kc block lands densely in shared memory.
 struct FilterLayout {
-    uint32_t K = 0, kc = 0, n_chunks = 0;
+    uint32_t K = 0, kc = 0, kt = 0, n_chunks = 0;  // kt: width of the last chunk (== kc unless the DMMA kernel runs)
     uint64_t n = 0, n_pad = 0, n_blocks = 0;
 };
 

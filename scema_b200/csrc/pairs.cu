@@ -126,26 +126,28 @@ __device__ __forceinline__ void warp_append_cand(bool keep, uint64_t packed, uns
 // prep: S[n][K] -> F[chunk][n_pad][ks] (zero padded), HN[n_pad] = -|row|^2/2, BM[block] = max |row|^2
 // one warp per row
 // ------------------------------------------------------------------------------------------------
+// The last chunk may be narrower (kt columns, row stride kst) than the others (kc, ks).
 __global__ void __launch_bounds__(256) k_prep(const double *__restrict__ S, uint64_t n, uint32_t K, uint64_t n_pad,
-                                              uint32_t kc, uint32_t ks, uint32_t n_chunks, double *__restrict__ F,
-                                              double *__restrict__ HN, unsigned long long *__restrict__ BM)
+                                              uint32_t kc, uint32_t ks, uint32_t kt, uint32_t kst, uint32_t n_chunks,
+                                              double *__restrict__ F, double *__restrict__ HN,
+                                              unsigned long long *__restrict__ BM)
 {
     const uint64_t row = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n_pad) return;
     double nrm = 0.0;
-    const uint32_t kp = kc * n_chunks;
     for (uint32_t c = 0; c < n_chunks; c++) {
-        double *dst = F + ((uint64_t)c * n_pad + row) * ks;
-        for (uint32_t q = lane; q < ks; q += 32) {
+        const bool tail = c == n_chunks - 1;
+        const uint32_t w = tail ? kt : kc, st = tail ? kst : ks;
+        double *dst = F + (uint64_t)c * n_pad * ks + row * st;
+        for (uint32_t q = lane; q < st; q += 32) {
             uint32_t k = c * kc + q;
             double v = 0.0;
-            if (q < kc && k < K && row < n) v = S[row * K + k];
+            if (q < w && k < K && row < n) v = S[row * K + k];
             dst[q] = v;
             nrm = fma(v, v, nrm);
         }
     }
-    (void)kp;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
     if (lane == 0) {
@@ -386,8 +388,9 @@ __global__ void __launch_bounds__(256, 1) k_filter(const FilterArgs a)
 struct StageMeta {
     uint32_t I, J, flags, lo_bound, span, pad0, pad1, pad2;
 };
-constexpr uint32_t META_FIRST = 1u, META_LAST = 2u, META_DONE = 4u;
+constexpr uint32_t META_FIRST = 1u, META_LAST = 2u, META_DONE = 4u;  // LAST also means: this is the (narrower) tail chunk
 
+// KC = columns of a chunk, KT = columns of the last chunk (KT <= KC; KT == KC when there is one chunk)
 template <int KC, bool MULTI>
 struct WsSmem {
     static constexpr size_t tile_bytes = (size_t)TILE * KC * 8;
@@ -408,14 +411,34 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 // works). Every scheduler partition hosts 2 consumer warps and 1 producer-group warp and owns 16384
 // registers, so the kernel is compiled for 168 registers/thread and re-balanced at run time with
 // setmaxnreg: producer group down to 40, consumers up to 232 (32*(2*232+40) = 16128).
-template <int KC, bool MULTI>
+// 64 x 32 warp tile += A[64 x KK] . B[32 x KK]^T out of shared memory (row stride KK, KK % 8 == 4)
+template <int KK>
+__device__ __forceinline__ void mma_warp_tile(double (&acc)[8][4][2], const double *__restrict__ ap, const double *__restrict__ bp)
+{
+#pragma unroll
+    for (int ks = 0; ks < KK / 4; ks++) {
+        double af[8], bf[4];
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) af[mi] = ap[mi * 8 * KK + ks * 4];
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) bf[ni] = bp[ni * 8 * KK + ks * 4];
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
+}
+
+template <int KC, int KT, bool MULTI>
 __global__ void __launch_bounds__(384, 1) k_filter_ws(const FilterArgs a)
 {
     using SM = WsSmem<KC, MULTI>;
     constexpr int NST = SM::NST;
     static_assert(NST >= 2, "need at least two stages");
+    static_assert(KT <= KC && (MULTI || KT == KC), "tail chunk");
     constexpr int KS = KC;
     constexpr uint32_t TILE_BYTES = (uint32_t)SM::tile_bytes;
+    constexpr uint32_t TAIL_BYTES = (uint32_t)((size_t)TILE * KT * 8);
     constexpr uint32_t HN_BYTES = TILE * 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [resident A (non-MULTI)] | stage 0 | stage 1 | ... | meta[NST] | full[NST] | empty[NST]
@@ -487,16 +510,20 @@ __global__ void __launch_bounds__(384, 1) k_filter_ws(const FilterArgs a)
                     m.flags = (c == 0 ? META_FIRST : 0u) | (c == a.n_chunks - 1 ? META_LAST : 0u);
                     m.lo_bound = lo_bound; m.span = span; m.pad0 = m.pad1 = m.pad2 = 0;
                     metas[st] = m;
-                    uint32_t bytes = TILE_BYTES + (c == 0 ? 2 * HN_BYTES : 0u);
-                    if (MULTI || new_A) bytes += TILE_BYTES;
+                    const bool tail = MULTI && c == a.n_chunks - 1;  // narrower last chunk: row stride KT
+                    const uint32_t tb = tail ? TAIL_BYTES : TILE_BYTES;
+                    const uint32_t kst = tail ? KT : KS;
+                    const double *Fc = a.F + (uint64_t)c * a.n_pad * KS;
+                    uint32_t bytes = tb + (c == 0 ? 2 * HN_BYTES : 0u);
+                    if (MULTI || new_A) bytes += tb;
                     mbar_expect_tx(&full[st], bytes);
-                    tma_bulk_g2s(stageB(st), a.F + ((uint64_t)c * a.n_pad + (uint64_t)J * TILE) * KS, TILE_BYTES, &full[st]);
+                    tma_bulk_g2s(stageB(st), Fc + (uint64_t)J * TILE * kst, tb, &full[st]);
                     if (c == 0) {
                         tma_bulk_g2s(stageHA(st), a.HN + (uint64_t)I * TILE, HN_BYTES, &full[st]);
                         tma_bulk_g2s(stageHB(st), a.HN + (uint64_t)J * TILE, HN_BYTES, &full[st]);
                     }
                     if (MULTI)
-                        tma_bulk_g2s(stageA(st), a.F + ((uint64_t)c * a.n_pad + (uint64_t)I * TILE) * KS, TILE_BYTES, &full[st]);
+                        tma_bulk_g2s(stageA(st), Fc + (uint64_t)I * TILE * kst, tb, &full[st]);
                     else if (new_A)
                         tma_bulk_g2s(As, a.F + (uint64_t)I * TILE * KS, TILE_BYTES, &full[st]);
                 }
@@ -541,22 +568,10 @@ __global__ void __launch_bounds__(384, 1) k_filter_ws(const FilterArgs a)
                 }
             }
         }
-        {
-            const double *ap = Ab + (wm * 64 + g) * KS + t4;
-            const double *bp = Bb + (wn * 32 + g) * KS + t4;
-#pragma unroll
-            for (int ks = 0; ks < KC / 4; ks++) {
-                double af[8], bf[4];
-#pragma unroll
-                for (int mi = 0; mi < 8; mi++) af[mi] = ap[mi * 8 * KS + ks * 4];
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++) bf[ni] = bp[ni * 8 * KS + ks * 4];
-#pragma unroll
-                for (int mi = 0; mi < 8; mi++)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ni++) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
-            }
-        }
+        if (KT != KC && (m.flags & META_LAST))
+            mma_warp_tile<KT>(acc, Ab + (wm * 64 + g) * KT + t4, Bb + (wn * 32 + g) * KT + t4);
+        else
+            mma_warp_tile<KC>(acc, Ab + (wm * 64 + g) * KC + t4, Bb + (wn * 32 + g) * KC + t4);
         // this warp is done with the stage's shared memory (and, at the last tile of an item, with A)
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
@@ -680,6 +695,27 @@ __global__ void __launch_bounds__(256) k_exact_all(const double *__restrict__ S,
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// Warp-specialised DMMA kernel: n-1 chunks of kc columns and a last one of kt <= kc, all from the
+// bank-conflict-free widths (== 4 mod 8); least padding first, then fewest chunks.
+static void choose_chunks_tail(uint32_t K, uint32_t *kc, uint32_t *kt, uint32_t *n_chunks)
+{
+    static const uint32_t widths[] = {12, 20, 28, 36, 44, 52, 60};
+    for (uint32_t w : widths)
+        if (K <= w) { *kc = w; *kt = w; *n_chunks = 1; return; }
+    static const uint32_t mains[] = {36, 44, 52};
+    uint64_t best_cost = ~0ull;
+    for (uint32_t m : mains) {
+        const uint32_t nn = (K + m - 1) / m;            // chunks when all but the last are m wide
+        const uint32_t rest = K - (nn - 1) * m;         // 1 .. m columns left for the tail
+        uint32_t t = m;
+        for (uint32_t w : widths)
+            if (w >= rest && w <= m) { t = w; break; }
+        const uint64_t padded = (uint64_t)(nn - 1) * m + t;
+        const uint64_t cost = padded * 64 + nn;          // padding dominates, chunk count breaks ties
+        if (cost < best_cost) { best_cost = cost; *kc = m; *kt = t; *n_chunks = nn; }
+    }
+}
+
 static void choose_chunks(uint32_t K, uint32_t *kc, uint32_t *n_chunks)
 {
     static const uint32_t single[] = {12, 20, 28, 36, 44, 52, 60};
@@ -711,10 +747,10 @@ static int launch_filter_t(scema_ctx *ctx, const FilterArgs &fa)
     return SCEMA_OK;
 }
 
-template <int KC, bool MULTI>
+template <int KC, int KT, bool MULTI>
 static int launch_filter_ws_t(scema_ctx *ctx, const FilterArgs &fa)
 {
-    auto kern = k_filter_ws<KC, MULTI>;
+    auto kern = k_filter_ws<KC, KT, MULTI>;
     const size_t smem = WsSmem<KC, MULTI>::bytes;
     if (smem > ctx->smem_optin) return fail(ctx, SCEMA_ERR_CUDA, "filter kernel shared memory exceeds device limit");
     SCEMA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -726,22 +762,37 @@ static int launch_filter_ws_t(scema_ctx *ctx, const FilterArgs &fa)
     return SCEMA_OK;
 }
 
-static int launch_filter_ws(scema_ctx *ctx, const FilterArgs &fa, uint32_t kc, bool multi)
+template <int KC>
+static int launch_filter_ws_tail(scema_ctx *ctx, const FilterArgs &fa, uint32_t kt)
+{
+    switch (kt) {
+    case 12: if (12 <= KC) return launch_filter_ws_t<KC, (12 <= KC ? 12 : KC), true>(ctx, fa); break;
+    case 20: if (20 <= KC) return launch_filter_ws_t<KC, (20 <= KC ? 20 : KC), true>(ctx, fa); break;
+    case 28: if (28 <= KC) return launch_filter_ws_t<KC, (28 <= KC ? 28 : KC), true>(ctx, fa); break;
+    case 36: if (36 <= KC) return launch_filter_ws_t<KC, (36 <= KC ? 36 : KC), true>(ctx, fa); break;
+    case 44: if (44 <= KC) return launch_filter_ws_t<KC, (44 <= KC ? 44 : KC), true>(ctx, fa); break;
+    case 52: if (52 <= KC) return launch_filter_ws_t<KC, (52 <= KC ? 52 : KC), true>(ctx, fa); break;
+    }
+    return fail(ctx, SCEMA_ERR_INVALID, "no filter kernel instantiation for this tail chunk size");
+}
+
+static int launch_filter_ws(scema_ctx *ctx, const FilterArgs &fa, uint32_t kc, uint32_t kt, bool multi)
 {
     if (!multi) {
         switch (kc) {
-        case 12: return launch_filter_ws_t<12, false>(ctx, fa);
-        case 20: return launch_filter_ws_t<20, false>(ctx, fa);
-        case 28: return launch_filter_ws_t<28, false>(ctx, fa);
-        case 36: return launch_filter_ws_t<36, false>(ctx, fa);
-        case 44: return launch_filter_ws_t<44, false>(ctx, fa);
-        case 52: return launch_filter_ws_t<52, false>(ctx, fa);
-        case 60: return launch_filter_ws_t<60, false>(ctx, fa);
+        case 12: return launch_filter_ws_t<12, 12, false>(ctx, fa);
+        case 20: return launch_filter_ws_t<20, 20, false>(ctx, fa);
+        case 28: return launch_filter_ws_t<28, 28, false>(ctx, fa);
+        case 36: return launch_filter_ws_t<36, 36, false>(ctx, fa);
+        case 44: return launch_filter_ws_t<44, 44, false>(ctx, fa);
+        case 52: return launch_filter_ws_t<52, 52, false>(ctx, fa);
+        case 60: return launch_filter_ws_t<60, 60, false>(ctx, fa);
         }
     } else {
         switch (kc) {
-        case 44: return launch_filter_ws_t<44, true>(ctx, fa);
-        case 52: return launch_filter_ws_t<52, true>(ctx, fa);
+        case 36: return launch_filter_ws_tail<36>(ctx, fa, kt);
+        case 44: return launch_filter_ws_tail<44>(ctx, fa, kt);
+        case 52: return launch_filter_ws_tail<52>(ctx, fa, kt);
         }
     }
     return fail(ctx, SCEMA_ERR_INVALID, "no filter kernel instantiation for this chunk size");
@@ -784,15 +835,19 @@ static int prepare_filter(scema_ctx *ctx, int variant)
         return SCEMA_OK;
     fl.K = ctx->K;
     fl.n = ctx->n;
-    choose_chunks(fl.K, &fl.kc, &fl.n_chunks);
+    static const char *k2_env = getenv("SCEMA_K2");
+    const bool ws = variant == SCEMA_PAIRS_DMMA && !(k2_env && strcmp(k2_env, "v1") == 0);
+    if (ws) choose_chunks_tail(fl.K, &fl.kc, &fl.kt, &fl.n_chunks);
+    else { choose_chunks(fl.K, &fl.kc, &fl.n_chunks); fl.kt = fl.kc; }
     fl.n_blocks = (fl.n + TILE - 1) / TILE;
     fl.n_pad = fl.n_blocks * TILE;
     const uint32_t ks = variant == SCEMA_PAIRS_DMMA ? fl.kc : fl.kc + 1;
+    const uint32_t kst = variant == SCEMA_PAIRS_DMMA ? fl.kt : fl.kt + 1;
     SCEMA_CUDA(ctx, ctx->d_filter.reserve((size_t)fl.n_chunks * fl.n_pad * ks * sizeof(double)));
     SCEMA_CUDA(ctx, ctx->d_halfnorm.reserve(fl.n_pad * sizeof(double)));
     SCEMA_CUDA(ctx, ctx->d_blockmax.reserve(fl.n_blocks * sizeof(double)));
     SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_blockmax.p, 0, fl.n_blocks * sizeof(double), ctx->stream));
-    k_prep<<<(unsigned)((fl.n_pad + 7) / 8), 256, 0, ctx->stream>>>(ctx->d_spline, fl.n, fl.K, fl.n_pad, fl.kc, ks,
+    k_prep<<<(unsigned)((fl.n_pad + 7) / 8), 256, 0, ctx->stream>>>(ctx->d_spline, fl.n, fl.K, fl.n_pad, fl.kc, ks, fl.kt, kst,
                                                                      fl.n_chunks, ctx->d_filter.as<double>(),
                                                                      ctx->d_halfnorm.as<double>(),
                                                                      ctx->d_blockmax.as<unsigned long long>());
@@ -906,7 +961,7 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
             // SCEMA_K2=v1 selects the barrier-synchronised DMMA kernel (kept for A/B measurements)
             static const char *k2_env = getenv("SCEMA_K2");
             const bool ws = !(k2_env && strcmp(k2_env, "v1") == 0);
-            rc = *variant == SCEMA_PAIRS_DMMA ? (ws ? launch_filter_ws(ctx, fa, fl.kc, fl.n_chunks > 1)
+            rc = *variant == SCEMA_PAIRS_DMMA ? (ws ? launch_filter_ws(ctx, fa, fl.kc, fl.kt, fl.n_chunks > 1)
                                                     : launch_filter<true>(ctx, fa, fl.kc, fl.n_chunks > 1))
                                               : launch_filter<false>(ctx, fa, fl.kc, fl.n_chunks > 1);
             if (rc) return rc;
