@@ -131,6 +131,12 @@ def cpu_pairs_step(lib, rows, r0, r1):
     return pairs, time.perf_counter() - t0, edges
 
 
+def cpu_pairs_step_threads(lib, rows, r0, r1, nthreads):
+    t0 = time.perf_counter()
+    edges, pairs = lib.all_pairs(rows, THR, r0, r1, nthreads, count_only=True)
+    return pairs, time.perf_counter() - t0, edges
+
+
 def run_reference(args, wl, wl_name):
     rank = env_int("RANK", 0)
     if rank != 0:
@@ -223,8 +229,8 @@ def run_ours(args, wl, wl_name):
             dist.barrier()
         torch.cuda.synchronize()
 
-    acc = {"filter": 0.0, "resample": 0.0, "exact": 0.0, "sort": 0.0, "prep": 0.0, "steps": 0, "edges": 0,
-           "survivors": 0}
+    acc = {"filter": 0.0, "resample": 0.0, "exact": 0.0, "sort": 0.0, "prep": 0.0, "allgather": 0.0, "steps": 0,
+           "edges": 0, "survivors": 0}
 
     streamed = {"edges": 0, "chunks": 0}
 
@@ -246,6 +252,8 @@ def run_ours(args, wl, wl_name):
             for k in ("filter", "exact", "sort", "prep"):
                 acc[k] += t[k]
             acc["resample"] += t["resample"] if world > 1 else t_res
+            if world > 1:
+                acc["allgather"] += sc.gather_events[0].elapsed_time(sc.gather_events[1])  # hc.timings() synchronised
             acc["steps"] += 1
             acc["edges"] = tot
             acc["survivors"] = hc.counters()["survivors"]
@@ -330,7 +338,8 @@ def run_ours(args, wl, wl_name):
                     "peak_source": "measured live on this GPU: FP64 %s issue-rate probe (scema_fp64_peak); "
                                    "MEASURED_PEAKS.json has no FP64 figure" % ("DMMA m8n8k4" if variant == 0 else "DFMA"),
                     "launch_ms": filt_ms,
-                    "other_kernels_ms": {k: acc[k] / max(acc["steps"], 1) for k in ("resample", "prep", "exact", "sort")}}
+                    "other_kernels_ms": {k: acc[k] / max(acc["steps"], 1)
+                                         for k in ("resample", "prep", "exact", "sort") + (("allgather",) if world > 1 else ())}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             m = min(n, 65536)
@@ -341,6 +350,17 @@ def run_ours(args, wl, wl_name):
             cpu = {"value": pairs / dt, "unit": "pairs/s", "cores": lib.max_threads(), "kind": kind,
                    "sample": f"first {m} of {n} histories; rows [0,{rps}) x all later rows = {pairs} pairs in {dt:.1f} s; "
                              f"reference splinify {m / t_spl:.0f} histories/s"}
+            # one core, for scale: the -O2 build and the as-shipped build (clustering/Makefile has no -O)
+            try:
+                p1, d1, _ = cpu_pairs_step_threads(lib, rows, 0, 24, 1)
+                cpu["single_core_O2"] = p1 / d1
+                if kind == "reference":
+                    from oracle.pyoracle import Reference
+                    lib0 = Reference(o0=True)
+                    p0, d0, _ = cpu_pairs_step_threads(lib0, rows, 0, 8, 1)
+                    cpu["single_core_O0_as_shipped"] = p0 / d0
+            except Exception as e:  # noqa: BLE001 - the extra figures are optional
+                cpu["single_core_note"] = repr(e)
         line = {
             "metric": "history pair comparisons/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

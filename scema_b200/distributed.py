@@ -88,7 +88,11 @@ class ShardedCluster:
             hc.resample(spline_points)
             n_local, K, ptr = hc.spline_info()
             local = torch.as_tensor(CudaView(ptr, (n_local, K)), device="cuda")
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
             full = gather_rows(local, n, self.world, self.group)
+            ev1.record()
+            self.gather_events = (ev0, ev1)  # ev0.elapsed_time(ev1) after a synchronize = the all-gather alone
             hc.set_spline(device_ptr=full.data_ptr(), n=n, k=K)
             if sink is not None:
                 ne = hc.compare_stream(threshold, sink, variant, shard=self.rank, n_shards=self.world)

@@ -429,3 +429,42 @@ def test_config3_ragged_200k_properties(hc, oracle):
         assert len(ei) == int(np.count_nonzero(a == r))
     hc.compare(THR, PAIRS_FMA)
     assert edges_equal(hc.get_edges(), (a, b, d))
+
+
+def test_config4_1M_properties(hc, oracle):
+    """BASELINE configs[3] at full size on one GPU: 1M histories x 6 x 10 (5e11 pairs). Size-independent
+    checks: (i) the filter-free exact kernel and the DMMA path emit the same edge list (ids, order, distance
+    bits) over the WHOLE problem, (ii) every emitted edge re-derived on the CPU by direct differences,
+    (iii) completeness of 200 full rows recomputed on the CPU, (iv) the streamed compare delivers the
+    same list, (v) a 20k-history spline subset bit-exact against the oracle."""
+    import torch
+    n, P = 1000000, 10
+    pert = synth.default_pert(THR, P)
+    off = synth.device_offsets(4, n, 16, 8, 64)
+    d_steps = synth.device_histories(4, n, 16, 5e-3, pert, off, device="cuda:0")
+    torch.cuda.synchronize()
+    hc.set_histories(None, off, device_ptr=d_steps.data_ptr())
+    hc.resample(P)
+    sp = hc.get_spline()
+    sub = np.sort(np.random.default_rng(0).choice(n, size=20000, replace=False))
+    sub_off = np.concatenate([[0], np.cumsum(off[sub + 1] - off[sub])]).astype(np.uint64)
+    h_steps = d_steps.cpu().numpy()
+    sub_steps = np.concatenate([h_steps[int(off[i]):int(off[i + 1])] for i in sub])
+    assert same_bits(sp[sub], oracle.splinify_batch(sub_steps, sub_off, P))
+    del h_steps, sub_steps
+    ne = hc.compare(THR, PAIRS_DMMA)
+    a, b, d = hc.get_edges()
+    assert ne > n and np.all(a < b) and np.all(np.diff(a.astype(np.int64) * n + b) > 0)  # sorted, unique
+    assert hc.counters()["survivors"] < ne + ne // 100  # the guard band stays a vanishing fraction
+    assert oracle.check_edges(sp, THR, a, b, d) == 0
+    for r in np.random.default_rng(1).choice(n - 1, size=200, replace=False).tolist():
+        ei, ej, ed, _ = oracle.all_pairs(sp, THR, r, r + 1)
+        lo, hi = np.searchsorted(a, r), np.searchsorted(a, r + 1)
+        assert np.array_equal(b[lo:hi], ej) and same_bits(d[lo:hi], ed), r
+    chunks = []
+    tot = hc.compare_stream(THR, lambda x, y, z: chunks.append((x, y, z)), PAIRS_DMMA)
+    assert tot == ne and len(chunks) > 4
+    assert edges_equal(tuple(np.concatenate([c[k] for c in chunks]) for k in range(3)), (a, b, d))
+    hc.compare(THR, PAIRS_EXACT)
+    assert edges_equal(hc.get_edges(), (a, b, d))
+    del d_steps

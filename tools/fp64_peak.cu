@@ -113,6 +113,29 @@ __global__ void __launch_bounds__(256) k_mixed(double *out, double a, double b)
     if (s == 123.456) out[0] = s;
 }
 
+// DMMA issue rate at the occupancy of the K2 filter: `blocks` CTAs of 256 threads with a large
+// dynamic shared-memory request (one CTA per SM -> 2 warps per scheduler), NACC independent
+// accumulator fragments per warp (the filter has 32).
+template <int NACC>
+__global__ void __launch_bounds__(256, 1) k_dmma_occ(double *out, double av, double bv)
+{
+    extern __shared__ double pad[];
+    double c[NACC][2];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) c[i][0] = c[i][1] = 0.0;
+    const double a = av + threadIdx.x * 1e-12, b = bv;
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < NACC; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s + pad[0];
+}
+
 // one warp, one thread active: dependent chain latency in cycles per op
 template <int OP>
 __global__ void k_lat(double *out, long long *cyc, double a, double b)
@@ -196,6 +219,27 @@ int main()
                    f_t / (t * 1e-3) / 1e12, f_v / (t * 1e-3) / 1e12, (f_t + f_v) / (t * 1e-3) / 1e12);
         }
         printf("]");
+    }
+    {
+        // one CTA per SM (180 KB of dynamic shared memory), 8 warps -> 2 per scheduler
+        cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        CK(cudaFuncSetAttribute(k_dmma_occ<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+        CK(cudaFuncSetAttribute(k_dmma_occ<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+        printf(", \"dmma_2warps_per_scheduler\": {");
+        for (int v = 0; v < 2; v++) {
+            float best = 1e30f;
+            for (int r = 0; r < 6; r++) {
+                CK(cudaEventRecord(e0));
+                if (v == 0) k_dmma_occ<8><<<sms, 256, 180 * 1024>>>(g_out, 1.0, 1e-9);
+                else k_dmma_occ<32><<<sms, 256, 180 * 1024>>>(g_out, 1.0, 1e-9);
+                CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+                float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                if (r && ms < best) best = ms;
+            }
+            const int nacc = v == 0 ? 8 : 32;
+            printf("%s\"nacc%d_tflops\": %.3f", v ? ", " : "", nacc, (double)sms * 8 * ITERS * nacc * 512.0 / (best * 1e-3) / 1e12);
+        }
+        printf("}");
     }
     k_lat<0><<<1, 1>>>(g_out, cyc, 1.0, 1e-9);
     k_lat<1><<<1, 1>>>(g_out, cyc, 1.0, 1.0000001);
