@@ -75,7 +75,9 @@ struct scema_ctx {
     scema::DevBuf d_tables, d_table_index;   // d_table_index: int64 [max_len+1] -> offset or -1
     uint64_t tables_used = 0;                // doubles
     uint32_t table_index_len = 0;
-    scema::DevBuf zscratch, d_order;
+    scema::DevBuf zscratch, d_order, d_chunks, d_chunk_counters;  // K1 work plan: padded group order, chunk list
+    std::vector<uint32_t> plan_chunk_begin;                        // [classes+1] into d_chunks
+    std::vector<uint64_t> plan_groups, plan_first_slot;            // per class: groups, first group slot
     uint64_t histories_version = 0, order_version = ~0ull;
 
     // ---- spline matrix S [n][K] (n == hn after a resample; set_spline may install any n)

@@ -375,22 +375,46 @@ inline void compare_batch(std::vector<Strain6D *> &hist, double threshold, const
     const size_t n = hist.size();
     for (size_t i = 0; i < n; i++) hist[i]->clear_most_similar_history();
     if (n == 0) return;
-    resolve_splines(hist);
-    const uint32_t K = (uint32_t)hist[0]->get_spline()->size();
-    std::vector<double> rows(n * (size_t)K);
+    scema_ctx *ctx = context();
     std::vector<uint32_t> ids(n);
     for (size_t i = 0; i < n; i++) {
-        std::vector<double> *sp = hist[i]->get_spline();
-        if (sp->size() != K) {
-            fprintf(stderr, "Error in compare_L2_norm(): given strain6D objects have different numbers of spline points (%u and %u)\n",
-                    K, (uint32_t)sp->size());
+        if (!hist[i]->b200_up_to_date()) {  // get_spline() of a stale object (strain2spline.h:214-221)
+            std::cout << "Spline is not up to date.\n";
             exit(1);
         }
-        if (K) memcpy(rows.data() + i * (size_t)K, sp->data(), K * sizeof(double));
         ids[i] = hist[i]->get_ID();
     }
-    scema_ctx *ctx = context();
-    check(scema_set_spline(ctx, rows.data(), 0, n, K, ids.data()), "compare_histories_with_all_ranks");
+    // Usual case (FE_problem.h:1187 then :1229, mpi_comparison_test.cc:83 then :96): every history still
+    // carries its deferred splinify(P) with the same P. The raw histories then go to the GPU once,
+    // K1 writes the spline matrix where K2 reads it, and nothing comes back but the edges; an object's
+    // own spline vector is only materialised if somebody asks for it (get_spline, print, ...).
+    bool direct = true;
+    const uint32_t P0 = hist[0]->get_num_spline_points_per_component();
+    for (size_t i = 0; i < n; i++) direct = direct && hist[i]->b200_pending() && hist[i]->get_num_spline_points_per_component() == P0;
+    if (direct && P0 > 0) {
+        std::vector<uint64_t> offsets(1, 0);
+        std::vector<double> flat;
+        for (size_t i = 0; i < n; i++) {
+            flat.insert(flat.end(), hist[i]->b200_steps().begin(), hist[i]->b200_steps().end());
+            offsets.push_back(offsets.back() + hist[i]->b200_num_steps());
+        }
+        check(scema_set_histories(ctx, flat.data(), 0, offsets.data(), ids.data(), n), "compare_histories_with_all_ranks");
+        check(scema_resample(ctx, P0), "compare_histories_with_all_ranks");
+    } else {
+        resolve_splines(hist);
+        const uint32_t K = (uint32_t)hist[0]->get_spline()->size();
+        std::vector<double> rows(n * (size_t)K);
+        for (size_t i = 0; i < n; i++) {
+            std::vector<double> *sp = hist[i]->get_spline();
+            if (sp->size() != K) {
+                fprintf(stderr, "Error in compare_L2_norm(): given strain6D objects have different numbers of spline points (%u and %u)\n",
+                        K, (uint32_t)sp->size());
+                exit(1);
+            }
+            if (K) memcpy(rows.data() + i * (size_t)K, sp->data(), K * sizeof(double));
+        }
+        check(scema_set_spline(ctx, rows.data(), 0, n, K, ids.data()), "compare_histories_with_all_ranks");
+    }
     const bool dense = keep_all_similar();
     uint64_t m = 0;
     check(scema_compare(ctx, dense ? std::numeric_limits<double>::infinity() : threshold, SCEMA_PAIRS_DMMA, 0, 1, &m),

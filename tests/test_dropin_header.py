@@ -1,0 +1,59 @@
+"""The drop-in header scema_b200/host/strain2spline_b200.h against the reference header itself: one
+caller (tests/helpers/dropin_driver.cc, written only against the MatHistPredict API and shaped like
+FE_problem.h:1091-1270) is compiled against both; stdout and every result file must be identical."""
+import filecmp
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "dropin_driver_ref")
+
+
+def build_ours(tmp_path):
+    exe = str(tmp_path / "dropin_driver_b200")
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-ffp-contract=off", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "scema_b200", "host"),
+                           os.path.join(ROOT, "tests", "helpers", "dropin_driver.cc"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "scema_b200"), "-lscema_hist",
+                           "-Wl,-rpath," + os.path.join(ROOT, "scema_b200")])
+    return exe
+
+
+@pytest.mark.parametrize("n_qp,n_steps,P,thr,seed", [(64, 12, 10, 1e-6, 5), (300, 21, 10, 4e-7, 9), (41, 7, 4, 1e-6, 2)])
+def test_same_caller_same_bytes(tmp_path, n_qp, n_steps, P, thr, seed):
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref not built")
+    ours_exe = build_ours(tmp_path)
+    outs = {}
+    for name, exe in (("ref", REF_BIN), ("ours", ours_exe)):
+        d = tmp_path / name
+        d.mkdir()
+        r = subprocess.run([exe, str(d), str(n_qp), str(n_steps), str(P), repr(thr), str(seed)], capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        outs[name] = r.stdout
+    assert outs["ours"] == outs["ref"]
+    assert "flagged" in outs["ref"] and "run_new_md" in outs["ref"]
+    files = sorted(os.listdir(tmp_path / "ref"))
+    assert files == sorted(os.listdir(tmp_path / "ours")) and len(files) > n_qp
+    match, mismatch, errors = filecmp.cmpfiles(tmp_path / "ref", tmp_path / "ours", files, shallow=False)
+    assert not mismatch and not errors
+    assert any(os.path.getsize(tmp_path / "ref" / f) > 0 for f in files if f.endswith("similar_hist"))
+
+
+def test_error_behaviour_matches(tmp_path):
+    """< 3 samples: both print the reference's message and exit(1) (strain2spline.h:142-148)."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref not built")
+    ours_exe = build_ours(tmp_path)
+    for n_steps in ("2", "0"):
+        res = []
+        for exe in (REF_BIN, ours_exe):
+            d = tmp_path / (os.path.basename(exe) + n_steps)
+            d.mkdir()
+            r = subprocess.run([exe, str(d), "16", n_steps, "10", "1e-6", "1"], capture_output=True, text=True, timeout=120)
+            res.append((r.returncode, r.stdout, r.stderr))
+        assert res[0] == res[1] and res[0][0] == 1 and "splinify" in res[0][2]
