@@ -36,6 +36,12 @@ extern "C" {
 #define SCEMA_PAIRS_DMMA 0  /* GEMM-form filter on FP64 mma.sync (DMMA) + exact recompute of survivors */
 #define SCEMA_PAIRS_FMA 1   /* GEMM-form filter on CUDA-core DFMA + exact recompute of survivors */
 #define SCEMA_PAIRS_EXACT 2 /* every pair by direct differences (compare_L2_norm order), no filter */
+/* GEMM-form filter on the 5th-generation tensor cores: FP64 rows split into two fp16 slices, tcgen05.mma
+ * kind::f16 with fp32 accumulators in tensor memory, row norms and threshold folded into spare operand
+ * columns so that the sign of the accumulator decides; survivors (edges + a guard band covering the
+ * slicing and accumulation error) take the same exact FP64 recompute. Same edge list, same distance
+ * bits. Needs 6 * spline_points <= 60; wider rows silently take SCEMA_PAIRS_DMMA. */
+#define SCEMA_PAIRS_TC 3
 
 typedef struct scema_ctx scema_ctx;
 
@@ -155,7 +161,7 @@ int scema_reduce_dir(const char *input_folder, const char *out_mapping_csv, uint
 /* ---- instrumentation ------------------------------------------------------------------------ */
 #define SCEMA_T_RESAMPLE 0 /* K1 kernel(s) */
 #define SCEMA_T_PREP 1     /* norms + filter-layout copy */
-#define SCEMA_T_FILTER 2   /* K2 GEMM-form filter (DMMA or FMA) or the exact all-pairs kernel */
+#define SCEMA_T_FILTER 2   /* K2 GEMM-form filter (tcgen05, DMMA or FMA) or the exact all-pairs kernel */
 #define SCEMA_T_EXACT 3    /* exact recompute of survivors + K3 compaction */
 #define SCEMA_T_SORT 4     /* canonical (a,b) ordering */
 #define SCEMA_T_COUNT 8
@@ -166,6 +172,14 @@ int scema_last_timings(scema_ctx *ctx, float ms[SCEMA_T_COUNT]);
 int scema_last_counters(scema_ctx *ctx, uint64_t counters[8]);
 /* Total kernels launched by this context so far. */
 uint64_t scema_kernel_launches(const scema_ctx *ctx);
+/* Validation hook of SCEMA_PAIRS_TC (tests only; n padded to 256 must be <= 8192): runs the instrumented
+ * tcgen05 kernel over the whole pair matrix of the current spline rows. acc_host[row * ld + col] receives
+ * every fp32 accumulator (a.b - h_row - h_col in the scaled units of the operands), operand_a_host /
+ * operand_b_host (n_pad * 256 bytes each, may be NULL) the fp16 operand copies as they sit in memory:
+ * blocks of 128 rows, each [hi slice | lo slice] of 128 rows x 128 bytes, 16-byte chunk c of row r
+ * stored at chunk c ^ (r & 7). */
+int scema_tc_debug(scema_ctx *ctx, double threshold, float *acc_host, uint64_t ld, void *operand_a_host,
+                   void *operand_b_host);
 /* Measured FP64 issue rates on the context's device (TFLOP/s): out[0] DFMA, out[1] DMMA m8n8k4. */
 int scema_fp64_peak(scema_ctx *ctx, double out[2]);
 

@@ -4,7 +4,7 @@ import os
 
 import numpy as np
 
-PAIRS_DMMA, PAIRS_FMA, PAIRS_EXACT = 0, 1, 2
+PAIRS_DMMA, PAIRS_FMA, PAIRS_EXACT, PAIRS_TC = 0, 1, 2, 3
 T_NAMES = ("resample", "prep", "filter", "exact", "sort")
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -63,6 +63,7 @@ def lib():
         "scema_last_counters": (i32, [vp, P(u64)]),
         "scema_kernel_launches": (u64, [vp]),
         "scema_fp64_peak": (i32, [vp, P(dbl)]),
+        "scema_tc_debug": (i32, [vp, dbl, vp, u64, vp, vp]),
         "scema_ingest_last_error": (C.c_char_p, []),
         "scema_batch_read_dir": (i32, [C.c_char_p, u32, P(vp)]),
         "scema_batch_read_files": (i32, [P(C.c_char_p), vp, u64, u32, P(vp)]),
@@ -93,7 +94,7 @@ EXPORTED = (
     "scema_store_reset scema_store_append scema_store_info scema_store_resample scema_select_rows "
     "scema_set_spline scema_get_spline scema_spline_info scema_compare scema_compare_stream scema_get_edges scema_edges_device "
     "scema_get_degrees scema_cluster scema_write_similar_hist scema_reduce_edges scema_reduce_calls scema_reduce_dir "
-    "scema_last_timings scema_last_counters scema_kernel_launches scema_fp64_peak scema_synth_offsets "
+    "scema_last_timings scema_last_counters scema_kernel_launches scema_fp64_peak scema_tc_debug scema_synth_offsets "
     "scema_synth_histories_device scema_synth_rows_device scema_ingest_last_error scema_batch_read_dir "
     "scema_batch_read_files scema_batch_from_lhistory scema_batch_count scema_batch_total_steps scema_batch_steps "
     "scema_batch_offsets scema_batch_ids scema_batch_name scema_batch_write_strain_files "
@@ -372,6 +373,16 @@ class HistCluster:
 
     def kernel_launches(self):
         return int(self._L.scema_kernel_launches(self._h))
+
+    def tc_debug(self, threshold, n):
+        """Accumulators and operand copies of the tcgen05 filter over the whole pair matrix (tests only).
+        Returns (acc [n_pad, n_pad] float32, A operand bytes, B operand bytes)."""
+        n_pad = (n + 255) // 256 * 256
+        acc = np.empty((n_pad, n_pad), dtype=np.float32)
+        ha = np.empty(n_pad * 256, dtype=np.uint8)
+        hb = np.empty(n_pad * 256, dtype=np.uint8)
+        self._ck(self._L.scema_tc_debug(self._h, float(threshold), _ptr(acc), n_pad, _ptr(ha), _ptr(hb)))
+        return acc, ha, hb
 
     def fp64_peak(self):
         out = (C.c_double * 2)()

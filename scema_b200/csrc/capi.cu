@@ -48,6 +48,7 @@ void scema_destroy(scema_ctx *c)
     c->d_blockmax.release(); c->d_panel_start.release(); c->d_cand.release(); c->d_counters.release();
     for (int b = 0; b < 2; b++) { c->d_edge_key[b].release(); c->d_edge_val[b].release(); }
     c->d_sort_tmp.release();
+    c->d_tc_a.release(); c->d_tc_b.release(); c->d_tc_nrm.release(); c->d_tc_misc.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (int k = 0; k < 2; k++) {
         if (c->h_stage_key[k]) cudaFreeHost(c->h_stage_key[k]);
@@ -368,6 +369,13 @@ int scema_fp64_peak(scema_ctx *c, double out[2])
     int rc = enter(c);
     if (rc) return rc;
     return fp64_peak_run(c, out);
+}
+
+int scema_tc_debug(scema_ctx *c, double threshold, float *acc_host, uint64_t ld, void *operand_a_host, void *operand_b_host)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    return tc_debug_run(c, threshold, acc_host, ld, (unsigned char *)operand_a_host, (unsigned char *)operand_b_host);
 }
 
 }  // extern "C"

@@ -931,6 +931,22 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
             ctx->launches++;
             t_end(ctx, SCEMA_T_FILTER);
             SCEMA_CUDA(ctx, cudaGetLastError());
+        } else if (*variant == SCEMA_PAIRS_TC) {
+            SCEMA_CUDA(ctx, ctx->d_cand.reserve(ctx->cand_cap * sizeof(uint64_t)));
+            t_begin(ctx, SCEMA_T_FILTER);
+            // one panel = PANEL_ROWBLOCKS * TILE = 2048 rows = 8 row tiles of 256
+            rc = tc_launch(ctx, p0 * (PANEL_ROWBLOCKS * TILE / 256), p1 * (PANEL_ROWBLOCKS * TILE / 256), shard, n_shards, d_cnt + 0,
+                           nullptr, 0);
+            if (rc) return rc;
+            t_end(ctx, SCEMA_T_FILTER);
+            t_begin(ctx, SCEMA_T_EXACT);
+            k_exact_queue<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->d_spline, K, ctx->d_cand.as<uint64_t>(), d_cnt + 0,
+                                                                      ctx->cand_cap, thr, ctx->key_shift, d_cnt + 1,
+                                                                      ctx->edge_cap, ctx->d_edge_key[0].as<uint64_t>(),
+                                                                      ctx->d_edge_val[0].as<double>());
+            ctx->launches++;
+            t_end(ctx, SCEMA_T_EXACT);
+            SCEMA_CUDA(ctx, cudaGetLastError());
         } else {
             const FilterLayout &fl = ctx->fl;
             SCEMA_CUDA(ctx, ctx->d_cand.reserve(ctx->cand_cap * sizeof(uint64_t)));
@@ -1024,11 +1040,13 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
 
 // Common front end: argument checks, buffers, filter copy and schedule. Returns 1 when there is
 // nothing to compare (result: no edges).
-static int compare_begin(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards, Schedule &sc)
+static int compare_begin(scema_ctx *ctx, double thr, int &variant, uint32_t shard, uint32_t n_shards, Schedule &sc)
 {
     if (!ctx->have_spline) return fail(ctx, SCEMA_ERR_STATE, "Spline is not up to date.");
     if (n_shards == 0 || shard >= n_shards) return fail(ctx, SCEMA_ERR_INVALID, "compare: bad shard");
-    if (variant < 0 || variant > 2) return fail(ctx, SCEMA_ERR_INVALID, "compare: bad variant");
+    if (variant < 0 || variant > 3) return fail(ctx, SCEMA_ERR_INVALID, "compare: bad variant");
+    // the tcgen05 filter holds one 64-column fp16 slice per operand row (K <= 60); wider rows take the DMMA filter
+    if (variant == SCEMA_PAIRS_TC && (ctx->have_spline && !tc_supported(ctx))) variant = SCEMA_PAIRS_DMMA;
     if (ctx->n >= (1ull << 32)) return fail(ctx, SCEMA_ERR_INVALID, "compare: more than 2^32-1 histories");
     for (int i = 0; i < 8; i++) ctx->counters[i] = 0;
     for (int w = SCEMA_T_PREP; w <= SCEMA_T_SORT; w++) { ctx->ev_used[w] = false; ctx->acc_ms[w] = 0.f; }
@@ -1046,7 +1064,13 @@ static int compare_begin(scema_ctx *ctx, double thr, int variant, uint32_t shard
     if (rc) return rc;
     make_schedule(ctx, n, sc);
     ctx->counters[4] = sc.tiles;
-    if (variant != SCEMA_PAIRS_EXACT) {
+    if (variant == SCEMA_PAIRS_TC) {
+        t_begin(ctx, SCEMA_T_PREP);
+        rc = tc_prepare(ctx, thr);
+        if (rc) return rc;
+        if (ctx->cand_cap == 0) ctx->cand_cap = std::max<uint64_t>(1ull << 20, 32 * n);
+        t_end(ctx, SCEMA_T_PREP);
+    } else if (variant != SCEMA_PAIRS_EXACT) {
         t_begin(ctx, SCEMA_T_PREP);
         rc = prepare_filter(ctx, variant);
         if (rc) return rc;

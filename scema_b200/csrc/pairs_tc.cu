@@ -1,0 +1,651 @@
+// K2, tensor-core filter on tcgen05 (SCEMA_PAIRS_TC) — the all-pairs distance of
+// compare_histories_with_all_ranks / compare_L2_norm (reference headers/strain2spline.h:546-614,
+// :469-484) filtered on the 5th-generation tensor cores, survivors recomputed exactly.
+//
+// sm_100a has no FP64 kind on tcgen05, so the FP64 contraction a.b of the GEMM form
+//        d^2 = |a|^2 + |b|^2 - 2 a.b
+// is evaluated on split operands: every scaled FP64 element is cut into two fp16 slices
+// a = a_hi + a_lo + r (|r| <= 2^-22 |a|), and one accumulator collects
+//        a_hi.b_hi + a_lo.b_hi + a_hi.b_lo            (kind::f16, fp32 accumulate in TMEM)
+// The four spare columns of every 64-wide slice carry the row terms, so the tensor core itself
+// produces   acc = a.b - h_i - h_j   with h_i = (|a_i|^2 (1 - 2^-13) - T'(1/2 + 2^-12) - e0) / 2, and
+// the pair is PROVABLY rejected by the reference iff acc < 0 — the epilogue only looks at sign bits
+// (one LOP3 per two pairs). Everything else (true edges + a guard band that covers the slicing
+// residual and the fp32 accumulation of the tensor core, DESIGN.md "K2-TC") is a survivor and goes
+// through the same exact FP64 recompute (k_exact_queue) as the DMMA path: the edge list and the
+// distance bits are identical to the reference's.
+//
+// Kernel: warp-specialised, persistent, one CTA per SM; CG = 2 pairs the two SMs of a TPC on one
+// 256 x 256 tile (tcgen05.mma.cta_group::2: each CTA holds 128 rows of A and 128 of the 256 B rows,
+// so B traffic from L2 and the shared-memory reads per SM are halved). Operand blocks are stored in
+// global memory exactly as the 128-byte-swizzled K-major image tcgen05 wants in shared memory, so one
+// block = one contiguous 1-D bulk copy of the TMA engine (no tensor map).
+#include "common.cuh"
+#include <cuda_fp16.h>
+#include <algorithm>
+
+namespace scema {
+namespace tc {
+
+constexpr uint32_t ROWS = 128;                     // rows per operand block
+constexpr uint32_t SLICE_BYTES = ROWS * 128;       // 128 rows x 64 fp16, SW128 K-major
+constexpr uint32_t BLOCK_BYTES = 2 * SLICE_BYTES;  // hi | lo
+constexpr uint32_t COLT = 256;                     // B rows (= pair-matrix columns) per tile
+constexpr uint32_t KMAX = 60;                      // data columns per slice (4 more carry the row terms)
+constexpr long long WAIT_TIMEOUT = 4000000000ll;   // cycles; a wait this long is a bug, trap instead of hanging
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void wait_timeout(uint32_t bar, uint32_t parity, int tag)
+{
+    printf("scema k_filter_tc: barrier wait timed out (block %d thread %d tag %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+           (int)threadIdx.x, tag, bar, parity);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > WAIT_TIMEOUT) wait_timeout(bar, parity, tag);
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta)
+{
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(bar),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int CG>
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    if (CG == 1)
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+// arrive on `bar` (same offset in every CTA of the group) once all MMAs issued so far have completed
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    if (CG == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                     "h"((uint16_t)3)
+                     : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols)
+{
+    if (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// 32 lanes x 64 consecutive fp32 columns: thread t of the warp gets row (lane base + t)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]),
+          "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]),
+          "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]),
+          "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),
+          "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 64-bit shared-memory matrix descriptor, K-major, 128-byte swizzle: 8-row groups 1024 bytes apart
+// (SBO), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B. Address and offsets in 16-byte units.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+}
+
+struct Args {
+    const unsigned char *HA, *HB;  // [n_pad/128][hi|lo][128 rows][128 bytes, 16-byte chunks XOR-swizzled by row & 7]
+    unsigned long long *cand_count;
+    uint64_t *cand;
+    uint64_t cand_cap;
+    uint64_t n;
+    uint32_t NT;       // column tiles (256 rows each)
+    uint32_t I0, I1;   // row range of this launch, in 256-row tiles
+    uint32_t strip_len;
+    uint32_t shard, n_shards;
+    float *dbg;        // debug: every accumulator of every tile, dbg[row * dbg_ld + col]
+    uint64_t dbg_ld;
+};
+
+// Static schedule, identical in every role: work item = (row tile I of 128*CG rows, the column tiles of
+// one strip at or right of the diagonal). Items are numbered strip by strip so that the clusters
+// working at the same time walk the same strip of B (shared through L2); item g belongs to shard
+// g % n_shards, and inside a shard cluster u takes the items u, u + n_units, ...
+template <int CG>
+struct Sched {
+    static constexpr uint32_t RPC = 2 / CG;  // row tiles per column tile
+    uint32_t S, NT, R0, R1, ns, s, shard, n_shards;
+    uint64_t cum, k, stride;
+    __device__ void init(const Args &a, uint32_t unit, uint32_t n_units)
+    {
+        S = a.strip_len; NT = a.NT; R0 = a.I0 * RPC; R1 = a.I1 * RPC;
+        ns = (NT + S - 1) / S; s = a.I0 / S; cum = 0; k = unit; stride = n_units;
+        shard = a.shard; n_shards = a.n_shards;
+    }
+    __device__ uint32_t count(uint32_t strip) const
+    {
+        const uint32_t ce = min((strip + 1) * S, NT) * RPC;
+        const uint32_t e = min(R1, ce);
+        return e > R0 ? e - R0 : 0u;
+    }
+    __device__ bool next(uint32_t &I, uint32_t &J0, uint32_t &J1)
+    {
+        const uint64_t g = k * n_shards + shard;
+        while (s < ns && g >= cum + count(s)) { cum += count(s); s++; }
+        if (s >= ns) return false;
+        I = R0 + (uint32_t)(g - cum);
+        J1 = min((s + 1) * S, NT);
+        J0 = max(I / RPC, s * S);
+        k += stride;
+        return true;
+    }
+};
+
+template <int CG>
+struct Smem {
+    static constexpr uint32_t NST = CG == 2 ? 4 : 2;              // B stages
+    static constexpr uint32_t B_ROWS = COLT / CG;                 // B rows held by one CTA
+    static constexpr uint32_t B_SLICE = B_ROWS * 128;             // bytes of one slice of a B stage
+    static constexpr uint32_t B_STAGE = 2 * B_SLICE;
+    static constexpr uint32_t off_A = 0;                          // 2 x BLOCK_BYTES (A double-buffered over items)
+    static constexpr uint32_t off_B = 2 * BLOCK_BYTES;
+    static constexpr uint32_t off_bar = off_B + NST * B_STAGE;
+    static constexpr uint32_t n_bars = 3 * NST + 6;               // full, pfull, empty | a_empty[2] tfull[2] tempty[2]
+    static constexpr uint32_t off_tmem = off_bar + n_bars * 8;
+    static constexpr uint32_t bytes = off_tmem + 16 + 1024;       // + slack to align the base to 1024
+};
+
+template <int CG, bool DBG>
+__global__ void __launch_bounds__(256, 1) k_filter_tc(const Args a)
+{
+    using SM = Smem<CG>;
+    constexpr uint32_t NST = SM::NST;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t sA = base + SM::off_A, sB = base + SM::off_B, sBar = base + SM::off_bar;
+    auto bar_full = [&](uint32_t i) { return sBar + 8 * i; };
+    auto bar_pfull = [&](uint32_t i) { return sBar + 8 * (NST + i); };
+    auto bar_empty = [&](uint32_t i) { return sBar + 8 * (2 * NST + i); };
+    auto bar_aempty = [&](uint32_t i) { return sBar + 8 * (3 * NST + i); };
+    auto bar_tfull = [&](uint32_t i) { return sBar + 8 * (3 * NST + 2 + i); };
+    auto bar_tempty = [&](uint32_t i) { return sBar + 8 * (3 * NST + 4 + i); };
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_raw + (base - raw) + SM::off_tmem);
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
+    const uint32_t unit = blockIdx.x / CG, n_units = gridDim.x / CG;
+
+    if (tid == 0) {
+        for (uint32_t i = 0; i < NST; i++) { mbar_init(bar_full(i), 1); mbar_init(bar_pfull(i), 1); mbar_init(bar_empty(i), 1); }
+        for (uint32_t i = 0; i < 2; i++) { mbar_init(bar_aempty(i), 1); mbar_init(bar_tfull(i), 1); mbar_init(bar_tempty(i), 4 * CG); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc<CG>(base + SM::off_tmem, 512);
+    fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer: TMA bulk copies
+        if (lane == 0) {
+            Sched<CG> sc;
+            sc.init(a, unit, n_units);
+            uint32_t I, J0, J1, t = 0, item = 0;
+            while (sc.next(I, J0, J1)) {
+                const uint32_t ab = item & 1u;
+                mbar_wait(bar_aempty(ab), ((item >> 1) & 1u) ^ 1u, 1);
+                for (uint32_t J = J0; J < J1; J++, t++) {
+                    const uint32_t st = t % NST;
+                    mbar_wait(bar_empty(st), ((t / NST) & 1u) ^ 1u, 2);
+                    const bool first = J == J0;
+                    mbar_expect_tx(bar_full(st), SM::B_STAGE + (first ? BLOCK_BYTES : 0u));
+                    if (first) bulk_g2s(sA + ab * BLOCK_BYTES, a.HA + (uint64_t)(I * CG + rank) * BLOCK_BYTES, BLOCK_BYTES, bar_full(st));
+                    const uint32_t dst = sB + st * SM::B_STAGE;
+                    if (CG == 2) {
+                        bulk_g2s(dst, a.HB + (uint64_t)(J * 2 + rank) * BLOCK_BYTES, BLOCK_BYTES, bar_full(st));
+                    } else {
+                        // 256 B rows of one CTA: the hi slices of both 128-row blocks, then both lo slices
+                        const unsigned char *b0 = a.HB + (uint64_t)(J * 2) * BLOCK_BYTES;
+                        bulk_g2s(dst, b0, SLICE_BYTES, bar_full(st));
+                        bulk_g2s(dst + SLICE_BYTES, b0 + BLOCK_BYTES, SLICE_BYTES, bar_full(st));
+                        bulk_g2s(dst + 2 * SLICE_BYTES, b0 + SLICE_BYTES, SLICE_BYTES, bar_full(st));
+                        bulk_g2s(dst + 3 * SLICE_BYTES, b0 + BLOCK_BYTES + SLICE_BYTES, SLICE_BYTES, bar_full(st));
+                    }
+                }
+                item++;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // -------------------------------------------------------------- MMA issuer (leader CTA)
+            // instruction descriptor: D fp32, A/B fp16, both K-major, N = 256, M = 128 * CG
+            const uint32_t idesc = (1u << 4) | ((COLT >> 3) << 17) | (((128u * CG) >> 4) << 24);
+            Sched<CG> sc;
+            sc.init(a, unit, n_units);
+            uint32_t I, J0, J1, t = 0, item = 0, tile = 0;
+            while (sc.next(I, J0, J1)) {
+                const uint32_t ab = item & 1u;
+                const uint64_t adesc = make_desc(sA + ab * BLOCK_BYTES);
+                for (uint32_t J = J0; J < J1; J++, t++, tile++) {
+                    const uint32_t as = tile & 1u;
+                    mbar_wait(bar_tempty(as), ((tile >> 1) & 1u) ^ 1u, 3);
+                    const uint32_t st = t % NST, ph = (t / NST) & 1u;
+                    mbar_wait(bar_full(st), ph, 4);
+                    if (CG == 2) mbar_wait(bar_pfull(st), ph, 5);
+                    fence_after();
+                    const uint64_t bdesc = make_desc(sB + st * SM::B_STAGE);
+                    const uint32_t d_tmem = tmem_base + as * COLT;
+#pragma unroll
+                    for (uint32_t term = 0; term < 3; term++) {
+                        // a_hi.b_hi, a_lo.b_hi, a_hi.b_lo
+                        const uint32_t a_off = (term == 1 ? SLICE_BYTES : 0u) >> 4;
+                        const uint32_t b_off = (term == 2 ? SM::B_SLICE : 0u) >> 4;
+#pragma unroll
+                        for (uint32_t kk = 0; kk < 4; kk++)
+                            umma_f16<CG>(d_tmem, adesc + a_off + 2 * kk, bdesc + b_off + 2 * kk, idesc, (term | kk) != 0 ? 1u : 0u);
+                    }
+                    umma_commit<CG>(bar_empty(st));
+                    umma_commit<CG>(bar_tfull(as));
+                    if (J == J1 - 1) umma_commit<CG>(bar_aempty(ab));
+                }
+                item++;
+            }
+        } else if (CG == 2 && lane == 0 && rank == 1) {
+            // ---------------------------- peer CTA: tell the leader when this CTA's half of a stage landed
+            Sched<CG> sc;
+            sc.init(a, unit, n_units);
+            uint32_t I, J0, J1, t = 0;
+            while (sc.next(I, J0, J1))
+                for (uint32_t J = J0; J < J1; J++, t++) {
+                    const uint32_t st = t % NST;
+                    mbar_wait(bar_full(st), (t / NST) & 1u, 6);
+                    mbar_arrive_cluster(bar_pfull(st), 0);
+                }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------------- epilogue (4 warps)
+        const uint32_t q = warp & 3u;  // TMEM lane quarter this warp may read
+        Sched<CG> sc;
+        sc.init(a, unit, n_units);
+        uint32_t I, J0, J1, tile = 0;
+        while (sc.next(I, J0, J1)) {
+            const uint64_t row = (uint64_t)(I * CG + rank) * ROWS + q * 32 + lane;
+            for (uint32_t J = J0; J < J1; J++, tile++) {
+                const uint32_t as = tile & 1u;
+                mbar_wait(bar_tfull(as), (tile >> 1) & 1u, 7);
+                fence_after();
+#pragma unroll 1
+                for (uint32_t ch = 0; ch < 4; ch++) {
+                    uint32_t v[64];
+                    tmem_ld64(tmem_base + ((q * 32u) << 16) + as * COLT + ch * 64u, v);
+                    tmem_ld_wait();
+                    // acc < 0 for every pair <=> the AND of the bit patterns keeps the sign bit
+                    uint32_t all_neg = v[0];
+#pragma unroll
+                    for (int c = 1; c < 64; c++) all_neg &= v[c];
+                    const uint64_t col0 = (uint64_t)J * COLT + ch * 64u;
+                    if (DBG && a.dbg) {
+#pragma unroll
+                        for (int c = 0; c < 64; c++) a.dbg[row * a.dbg_ld + col0 + c] = __uint_as_float(v[c]);
+                    }
+                    if (__any_sync(0xffffffffu, (all_neg >> 31) == 0u)) {
+#pragma unroll
+                        for (int c = 0; c < 64; c++) {
+                            const uint64_t col = col0 + c;
+                            const bool keep = (v[c] >> 31) == 0u && row < col && col < a.n;
+                            const unsigned m = __ballot_sync(0xffffffffu, keep);
+                            if (m) {
+                                const int leader = __ffs(m) - 1;
+                                unsigned long long pos = 0;
+                                if ((int)lane == leader) pos = atomicAdd(a.cand_count, (unsigned long long)__popc(m));
+                                pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(m & ((1u << lane) - 1u));
+                                if (keep && pos < a.cand_cap) a.cand[pos] = (row << 32) | col;
+                            }
+                        }
+                    }
+                }
+                // the accumulator stage is free again
+                fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_cluster(bar_tempty(as), 0);
+                    else mbar_arrive_local(bar_tempty(as));
+                }
+            }
+        }
+    }
+
+    // teardown: nobody may leave (or free TMEM) while its partner CTA can still signal it
+    fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    fence_after();
+    if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand preparation
+// ------------------------------------------------------------------------------------------------
+// pass 1: row norms (FP64) and the largest finite magnitude of the matrix
+__global__ void __launch_bounds__(256) k_tc_rowstats(const double *__restrict__ S, uint64_t n, uint32_t K,
+                                                     double *__restrict__ NRM, unsigned long long *__restrict__ gmax)
+{
+    const uint64_t row = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double nrm = 0.0, m = 0.0;
+    for (uint32_t k = lane; k < K; k += 32) {
+        const double v = S[row * K + k];
+        nrm = fma(v, v, nrm);
+        m = fmax(m, fabs(v));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    if (lane == 0) {
+        NRM[row] = nrm;
+        if (isfinite(nrm)) atomicMax(gmax, (unsigned long long)__double_as_longlong(m));  // non-negative doubles order as integers
+    }
+}
+
+// Power-of-two scale that brings the largest finite magnitude into [2^11, 2^12).
+__device__ __forceinline__ double tc_scale(double maxabs)
+{
+    if (!(maxabs > 0.0)) return 1.0;
+    int se = 11 - ilogb(maxabs);
+    se = max(-1000, min(1000, se));
+    return scalbn(1.0, se);
+}
+
+// pass 2: one warp per row. Writes the row's hi and lo fp16 slices (60 data columns + 4 columns
+// carrying the row term -h_i split three ways against the constant 2^14 on the other operand) into
+// the A-flavoured and the B-flavoured copy, already in the swizzled shared-memory image.
+//   A hi: [x0 x1 P P]   A lo: [x2 0 0 0]        B hi: [P P x0 x1]   B lo: [0 0 x2 0]
+// so that  A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  adds  P (x0 + x1 + x2)_i + P (x0 + x1 + x2)_j = -h_i - h_j.
+__global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, uint64_t n, uint64_t n_pad, uint32_t K,
+                                                 const double *__restrict__ NRM, const unsigned long long *__restrict__ gmax,
+                                                 double T0, unsigned char *__restrict__ HA, unsigned char *__restrict__ HB)
+{
+    const uint64_t row = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    const double s = tc_scale(__longlong_as_double((long long)*gmax));
+    const bool real = row < n;
+    const bool wild = real && !isfinite(NRM[row]);
+    double v[2] = {0.0, 0.0};
+    double nrm = 0.0;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const uint32_t k = lane + 32 * e;
+        if (real && !wild && k < K) v[e] = S[row * K + k] * s;
+        nrm = fma(v[e], v[e], nrm);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    // row term
+    const double T0s = (T0 * s) * s;
+    const double e0 = (double)K * 9.5367431640625e-07;                                   // K 2^-20
+    const double h = 0.5 * (nrm * (1.0 - 0.0001220703125) - T0s * (0.5 + 0.000244140625) - e0);  // 2^-13, 2^-12
+    const double x = -h * 6.103515625e-05;                                               // / 2^14
+    double x0, x1, x2;
+    if (!real) { x0 = x1 = -65504.0; x2 = 0.0; }            // padding row: never a survivor
+    else if (wild || !(x <= 65000.0)) { x0 = x1 = 65504.0; x2 = 0.0; }  // NaN/inf row, or threshold beyond every distance: always
+    else {
+        x0 = (double)__half2float(__double2half(x));
+        x1 = (double)__half2float(__double2half(x - x0));
+        x2 = (double)__half2float(__double2half(x - x0 - x1));
+    }
+    const uint64_t blk = row / ROWS;
+    const uint32_t r = (uint32_t)(row % ROWS);
+    unsigned char *a_hi = HA + blk * BLOCK_BYTES + (uint64_t)r * 128, *a_lo = a_hi + SLICE_BYTES;
+    unsigned char *b_hi = HB + blk * BLOCK_BYTES + (uint64_t)r * 128, *b_lo = b_hi + SLICE_BYTES;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const uint32_t k = lane + 32 * e;  // column 0..63 of the slice
+        const __half hi = __double2half(v[e]);
+        const __half lo = __double2half(v[e] - (double)__half2float(hi));
+        __half ahi = hi, alo = lo, bhi = hi, blo = lo;
+        if (k >= KMAX) {
+            const double P = 16384.0, Z = 0.0;
+            const uint32_t c = k - KMAX;
+            ahi = __double2half(c == 0 ? x0 : c == 1 ? x1 : P);
+            alo = __double2half(c == 0 ? x2 : Z);
+            bhi = __double2half(c == 2 ? x0 : c == 3 ? x1 : P);
+            blo = __double2half(c == 2 ? x2 : Z);
+        }
+        const uint32_t off = ((((k >> 3) ^ (r & 7u)) << 4) | ((k & 7u) << 1));  // swizzled 16-byte chunk, element in chunk
+        *reinterpret_cast<__half *>(a_hi + off) = ahi;
+        *reinterpret_cast<__half *>(a_lo + off) = alo;
+        *reinterpret_cast<__half *>(b_hi + off) = bhi;
+        *reinterpret_cast<__half *>(b_lo + off) = blo;
+    }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+bool tc_supported(const scema_ctx *ctx) { return ctx->K >= 1 && ctx->K <= tc::KMAX; }
+
+// Builds (or reuses) the fp16 operand copies for the current spline matrix and threshold.
+int tc_prepare(scema_ctx *ctx, double thr)
+{
+    const uint64_t n = ctx->n;
+    const uint32_t K = ctx->K;
+    const uint64_t n_pad = (n + tc::COLT - 1) / tc::COLT * tc::COLT;
+    if (ctx->tc_for_version == ctx->spline_version && ctx->tc_thr == thr && ctx->tc_n == n && ctx->tc_K == K && ctx->tc_valid)
+        return SCEMA_OK;
+    SCEMA_CUDA(ctx, ctx->d_tc_a.reserve(n_pad * 256));
+    SCEMA_CUDA(ctx, ctx->d_tc_b.reserve(n_pad * 256));
+    SCEMA_CUDA(ctx, ctx->d_tc_nrm.reserve(n_pad * sizeof(double)));
+    SCEMA_CUDA(ctx, ctx->d_tc_misc.reserve(64));
+    SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_tc_misc.p, 0, 64, ctx->stream));
+    tc::k_tc_rowstats<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(ctx->d_spline, n, K, ctx->d_tc_nrm.as<double>(),
+                                                                        ctx->d_tc_misc.as<unsigned long long>());
+    const double eps = 1.1102230246251565e-16;  // 2^-53
+    const double T0 = thr * thr * (1.0 + (2.0 * K + 16.0) * eps) * (1.0 + 4.0 * eps);
+    tc::k_tc_prep<<<(unsigned)((n_pad + 7) / 8), 256, 0, ctx->stream>>>(ctx->d_spline, n, n_pad, K, ctx->d_tc_nrm.as<double>(),
+                                                                        ctx->d_tc_misc.as<unsigned long long>(), T0,
+                                                                        ctx->d_tc_a.as<unsigned char>(), ctx->d_tc_b.as<unsigned char>());
+    ctx->launches += 2;
+    SCEMA_CUDA(ctx, cudaGetLastError());
+    ctx->tc_for_version = ctx->spline_version;
+    ctx->tc_thr = thr;
+    ctx->tc_n = n;
+    ctx->tc_K = K;
+    ctx->tc_valid = true;
+    return SCEMA_OK;
+}
+
+template <int CG, bool DBG>
+static int tc_launch_t(scema_ctx *ctx, const tc::Args &a, uint64_t items)
+{
+    auto kern = tc::k_filter_tc<CG, DBG>;
+    const size_t smem = tc::Smem<CG>::bytes;
+    if (smem > ctx->smem_optin) return fail(ctx, SCEMA_ERR_CUDA, "tensor-core filter: shared memory exceeds device limit");
+    SCEMA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint64_t units = std::min<uint64_t>((uint64_t)ctx->sm_count / CG, std::max<uint64_t>(items, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(units * CG));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SCEMA_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, a));
+    ctx->launches++;
+    return SCEMA_OK;
+}
+
+// Filter the pairs of the row tiles [I0, I1) (256-row units) that belong to this shard; survivors go
+// to the candidate queue (cand_count is d_counters[0]). dbg != nullptr selects the instrumented kernel.
+int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t shard, uint32_t n_shards, unsigned long long *cand_count,
+              float *dbg, uint64_t dbg_ld)
+{
+    tc::Args a;
+    a.HA = ctx->d_tc_a.as<unsigned char>();
+    a.HB = ctx->d_tc_b.as<unsigned char>();
+    a.cand_count = cand_count;
+    a.cand = ctx->d_cand.as<uint64_t>();
+    a.cand_cap = ctx->cand_cap;
+    a.n = ctx->n;
+    a.NT = (uint32_t)((ctx->n + tc::COLT - 1) / tc::COLT);
+    a.I0 = I0;
+    a.I1 = std::min<uint32_t>(I1, a.NT);
+    a.shard = shard;
+    a.n_shards = n_shards;
+    a.dbg = dbg;
+    a.dbg_ld = dbg_ld;
+    static const char *cg_env = getenv("SCEMA_TC_CG");
+    const int cg = (cg_env && atoi(cg_env) == 1) ? 1 : 2;
+    // strips: long enough to amortise the A tile, short enough to leave every cluster many items
+    const uint64_t rows = a.I1 > a.I0 ? a.I1 - a.I0 : 0;
+    const uint64_t tiles = rows * a.NT;  // upper bound
+    const uint64_t units = (uint64_t)ctx->sm_count / cg;
+    a.strip_len = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, tiles / (units * 32 * std::max<uint32_t>(n_shards, 1))));
+    if (rows == 0) return SCEMA_OK;
+    // items of this shard (upper bound is enough to size the grid)
+    const uint64_t n_strips = (a.NT + a.strip_len - 1) / a.strip_len;
+    const uint64_t items = std::max<uint64_t>(1, rows * (2 / cg) * n_strips / std::max<uint32_t>(n_shards, 1));
+    if (cg == 1) return dbg ? tc_launch_t<1, true>(ctx, a, items) : tc_launch_t<1, false>(ctx, a, items);
+    return dbg ? tc_launch_t<2, true>(ctx, a, items) : tc_launch_t<2, false>(ctx, a, items);
+}
+
+// Debug / validation entry (scema_tc_debug): runs the instrumented kernel over the whole pair matrix
+// and returns every accumulator (acc_host[row * ld + col], ld >= n_pad) and the operand copies, so a
+// test can redo the sliced contraction in FP64 and check the layout, the fold columns and the
+// accumulation-error model against the hardware.
+int tc_debug_run(scema_ctx *ctx, double thr, float *acc_host, uint64_t ld, unsigned char *ha_host, unsigned char *hb_host)
+{
+    if (!ctx->have_spline) return fail(ctx, SCEMA_ERR_STATE, "Spline is not up to date.");
+    if (!tc_supported(ctx)) return fail(ctx, SCEMA_ERR_INVALID, "tensor-core filter needs 1 <= K <= 60");
+    const uint64_t n_pad = (ctx->n + tc::COLT - 1) / tc::COLT * tc::COLT;
+    if (ld < n_pad) return fail(ctx, SCEMA_ERR_INVALID, "tc_debug: ld < padded n");
+    if (n_pad > 8192) return fail(ctx, SCEMA_ERR_INVALID, "tc_debug: at most 8192 rows");
+    int rc = tc_prepare(ctx, thr);
+    if (rc) return rc;
+    SCEMA_CUDA(ctx, ctx->d_counters.reserve(8 * sizeof(uint64_t)));
+    SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(uint64_t), ctx->stream));
+    if (ctx->cand_cap == 0) ctx->cand_cap = 1ull << 20;
+    SCEMA_CUDA(ctx, ctx->d_cand.reserve(ctx->cand_cap * sizeof(uint64_t)));
+    DevBuf dbg;
+    SCEMA_CUDA(ctx, dbg.reserve(n_pad * n_pad * sizeof(float)));
+    SCEMA_CUDA(ctx, cudaMemsetAsync(dbg.p, 0xFF, n_pad * n_pad * sizeof(float), ctx->stream));  // NaN = never written
+    rc = tc_launch(ctx, 0, (uint32_t)(n_pad / tc::COLT), 0, 1, ctx->d_counters.as<unsigned long long>(), dbg.as<float>(), n_pad);
+    if (rc) { dbg.release(); return rc; }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && acc_host)
+        e = cudaMemcpy2D(acc_host, ld * sizeof(float), dbg.p, n_pad * sizeof(float), n_pad * sizeof(float), n_pad, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && ha_host) e = cudaMemcpy(ha_host, ctx->d_tc_a.p, n_pad * 256, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && hb_host) e = cudaMemcpy(hb_host, ctx->d_tc_b.p, n_pad * 256, cudaMemcpyDeviceToHost);
+    dbg.release();
+    if (e != cudaSuccess) return fail(ctx, SCEMA_ERR_CUDA, std::string("tc_debug: ") + cudaGetErrorString(e));
+    return SCEMA_OK;
+}
+
+}  // namespace scema
