@@ -5,7 +5,8 @@
   python bench.py --impl reference --gpus N --steps K --warmup W
 
 A "step" is one pass of the hot path over the synthetic batch: K1 ragged spline resample of every
-history -> (N>1: one NCCL all-gather of the resampled rows) -> K2 all-pairs GEMM-form filter (DMMA)
+history -> (N>1: one NCCL all-gather of the resampled rows) -> K2 all-pairs GEMM-form filter (tcgen05
+split-fp16 tensor-core filter; --variant dmma selects the FP64 DMMA filter)
 + exact recompute of the survivors -> K3 edge compaction -> canonical sort (-> N>1: all-gather of
 the edge counts). Workload (BASELINE.json configs[3], the one the 1/2/4/8 scaling is quoted on; it
 fits one GPU): 1M histories x 6 components x 10 spline points, all-pairs = 5.0e11 unordered pairs,
@@ -203,7 +204,9 @@ def run_ours(args, wl, wl_name):
         dist.init_process_group("nccl", device_id=dev)
     n, P = wl["n"], wl["P"]
     K = 6 * P
-    variant = {"dmma": 0, "fma": 1, "exact": 2}[args.variant]
+    variant = {"dmma": 0, "fma": 1, "exact": 2, "tc": 3}[args.variant]
+    # the tcgen05 filter holds one 64-column fp16 slice per row: wider rows (config 5) take the DMMA filter
+    eff_variant = "dmma" if (args.variant == "tc" and K > 60) else args.variant
     pert = synth.default_pert(THR, P)
     b, e = shard_bounds(n, world)[rank]
     n_local = e - b
@@ -320,26 +323,63 @@ def run_ours(args, wl, wl_name):
         pairs_this_rank = total_pairs / world
         filt_ms = acc["filter"] / max(acc["steps"], 1)
         achieved = pairs_this_rank * 2 * K / (filt_ms * 1e-3) / 1e12 if filt_ms > 0 else None
-        # issue-rate probe, taken twice (the first call also warms the clocks back up after the host-side
-        # bookkeeping above); the better of the two is the denominator
-        peaks = [hc.fp64_peak() for _ in range(2)]
-        key = "dmma_tflops" if variant == 0 else "dfma_tflops"
-        peak = max(p[key] for p in peaks)
+        NT = (n + 255) // 256
+        if eff_variant == "tc":
+            # tensor roofline: the denominators are the driver-measured cuBLAS bf16 figures (fp16 runs at the
+            # same rate). `achieved` stays ALGORITHMIC (2K flops per unordered pair); the filter executes 3
+            # sliced products of 64 columns over whole 256 x 256 tiles of the upper triangle = `executed`.
+            mp, src = {}, "fallback"
+            try:
+                mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                src = "measured"
+            except Exception:
+                mp = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+            peak = float(mp.get("bf16_tflops", 1590.0))
+            tc_slices = hc.counters().get("tc_slices", 2) or 2
+            n_products = 1 if tc_slices == 1 else 3
+            executed = (NT * (NT + 1) / 2) / world * 256 * 256 * n_products * 64 * 2 / (filt_ms * 1e-3) / 1e12 if filt_ms > 0 else None
+            extra = {"tc_slices": tc_slices, "executed_tflops": executed, "frac_executed": (executed / peak) if executed else None,
+                     "peak_sustained": mp.get("bf16_tflops_sustained"),
+                     "kernel": "k_filter_tc (K2 GEMM-form filter on tcgen05, split fp16, fp32 accumulate in TMEM)",
+                     "peak_source": "of %s: MEASURED_PEAKS.json bf16_tflops (cuBLAS bf16 8192^3 burst); the kernel is timed "
+                                    "alone per launch (CUDA events around it); sustained figure beside it" % src}
+            if tc_slices == 1:
+                # what actually bounds the one-slice kernel: every pair's fp32 accumulator has to come out of tensor
+                # memory once (tcgen05.ld moves 128 B/clk/SM = 32 pairs/clk/SM; ncu: tensor pipe 48 % busy)
+                mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+                ceiling = 148 * 32 * mhz * 1e6
+                extra["limiter"] = {"what": "TMEM read-out of the accumulators (tcgen05.ld, 4 bytes per pair, 128 B/clk/SM)",
+                                    "ceiling_pairs_per_s": ceiling,
+                                    "frac_of_ceiling": (pairs_this_rank / (filt_ms * 1e-3)) / ceiling if filt_ms > 0 else None}
+            else:
+                extra["limiter"] = {"what": "tensor pipe (ncu: 90 % busy, SM clock pulled to 1.70 GHz by the power cap)"}
+            fp64 = max(hc.fp64_peak()["dmma_tflops"] for _ in range(2))
+            extra["fp64_dmma_peak_tflops"] = fp64
+            extra["achieved_over_fp64_peak"] = (achieved / fp64) if achieved else None
+            tkey = f"tc:{wl_name}:{n}"
+        else:
+            # issue-rate probe, taken twice (the first call also warms the clocks back up after the host-side
+            # bookkeeping above); the better of the two is the denominator
+            peaks = [hc.fp64_peak() for _ in range(2)]
+            key = "dmma_tflops" if eff_variant == "dmma" else "dfma_tflops"
+            peak = max(p[key] for p in peaks)
+            extra = {"kernel": "k_filter (K2 GEMM-form filter, %s)" % eff_variant,
+                     "peak_source": "measured live on this GPU: FP64 %s issue-rate probe (scema_fp64_peak); "
+                                    "MEASURED_PEAKS.json has no FP64 figure" % ("DMMA m8n8k4" if eff_variant == "dmma" else "DFMA")}
+            tkey = f"{wl_name}:{n}"
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "filter_traffic.json")
         if world == 1 and os.path.exists(tfile):
             try:
-                traffic = json.load(open(tfile)).get(f"{wl_name}:{n}")
+                traffic = json.load(open(tfile)).get(tkey)
             except Exception:
                 traffic = None
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                    "kernel": "k_filter (K2 GEMM-form filter, %s)" % args.variant,
-                    "peak_source": "measured live on this GPU: FP64 %s issue-rate probe (scema_fp64_peak); "
-                                   "MEASURED_PEAKS.json has no FP64 figure" % ("DMMA m8n8k4" if variant == 0 else "DFMA"),
                     "launch_ms": filt_ms,
                     "other_kernels_ms": {k: acc[k] / max(acc["steps"], 1)
                                          for k in ("resample", "prep", "exact", "sort") + (("allgather",) if world > 1 else ())}}
+        roofline.update(extra)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             m = min(n, 65536)
@@ -365,8 +405,11 @@ def run_ours(args, wl, wl_name):
             "metric": "history pair comparisons/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{wl_name}: {wl['desc']}", "histories": n, "spline_points": P, "threshold": THR,
-                       "raw_steps_per_history": [wl["lmin"], wl["lmax"]], "cluster_size": CLUSTER, "variant": args.variant,
+            "config": {"workload": f"{wl_name}: {wl['desc']}", "histories": n,
+                       "filter_arithmetic": ("fp16 x2 split operands on tcgen05, fp32 accumulate; every survivor and every emitted "
+                                             "distance recomputed in f64 in the reference's operation order")
+                       if eff_variant == "tc" else "f64", "spline_points": P, "threshold": THR,
+                       "raw_steps_per_history": [wl["lmin"], wl["lmax"]], "cluster_size": CLUSTER, "variant": eff_variant,
                        "parallelism": f"tile-shard x{world}", "l2": "inputs (raw histories + spline matrix) larger than L2",
                        "edges": acc["edges"], "survivors_last_rank0": acc["survivors"]},
             "clocks": clocks,
@@ -410,7 +453,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", default="dmma", choices=["dmma", "fma", "exact"])
+    ap.add_argument("--variant", default="tc", choices=["tc", "dmma", "fma", "exact"])
     ap.add_argument("--histories", type=int, default=0, help="override the workload's history count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stream", type=int, default=-1,

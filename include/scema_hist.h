@@ -40,7 +40,10 @@ extern "C" {
  * kind::f16 with fp32 accumulators in tensor memory, row norms and threshold folded into spare operand
  * columns so that the sign of the accumulator decides; survivors (edges + a guard band covering the
  * slicing and accumulation error) take the same exact FP64 recompute. Same edge list, same distance
- * bits. Needs 6 * spline_points <= 60; wider rows silently take SCEMA_PAIRS_DMMA. */
+ * bits. Needs 6 * spline_points <= 60; wider rows silently take SCEMA_PAIRS_DMMA. The filter starts
+ * with the hi slices alone (a third of the tensor work, guard band 2^-9 of the squared norms) and
+ * repeats with both slices (2^-13) when the survivors overflow the candidate queue;
+ * SCEMA_TC_SLICES=1|2 in the environment pins the choice. */
 #define SCEMA_PAIRS_TC 3
 
 typedef struct scema_ctx scema_ctx;
@@ -168,18 +171,20 @@ int scema_reduce_dir(const char *input_folder, const char *out_mapping_csv, uint
 /* CUDA-event durations (ms) of the phases of the last resample/compare on this context. */
 int scema_last_timings(scema_ctx *ctx, float ms[SCEMA_T_COUNT]);
 /* Counters of the last compare: [0] pairs evaluated by the filter, [1] survivors recomputed
- * exactly, [2] edges, [3] passes (>1 when a buffer had to grow), [4] tiles. */
+ * exactly, [2] edges, [3] passes (>1 when a buffer had to grow), [4] tiles, [5] fp16 slices the
+ * tcgen05 filter ended up using (SCEMA_PAIRS_TC only). */
 int scema_last_counters(scema_ctx *ctx, uint64_t counters[8]);
 /* Total kernels launched by this context so far. */
 uint64_t scema_kernel_launches(const scema_ctx *ctx);
 /* Validation hook of SCEMA_PAIRS_TC (tests only; n padded to 256 must be <= 8192): runs the instrumented
  * tcgen05 kernel over the whole pair matrix of the current spline rows. acc_host[row * ld + col] receives
- * every fp32 accumulator (a.b - h_row - h_col in the scaled units of the operands), operand_a_host /
+ * every fp32 accumulator (a.b - h_row - h_col in the scaled units of the operands; slices = 2: all three
+ * sliced products, slices = 1: a_hi.b_hi only, with the wider guard band folded in), operand_a_host /
  * operand_b_host (n_pad * 256 bytes each, may be NULL) the fp16 operand copies as they sit in memory:
  * blocks of 128 rows, each [hi slice | lo slice] of 128 rows x 128 bytes, 16-byte chunk c of row r
  * stored at chunk c ^ (r & 7). */
-int scema_tc_debug(scema_ctx *ctx, double threshold, float *acc_host, uint64_t ld, void *operand_a_host,
-                   void *operand_b_host);
+int scema_tc_debug(scema_ctx *ctx, double threshold, uint32_t slices, float *acc_host, uint64_t ld,
+                   void *operand_a_host, void *operand_b_host);
 /* Measured FP64 issue rates on the context's device (TFLOP/s): out[0] DFMA, out[1] DMMA m8n8k4. */
 int scema_fp64_peak(scema_ctx *ctx, double out[2]);
 

@@ -15,10 +15,11 @@ from .binding import (  # noqa: F401
     PAIRS_DMMA,
     PAIRS_FMA,
     PAIRS_EXACT,
+    PAIRS_TC,
     lib,
     lib_path,
     reduce_dir,
 )
 
-__all__ = ["HistCluster", "ScemaError", "PAIRS_DMMA", "PAIRS_FMA", "PAIRS_EXACT", "lib", "lib_path",
+__all__ = ["HistCluster", "ScemaError", "PAIRS_DMMA", "PAIRS_FMA", "PAIRS_EXACT", "PAIRS_TC", "lib", "lib_path",
            "reduce_dir"]

@@ -63,7 +63,7 @@ def lib():
         "scema_last_counters": (i32, [vp, P(u64)]),
         "scema_kernel_launches": (u64, [vp]),
         "scema_fp64_peak": (i32, [vp, P(dbl)]),
-        "scema_tc_debug": (i32, [vp, dbl, vp, u64, vp, vp]),
+        "scema_tc_debug": (i32, [vp, dbl, u32, vp, u64, vp, vp]),
         "scema_ingest_last_error": (C.c_char_p, []),
         "scema_batch_read_dir": (i32, [C.c_char_p, u32, P(vp)]),
         "scema_batch_read_files": (i32, [P(C.c_char_p), vp, u64, u32, P(vp)]),
@@ -289,13 +289,13 @@ class HistCluster:
         return out
 
     # ---- compare ----
-    def compare(self, threshold, variant=PAIRS_DMMA, shard=0, n_shards=1):
+    def compare(self, threshold, variant=PAIRS_TC, shard=0, n_shards=1):
         ne = C.c_uint64(0)
         self._ck(self._L.scema_compare(self._h, float(threshold), int(variant), int(shard), int(n_shards), C.byref(ne)))
         self.n_edges = int(ne.value)
         return self.n_edges
 
-    def compare_stream(self, threshold, sink, variant=PAIRS_DMMA, shard=0, n_shards=1, panels_per_chunk=0):
+    def compare_stream(self, threshold, sink, variant=PAIRS_TC, shard=0, n_shards=1, panels_per_chunk=0):
         """Chunked compare; sink(a, b, d) is called with numpy copies of every chunk's sorted edges.
         -> total number of edges."""
         SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_double),
@@ -340,7 +340,7 @@ class HistCluster:
         self._ck(self._L.scema_get_degrees(self._h, _ptr(out)))
         return out
 
-    def cluster(self, steps, offsets, ids, spline_points, threshold, variant=PAIRS_DMMA):
+    def cluster(self, steps, offsets, ids, spline_points, threshold, variant=PAIRS_TC):
         steps = np.ascontiguousarray(steps, dtype=np.float64)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)
@@ -369,19 +369,20 @@ class HistCluster:
     def counters(self):
         c = (C.c_uint64 * 8)()
         self._ck(self._L.scema_last_counters(self._h, c))
-        return {"pairs": int(c[0]), "survivors": int(c[1]), "edges": int(c[2]), "passes": int(c[3]), "tiles": int(c[4])}
+        return {"pairs": int(c[0]), "survivors": int(c[1]), "edges": int(c[2]), "passes": int(c[3]), "tiles": int(c[4]),
+                "tc_slices": int(c[5])}
 
     def kernel_launches(self):
         return int(self._L.scema_kernel_launches(self._h))
 
-    def tc_debug(self, threshold, n):
+    def tc_debug(self, threshold, n, slices=2):
         """Accumulators and operand copies of the tcgen05 filter over the whole pair matrix (tests only).
         Returns (acc [n_pad, n_pad] float32, A operand bytes, B operand bytes)."""
         n_pad = (n + 255) // 256 * 256
         acc = np.empty((n_pad, n_pad), dtype=np.float32)
         ha = np.empty(n_pad * 256, dtype=np.uint8)
         hb = np.empty(n_pad * 256, dtype=np.uint8)
-        self._ck(self._L.scema_tc_debug(self._h, float(threshold), _ptr(acc), n_pad, _ptr(ha), _ptr(hb)))
+        self._ck(self._L.scema_tc_debug(self._h, float(threshold), int(slices), _ptr(acc), n_pad, _ptr(ha), _ptr(hb)))
         return acc, ha, hb
 
     def fp64_peak(self):

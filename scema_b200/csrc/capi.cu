@@ -371,11 +371,12 @@ int scema_fp64_peak(scema_ctx *c, double out[2])
     return fp64_peak_run(c, out);
 }
 
-int scema_tc_debug(scema_ctx *c, double threshold, float *acc_host, uint64_t ld, void *operand_a_host, void *operand_b_host)
+int scema_tc_debug(scema_ctx *c, double threshold, uint32_t slices, float *acc_host, uint64_t ld, void *operand_a_host,
+                   void *operand_b_host)
 {
     int rc = enter(c);
     if (rc) return rc;
-    return tc_debug_run(c, threshold, acc_host, ld, (unsigned char *)operand_a_host, (unsigned char *)operand_b_host);
+    return tc_debug_run(c, threshold, slices, acc_host, ld, (unsigned char *)operand_a_host, (unsigned char *)operand_b_host);
 }
 
 }  // extern "C"

@@ -105,7 +105,8 @@ struct scema_ctx {
     // ---- K2 tensor-core filter (SCEMA_PAIRS_TC): fp16 split operands, A- and B-flavoured
     scema::DevBuf d_tc_a, d_tc_b, d_tc_nrm, d_tc_misc;
     uint64_t tc_for_version = 0, tc_n = 0;
-    uint32_t tc_K = 0;
+    uint32_t tc_K = 0, tc_slices = 0;
+    uint32_t tc_mode = 0;  // slices the next compare starts with (auto: 1, falling back to 2 when survivors overflow)
     double tc_thr = 0.0;
     bool tc_valid = false;
 
@@ -164,10 +165,11 @@ int compare_stream_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, 
 int fp64_peak_run(scema_ctx *ctx, double out[2]);
 // pairs_tc.cu
 bool tc_supported(const scema_ctx *ctx);
-int tc_prepare(scema_ctx *ctx, double thr);
+int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices);
 int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t shard, uint32_t n_shards, unsigned long long *cand_count,
               float *dbg, uint64_t dbg_ld);
-int tc_debug_run(scema_ctx *ctx, double thr, float *acc_host, uint64_t ld, unsigned char *ha_host, unsigned char *hb_host);
+int tc_debug_run(scema_ctx *ctx, double thr, uint32_t slices, float *acc_host, uint64_t ld, unsigned char *ha_host,
+                 unsigned char *hb_host);
 // host_io.cc
 int write_similar_hist(scema_ctx *ctx, const char *pattern);
 int reduce_graph_calls(const uint32_t *eu, const uint32_t *ev, uint64_t n_calls, uint32_t num_gps,

@@ -999,6 +999,12 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
         }
         SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         const uint64_t n_cand = ctx->h_counters[0], n_edge = ctx->h_counters[1];
+        if (*variant == SCEMA_PAIRS_TC && ctx->tc_slices == 1 && ctx->tc_mode == 1 && n_cand > ctx->cand_cap) {
+            // the one-slice guard band keeps too much of this data: filter with both slices before growing the queue
+            rc = tc_prepare(ctx, thr, 2);
+            if (rc) return rc;
+            continue;
+        }
         if (*variant != SCEMA_PAIRS_EXACT && n_cand > ctx->cand_cap) {
             SCEMA_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
             const uint64_t want = n_cand + n_cand / 4;
@@ -1016,6 +1022,7 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
         }
         ctx->counters[1] += n_cand;
         ctx->counters[3] += passes;
+        if (*variant == SCEMA_PAIRS_TC) ctx->counters[5] = ctx->tc_slices;
         ctx->n_edges = n_edge;
         break;
     }
@@ -1066,7 +1073,16 @@ static int compare_begin(scema_ctx *ctx, double thr, int &variant, uint32_t shar
     ctx->counters[4] = sc.tiles;
     if (variant == SCEMA_PAIRS_TC) {
         t_begin(ctx, SCEMA_T_PREP);
-        rc = tc_prepare(ctx, thr);
+        // Start with the hi slices alone unless the environment pins the choice or these very rows and
+        // threshold already needed both slices (compare_panels falls back when the survivors overflow).
+        static const char *sl_env = getenv("SCEMA_TC_SLICES");
+        const int pin = sl_env ? atoi(sl_env) : 0;
+        uint32_t slices = pin == 2 ? 2u : 1u;
+        if (pin != 1 && pin != 2 && ctx->tc_valid && ctx->tc_for_version == ctx->spline_version && ctx->tc_thr == thr &&
+            ctx->tc_n == n && ctx->tc_K == ctx->K)
+            slices = ctx->tc_slices;
+        ctx->tc_mode = (pin == 1 || pin == 2) ? 0u : 1u;  // 1: may fall back to two slices
+        rc = tc_prepare(ctx, thr, slices);
         if (rc) return rc;
         if (ctx->cand_cap == 0) ctx->cand_cap = std::max<uint64_t>(1ull << 20, 32 * n);
         t_end(ctx, SCEMA_T_PREP);

@@ -8,7 +8,7 @@
 // a = a_hi + a_lo + r (|r| <= 2^-22 |a|), and one accumulator collects
 //        a_hi.b_hi + a_lo.b_hi + a_hi.b_lo            (kind::f16, fp32 accumulate in TMEM)
 // The four spare columns of every 64-wide slice carry the row terms, so the tensor core itself
-// produces   acc = a.b - h_i - h_j   with h_i = (|a_i|^2 (1 - 2^-13) - T'(1/2 + 2^-12) - e0) / 2, and
+// produces   acc = a.b - h_i - h_j   with h_i = (|a_i|^2 (1 - c) - T'(1/2 + 2c) - e0) / 2, c = 2^-13, and
 // the pair is PROVABLY rejected by the reference iff acc < 0 — the epilogue only looks at sign bits
 // (one LOP3 per two pairs). Everything else (true edges + a guard band that covers the slicing
 // residual and the fp32 accumulation of the tensor core, DESIGN.md "K2-TC") is a survivor and goes
@@ -197,6 +197,7 @@ struct Args {
     uint32_t I0, I1;   // row range of this launch, in 256-row tiles
     uint32_t strip_len;
     uint32_t shard, n_shards;
+    uint32_t slices;   // 2: a_hi.b_hi + a_lo.b_hi + a_hi.b_lo; 1: a_hi.b_hi only (coarser guard band, a third of the MMAs)
     float *dbg;        // debug: every accumulator of every tile, dbg[row * dbg_ld + col]
     uint64_t dbg_ld;
 };
@@ -244,26 +245,32 @@ struct Smem {
     static constexpr uint32_t off_A = 0;                          // 2 x BLOCK_BYTES (A double-buffered over items)
     static constexpr uint32_t off_B = 2 * BLOCK_BYTES;
     static constexpr uint32_t off_bar = off_B + NST * B_STAGE;
-    static constexpr uint32_t n_bars = 3 * NST + 6;               // full, pfull, empty | a_empty[2] tfull[2] tempty[2]
+    static constexpr uint32_t MAXST = 2 * NST;                    // one-slice mode: twice as many half-size stages
+    static constexpr uint32_t n_bars = 3 * MAXST + 6;             // full, pfull, empty | a_empty[2] tfull[2] tempty[2]
     static constexpr uint32_t off_tmem = off_bar + n_bars * 8;
     static constexpr uint32_t bytes = off_tmem + 16 + 1024;       // + slack to align the base to 1024
 };
 
 template <int CG, bool DBG>
-__global__ void __launch_bounds__(256, 1) k_filter_tc(const Args a)
+__global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
 {
     using SM = Smem<CG>;
-    constexpr uint32_t NST = SM::NST;
+    constexpr uint32_t MAXST = SM::MAXST;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const uint32_t sA = base + SM::off_A, sB = base + SM::off_B, sBar = base + SM::off_bar;
     auto bar_full = [&](uint32_t i) { return sBar + 8 * i; };
-    auto bar_pfull = [&](uint32_t i) { return sBar + 8 * (NST + i); };
-    auto bar_empty = [&](uint32_t i) { return sBar + 8 * (2 * NST + i); };
-    auto bar_aempty = [&](uint32_t i) { return sBar + 8 * (3 * NST + i); };
-    auto bar_tfull = [&](uint32_t i) { return sBar + 8 * (3 * NST + 2 + i); };
-    auto bar_tempty = [&](uint32_t i) { return sBar + 8 * (3 * NST + 4 + i); };
+    auto bar_pfull = [&](uint32_t i) { return sBar + 8 * (MAXST + i); };
+    auto bar_empty = [&](uint32_t i) { return sBar + 8 * (2 * MAXST + i); };
+    auto bar_aempty = [&](uint32_t i) { return sBar + 8 * (3 * MAXST + i); };
+    auto bar_tfull = [&](uint32_t i) { return sBar + 8 * (3 * MAXST + 2 + i); };
+    auto bar_tempty = [&](uint32_t i) { return sBar + 8 * (3 * MAXST + 4 + i); };
+    // B ring: with one slice a stage only holds the hi rows, so the same memory gives twice the stages
+    // (the TMA round trip is then hidden behind 7 instead of 3 tiles of a third of the MMA work each)
+    const uint32_t lg_nst = a.slices == 1 ? (CG == 2 ? 3u : 2u) : (CG == 2 ? 2u : 1u);
+    const uint32_t nst_mask = (1u << lg_nst) - 1u;
+    const uint32_t stage_bytes = a.slices == 1 ? SM::B_SLICE : SM::B_STAGE;
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_raw + (base - raw) + SM::off_tmem);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -271,8 +278,8 @@ __global__ void __launch_bounds__(256, 1) k_filter_tc(const Args a)
     const uint32_t unit = blockIdx.x / CG, n_units = gridDim.x / CG;
 
     if (tid == 0) {
-        for (uint32_t i = 0; i < NST; i++) { mbar_init(bar_full(i), 1); mbar_init(bar_pfull(i), 1); mbar_init(bar_empty(i), 1); }
-        for (uint32_t i = 0; i < 2; i++) { mbar_init(bar_aempty(i), 1); mbar_init(bar_tfull(i), 1); mbar_init(bar_tempty(i), 4 * CG); }
+        for (uint32_t i = 0; i < MAXST; i++) { mbar_init(bar_full(i), 1); mbar_init(bar_pfull(i), 1); mbar_init(bar_empty(i), 1); }
+        for (uint32_t i = 0; i < 2; i++) { mbar_init(bar_aempty(i), 1); mbar_init(bar_tfull(i), 1); mbar_init(bar_tempty(i), 8 * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc<CG>(base + SM::off_tmem, 512);
@@ -291,21 +298,25 @@ __global__ void __launch_bounds__(256, 1) k_filter_tc(const Args a)
                 const uint32_t ab = item & 1u;
                 mbar_wait(bar_aempty(ab), ((item >> 1) & 1u) ^ 1u, 1);
                 for (uint32_t J = J0; J < J1; J++, t++) {
-                    const uint32_t st = t % NST;
-                    mbar_wait(bar_empty(st), ((t / NST) & 1u) ^ 1u, 2);
+                    const uint32_t st = t & nst_mask;
+                    mbar_wait(bar_empty(st), ((t >> lg_nst) & 1u) ^ 1u, 2);
                     const bool first = J == J0;
-                    mbar_expect_tx(bar_full(st), SM::B_STAGE + (first ? BLOCK_BYTES : 0u));
-                    if (first) bulk_g2s(sA + ab * BLOCK_BYTES, a.HA + (uint64_t)(I * CG + rank) * BLOCK_BYTES, BLOCK_BYTES, bar_full(st));
-                    const uint32_t dst = sB + st * SM::B_STAGE;
+                    // one slice (hi) or both (hi | lo, contiguous in a block)
+                    const uint32_t blk_bytes = a.slices == 1 ? SLICE_BYTES : BLOCK_BYTES;
+                    mbar_expect_tx(bar_full(st), (COLT / CG / ROWS) * blk_bytes + (first ? blk_bytes : 0u));
+                    if (first) bulk_g2s(sA + ab * BLOCK_BYTES, a.HA + (uint64_t)(I * CG + rank) * BLOCK_BYTES, blk_bytes, bar_full(st));
+                    const uint32_t dst = sB + st * stage_bytes;
                     if (CG == 2) {
-                        bulk_g2s(dst, a.HB + (uint64_t)(J * 2 + rank) * BLOCK_BYTES, BLOCK_BYTES, bar_full(st));
+                        bulk_g2s(dst, a.HB + (uint64_t)(J * 2 + rank) * BLOCK_BYTES, blk_bytes, bar_full(st));
                     } else {
                         // 256 B rows of one CTA: the hi slices of both 128-row blocks, then both lo slices
                         const unsigned char *b0 = a.HB + (uint64_t)(J * 2) * BLOCK_BYTES;
                         bulk_g2s(dst, b0, SLICE_BYTES, bar_full(st));
                         bulk_g2s(dst + SLICE_BYTES, b0 + BLOCK_BYTES, SLICE_BYTES, bar_full(st));
-                        bulk_g2s(dst + 2 * SLICE_BYTES, b0 + SLICE_BYTES, SLICE_BYTES, bar_full(st));
-                        bulk_g2s(dst + 3 * SLICE_BYTES, b0 + BLOCK_BYTES + SLICE_BYTES, SLICE_BYTES, bar_full(st));
+                        if (a.slices != 1) {
+                            bulk_g2s(dst + 2 * SLICE_BYTES, b0 + SLICE_BYTES, SLICE_BYTES, bar_full(st));
+                            bulk_g2s(dst + 3 * SLICE_BYTES, b0 + BLOCK_BYTES + SLICE_BYTES, SLICE_BYTES, bar_full(st));
+                        }
                     }
                 }
                 item++;
@@ -326,14 +337,15 @@ __global__ void __launch_bounds__(256, 1) k_filter_tc(const Args a)
                 for (uint32_t J = J0; J < J1; J++, t++, tile++) {
                     const uint32_t as = tile & 1u;
                     mbar_wait(bar_tempty(as), ((tile >> 1) & 1u) ^ 1u, 3);
-                    const uint32_t st = t % NST, ph = (t / NST) & 1u;
+                    const uint32_t st = t & nst_mask, ph = (t >> lg_nst) & 1u;
                     mbar_wait(bar_full(st), ph, 4);
                     if (CG == 2) mbar_wait(bar_pfull(st), ph, 5);
                     fence_after();
-                    const uint64_t bdesc = make_desc(sB + st * SM::B_STAGE);
+                    const uint64_t bdesc = make_desc(sB + st * stage_bytes);
                     const uint32_t d_tmem = tmem_base + as * COLT;
-#pragma unroll
-                    for (uint32_t term = 0; term < 3; term++) {
+                    const uint32_t n_terms = a.slices == 1 ? 1u : 3u;
+#pragma unroll 1
+                    for (uint32_t term = 0; term < n_terms; term++) {
                         // a_hi.b_hi, a_lo.b_hi, a_hi.b_lo
                         const uint32_t a_off = (term == 1 ? SLICE_BYTES : 0u) >> 4;
                         const uint32_t b_off = (term == 2 ? SM::B_SLICE : 0u) >> 4;
@@ -354,15 +366,16 @@ __global__ void __launch_bounds__(256, 1) k_filter_tc(const Args a)
             uint32_t I, J0, J1, t = 0;
             while (sc.next(I, J0, J1))
                 for (uint32_t J = J0; J < J1; J++, t++) {
-                    const uint32_t st = t % NST;
-                    mbar_wait(bar_full(st), (t / NST) & 1u, 6);
+                    const uint32_t st = t & nst_mask;
+                    mbar_wait(bar_full(st), (t >> lg_nst) & 1u, 6);
                     mbar_arrive_cluster(bar_pfull(st), 0);
                 }
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ---------------------------------------------------------------------- epilogue (4 warps)
-        const uint32_t q = warp & 3u;  // TMEM lane quarter this warp may read
+        // ---------------------------------------------------------------------- epilogue (8 warps)
+        // warp -> (TMEM lane quarter it may read, column half of the tile)
+        const uint32_t q = warp & 3u, half = (warp - 4u) >> 2;
         Sched<CG> sc;
         sc.init(a, unit, n_units);
         uint32_t I, J0, J1, tile = 0;
@@ -372,42 +385,45 @@ __global__ void __launch_bounds__(256, 1) k_filter_tc(const Args a)
                 const uint32_t as = tile & 1u;
                 mbar_wait(bar_tfull(as), (tile >> 1) & 1u, 7);
                 fence_after();
-#pragma unroll 1
-                for (uint32_t ch = 0; ch < 4; ch++) {
-                    uint32_t v[64];
-                    tmem_ld64(tmem_base + ((q * 32u) << 16) + as * COLT + ch * 64u, v);
-                    tmem_ld_wait();
-                    // acc < 0 for every pair <=> the AND of the bit patterns keeps the sign bit
-                    uint32_t all_neg = v[0];
-#pragma unroll
-                    for (int c = 1; c < 64; c++) all_neg &= v[c];
-                    const uint64_t col0 = (uint64_t)J * COLT + ch * 64u;
-                    if (DBG && a.dbg) {
-#pragma unroll
-                        for (int c = 0; c < 64; c++) a.dbg[row * a.dbg_ld + col0 + c] = __uint_as_float(v[c]);
-                    }
-                    if (__any_sync(0xffffffffu, (all_neg >> 31) == 0u)) {
-#pragma unroll
-                        for (int c = 0; c < 64; c++) {
-                            const uint64_t col = col0 + c;
-                            const bool keep = (v[c] >> 31) == 0u && row < col && col < a.n;
-                            const unsigned m = __ballot_sync(0xffffffffu, keep);
-                            if (m) {
-                                const int leader = __ffs(m) - 1;
-                                unsigned long long pos = 0;
-                                if ((int)lane == leader) pos = atomicAdd(a.cand_count, (unsigned long long)__popc(m));
-                                pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(m & ((1u << lane) - 1u));
-                                if (keep && pos < a.cand_cap) a.cand[pos] = (row << 32) | col;
-                            }
-                        }
-                    }
-                }
-                // the accumulator stage is free again
+                uint32_t v0[64], v1[64];
+                const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * COLT + half * 128u;
+                tmem_ld64(taddr, v0);
+                tmem_ld64(taddr + 64u, v1);
+                tmem_ld_wait();
+                // the accumulator stage is free again as soon as the values sit in registers
                 fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     if (CG == 2) mbar_arrive_cluster(bar_tempty(as), 0);
                     else mbar_arrive_local(bar_tempty(as));
+                }
+                // acc < 0 for every pair <=> the AND of the bit patterns keeps the sign bit
+                uint32_t all_neg = v0[0] & v1[0];
+#pragma unroll
+                for (int c = 1; c < 64; c++) all_neg &= v0[c] & v1[c];
+                const uint64_t col0 = (uint64_t)J * COLT + half * 128u;
+                if (DBG && a.dbg) {
+#pragma unroll
+                    for (int c = 0; c < 64; c++) {
+                        a.dbg[row * a.dbg_ld + col0 + c] = __uint_as_float(v0[c]);
+                        a.dbg[row * a.dbg_ld + col0 + 64 + c] = __uint_as_float(v1[c]);
+                    }
+                }
+                if (__any_sync(0xffffffffu, (all_neg >> 31) == 0u)) {
+#pragma unroll
+                    for (int c = 0; c < 128; c++) {
+                        const uint64_t col = col0 + c;
+                        const uint32_t bitsv = c < 64 ? v0[c & 63] : v1[c & 63];
+                        const bool keep = (bitsv >> 31) == 0u && row < col && col < a.n;
+                        const unsigned m = __ballot_sync(0xffffffffu, keep);
+                        if (m) {
+                            const int leader = __ffs(m) - 1;
+                            unsigned long long pos = 0;
+                            if ((int)lane == leader) pos = atomicAdd(a.cand_count, (unsigned long long)__popc(m));
+                            pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(m & ((1u << lane) - 1u));
+                            if (keep && pos < a.cand_cap) a.cand[pos] = (row << 32) | col;
+                        }
+                    }
                 }
             }
         }
@@ -456,14 +472,24 @@ __device__ __forceinline__ double tc_scale(double maxabs)
     return scalbn(1.0, se);
 }
 
+// fp16 rounding with subnormal results flushed to zero: the operands never contain an fp16 subnormal, so
+// whether the tensor core would flush them itself does not matter (the error bound budgets 2^-14 per element)
+__device__ __forceinline__ double h16z(double v)
+{
+    const float f = __half2float(__double2half(v));
+    return fabsf(f) < 6.103515625e-05f ? 0.0 : (double)f;
+}
+
 // pass 2: one warp per row. Writes the row's hi and lo fp16 slices (60 data columns + 4 columns
-// carrying the row term -h_i split three ways against the constant 2^14 on the other operand) into
-// the A-flavoured and the B-flavoured copy, already in the swizzled shared-memory image.
-//   A hi: [x0 x1 P P]   A lo: [x2 0 0 0]        B hi: [P P x0 x1]   B lo: [0 0 x2 0]
-// so that  A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  adds  P (x0 + x1 + x2)_i + P (x0 + x1 + x2)_j = -h_i - h_j.
+// carrying the row term -h_i, split three ways against the constants P = 2^15 and Q = 2^3 on the other
+// operand) into the A-flavoured and the B-flavoured copy, already in the swizzled shared-memory image.
+//   A hi: [x0 x1 P Q]   A lo: [0 x2 0 0]        B hi: [P Q x0 x1]   B lo: [0 0 0 x2]
+// so that  A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  adds  (P x0 + Q x1 + Q x2)_i + (P x0 + Q x1 + Q x2)_j = -h_i - h_j
+// (to 2^-33 |h| + 2^-11; with the hi slices alone the x2 terms drop out: 2^-22 |h| + 2^-11).
 __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, uint64_t n, uint64_t n_pad, uint32_t K,
                                                  const double *__restrict__ NRM, const unsigned long long *__restrict__ gmax,
-                                                 double T0, unsigned char *__restrict__ HA, unsigned char *__restrict__ HB)
+                                                 double T0, double cguard, unsigned char *__restrict__ HA,
+                                                 unsigned char *__restrict__ HB)
 {
     const uint64_t row = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -482,17 +508,17 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
     // row term
+    const double P = 32768.0, Q = 8.0;
     const double T0s = (T0 * s) * s;
-    const double e0 = (double)K * 9.5367431640625e-07;                                   // K 2^-20
-    const double h = 0.5 * (nrm * (1.0 - 0.0001220703125) - T0s * (0.5 + 0.000244140625) - e0);  // 2^-13, 2^-12
-    const double x = -h * 6.103515625e-05;                                               // / 2^14
+    const double e0 = (double)K * 0.0078125;  // K 2^-7: flushed fp16 subnormals (data and fold slices)
+    const double h = 0.5 * (nrm * (1.0 - cguard) - T0s * (0.5 + 2.0 * cguard) - e0);
     double x0, x1, x2;
-    if (!real) { x0 = x1 = -65504.0; x2 = 0.0; }            // padding row: never a survivor
-    else if (wild || !(x <= 65000.0)) { x0 = x1 = 65504.0; x2 = 0.0; }  // NaN/inf row, or threshold beyond every distance: always
+    if (!real) { x0 = -65504.0; x1 = x2 = 0.0; }                              // padding row: never a survivor
+    else if (wild || !(-h <= 32768.0 * P)) { x0 = 65504.0; x1 = x2 = 0.0; }   // NaN/inf row, or threshold beyond every distance: always
     else {
-        x0 = (double)__half2float(__double2half(x));
-        x1 = (double)__half2float(__double2half(x - x0));
-        x2 = (double)__half2float(__double2half(x - x0 - x1));
+        x0 = h16z(-h / P);
+        x1 = h16z((-h - P * x0) / Q);
+        x2 = h16z((-h - P * x0 - Q * x1) / Q);
     }
     const uint64_t blk = row / ROWS;
     const uint32_t r = (uint32_t)(row % ROWS);
@@ -501,22 +527,21 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
 #pragma unroll
     for (int e = 0; e < 2; e++) {
         const uint32_t k = lane + 32 * e;  // column 0..63 of the slice
-        const __half hi = __double2half(v[e]);
-        const __half lo = __double2half(v[e] - (double)__half2float(hi));
-        __half ahi = hi, alo = lo, bhi = hi, blo = lo;
+        const double hi = h16z(v[e]);
+        const double lo = h16z(v[e] - hi);
+        double ahi = hi, alo = lo, bhi = hi, blo = lo;
         if (k >= KMAX) {
-            const double P = 16384.0, Z = 0.0;
             const uint32_t c = k - KMAX;
-            ahi = __double2half(c == 0 ? x0 : c == 1 ? x1 : P);
-            alo = __double2half(c == 0 ? x2 : Z);
-            bhi = __double2half(c == 2 ? x0 : c == 3 ? x1 : P);
-            blo = __double2half(c == 2 ? x2 : Z);
+            ahi = c == 0 ? x0 : c == 1 ? x1 : c == 2 ? P : Q;
+            alo = c == 1 ? x2 : 0.0;
+            bhi = c == 0 ? P : c == 1 ? Q : c == 2 ? x0 : x1;
+            blo = c == 3 ? x2 : 0.0;
         }
         const uint32_t off = ((((k >> 3) ^ (r & 7u)) << 4) | ((k & 7u) << 1));  // swizzled 16-byte chunk, element in chunk
-        *reinterpret_cast<__half *>(a_hi + off) = ahi;
-        *reinterpret_cast<__half *>(a_lo + off) = alo;
-        *reinterpret_cast<__half *>(b_hi + off) = bhi;
-        *reinterpret_cast<__half *>(b_lo + off) = blo;
+        *reinterpret_cast<__half *>(a_hi + off) = __double2half(ahi);
+        *reinterpret_cast<__half *>(a_lo + off) = __double2half(alo);
+        *reinterpret_cast<__half *>(b_hi + off) = __double2half(bhi);
+        *reinterpret_cast<__half *>(b_lo + off) = __double2half(blo);
     }
 }
 
@@ -528,12 +553,13 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
 bool tc_supported(const scema_ctx *ctx) { return ctx->K >= 1 && ctx->K <= tc::KMAX; }
 
 // Builds (or reuses) the fp16 operand copies for the current spline matrix and threshold.
-int tc_prepare(scema_ctx *ctx, double thr)
+int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices)
 {
     const uint64_t n = ctx->n;
     const uint32_t K = ctx->K;
     const uint64_t n_pad = (n + tc::COLT - 1) / tc::COLT * tc::COLT;
-    if (ctx->tc_for_version == ctx->spline_version && ctx->tc_thr == thr && ctx->tc_n == n && ctx->tc_K == K && ctx->tc_valid)
+    if (ctx->tc_for_version == ctx->spline_version && ctx->tc_thr == thr && ctx->tc_n == n && ctx->tc_K == K &&
+        ctx->tc_slices == slices && ctx->tc_valid)
         return SCEMA_OK;
     SCEMA_CUDA(ctx, ctx->d_tc_a.reserve(n_pad * 256));
     SCEMA_CUDA(ctx, ctx->d_tc_b.reserve(n_pad * 256));
@@ -543,9 +569,17 @@ int tc_prepare(scema_ctx *ctx, double thr)
     tc::k_tc_rowstats<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(ctx->d_spline, n, K, ctx->d_tc_nrm.as<double>(),
                                                                         ctx->d_tc_misc.as<unsigned long long>());
     const double eps = 1.1102230246251565e-16;  // 2^-53
-    const double T0 = thr * thr * (1.0 + (2.0 * K + 16.0) * eps) * (1.0 + 4.0 * eps);
+    // The operands are rescaled, so the reference's underflow must be budgeted explicitly: each squared
+    // difference of compare_L2_norm may lose up to half a subnormal ulp, i.e. the reference's sum can sit
+    // K 2^-1075 below d^2 (and thr * thr itself rounds there too).
+    const double T0 = thr * thr * (1.0 + (2.0 * K + 16.0) * eps) * (1.0 + 4.0 * eps) + (2.0 * K + 4.0) * 4.9406564584124654e-324;
+    // Guard band (DESIGN.md "K2-TC"): relative to |a_i|^2 + |a_j|^2 the computed accumulator is off by at most
+    //   two slices: 3.1 2^-22 (slicing) + 13 2^-18 (12 MMA steps, fp32 accumulate)          < 2^-14
+    //   one slice : 2^-11 (dropping a_lo, b_lo) + 5 2^-18 (4 steps) + 2^-23 (two-slice fold)  < 2^-10.9
+    // and the band must be twice that.
+    const double cguard = slices == 1 ? 0.001953125 : 0.0001220703125;  // 2^-9, 2^-13
     tc::k_tc_prep<<<(unsigned)((n_pad + 7) / 8), 256, 0, ctx->stream>>>(ctx->d_spline, n, n_pad, K, ctx->d_tc_nrm.as<double>(),
-                                                                        ctx->d_tc_misc.as<unsigned long long>(), T0,
+                                                                        ctx->d_tc_misc.as<unsigned long long>(), T0, cguard,
                                                                         ctx->d_tc_a.as<unsigned char>(), ctx->d_tc_b.as<unsigned char>());
     ctx->launches += 2;
     SCEMA_CUDA(ctx, cudaGetLastError());
@@ -553,6 +587,7 @@ int tc_prepare(scema_ctx *ctx, double thr)
     ctx->tc_thr = thr;
     ctx->tc_n = n;
     ctx->tc_K = K;
+    ctx->tc_slices = slices;
     ctx->tc_valid = true;
     return SCEMA_OK;
 }
@@ -567,7 +602,7 @@ static int tc_launch_t(scema_ctx *ctx, const tc::Args &a, uint64_t items)
     uint64_t units = std::min<uint64_t>((uint64_t)ctx->sm_count / CG, std::max<uint64_t>(items, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(units * CG));
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(384);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
@@ -587,6 +622,7 @@ static int tc_launch_t(scema_ctx *ctx, const tc::Args &a, uint64_t items)
 int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t shard, uint32_t n_shards, unsigned long long *cand_count,
               float *dbg, uint64_t dbg_ld)
 {
+    if (!ctx->tc_valid) return fail(ctx, SCEMA_ERR_STATE, "tensor-core filter: operands not prepared");
     tc::Args a;
     a.HA = ctx->d_tc_a.as<unsigned char>();
     a.HB = ctx->d_tc_b.as<unsigned char>();
@@ -599,6 +635,7 @@ int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t shard, uint32_t
     a.I1 = std::min<uint32_t>(I1, a.NT);
     a.shard = shard;
     a.n_shards = n_shards;
+    a.slices = ctx->tc_slices;
     a.dbg = dbg;
     a.dbg_ld = dbg_ld;
     static const char *cg_env = getenv("SCEMA_TC_CG");
@@ -620,14 +657,16 @@ int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t shard, uint32_t
 // and returns every accumulator (acc_host[row * ld + col], ld >= n_pad) and the operand copies, so a
 // test can redo the sliced contraction in FP64 and check the layout, the fold columns and the
 // accumulation-error model against the hardware.
-int tc_debug_run(scema_ctx *ctx, double thr, float *acc_host, uint64_t ld, unsigned char *ha_host, unsigned char *hb_host)
+int tc_debug_run(scema_ctx *ctx, double thr, uint32_t slices, float *acc_host, uint64_t ld, unsigned char *ha_host,
+                 unsigned char *hb_host)
 {
+    if (slices != 1 && slices != 2) return fail(ctx, SCEMA_ERR_INVALID, "tc_debug: slices must be 1 or 2");
     if (!ctx->have_spline) return fail(ctx, SCEMA_ERR_STATE, "Spline is not up to date.");
     if (!tc_supported(ctx)) return fail(ctx, SCEMA_ERR_INVALID, "tensor-core filter needs 1 <= K <= 60");
     const uint64_t n_pad = (ctx->n + tc::COLT - 1) / tc::COLT * tc::COLT;
     if (ld < n_pad) return fail(ctx, SCEMA_ERR_INVALID, "tc_debug: ld < padded n");
     if (n_pad > 8192) return fail(ctx, SCEMA_ERR_INVALID, "tc_debug: at most 8192 rows");
-    int rc = tc_prepare(ctx, thr);
+    int rc = tc_prepare(ctx, thr, slices);
     if (rc) return rc;
     SCEMA_CUDA(ctx, ctx->d_counters.reserve(8 * sizeof(uint64_t)));
     SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(uint64_t), ctx->stream));

@@ -78,7 +78,7 @@ class ShardedCluster:
             return torch.cuda.default_stream()
         return torch.cuda.ExternalStream(ptr)
 
-    def run(self, n, spline_points, threshold, variant=0, sink=None):
+    def run(self, n, spline_points, threshold, variant=3, sink=None):
         """The local share of the histories must already be set on self.hc (set_histories).
         sink: callable(a, b, d) -> the shard's edges are streamed chunk by chunk
         (scema_compare_stream) instead of being kept on the device.

@@ -87,7 +87,7 @@ int main(int argc, char **argv)
         } else {
             MatHistPredict::b200::check(scema_resample(ctx, spline_points), "splinify");
         }
-        MatHistPredict::b200::check(scema_compare(ctx, threshold, SCEMA_PAIRS_DMMA, 0, 1, &n_edges), "compare_histories_with_all_ranks");
+        MatHistPredict::b200::check(scema_compare(ctx, threshold, SCEMA_PAIRS_TC, 0, 1, &n_edges), "compare_histories_with_all_ranks");
         // most_similar_histories_to_file per history (:99-103); fails like the reference's ofstream
         // when __results/ does not exist
         if (scema_write_similar_hist(ctx, "__results/ID_%u.txt") != SCEMA_OK) die(scema_last_error(ctx));

@@ -417,7 +417,7 @@ inline void compare_batch(std::vector<Strain6D *> &hist, double threshold, const
     }
     const bool dense = keep_all_similar();
     uint64_t m = 0;
-    check(scema_compare(ctx, dense ? std::numeric_limits<double>::infinity() : threshold, SCEMA_PAIRS_DMMA, 0, 1, &m),
+    check(scema_compare(ctx, dense ? std::numeric_limits<double>::infinity() : threshold, dense ? SCEMA_PAIRS_EXACT : SCEMA_PAIRS_TC, 0, 1, &m),
           "compare_histories_with_all_ranks");
     std::vector<uint32_t> a(m), b(m);
     std::vector<double> d(m);

@@ -10,11 +10,11 @@ import numpy as np
 import pytest
 
 import scema_b200
-from scema_b200 import synth, PAIRS_DMMA, PAIRS_FMA, PAIRS_EXACT
+from scema_b200 import synth, PAIRS_DMMA, PAIRS_FMA, PAIRS_EXACT, PAIRS_TC
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-VARIANTS = [("dmma", PAIRS_DMMA), ("fma", PAIRS_FMA), ("exact", PAIRS_EXACT)]
+VARIANTS = [("tc", PAIRS_TC), ("dmma", PAIRS_DMMA), ("fma", PAIRS_FMA), ("exact", PAIRS_EXACT)]
 THR = 1e-6
 
 
@@ -267,7 +267,7 @@ def test_k2_huge_threshold_all_pairs(hc, oracle):
     assert edges_equal(hc.get_edges(), want)
 
 
-@pytest.mark.parametrize("vname,variant", [("dmma", 0), ("fma", 1), ("exact", 2)])
+@pytest.mark.parametrize("vname,variant", VARIANTS)
 def test_compare_stream_concatenates_to_compare(hc, vname, variant):
     """Edge streaming (config 5's mode): chunks of panels, delivered through the sink, concatenate
     to exactly the sorted list of the one-shot compare; also per shard."""
@@ -332,7 +332,9 @@ def test_sharded_compare_union(hc, oracle):
             d = np.concatenate([p[2] for p in parts])
             o = np.lexsort((b, a))
             assert edges_equal((a[o], b[o], d[o]), want), (variant, world)
-            if variant != PAIRS_EXACT and world <= 3:
+            # (the tcgen05 filter deals items out strip by strip; with every edge on the diagonal of this small
+            # case one of three shards may legitimately get none)
+            if variant not in (PAIRS_EXACT, PAIRS_TC) and world <= 3:
                 assert all(len(p[0]) > 0 for p in parts)
 
 
@@ -429,6 +431,8 @@ def test_config3_ragged_200k_properties(hc, oracle):
         assert len(ei) == int(np.count_nonzero(a == r))
     hc.compare(THR, PAIRS_FMA)
     assert edges_equal(hc.get_edges(), (a, b, d))
+    hc.compare(THR, PAIRS_TC)
+    assert edges_equal(hc.get_edges(), (a, b, d))
 
 
 def test_config4_1M_properties(hc, oracle):
@@ -467,4 +471,12 @@ def test_config4_1M_properties(hc, oracle):
     assert edges_equal(tuple(np.concatenate([c[k] for c in chunks]) for k in range(3)), (a, b, d))
     hc.compare(THR, PAIRS_EXACT)
     assert edges_equal(hc.get_edges(), (a, b, d))
+    # the tcgen05 filter: same list over the whole problem, one-shot and streamed; its guard band is wider
+    # (fp16 slices, fp32 accumulation) but still only keeps pairs of the same cluster
+    assert hc.compare(THR, PAIRS_TC) == ne
+    assert edges_equal(hc.get_edges(), (a, b, d))
+    assert hc.counters()["survivors"] <= n * 15 // 2 + n // 100
+    chunks = []
+    tot = hc.compare_stream(THR, lambda x, y, z: chunks.append((x, y, z)), PAIRS_TC)
+    assert tot == ne and edges_equal(tuple(np.concatenate([c[k] for c in chunks]) for k in range(3)), (a, b, d))
     del d_steps

@@ -1,0 +1,234 @@
+"""The tcgen05 filter (SCEMA_PAIRS_TC): operand layout, fold columns, the accumulation-error model its
+guard band relies on, and edge-list parity on inputs chosen to stress it (wide dynamic range, heavy
+cancellation, pairs planted a few ulp either side of the threshold at several norm scales).
+
+The filter's soundness argument (DESIGN.md "K2-TC") ASSUMES that one tcgen05.mma kind::f16 step returns
+c + sum of 16 exact products with an error of at most 2^-18 (|c| + sum |products|). The first test pins
+that assumption on the hardware with a 4x margin; everything else is bit-exact parity with the oracle.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import scema_b200
+from scema_b200 import synth, PAIRS_TC, PAIRS_EXACT
+
+pytestmark = pytest.mark.gpu
+THR = 1e-6
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def edges_equal(got, want):
+    return (len(got[0]) == len(want[0]) and np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+            and np.array_equal(bits(got[2]), bits(want[2])))
+
+
+def unswizzle(buf, n_pad):
+    """operand bytes as they sit in memory -> (hi, lo) float64 [n_pad, 64]"""
+    b = buf.reshape(n_pad // 128, 2, 128, 8, 16)  # block, slice, row, stored 16-byte chunk, bytes
+    out = np.empty_like(b)
+    r = np.arange(128)
+    for c in range(8):
+        out[:, :, r, c, :] = b[:, :, r, c ^ (r & 7), :]
+    h = out.reshape(n_pad // 128, 2, 128, 128).view(np.float16).astype(np.float64)
+    return h[:, 0].reshape(n_pad, 64), h[:, 1].reshape(n_pad, 64)
+
+
+def datasets():
+    rng = np.random.default_rng(3)
+    n = 1100
+    yield "clusters", synth.rows(11, n, 16, 10, 5e-3, synth.default_pert(THR, 10)), THR
+    yield "gauss", rng.standard_normal((n, 60)) * 1e-3, 1e-3
+    alt = np.tile(np.array([1.0, -1.0]), 30)[None, :] * (1e-2 + 1e-6 * rng.standard_normal((n, 60)))
+    yield "cancel", alt * np.where(rng.random((n, 1)) < 0.5, 1.0, -1.0), 1e-5   # a.b = +-|a||b|: worst cancellation
+    yield "ranges", rng.standard_normal((n, 60)) * 10.0 ** rng.integers(-12, -2, size=(n, 1)), 1e-7
+    yield "k18", rng.standard_normal((n, 18)) * 1e-2, 1e-2
+
+
+@pytest.mark.parametrize("slices", [2, 1])
+@pytest.mark.parametrize("name,rows,thr", list(datasets()), ids=[d[0] for d in datasets()])
+def test_tc_accumulators_match_sliced_fp64(hc, name, rows, thr, slices):
+    """Every accumulator the tensor core produced == the same sliced products summed in FP64 from the
+    operand copies, within a quarter of the error the guard band budgets for; the operand copies
+    reproduce s*a to 2^-22 and fold -h_i-h_j as documented; and no true edge has a negative accumulator."""
+    n, K = rows.shape
+    hc.set_spline(rows)
+    acc, ha, hb = hc.tc_debug(thr, n, slices)
+    n_pad = acc.shape[0]
+    ahi, alo = unswizzle(ha, n_pad)
+    bhi, blo = unswizzle(hb, n_pad)
+    want = ahi @ bhi.T
+    absum = np.abs(ahi) @ np.abs(bhi).T
+    if slices == 2:
+        want = want + alo @ bhi.T + ahi @ blo.T
+        absum = absum + np.abs(alo) @ np.abs(bhi).T + np.abs(ahi) @ np.abs(blo).T
+    steps = 12 if slices == 2 else 4
+    ti = np.arange(n_pad)[:, None] // 256
+    tj = np.arange(n_pad)[None, :] // 256
+    must = tj >= ti
+    assert not np.any(np.isnan(acc[must])), "a tile of the upper triangle was not written"
+    assert np.all(np.isnan(acc[~must])), "a tile below the diagonal was computed"
+    err = np.abs(acc.astype(np.float64) - want)
+    budget = (steps + 1) * 2.0 ** -18 * absum
+    assert np.all(err[must] <= 0.25 * budget[must] + 1e-30), float(np.max(err[must] / np.maximum(budget[must], 1e-300)))
+    # data columns: hi + lo == s * a to 2^-22 relative (+ the fp16 subnormal floor), same in both copies
+    finite = np.isfinite((rows ** 2).sum(1))
+    M = np.abs(rows[finite]).max()
+    s = 2.0 ** (11 - int(np.floor(np.log2(M))))
+    a_s = np.zeros((n_pad, 64))
+    a_s[:n, :K] = rows * s
+    rec = (ahi + alo)[:, :60]
+    assert np.all(np.abs(rec[:n] - a_s[:n, :60]) <= 2.0 ** -22 * np.abs(a_s[:n, :60]) + 2.0 ** -13)
+    assert np.array_equal(ahi[:, :60], bhi[:, :60]) and np.array_equal(alo[:, :60], blo[:, :60])
+    assert np.abs(ahi[:n, :60]).max() < 4096
+    # no fp16 subnormal anywhere in the operands (the prep flushes them; the bound budgets for that)
+    for arr in (ahi, alo, bhi, blo):
+        nz = np.abs(arr[arr != 0])
+        assert nz.size == 0 or nz.min() >= 2.0 ** -14
+    # fold columns: P x0 + Q x1 + Q x2 == -h_i to 2^-30 relative, h_i as documented (guard 2^-13 / 2^-9)
+    P, Q = 32768.0, 8.0
+    cg = 2.0 ** -13 if slices == 2 else 2.0 ** -9
+    nrm = (a_s[:n] ** 2).sum(1)
+    T0 = thr * thr * (1 + (2 * K + 16) * 2.0 ** -53) * (1 + 4 * 2.0 ** -53) * s * s
+    h = 0.5 * (nrm * (1 - cg) - T0 * (0.5 + 2 * cg) - K * 2.0 ** -7)
+    fold_a = P * ahi[:n, 60] + Q * ahi[:n, 61] + Q * alo[:n, 61]
+    fold_b = P * bhi[:n, 62] + Q * bhi[:n, 63] + Q * blo[:n, 63]
+    normal = -h <= 32768.0 * P
+    assert np.all(np.abs(fold_a[normal] + h[normal]) <= 2.0 ** -30 * np.abs(h[normal]) + 2.0 ** -10)
+    assert np.array_equal(fold_a, fold_b)
+    assert np.all(ahi[:n, 62] == P) and np.all(ahi[:n, 63] == Q) and np.all(bhi[:n, 60] == P) and np.all(bhi[:n, 61] == Q)
+    assert np.all(alo[:, 60] == 0) and np.all(alo[:, 62:] == 0) and np.all(blo[:, 60:63] == 0)
+    assert np.all(ahi[n:, 60] == -65504.0)  # padding rows can never survive
+    # soundness on this data: every true edge (FP64 direct differences) has a non-negative accumulator
+    for r0 in range(0, n, 256):
+        d2 = ((rows[r0:r0 + 256, None, :] - rows[None, :, :]) ** 2).sum(-1)
+        edge = (np.sqrt(d2) < thr) & (np.arange(r0, min(r0 + 256, n))[:, None] < np.arange(n)[None, :])
+        a_blk = acc[r0:r0 + 256, :n][: edge.shape[0]]
+        assert not np.any(edge & (np.signbit(a_blk))), "a true edge was rejected by the filter"
+
+
+def test_tc_falls_back_to_two_slices_when_one_slice_keeps_too_much():
+    """A cloud whose pairwise distances are ~3 % of the norms sits inside the one-slice guard band (6 %) but
+    outside the two-slice band (1.6 %): the survivors overflow the queue and the compare repeats with both slices."""
+    from oracle.pyoracle import Oracle
+    rng = np.random.default_rng(2)
+    n = 2600
+    base = 5e-3 * rng.standard_normal(60)
+    rows = base[None, :] * (1 + 0.03 / np.sqrt(2) * rng.standard_normal((n, 60)))
+    rows[::50] = rows[1::50][: len(rows[::50])] + 1e-8 * rng.standard_normal((len(rows[::50]), 60))  # a few true edges
+    want = Oracle().all_pairs(rows, THR)
+    h = scema_b200.HistCluster(0)  # fresh context: default queue capacity
+    h.set_spline(rows)
+    assert h.compare(THR, PAIRS_TC) == len(want[0])
+    assert edges_equal(h.get_edges(), want)
+    c = h.counters()
+    assert c["tc_slices"] == 2 and c["passes"] >= 2 and len(want[0]) >= 40
+    assert c["survivors"] < n * 8
+    # the same rows and threshold again start with both slices straight away
+    assert h.compare(THR, PAIRS_TC) == len(want[0]) and h.counters()["passes"] == 1
+    h.close()
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-150, 1e140, 1e-300])
+def test_tc_edges_across_magnitudes(hc, oracle, scale):
+    """Same clustered problem at very different magnitudes (rows and threshold scaled together by a power
+    of two would be exactly equivalent; a decimal factor is not) — the edge list must equal the oracle's."""
+    # at 1e-300 every squared difference underflows in the reference: ALL pairs are edges there
+    n = 3000 if scale != 1e-300 else 1200
+    rows = synth.rows(21, n, 16, 10, 5e-3, synth.default_pert(THR, 10)) * scale
+    thr = THR * scale
+    rng = np.random.default_rng(4)
+    for q in range(300):  # pairs a few ulp either side of the threshold
+        a = int(rng.integers(0, n)); b = (a + n // 2) % n
+        u = rng.standard_normal(60); u /= np.linalg.norm(u)
+        rows[b] = rows[a] + u * thr * (1 + (q - 150) * 3e-16)
+    want = oracle.all_pairs(rows, thr)
+    hc.set_spline(rows)
+    assert hc.compare(thr, PAIRS_TC) == len(want[0])
+    assert edges_equal(hc.get_edges(), want)
+    assert len(want[0]) > 1000
+    if scale == 1e-300:
+        assert len(want[0]) == n * (n - 1) // 2
+
+
+def test_tc_mixed_norm_scales_and_dense_neighbourhoods(hc, oracle):
+    """Rows of very different norms in one batch (the guard band scales with each row's own norm), small
+    rows whose fp16 image is zero, and a dense cloud well inside the guard band but outside the threshold."""
+    rng = np.random.default_rng(8)
+    n = 4000
+    rows = rng.standard_normal((n, 60)) * 10.0 ** rng.integers(-9, -1, size=(n, 1))
+    rows[:600] = 0.3 + 2e-6 * rng.standard_normal((600, 60))        # |a| ~ 2.3, distances ~ 2e-5: all inside the guard band
+    rows[600:900] = 1e-14 * rng.standard_normal((300, 60))          # vanish in fp16 next to the 0.3 rows; all mutual edges
+    rows[900] = rows[901] = 0.0
+    for q in range(400):
+        a = int(rng.integers(1000, n)); b = int(rng.integers(1000, n))
+        if a == b:
+            continue
+        u = rng.standard_normal(60); u /= np.linalg.norm(u)
+        rows[b] = rows[a] + u * THR * (1 + (q - 200) * 2e-16)
+    want = oracle.all_pairs(rows, THR)
+    hc.set_spline(rows)
+    assert hc.compare(THR, PAIRS_TC) == len(want[0])
+    assert edges_equal(hc.get_edges(), want)
+    c = hc.counters()
+    assert c["survivors"] >= 600 * 599 // 2          # the cloud really went through the exact path
+    assert len(want[0]) >= 300 * 299 // 2 + 150
+
+
+def test_tc_threshold_beyond_all_distances(hc, oracle):
+    """thr so large relative to the data that the folded row term saturates: every pair must survive."""
+    rows = synth.rows(1, 900, 16, 10, 5e-3, 1e-7)
+    for thr in (10.0, 1e30, float("inf")):
+        hc.set_spline(rows)
+        assert hc.compare(thr, PAIRS_TC) == 900 * 899 // 2
+    want = oracle.all_pairs(rows, 10.0)
+    hc.compare(10.0, PAIRS_TC)
+    assert edges_equal(hc.get_edges(), want)
+
+
+def test_tc_wide_rows_fall_back(hc, oracle):
+    """K > 60 does not fit the 64-column fp16 slice: the variant silently takes the DMMA filter."""
+    rows = synth.rows(5, 1500, 16, 50, 5e-3, synth.default_pert(THR, 50))
+    want = oracle.all_pairs(rows, THR)
+    hc.set_spline(rows)
+    assert hc.compare(THR, PAIRS_TC) == len(want[0])
+    assert edges_equal(hc.get_edges(), want)
+    with pytest.raises(scema_b200.ScemaError):
+        hc.tc_debug(THR, 1500)
+
+
+def test_tc_threshold_change_rebuilds_operands(hc, oracle):
+    """The threshold is baked into the operand copies; a second compare with another threshold on the same
+    rows must not reuse them."""
+    rows = synth.rows(6, 2500, 16, 10, 5e-3, synth.default_pert(THR, 10))
+    hc.set_spline(rows)
+    for thr in (THR, 0.3 * THR, 40 * THR, THR):
+        want = oracle.all_pairs(rows, thr)
+        assert hc.compare(thr, PAIRS_TC) == len(want[0])
+        assert edges_equal(hc.get_edges(), want)
+
+
+def test_tc_single_cta_kernel_and_pinned_slices_match(tmp_path):
+    """SCEMA_TC_CG=1 selects the cta_group::1 kernel (one SM per 128 x 256 tile), SCEMA_TC_SLICES pins the
+    number of fp16 slices; every combination emits the exact kernel's edge list."""
+    code = (
+        "import numpy as np, scema_b200\n"
+        "from scema_b200 import synth, PAIRS_TC, PAIRS_EXACT\n"
+        "rows = synth.rows(31, 7000, 16, 10, 5e-3, synth.default_pert(1e-6, 10))\n"
+        "hc = scema_b200.HistCluster(0); hc.set_spline(rows)\n"
+        "n1 = hc.compare(1e-6, PAIRS_TC); e1 = hc.get_edges(); assert hc.counters()['tc_slices'] == int(__import__('os').environ['SCEMA_TC_SLICES'])\n"
+        "n2 = hc.compare(1e-6, PAIRS_EXACT); e2 = hc.get_edges()\n"
+        "assert n1 == n2 and n1 > 7000\n"
+        "assert all(np.array_equal(x.view(np.uint64) if x.dtype == np.float64 else x, y.view(np.uint64) if y.dtype == np.float64 else y) for x, y in zip(e1, e2))\n"
+        "print('ok', n1)\n")
+    for cg, sl in (("1", "1"), ("1", "2"), ("2", "1"), ("2", "2")):
+        env = dict(os.environ, SCEMA_TC_CG=cg, SCEMA_TC_SLICES=sl, PYTHONPATH=ROOT)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and r.stdout.startswith("ok"), (cg, sl, r.stdout, r.stderr)

@@ -32,16 +32,20 @@ def main():
     n_big = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     thr, P = 1e-6, 10
     cg = os.environ.get("SCEMA_TC_CG", "2")
-    print(f"== tc_probe CG={cg} n={n}", flush=True)
+    print(f"== tc_probe CG={cg} slices={os.environ.get('SCEMA_TC_SLICES', 'auto')} n={n}", flush=True)
     rows = synth.rows(11, n, 16, P, 5e-3, synth.default_pert(thr, P))
     hc = scema_b200.HistCluster(0)
     hc.set_spline(rows)
-    acc, ha, hb = hc.tc_debug(thr, n)
+    slices = int(os.environ.get("SCEMA_TC_SLICES", "2"))
+    acc, ha, hb = hc.tc_debug(thr, n, slices)
     n_pad = acc.shape[0]
     ahi, alo = unswizzle(ha, n_pad)
     bhi, blo = unswizzle(hb, n_pad)
-    want = ahi @ bhi.T + alo @ bhi.T + ahi @ blo.T
-    absum = np.abs(ahi) @ np.abs(bhi).T + np.abs(alo) @ np.abs(bhi).T + np.abs(ahi) @ np.abs(blo).T
+    want = ahi @ bhi.T
+    absum = np.abs(ahi) @ np.abs(bhi).T
+    if slices == 2:
+        want = want + alo @ bhi.T + ahi @ blo.T
+        absum = absum + np.abs(alo) @ np.abs(bhi).T + np.abs(ahi) @ np.abs(blo).T
     written = ~np.isnan(acc)
     # which tiles must have been written: column tile J >= row tile I (256-row units)
     ti = np.arange(n_pad)[:, None] // 256
@@ -95,7 +99,7 @@ def main():
             c = hc.counters()
             pairs = n_big * (n_big - 1) / 2
             print(f"big n={n_big} {name}: edges {ne} survivors {c['survivors']} filter {tm['filter']:.2f} ms prep {tm['prep']:.2f} ms "
-                  f"exact {tm['exact']:.2f} ms wall {wall*1e3:.1f} ms -> {pairs / (tm['filter'] * 1e-3):.3e} pairs/s (filter)", flush=True)
+                  f"slices {c['tc_slices']} passes {c['passes']} exact {tm['exact']:.2f} ms wall {wall*1e3:.1f} ms -> {pairs / (tm['filter'] * 1e-3):.3e} pairs/s (filter)", flush=True)
     hc.close()
     print("== done", flush=True)
 
