@@ -15,9 +15,9 @@
 // through the same exact FP64 recompute (k_exact_queue) as the DMMA path: the edge list and the
 // distance bits are identical to the reference's.
 //
-// Kernel: warp-specialised, persistent, one CTA per SM; CG = 2 pairs the two SMs of a TPC on one
-// 256 x 256 tile (tcgen05.mma.cta_group::2: each CTA holds 128 rows of A and 128 of the 256 B rows,
-// so B traffic from L2 and the shared-memory reads per SM are halved). Operand blocks are stored in
+// Kernel: warp-specialised, persistent, one CTA per SM, one 128 x 256 tile per CTA (CG = 1, the default) or
+// CG = 2: the two SMs of a TPC on one 256 x 256 tile (tcgen05.mma.cta_group::2: each CTA holds 128 rows of A
+// and 128 of the 256 B rows, so B traffic from L2 and the shared-memory reads per SM are halved). Operand blocks are stored in
 // global memory exactly as the 128-byte-swizzled K-major image tcgen05 wants in shared memory, so one
 // block = one contiguous 1-D bulk copy of the TMA engine (no tensor map).
 #include "common.cuh"
@@ -639,7 +639,10 @@ int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t shard, uint32_t
     a.dbg = dbg;
     a.dbg_ld = dbg_ld;
     static const char *cg_env = getenv("SCEMA_TC_CG");
-    const int cg = (cg_env && atoi(cg_env) == 1) ? 1 : 2;
+    // cta_group::2 pairs halve the B traffic and the shared-memory reads per SM, but neither bounds this kernel
+    // (the TMEM read-out resp. the tensor pipe do) and the pair pays a forwarder hop per stage: measured 61.0 ms
+    // against 56.4 ms for one CTA per tile at 1M histories, so single CTAs are the default.
+    const int cg = (cg_env && atoi(cg_env) == 2) ? 2 : 1;
     // strips: long enough to amortise the A tile, short enough to leave every cluster many items
     const uint64_t rows = a.I1 > a.I0 ? a.I1 - a.I0 : 0;
     const uint64_t tiles = rows * a.NT;  // upper bound

@@ -216,7 +216,7 @@ def test_tc_threshold_change_rebuilds_operands(hc, oracle):
 
 
 def test_tc_single_cta_kernel_and_pinned_slices_match(tmp_path):
-    """SCEMA_TC_CG=1 selects the cta_group::1 kernel (one SM per 128 x 256 tile), SCEMA_TC_SLICES pins the
+    """SCEMA_TC_CG=2 selects the cta_group::2 kernel (an SM pair per 256 x 256 tile), SCEMA_TC_SLICES pins the
     number of fp16 slices; every combination emits the exact kernel's edge list."""
     code = (
         "import numpy as np, scema_b200\n"
