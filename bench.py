@@ -263,6 +263,12 @@ def run_ours(args, wl, wl_name):
         return tot
 
     def step_e2e():
+        if world == 1 and not args.stream:
+            # the one-call host API (scema_cluster): pinned host -> device copy, K1, K2, K3 — pipelined range by
+            # range inside the library when the tcgen05 filter applies
+            ne = hc.cluster(h_steps_np, off, None, P, THR, variant)
+            hc.get_edges()                           # device -> host read of the result
+            return ne
         hc.set_histories(h_steps_np, off)            # pinned host -> device inside the timed region
         if world > 1:
             ne, counts, offs, _ = sc.run(n, P, THR, variant, sink=sink if args.stream else None)
@@ -414,7 +420,8 @@ def run_ours(args, wl, wl_name):
                        "edges": acc["edges"], "survivors_last_rank0": acc["survivors"]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                    "pipeline_ranges": hc.counters().get("pipeline_ranges", 0) if world == 1 else 0},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -136,7 +136,11 @@ int scema_edges_device(scema_ctx *ctx, const uint64_t **keys, const double **dif
 /* Per-history number of partners (size of most_similar_histories, strain2spline.h:429). */
 int scema_get_degrees(scema_ctx *ctx, uint32_t *degree_host);
 
-/* One call for a host caller: set_histories + resample + compare. */
+/* One call for a host caller: set_histories + resample + compare. With SCEMA_PAIRS_TC, 6 * spline_points <= 60
+ * and a large batch (>= 65536 histories; SCEMA_PIPELINE=0 disables, SCEMA_PIPELINE_MIN_N moves the limit) the three
+ * steps are pipelined range by range behind the host->device copy of the raw steps: range c is resampled and compared
+ * with itself and all earlier ranges while range c+1 is still on the bus. Same spline matrix and edge list; the
+ * per-phase timings then report the whole overlapped region as "filter". */
 int scema_cluster(scema_ctx *ctx, const double *steps, const uint64_t *offsets, const uint32_t *ids,
                   uint64_t n, uint32_t spline_points, double threshold, int variant, uint64_t *n_edges);
 
@@ -172,7 +176,8 @@ int scema_reduce_dir(const char *input_folder, const char *out_mapping_csv, uint
 int scema_last_timings(scema_ctx *ctx, float ms[SCEMA_T_COUNT]);
 /* Counters of the last compare: [0] pairs evaluated by the filter, [1] survivors recomputed
  * exactly, [2] edges, [3] passes (>1 when a buffer had to grow), [4] tiles, [5] fp16 slices the
- * tcgen05 filter ended up using (SCEMA_PAIRS_TC only). */
+ * tcgen05 filter ended up using (SCEMA_PAIRS_TC only), [6] ranges of the host-buffer pipeline of
+ * scema_cluster (0: the batch was not pipelined). */
 int scema_last_counters(scema_ctx *ctx, uint64_t counters[8]);
 /* Total kernels launched by this context so far. */
 uint64_t scema_kernel_launches(const scema_ctx *ctx);

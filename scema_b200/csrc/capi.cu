@@ -56,6 +56,8 @@ void scema_destroy(scema_ctx *c)
         if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
     }
     for (int i = 0; i < 2 * SCEMA_T_COUNT; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -84,9 +86,12 @@ static void set_ids(std::vector<uint32_t> &dst, const uint32_t *ids, uint64_t n)
     else for (uint64_t i = 0; i < n; i++) dst[i] = (uint32_t)i;
 }
 
-int scema_set_histories(scema_ctx *c, const double *steps, int steps_on_device, const uint64_t *offsets,
-                        const uint32_t *ids, uint64_t n)
+// steps_mode: 0 = copy the host steps now, 1 = borrow the device pointer, 2 = only reserve the device buffer
+// (the caller copies the steps itself, range by range: cluster_pipelined)
+static int set_histories_impl(scema_ctx *c, const double *steps, int steps_mode, const uint64_t *offsets,
+                              const uint32_t *ids, uint64_t n)
 {
+    const int steps_on_device = steps_mode == 1;
     int rc = enter(c);
     if (rc) return rc;
     if (n && (!offsets || !steps)) return fail(c, SCEMA_ERR_INVALID, "set_histories: null pointer");
@@ -117,7 +122,7 @@ int scema_set_histories(scema_ctx *c, const double *steps, int steps_on_device, 
     } else {
         const uint64_t last = n ? offsets[n] : 0;
         SCEMA_CUDA(c, c->steps_own.reserve(std::max<uint64_t>(last, 1) * 6 * sizeof(double)));
-        if (last)
+        if (last && steps_mode == 0)
             SCEMA_CUDA(c, cudaMemcpyAsync(c->steps_own.p, steps, last * 6 * sizeof(double), cudaMemcpyHostToDevice,
                                           c->stream));
         c->d_steps = c->steps_own.as<double>();
@@ -126,6 +131,12 @@ int scema_set_histories(scema_ctx *c, const double *steps, int steps_on_device, 
     c->have_histories = true;
     c->histories_version++;
     return SCEMA_OK;
+}
+
+int scema_set_histories(scema_ctx *c, const double *steps, int steps_on_device, const uint64_t *offsets,
+                        const uint32_t *ids, uint64_t n)
+{
+    return set_histories_impl(c, steps, steps_on_device ? 1 : 0, offsets, ids, n);
 }
 
 int scema_resample(scema_ctx *c, uint32_t spline_points)
@@ -295,6 +306,25 @@ int scema_get_degrees(scema_ctx *c, uint32_t *degree_host)
 int scema_cluster(scema_ctx *c, const double *steps, const uint64_t *offsets, const uint32_t *ids, uint64_t n,
                   uint32_t spline_points, double threshold, int variant, uint64_t *n_edges)
 {
+    // Large host batches on the tcgen05 path are pipelined: the raw steps travel to the device range by range
+    // and every range is resampled and compared against everything that arrived before it while the next one
+    // is still on the bus (cluster_pipelined, pairs.cu). Same spline matrix, same edge list.
+    if (c && steps && offsets && variant == SCEMA_PAIRS_TC && spline_points >= 1 && spline_points <= 10 && threshold > 0.0 &&
+        pipeline_wanted(n)) {
+        int rc = set_histories_impl(c, steps, 2, offsets, ids, n);
+        if (rc) return rc;
+        bool done = false;
+        rc = cluster_pipelined(c, steps, spline_points, threshold, &done);
+        if (rc) { c->have_edges = false; return rc; }
+        if (done) {
+            if (n_edges) *n_edges = c->n_edges;
+            return SCEMA_OK;
+        }
+        // not done (e.g. the survivors overflowed the queue): every step is on the device by now, carry on in order
+        rc = scema_resample(c, spline_points);
+        if (rc) return rc;
+        return scema_compare(c, threshold, variant, 0, 1, n_edges);
+    }
     int rc = scema_set_histories(c, steps, 0, offsets, ids, n);
     if (rc) return rc;
     rc = scema_resample(c, spline_points);

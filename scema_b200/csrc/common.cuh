@@ -77,7 +77,9 @@ struct scema_ctx {
     uint32_t table_index_len = 0;
     scema::DevBuf zscratch, d_order, d_chunks, d_chunk_counters;  // K1 work plan: padded group order, chunk list
     std::vector<uint32_t> plan_chunk_begin;                        // [classes+1] into d_chunks
-    std::vector<uint64_t> plan_groups, plan_first_slot;            // per class: groups, first group slot
+    std::vector<uint64_t> plan_groups, plan_first_slot;            // per range and class: groups, first group slot
+    std::vector<uint64_t> plan_bounds, plan_steps;                 // history ranges the plan was built for; raw steps per range
+    std::vector<uint32_t> plan_max_len;                            // per range
     uint64_t histories_version = 0, order_version = ~0ull;
 
     // ---- spline matrix S [n][K] (n == hn after a resample; set_spline may install any n)
@@ -107,7 +109,7 @@ struct scema_ctx {
     uint64_t tc_for_version = 0, tc_n = 0;
     uint32_t tc_K = 0, tc_slices = 0;
     uint32_t tc_mode = 0;  // slices the next compare starts with (auto: 1, falling back to 2 when survivors overflow)
-    double tc_thr = 0.0;
+    double tc_thr = 0.0, tc_T0 = 0.0, tc_cguard = 0.0;
     bool tc_valid = false;
 
     // ---- candidate queue + edges
@@ -124,6 +126,10 @@ struct scema_ctx {
     double *h_stage_val[2] = {nullptr, nullptr};
     uint64_t stage_cap[2] = {0, 0};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+
+    // ---- host-buffer pipeline of scema_cluster: copy stream + one event per range
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_events;
 
     // ---- instrumentation
     cudaEvent_t ev[2 * SCEMA_T_COUNT] = {};
@@ -154,6 +160,8 @@ inline void t_end(scema_ctx *c, int which) { cudaEventRecord(c->ev[2 * which + 1
 
 // resample.cu
 int resample_run(scema_ctx *ctx, uint32_t P);
+int resample_prepare(scema_ctx *ctx, uint32_t P, const std::vector<uint64_t> &bounds);
+int resample_launch_range(scema_ctx *ctx, uint32_t P, size_t r);
 int store_reset(scema_ctx *ctx, uint64_t n, const uint32_t *ids, uint32_t capacity_steps);
 int store_append(scema_ctx *ctx, const double *strain, int on_device);
 int store_resample(scema_ctx *ctx, uint32_t P);
@@ -163,11 +171,17 @@ int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_
 int compare_stream_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards, uint32_t panels_per_chunk,
                        scema_edge_sink sink, void *user, uint64_t *n_total);
 int fp64_peak_run(scema_ctx *ctx, double out[2]);
+bool pipeline_wanted(uint64_t n);
+int cluster_pipelined(scema_ctx *ctx, const double *steps_host, uint32_t P, double thr, bool *done);
 // pairs_tc.cu
 bool tc_supported(const scema_ctx *ctx);
 int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices);
-int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t shard, uint32_t n_shards, unsigned long long *cand_count,
-              float *dbg, uint64_t dbg_ld);
+int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices);
+int tc_stats_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1, bool into_scale);
+int tc_fix_scale(scema_ctx *ctx, int headroom);
+int tc_prep_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1);
+int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t C0, uint32_t C1, uint32_t shard, uint32_t n_shards,
+              unsigned long long *cand_count, float *dbg, uint64_t dbg_ld);
 int tc_debug_run(scema_ctx *ctx, double thr, uint32_t slices, float *acc_host, uint64_t ld, unsigned char *ha_host,
                  unsigned char *hb_host);
 // host_io.cc

@@ -869,6 +869,8 @@ static int ensure_edge_buffers(scema_ctx *ctx, uint64_t cap)
     return SCEMA_OK;
 }
 
+static int sort_edges(scema_ctx *ctx);
+
 // Schedule of one compare: panels of PANEL_ROWBLOCKS row blocks, column strips of strip_len tiles.
 struct Schedule {
     uint64_t nb = 0, tiles = 0, groups = 0;
@@ -935,8 +937,8 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
             SCEMA_CUDA(ctx, ctx->d_cand.reserve(ctx->cand_cap * sizeof(uint64_t)));
             t_begin(ctx, SCEMA_T_FILTER);
             // one panel = PANEL_ROWBLOCKS * TILE = 2048 rows = 8 row tiles of 256
-            rc = tc_launch(ctx, p0 * (PANEL_ROWBLOCKS * TILE / 256), p1 * (PANEL_ROWBLOCKS * TILE / 256), shard, n_shards, d_cnt + 0,
-                           nullptr, 0);
+            rc = tc_launch(ctx, p0 * (PANEL_ROWBLOCKS * TILE / 256), p1 * (PANEL_ROWBLOCKS * TILE / 256), 0, 0xffffffffu, shard, n_shards,
+                           d_cnt + 0, nullptr, 0);
             if (rc) return rc;
             t_end(ctx, SCEMA_T_FILTER);
             t_begin(ctx, SCEMA_T_EXACT);
@@ -1026,7 +1028,12 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
         ctx->n_edges = n_edge;
         break;
     }
-    // canonical order: ascending (a,b) == ascending packed key
+    return sort_edges(ctx);
+}
+
+// canonical order: ascending (a,b) == ascending packed key
+static int sort_edges(scema_ctx *ctx)
+{
     if (ctx->n_edges > 1) {
         t_begin(ctx, SCEMA_T_SORT);
         cub::DoubleBuffer<uint64_t> dk(ctx->d_edge_key[0].as<uint64_t>(), ctx->d_edge_key[1].as<uint64_t>());
@@ -1111,6 +1118,143 @@ int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_
     ctx->counters[2] = ctx->n_edges;
     if (n_shards == 1) ctx->counters[0] = ctx->n * (ctx->n - 1) / 2;
     return SCEMA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scema_cluster from host buffers, pipelined (SCEMA_PAIRS_TC, K <= 60)
+//
+// The raw steps of a large batch take longer to cross PCIe than the whole clustering takes on the GPU
+// (config 4: 1.7 GB, ~65 ms, against ~65 ms of kernels), so the batch is cut into ranges of histories.
+// Range c is copied on a second stream; as soon as it has landed it is resampled (K1 plan per range),
+// its fp16 operand copies are built, and the tcgen05 filter evaluates the COLUMN panel of the pair
+// matrix that pairs range c with itself and every earlier range — all of which is on the device by
+// then — while range c+1 is still on the bus. The survivors of all panels share one queue; the exact
+// recompute and the sort run once at the end. The operand scale has to be one power of two for all rows
+// but the rows are not all there when the first panel starts: it is frozen after range 0 with six
+// binades of headroom (rows that still outgrow it lose their fp16 image and survive against everybody,
+// k_tc_prep), which changes which pairs survive, never the edge list.
+// ------------------------------------------------------------------------------------------------
+bool pipeline_wanted(uint64_t n)
+{
+    const char *e = getenv("SCEMA_PIPELINE");         // 0 disables
+    if (e && atoi(e) == 0) return false;
+    const char *m = getenv("SCEMA_PIPELINE_MIN_N");    // smallest batch that is pipelined (tests lower it)
+    const uint64_t min_n = m ? (uint64_t)atoll(m) : 65536;
+    return n >= min_n && n >= 4096;
+}
+
+static int cluster_pipelined_impl(scema_ctx *ctx, const double *steps_host, uint32_t P, double thr, bool *done)
+{
+    *done = false;
+    const uint64_t n = ctx->hn;
+    const uint64_t panel_rows = (uint64_t)PANEL_ROWBLOCKS * TILE;  // 2048: range boundaries are whole panels (and 256-row tiles)
+    uint64_t n_ranges = std::min<uint64_t>(16, std::max<uint64_t>(2, n / 65536));
+    uint64_t per = ((n + n_ranges - 1) / n_ranges + panel_rows - 1) / panel_rows * panel_rows;
+    std::vector<uint64_t> bounds(1, 0);
+    while (bounds.back() < n) bounds.push_back(std::min<uint64_t>(n, bounds.back() + per));
+    n_ranges = bounds.size() - 1;
+
+    // ---- the first two ranges start travelling at once; the host-side preparation below (factor tables, K1 plan:
+    //      a few ms of host work with small host->device copies of its own, which queue behind what is already on
+    //      the copy engine) runs meanwhile, and only then are the remaining ranges queued
+    if (!ctx->copy_stream) SCEMA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    while (ctx->copy_events.size() < n_ranges) {
+        cudaEvent_t e;
+        SCEMA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->copy_events.push_back(e);
+    }
+    auto queue_copy = [&](uint64_t r) -> int {
+        const uint64_t s0 = ctx->h_offsets[bounds[r]], s1 = ctx->h_offsets[bounds[r + 1]];
+        if (s1 > s0)
+            SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->steps_own.as<double>() + s0 * 6, steps_host + s0 * 6, (s1 - s0) * 6 * sizeof(double),
+                                            cudaMemcpyHostToDevice, ctx->copy_stream));
+        SCEMA_CUDA(ctx, cudaEventRecord(ctx->copy_events[r], ctx->copy_stream));
+        return SCEMA_OK;
+    };
+    const uint64_t early = std::min<uint64_t>(2, n_ranges);
+    int rc;
+    for (uint64_t r = 0; r < early; r++)
+        if ((rc = queue_copy(r))) return rc;
+    rc = resample_prepare(ctx, P, bounds);
+    if (rc) return rc;
+    for (int i = 0; i < 8; i++) ctx->counters[i] = 0;
+    for (int w = SCEMA_T_RESAMPLE; w <= SCEMA_T_SORT; w++) { ctx->ev_used[w] = false; ctx->acc_ms[w] = 0.f; }
+    ctx->n_edges = 0;
+    ctx->edge_cur = 0;
+    ctx->key_shift = bits_for(n);
+    SCEMA_CUDA(ctx, ctx->d_counters.reserve(8 * sizeof(uint64_t)));
+    if (!ctx->h_counters) SCEMA_CUDA(ctx, cudaMallocHost(&ctx->h_counters, 8 * sizeof(uint64_t)));
+    rc = ensure_edge_buffers(ctx, std::max<uint64_t>(1ull << 20, 16 * n));
+    if (rc) return rc;
+    if (ctx->cand_cap == 0) ctx->cand_cap = std::max<uint64_t>(1ull << 20, 32 * n);
+    SCEMA_CUDA(ctx, ctx->d_cand.reserve(ctx->cand_cap * sizeof(uint64_t)));
+    rc = tc_prepare_begin(ctx, thr, 1);
+    if (rc) return rc;
+    unsigned long long *d_cnt = ctx->d_counters.as<unsigned long long>();
+    SCEMA_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 8 * sizeof(uint64_t), ctx->stream));
+    SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+    // ---- queue the remaining copies, then the per-range work
+    for (uint64_t r = early; r < n_ranges; r++)
+        if ((rc = queue_copy(r))) return rc;
+    const uint64_t n_pad = (n + 255) / 256 * 256;
+    t_begin(ctx, SCEMA_T_FILTER);  // in this mode "filter" spans the whole overlapped region (K1, operand prep and filter of every range)
+    for (uint64_t r = 0; r < n_ranges; r++) {
+        SCEMA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_events[r], 0));
+        rc = resample_launch_range(ctx, P, r);
+        if (rc) return rc;
+        const uint64_t r0 = bounds[r], r1 = bounds[r + 1];
+        const uint64_t r1p = r + 1 == n_ranges ? n_pad : r1;  // the last range also writes the padding rows
+        rc = tc_stats_rows(ctx, r0, r1, r == 0);
+        if (!rc && r == 0) rc = tc_fix_scale(ctx, 6);
+        if (!rc) rc = tc_prep_rows(ctx, r0, r1p);
+        if (!rc) rc = tc_launch(ctx, 0, (uint32_t)(r1p / 256), (uint32_t)(r0 / 256), (uint32_t)(r1p / 256), 0, 1, d_cnt + 0, nullptr, 0);
+        if (rc) return rc;
+    }
+    t_end(ctx, SCEMA_T_FILTER);
+
+    // ---- survivors -> edges (repeated only if the edge buffers were too small)
+    for (int pass = 0; pass < 4; pass++) {
+        SCEMA_CUDA(ctx, cudaMemsetAsync(d_cnt + 1, 0, sizeof(uint64_t), ctx->stream));
+        t_begin(ctx, SCEMA_T_EXACT);
+        k_exact_queue<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->d_spline, ctx->K, ctx->d_cand.as<uint64_t>(), d_cnt + 0, ctx->cand_cap,
+                                                                  thr, ctx->key_shift, d_cnt + 1, ctx->edge_cap,
+                                                                  ctx->d_edge_key[0].as<uint64_t>(), ctx->d_edge_val[0].as<double>());
+        ctx->launches++;
+        t_end(ctx, SCEMA_T_EXACT);
+        SCEMA_CUDA(ctx, cudaGetLastError());
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, d_cnt, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const uint64_t n_cand = ctx->h_counters[0], n_edge = ctx->h_counters[1];
+        if (n_cand > ctx->cand_cap) return SCEMA_OK;  // too many survivors for the one-slice band: the ordinary path sorts it out
+        if (n_edge > ctx->edge_cap) {
+            rc = ensure_edge_buffers(ctx, n_edge + n_edge / 8);
+            if (rc) return rc;
+            continue;
+        }
+        ctx->counters[1] = n_cand;
+        ctx->counters[3] = (uint64_t)pass + 1;
+        ctx->counters[5] = 1;
+        ctx->counters[6] = n_ranges;
+        ctx->n_edges = n_edge;
+        rc = sort_edges(ctx);
+        if (rc) return rc;
+        ctx->counters[0] = n * (n - 1) / 2;
+        ctx->counters[2] = ctx->n_edges;
+        ctx->have_edges = true;
+        *done = true;
+        return SCEMA_OK;
+    }
+    return SCEMA_OK;
+}
+
+int cluster_pipelined(scema_ctx *ctx, const double *steps_host, uint32_t P, double thr, bool *done)
+{
+    const int rc = cluster_pipelined_impl(ctx, steps_host, P, thr, done);
+    // on failure copies of the caller's buffer may still be in flight; the buffer is the caller's again on return
+    if (rc && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (!rc && !*done && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    return rc;
 }
 
 // Streaming compare: the panels are evaluated in chunks of panels_per_chunk; each chunk's sorted

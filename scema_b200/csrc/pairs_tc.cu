@@ -195,6 +195,7 @@ struct Args {
     uint64_t n;
     uint32_t NT;       // column tiles (256 rows each)
     uint32_t I0, I1;   // row range of this launch, in 256-row tiles
+    uint32_t C0, C1;   // column range of this launch, in 256-row tiles (all pairs: 0 .. NT)
     uint32_t strip_len;
     uint32_t shard, n_shards;
     uint32_t slices;   // 2: a_hi.b_hi + a_lo.b_hi + a_hi.b_lo; 1: a_hi.b_hi only (coarser guard band, a third of the MMAs)
@@ -209,12 +210,12 @@ struct Args {
 template <int CG>
 struct Sched {
     static constexpr uint32_t RPC = 2 / CG;  // row tiles per column tile
-    uint32_t S, NT, R0, R1, ns, s, shard, n_shards;
+    uint32_t S, NT, C0, R0, R1, ns, s, shard, n_shards;  // NT: end of the column range
     uint64_t cum, k, stride;
     __device__ void init(const Args &a, uint32_t unit, uint32_t n_units)
     {
-        S = a.strip_len; NT = a.NT; R0 = a.I0 * RPC; R1 = a.I1 * RPC;
-        ns = (NT + S - 1) / S; s = a.I0 / S; cum = 0; k = unit; stride = n_units;
+        S = a.strip_len; NT = min(a.NT, a.C1); C0 = a.C0; R0 = a.I0 * RPC; R1 = a.I1 * RPC;
+        ns = (NT + S - 1) / S; s = max(a.I0, a.C0) / S; cum = 0; k = unit; stride = n_units;
         shard = a.shard; n_shards = a.n_shards;
     }
     __device__ uint32_t count(uint32_t strip) const
@@ -230,7 +231,7 @@ struct Sched {
         if (s >= ns) return false;
         I = R0 + (uint32_t)(g - cum);
         J1 = min((s + 1) * S, NT);
-        J0 = max(I / RPC, s * S);
+        J0 = max(max(I / RPC, s * S), C0);
         k += stride;
         return true;
     }
@@ -439,37 +440,51 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
 // ------------------------------------------------------------------------------------------------
 // operand preparation
 // ------------------------------------------------------------------------------------------------
-// pass 1: row norms (FP64) and the largest finite magnitude of the matrix
-__global__ void __launch_bounds__(256) k_tc_rowstats(const double *__restrict__ S, uint64_t n, uint32_t K,
+// pass 1: row norms (FP64) and the largest finite magnitude of the rows [r0, r1)
+__global__ void __launch_bounds__(256) k_tc_rowstats(const double *__restrict__ S, uint64_t r0, uint64_t r1, uint32_t K,
                                                      double *__restrict__ NRM, unsigned long long *__restrict__ gmax)
 {
-    const uint64_t row = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= n) return;
+    __shared__ double s_max[8];
+    const uint64_t row = r0 + (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double nrm = 0.0, m = 0.0;
-    for (uint32_t k = lane; k < K; k += 32) {
-        const double v = S[row * K + k];
-        nrm = fma(v, v, nrm);
-        m = fmax(m, fabs(v));
-    }
+    if (row < r1)
+        for (uint32_t k = lane; k < K; k += 32) {
+            const double v = S[row * K + k];
+            nrm = fma(v, v, nrm);
+            m = fmax(m, fabs(v));
+        }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
         m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     }
     if (lane == 0) {
-        NRM[row] = nrm;
-        if (isfinite(nrm)) atomicMax(gmax, (unsigned long long)__double_as_longlong(m));  // non-negative doubles order as integers
+        if (row < r1) NRM[row] = nrm;
+        s_max[warp] = (row < r1 && isfinite(nrm)) ? m : 0.0;  // rows with a non-finite norm take no part in the scale
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double bm = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) bm = fmax(bm, s_max[w]);
+        if (gmax && bm > 0.0) atomicMax(gmax, (unsigned long long)__double_as_longlong(bm));  // non-negative doubles order as integers
     }
 }
 
-// Power-of-two scale that brings the largest finite magnitude into [2^11, 2^12).
-__device__ __forceinline__ double tc_scale(double maxabs)
+// Power-of-two scale that brings the largest finite magnitude into [2^(11-headroom), 2^(12-headroom)).
+// misc[0] = largest magnitude seen (bits), misc[1] = the scale (double bits), misc[2] = rows whose scaled
+// magnitude reached 2^12 (only possible when the scale was fixed before all rows were seen).
+__global__ void k_tc_fix_scale(unsigned long long *misc, int headroom)
 {
-    if (!(maxabs > 0.0)) return 1.0;
-    int se = 11 - ilogb(maxabs);
-    se = max(-1000, min(1000, se));
-    return scalbn(1.0, se);
+    const double maxabs = __longlong_as_double((long long)misc[0]);
+    double s = 1.0;
+    if (maxabs > 0.0) {
+        int se = 11 - headroom - ilogb(maxabs);
+        se = max(-1000, min(1000, se));
+        s = scalbn(1.0, se);
+    }
+    misc[1] = (unsigned long long)__double_as_longlong(s);
 }
 
 // fp16 rounding with subnormal results flushed to zero: the operands never contain an fp16 subnormal, so
@@ -486,25 +501,31 @@ __device__ __forceinline__ double h16z(double v)
 //   A hi: [x0 x1 P Q]   A lo: [0 x2 0 0]        B hi: [P Q x0 x1]   B lo: [0 0 0 x2]
 // so that  A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  adds  (P x0 + Q x1 + Q x2)_i + (P x0 + Q x1 + Q x2)_j = -h_i - h_j
 // (to 2^-33 |h| + 2^-11; with the hi slices alone the x2 terms drop out: 2^-22 |h| + 2^-11).
-__global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, uint64_t n, uint64_t n_pad, uint32_t K,
-                                                 const double *__restrict__ NRM, const unsigned long long *__restrict__ gmax,
+__global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, uint64_t n, uint64_t r0, uint64_t r1, uint32_t K,
+                                                 const double *__restrict__ NRM, unsigned long long *__restrict__ misc,
                                                  double T0, double cguard, unsigned char *__restrict__ HA,
                                                  unsigned char *__restrict__ HB)
 {
-    const uint64_t row = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint64_t row = r0 + (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= n_pad) return;
-    const double s = tc_scale(__longlong_as_double((long long)*gmax));
+    if (row >= r1) return;
+    const double s = __longlong_as_double((long long)misc[1]);
     const bool real = row < n;
     const bool wild = real && !isfinite(NRM[row]);
     double v[2] = {0.0, 0.0};
-    double nrm = 0.0;
 #pragma unroll
     for (int e = 0; e < 2; e++) {
         const uint32_t k = lane + 32 * e;
         if (real && !wild && k < K) v[e] = S[row * K + k] * s;
-        nrm = fma(v[e], v[e], nrm);
     }
+    // a row beyond the range the scale was chosen for (possible only when the scale was fixed before every
+    // row had been seen): no fp16 image; it survives against everybody like a row with a non-finite norm
+    const bool too_big = __any_sync(0xffffffffu, fabs(v[0]) >= 4096.0 || fabs(v[1]) >= 4096.0);
+    if (too_big) {
+        v[0] = v[1] = 0.0;
+        if (lane == 0) atomicAdd(misc + 2, 1ull);
+    }
+    double nrm = fma(v[1], v[1], v[0] * v[0]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
     // row term
@@ -514,7 +535,7 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
     const double h = 0.5 * (nrm * (1.0 - cguard) - T0s * (0.5 + 2.0 * cguard) - e0);
     double x0, x1, x2;
     if (!real) { x0 = -65504.0; x1 = x2 = 0.0; }                              // padding row: never a survivor
-    else if (wild || !(-h <= 32768.0 * P)) { x0 = 65504.0; x1 = x2 = 0.0; }   // NaN/inf row, or threshold beyond every distance: always
+    else if (wild || too_big || !(-h <= 32768.0 * P)) { x0 = 65504.0; x1 = x2 = 0.0; }   // NaN/inf row, or threshold beyond every distance: always
     else {
         x0 = h16z(-h / P);
         x1 = h16z((-h - P * x0) / Q);
@@ -552,42 +573,82 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
 // ------------------------------------------------------------------------------------------------
 bool tc_supported(const scema_ctx *ctx) { return ctx->K >= 1 && ctx->K <= tc::KMAX; }
 
-// Builds (or reuses) the fp16 operand copies for the current spline matrix and threshold.
-int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices)
+// Operand preparation in three steps so that the host-buffer pipeline can run it range by range:
+//   tc_prepare_begin : buffers, threshold constants, guard band of the slice count
+//   tc_stats_rows    : norms of rows [r0, r1) (and, if wanted, their largest magnitude into the scale input)
+//   tc_fix_scale     : freeze the power-of-two scale (headroom = binades left for rows not seen yet)
+//   tc_prep_rows     : fp16 operand copies of rows [r0, r1) (r1 may run into the padding)
+int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices)
 {
     const uint64_t n = ctx->n;
     const uint32_t K = ctx->K;
     const uint64_t n_pad = (n + tc::COLT - 1) / tc::COLT * tc::COLT;
-    if (ctx->tc_for_version == ctx->spline_version && ctx->tc_thr == thr && ctx->tc_n == n && ctx->tc_K == K &&
-        ctx->tc_slices == slices && ctx->tc_valid)
-        return SCEMA_OK;
+    ctx->tc_valid = false;
     SCEMA_CUDA(ctx, ctx->d_tc_a.reserve(n_pad * 256));
     SCEMA_CUDA(ctx, ctx->d_tc_b.reserve(n_pad * 256));
     SCEMA_CUDA(ctx, ctx->d_tc_nrm.reserve(n_pad * sizeof(double)));
     SCEMA_CUDA(ctx, ctx->d_tc_misc.reserve(64));
     SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_tc_misc.p, 0, 64, ctx->stream));
-    tc::k_tc_rowstats<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(ctx->d_spline, n, K, ctx->d_tc_nrm.as<double>(),
-                                                                        ctx->d_tc_misc.as<unsigned long long>());
     const double eps = 1.1102230246251565e-16;  // 2^-53
     // The operands are rescaled, so the reference's underflow must be budgeted explicitly: each squared
     // difference of compare_L2_norm may lose up to half a subnormal ulp, i.e. the reference's sum can sit
     // K 2^-1075 below d^2 (and thr * thr itself rounds there too).
-    const double T0 = thr * thr * (1.0 + (2.0 * K + 16.0) * eps) * (1.0 + 4.0 * eps) + (2.0 * K + 4.0) * 4.9406564584124654e-324;
+    ctx->tc_T0 = thr * thr * (1.0 + (2.0 * K + 16.0) * eps) * (1.0 + 4.0 * eps) + (2.0 * K + 4.0) * 4.9406564584124654e-324;
     // Guard band (DESIGN.md "K2-TC"): relative to |a_i|^2 + |a_j|^2 the computed accumulator is off by at most
     //   two slices: 3.1 2^-22 (slicing) + 13 2^-18 (12 MMA steps, fp32 accumulate)          < 2^-14
     //   one slice : 2^-11 (dropping a_lo, b_lo) + 5 2^-18 (4 steps) + 2^-23 (two-slice fold)  < 2^-10.9
     // and the band must be twice that.
-    const double cguard = slices == 1 ? 0.001953125 : 0.0001220703125;  // 2^-9, 2^-13
-    tc::k_tc_prep<<<(unsigned)((n_pad + 7) / 8), 256, 0, ctx->stream>>>(ctx->d_spline, n, n_pad, K, ctx->d_tc_nrm.as<double>(),
-                                                                        ctx->d_tc_misc.as<unsigned long long>(), T0, cguard,
-                                                                        ctx->d_tc_a.as<unsigned char>(), ctx->d_tc_b.as<unsigned char>());
-    ctx->launches += 2;
-    SCEMA_CUDA(ctx, cudaGetLastError());
-    ctx->tc_for_version = ctx->spline_version;
+    ctx->tc_cguard = slices == 1 ? 0.001953125 : 0.0001220703125;  // 2^-9, 2^-13
     ctx->tc_thr = thr;
     ctx->tc_n = n;
     ctx->tc_K = K;
     ctx->tc_slices = slices;
+    ctx->tc_for_version = ctx->spline_version;
+    return SCEMA_OK;
+}
+
+int tc_stats_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1, bool into_scale)
+{
+    if (r1 <= r0) return SCEMA_OK;
+    tc::k_tc_rowstats<<<(unsigned)((r1 - r0 + 7) / 8), 256, 0, ctx->stream>>>(
+        ctx->d_spline, r0, r1, ctx->K, ctx->d_tc_nrm.as<double>(), into_scale ? ctx->d_tc_misc.as<unsigned long long>() : nullptr);
+    ctx->launches++;
+    SCEMA_CUDA(ctx, cudaGetLastError());
+    return SCEMA_OK;
+}
+
+int tc_fix_scale(scema_ctx *ctx, int headroom)
+{
+    tc::k_tc_fix_scale<<<1, 1, 0, ctx->stream>>>(ctx->d_tc_misc.as<unsigned long long>(), headroom);
+    ctx->launches++;
+    SCEMA_CUDA(ctx, cudaGetLastError());
+    return SCEMA_OK;
+}
+
+int tc_prep_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1)
+{
+    if (r1 <= r0) return SCEMA_OK;
+    tc::k_tc_prep<<<(unsigned)((r1 - r0 + 7) / 8), 256, 0, ctx->stream>>>(
+        ctx->d_spline, ctx->n, r0, r1, ctx->K, ctx->d_tc_nrm.as<double>(), ctx->d_tc_misc.as<unsigned long long>(), ctx->tc_T0,
+        ctx->tc_cguard, ctx->d_tc_a.as<unsigned char>(), ctx->d_tc_b.as<unsigned char>());
+    ctx->launches++;
+    SCEMA_CUDA(ctx, cudaGetLastError());
+    return SCEMA_OK;
+}
+
+// Builds (or reuses) the fp16 operand copies for the current spline matrix and threshold.
+int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices)
+{
+    const uint64_t n = ctx->n;
+    const uint64_t n_pad = (n + tc::COLT - 1) / tc::COLT * tc::COLT;
+    if (ctx->tc_for_version == ctx->spline_version && ctx->tc_thr == thr && ctx->tc_n == n && ctx->tc_K == ctx->K &&
+        ctx->tc_slices == slices && ctx->tc_valid)
+        return SCEMA_OK;
+    int rc = tc_prepare_begin(ctx, thr, slices);
+    if (!rc) rc = tc_stats_rows(ctx, 0, n, true);
+    if (!rc) rc = tc_fix_scale(ctx, 0);
+    if (!rc) rc = tc_prep_rows(ctx, 0, n_pad);
+    if (rc) return rc;
     ctx->tc_valid = true;
     return SCEMA_OK;
 }
@@ -619,10 +680,9 @@ static int tc_launch_t(scema_ctx *ctx, const tc::Args &a, uint64_t items)
 
 // Filter the pairs of the row tiles [I0, I1) (256-row units) that belong to this shard; survivors go
 // to the candidate queue (cand_count is d_counters[0]). dbg != nullptr selects the instrumented kernel.
-int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t shard, uint32_t n_shards, unsigned long long *cand_count,
-              float *dbg, uint64_t dbg_ld)
+int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t C0, uint32_t C1, uint32_t shard, uint32_t n_shards,
+              unsigned long long *cand_count, float *dbg, uint64_t dbg_ld)
 {
-    if (!ctx->tc_valid) return fail(ctx, SCEMA_ERR_STATE, "tensor-core filter: operands not prepared");
     tc::Args a;
     a.HA = ctx->d_tc_a.as<unsigned char>();
     a.HB = ctx->d_tc_b.as<unsigned char>();
@@ -633,6 +693,8 @@ int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t shard, uint32_t
     a.NT = (uint32_t)((ctx->n + tc::COLT - 1) / tc::COLT);
     a.I0 = I0;
     a.I1 = std::min<uint32_t>(I1, a.NT);
+    a.C0 = C0;
+    a.C1 = std::min<uint32_t>(C1, a.NT);
     a.shard = shard;
     a.n_shards = n_shards;
     a.slices = ctx->tc_slices;
@@ -645,12 +707,13 @@ int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t shard, uint32_t
     const int cg = (cg_env && atoi(cg_env) == 2) ? 2 : 1;
     // strips: long enough to amortise the A tile, short enough to leave every cluster many items
     const uint64_t rows = a.I1 > a.I0 ? a.I1 - a.I0 : 0;
-    const uint64_t tiles = rows * a.NT;  // upper bound
+    const uint64_t cols = a.C1 > a.C0 ? a.C1 - a.C0 : 0;
+    const uint64_t tiles = rows * cols;  // upper bound
     const uint64_t units = (uint64_t)ctx->sm_count / cg;
     a.strip_len = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, tiles / (units * 32 * std::max<uint32_t>(n_shards, 1))));
-    if (rows == 0) return SCEMA_OK;
+    if (rows == 0 || cols == 0) return SCEMA_OK;
     // items of this shard (upper bound is enough to size the grid)
-    const uint64_t n_strips = (a.NT + a.strip_len - 1) / a.strip_len;
+    const uint64_t n_strips = (cols + a.strip_len - 1) / a.strip_len + 1;
     const uint64_t items = std::max<uint64_t>(1, rows * (2 / cg) * n_strips / std::max<uint32_t>(n_shards, 1));
     if (cg == 1) return dbg ? tc_launch_t<1, true>(ctx, a, items) : tc_launch_t<1, false>(ctx, a, items);
     return dbg ? tc_launch_t<2, true>(ctx, a, items) : tc_launch_t<2, false>(ctx, a, items);
@@ -678,7 +741,8 @@ int tc_debug_run(scema_ctx *ctx, double thr, uint32_t slices, float *acc_host, u
     DevBuf dbg;
     SCEMA_CUDA(ctx, dbg.reserve(n_pad * n_pad * sizeof(float)));
     SCEMA_CUDA(ctx, cudaMemsetAsync(dbg.p, 0xFF, n_pad * n_pad * sizeof(float), ctx->stream));  // NaN = never written
-    rc = tc_launch(ctx, 0, (uint32_t)(n_pad / tc::COLT), 0, 1, ctx->d_counters.as<unsigned long long>(), dbg.as<float>(), n_pad);
+    rc = tc_launch(ctx, 0, (uint32_t)(n_pad / tc::COLT), 0, (uint32_t)(n_pad / tc::COLT), 0, 1,
+                   ctx->d_counters.as<unsigned long long>(), dbg.as<float>(), n_pad);
     if (rc) { dbg.release(); return rc; }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess && acc_host)

@@ -539,42 +539,59 @@ static int ensure_tables_present(scema_ctx *ctx, uint32_t P, const std::vector<u
 static const uint32_t K1_CAPS[] = {64, SMEM_TAB_MAX_L, 2048, 16384, 131072};
 constexpr int K1_NCLS = sizeof(K1_CAPS) / sizeof(K1_CAPS[0]) + 1;  // last class: global-scratch fallback
 
-static int build_plan(scema_ctx *ctx)
+// The plan covers one or more contiguous RANGES of histories; every range has its own groups, chunks
+// and per-class launch set, so a range can be resampled as soon as its raw steps are on the device
+// (the host-buffer pipeline of scema_cluster) while the default path is the single range [0, n).
+static int build_plan(scema_ctx *ctx, const std::vector<uint64_t> &bounds)
 {
-    if (ctx->order_version == ctx->histories_version) return SCEMA_OK;
-    const uint64_t n = ctx->hn;
-    std::vector<uint64_t> len_count((size_t)ctx->max_len + 2, 0);
-    for (uint64_t i = 0; i < n; i++) len_count[ctx->h_offsets[i + 1] - ctx->h_offsets[i]]++;
-    // group slots per length, in ascending length
-    std::vector<uint64_t> group_first((size_t)ctx->max_len + 2, 0);
-    for (uint32_t L = 0; L <= ctx->max_len; L++) group_first[L + 1] = group_first[L] + (len_count[L] + GROUP - 1) / GROUP;
-    const uint64_t n_groups = group_first[ctx->max_len + 1];
-    std::vector<uint32_t> order(std::max<uint64_t>(n_groups * GROUP, 1), 0xffffffffu);
-    std::vector<uint64_t> fill((size_t)ctx->max_len + 1, 0);
-    for (uint64_t i = 0; i < n; i++) {
-        const uint64_t L = ctx->h_offsets[i + 1] - ctx->h_offsets[i];
-        order[group_first[L] * GROUP + fill[L]++] = (uint32_t)i;
-    }
+    if (ctx->order_version == ctx->histories_version && ctx->plan_bounds == bounds) return SCEMA_OK;
+    const size_t n_ranges = bounds.size() - 1;
     auto cls_of = [&](uint32_t L) { int k = 0; while (k < K1_NCLS - 1 && L > K1_CAPS[k]) k++; return k; };
+    std::vector<uint32_t> order;
     std::vector<K1Chunk> chunks;
-    ctx->plan_chunk_begin.assign(K1_NCLS + 1, 0);
-    ctx->plan_groups.assign(K1_NCLS, 0);
-    ctx->plan_first_slot.assign(K1_NCLS, 0);
-    for (int k = 0; k < K1_NCLS; k++) {
-        ctx->plan_chunk_begin[k] = (uint32_t)chunks.size();
-        bool first = true;
-        for (uint32_t L = ctx->max_len; L >= 3; L--) {  // longest first
-            if (cls_of(L) != k || !len_count[L]) continue;
-            const uint64_t g0 = group_first[L], g1 = group_first[L + 1];
-            if (first) { ctx->plan_first_slot[k] = g0; first = false; }
-            ctx->plan_first_slot[k] = std::min<uint64_t>(ctx->plan_first_slot[k], g0);
-            ctx->plan_groups[k] += g1 - g0;
-            for (uint64_t g = g0; g < g1; g += CHUNK_GROUPS)
-                chunks.push_back(K1Chunk{(uint32_t)g, (uint32_t)std::min<uint64_t>(CHUNK_GROUPS, g1 - g), L, 0});
+    ctx->plan_chunk_begin.assign(n_ranges * (K1_NCLS + 1), 0);
+    ctx->plan_groups.assign(n_ranges * K1_NCLS, 0);
+    ctx->plan_first_slot.assign(n_ranges * K1_NCLS, 0);
+    ctx->plan_max_len.assign(n_ranges, 0);
+    ctx->plan_steps.assign(n_ranges, 0);
+    std::vector<uint64_t> len_count, group_first, fill;
+    for (size_t r = 0; r < n_ranges; r++) {
+        const uint64_t h0 = bounds[r], h1 = bounds[r + 1];
+        uint32_t max_len = 0;
+        for (uint64_t i = h0; i < h1; i++) max_len = std::max<uint32_t>(max_len, (uint32_t)(ctx->h_offsets[i + 1] - ctx->h_offsets[i]));
+        ctx->plan_max_len[r] = max_len;
+        ctx->plan_steps[r] = ctx->h_offsets[h1] - ctx->h_offsets[h0];
+        len_count.assign((size_t)max_len + 2, 0);
+        for (uint64_t i = h0; i < h1; i++) len_count[ctx->h_offsets[i + 1] - ctx->h_offsets[i]]++;
+        // group slots per length, in ascending length; slot numbers are global over all ranges
+        const uint64_t base = order.size() / GROUP;
+        group_first.assign((size_t)max_len + 2, base);
+        for (uint32_t L = 0; L <= max_len; L++) group_first[L + 1] = group_first[L] + (len_count[L] + GROUP - 1) / GROUP;
+        const uint64_t n_groups = group_first[max_len + 1] - base;
+        order.resize((base + n_groups) * GROUP, 0xffffffffu);
+        fill.assign((size_t)max_len + 1, 0);
+        for (uint64_t i = h0; i < h1; i++) {
+            const uint64_t L = ctx->h_offsets[i + 1] - ctx->h_offsets[i];
+            order[group_first[L] * GROUP + fill[L]++] = (uint32_t)i;
         }
+        for (int k = 0; k < K1_NCLS; k++) {
+            ctx->plan_chunk_begin[r * (K1_NCLS + 1) + k] = (uint32_t)chunks.size();
+            bool first = true;
+            for (uint32_t L = max_len; L >= 3; L--) {  // longest first
+                if (cls_of(L) != k || !len_count[L]) continue;
+                const uint64_t g0 = group_first[L], g1 = group_first[L + 1];
+                uint64_t &fs = ctx->plan_first_slot[r * K1_NCLS + k];
+                if (first) { fs = g0; first = false; }
+                fs = std::min<uint64_t>(fs, g0);
+                ctx->plan_groups[r * K1_NCLS + k] += g1 - g0;
+                for (uint64_t g = g0; g < g1; g += CHUNK_GROUPS)
+                    chunks.push_back(K1Chunk{(uint32_t)g, (uint32_t)std::min<uint64_t>(CHUNK_GROUPS, g1 - g), L, 0});
+            }
+        }
+        ctx->plan_chunk_begin[r * (K1_NCLS + 1) + K1_NCLS] = (uint32_t)chunks.size();
     }
-    ctx->plan_chunk_begin[K1_NCLS] = (uint32_t)chunks.size();
-    if (n_groups * GROUP >= (1ull << 32)) return fail(ctx, SCEMA_ERR_INVALID, "resample: too many histories");
+    if (order.size() >= (1ull << 32)) return fail(ctx, SCEMA_ERR_INVALID, "resample: too many histories");
+    if (order.empty()) order.push_back(0xffffffffu);
     SCEMA_CUDA(ctx, ctx->d_order.reserve(order.size() * sizeof(uint32_t)));
     SCEMA_CUDA(ctx, ctx->d_chunks.reserve(std::max<size_t>(chunks.size(), 1) * sizeof(K1Chunk)));
     SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_order.p, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -583,6 +600,7 @@ static int build_plan(scema_ctx *ctx)
                                         ctx->stream));
     SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // order / chunks are stack-lifetime host buffers
     ctx->order_version = ctx->histories_version;
+    ctx->plan_bounds = bounds;
     return SCEMA_OK;
 }
 
@@ -612,7 +630,9 @@ static int launch_stream(scema_ctx *ctx, const double *steps, const uint64_t *of
     return SCEMA_OK;
 }
 
-int resample_run(scema_ctx *ctx, uint32_t P)
+// Everything a resample needs before the first kernel: output matrix, factor tables, plan over the
+// given ranges of histories (bounds[0] = 0 < ... < bounds.back() = n), scratch, zeroed chunk counters.
+int resample_prepare(scema_ctx *ctx, uint32_t P, const std::vector<uint64_t> &bounds)
 {
     if (!ctx->have_histories) return fail(ctx, SCEMA_ERR_STATE, "resample: no histories set");
     if (P == 0) return fail(ctx, SCEMA_ERR_INVALID, "resample: spline_points must be >= 1");
@@ -632,45 +652,60 @@ int resample_run(scema_ctx *ctx, uint32_t P)
 
     int rc = ensure_tables(ctx, P);
     if (rc) return rc;
-    rc = build_plan(ctx);
+    rc = build_plan(ctx, bounds);
     if (rc) return rc;
-
-    uint64_t warps[K1_NCLS] = {};
+    const size_t n_ranges = bounds.size() - 1;
     uint64_t scratch_need = 0;
-    for (int k = 0; k < K1_NCLS; k++) {
-        if (!ctx->plan_groups[k]) continue;
-        if (k == K1_NCLS - 1) { scratch_need = std::max<uint64_t>(scratch_need, (uint64_t)ctx->total_steps * 6 * sizeof(double)); continue; }
-        const uint32_t cap = std::min<uint32_t>(K1_CAPS[k], ctx->max_len);
-        warps[k] = stream_warps_for(ctx, ctx->plan_groups[k], cap);
-        scratch_need = std::max<uint64_t>(scratch_need, warps[k] * cap * 256);
-    }
+    for (size_t r = 0; r < n_ranges; r++)
+        for (int k = 0; k < K1_NCLS; k++) {
+            if (!ctx->plan_groups[r * K1_NCLS + k]) continue;
+            if (k == K1_NCLS - 1) { scratch_need = std::max<uint64_t>(scratch_need, (uint64_t)ctx->total_steps * 6 * sizeof(double)); continue; }
+            const uint32_t cap = std::min<uint32_t>(K1_CAPS[k], ctx->plan_max_len[r]);
+            scratch_need = std::max<uint64_t>(scratch_need, stream_warps_for(ctx, ctx->plan_groups[r * K1_NCLS + k], cap) * cap * 256);
+        }
     if (scratch_need) SCEMA_CUDA(ctx, ctx->zscratch.reserve(scratch_need));
-    SCEMA_CUDA(ctx, ctx->d_chunk_counters.reserve(K1_NCLS * sizeof(unsigned int)));
-    SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_chunk_counters.p, 0, K1_NCLS * sizeof(unsigned int), ctx->stream));
+    SCEMA_CUDA(ctx, ctx->d_chunk_counters.reserve(n_ranges * K1_NCLS * sizeof(unsigned int)));
+    SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_chunk_counters.p, 0, n_ranges * K1_NCLS * sizeof(unsigned int), ctx->stream));
+    return SCEMA_OK;
+}
 
-    t_begin(ctx, SCEMA_T_RESAMPLE);
+// K1 launches of range r of the prepared plan.
+int resample_launch_range(scema_ctx *ctx, uint32_t P, size_t r)
+{
+    int rc;
     for (int k = 0; k < K1_NCLS; k++) {
-        if (!ctx->plan_groups[k]) continue;
+        const uint64_t n_groups = ctx->plan_groups[r * K1_NCLS + k];
+        if (!n_groups) continue;
         if (k < K1_NCLS - 1) {
-            const uint32_t cap = std::min<uint32_t>(K1_CAPS[k], ctx->max_len);
+            const uint32_t cap = std::min<uint32_t>(K1_CAPS[k], ctx->plan_max_len[r]);
+            const uint32_t cb = ctx->plan_chunk_begin[r * (K1_NCLS + 1) + k], ce = ctx->plan_chunk_begin[r * (K1_NCLS + 1) + k + 1];
             rc = launch_stream(ctx, ctx->d_steps, ctx->d_offsets.as<uint64_t>(), ctx->d_order.as<uint32_t>(), ctx->hn,
-                               ctx->d_chunks.as<K1Chunk>() + ctx->plan_chunk_begin[k],
-                               ctx->plan_chunk_begin[k + 1] - ctx->plan_chunk_begin[k],
-                               ctx->d_chunk_counters.as<unsigned int>() + k, P, warps[k], cap, 6, 0);
+                               ctx->d_chunks.as<K1Chunk>() + cb, ce - cb, ctx->d_chunk_counters.as<unsigned int>() + r * K1_NCLS + k, P,
+                               stream_warps_for(ctx, n_groups, cap), cap, 6, 0);
             if (rc) return rc;
         } else {
             // histories longer than the last class: sweeps through a global scratch of the input's shape
-            const uint64_t n_groups = ctx->plan_groups[k];
             uint64_t grid = std::min<uint64_t>((uint64_t)ctx->sm_count * 32, n_groups);
             k_resample_global<<<(unsigned)grid, 32, 0, ctx->stream>>>(
-                ctx->d_steps, ctx->d_offsets.as<uint64_t>(), ctx->d_order.as<uint32_t>(), ctx->plan_first_slot[k] * GROUP,
+                ctx->d_steps, ctx->d_offsets.as<uint64_t>(), ctx->d_order.as<uint32_t>(), ctx->plan_first_slot[r * K1_NCLS + k] * GROUP,
                 n_groups * GROUP, ctx->d_table_index.as<int64_t>(), ctx->d_tables.as<double>(), P,
                 ctx->spline_own.as<double>(), ctx->zscratch.as<double>());
             ctx->launches++;
         }
     }
-    t_end(ctx, SCEMA_T_RESAMPLE);
     SCEMA_CUDA(ctx, cudaGetLastError());
+    return SCEMA_OK;
+}
+
+int resample_run(scema_ctx *ctx, uint32_t P)
+{
+    const std::vector<uint64_t> bounds = {0, ctx->hn};
+    int rc = resample_prepare(ctx, P, bounds);
+    if (rc || ctx->hn == 0) return rc;
+    t_begin(ctx, SCEMA_T_RESAMPLE);
+    rc = resample_launch_range(ctx, P, 0);
+    if (rc) return rc;
+    t_end(ctx, SCEMA_T_RESAMPLE);
     return SCEMA_OK;
 }
 

@@ -232,3 +232,46 @@ def test_tc_single_cta_kernel_and_pinned_slices_match(tmp_path):
         env = dict(os.environ, SCEMA_TC_CG=cg, SCEMA_TC_SLICES=sl, PYTHONPATH=ROOT)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and r.stdout.startswith("ok"), (cg, sl, r.stdout, r.stderr)
+
+
+def test_cluster_from_host_buffers_is_pipelined_and_identical(oracle, monkeypatch):
+    """scema_cluster on a large host batch copies, resamples and compares range by range (cluster_pipelined):
+    same spline matrix and edge list as the step-by-step calls; rows that outgrow the scale frozen after the
+    first range, and a batch whose survivors overflow the queue (fall back to the ordinary path), included."""
+    monkeypatch.setenv("SCEMA_PIPELINE_MIN_N", "4096")
+    P = 10
+    n = 21000  # ranges of 12288 + 8712 histories
+    off = synth.offsets(13, n, 16, 6, 90)
+    steps = synth.histories(13, n, 16, 5e-3, synth.default_pert(THR, P), off)
+    cases = {"plain": steps}
+    big = steps.copy()
+    big[int(off[15000]):int(off[15020])] *= 3000.0      # later rows 3000x larger than anything in the first range
+    big[int(off[20000]):int(off[20004])] *= 1e6
+    cases["outgrows_scale"] = big
+    for name, st in cases.items():
+        h = scema_b200.HistCluster(0)
+        ne = h.cluster(st, off, None, P, THR)
+        c = h.counters()
+        assert c["pipeline_ranges"] == 2, (name, c)
+        got, sp = h.get_edges(), h.get_spline()
+        want_sp = oracle.splinify_batch(st, off, P)
+        assert np.array_equal(bits(sp), bits(want_sp)), name
+        h.set_histories(st, off)
+        h.resample(P)
+        assert h.compare(THR, PAIRS_EXACT) == ne and edges_equal(h.get_edges(), got), name
+        assert ne > n // 4
+        # a second call on the same context reuses streams/events
+        assert h.cluster(st, off, None, P, THR) == ne and edges_equal(h.get_edges(), got)
+        h.close()
+    # survivors overflow the queue -> the pipeline hands over to the ordinary path (which grows the buffers)
+    n2 = 6000
+    off2 = (np.arange(n2 + 1, dtype=np.uint64) * 7)
+    st2 = np.tile(np.linspace(0, 1e-3, 7)[:, None], (n2, 6)) + 1e-10 * np.random.default_rng(0).standard_normal((n2 * 7, 6))
+    h = scema_b200.HistCluster(0)
+    assert h.cluster(st2, off2, None, P, THR) == n2 * (n2 - 1) // 2
+    assert h.counters()["pipeline_ranges"] == 0
+    h.close()
+    monkeypatch.setenv("SCEMA_PIPELINE", "0")
+    h = scema_b200.HistCluster(0)
+    assert h.cluster(steps, off, None, P, THR) > 0 and h.counters()["pipeline_ranges"] == 0
+    h.close()
