@@ -205,8 +205,8 @@ def run_ours(args, wl, wl_name):
     n, P = wl["n"], wl["P"]
     K = 6 * P
     variant = {"dmma": 0, "fma": 1, "exact": 2, "tc": 3}[args.variant]
-    # the tcgen05 filter holds one 64-column fp16 slice per row: wider rows (config 5) take the DMMA filter
-    eff_variant = "dmma" if (args.variant == "tc" and K > 60) else args.variant
+    # the tcgen05 filter takes rows of up to 10 chunks of 64 columns; wider rows take the DMMA filter
+    eff_variant = "dmma" if (args.variant == "tc" and K > 636) else args.variant
     pert = synth.default_pert(THR, P)
     b, e = shard_bounds(n, world)[rank]
     n_local = e - b
@@ -343,13 +343,15 @@ def run_ours(args, wl, wl_name):
             peak = float(mp.get("bf16_tflops", 1590.0))
             tc_slices = hc.counters().get("tc_slices", 2) or 2
             n_products = 1 if tc_slices == 1 else 3
-            executed = (NT * (NT + 1) / 2) / world * 256 * 256 * n_products * 64 * 2 / (filt_ms * 1e-3) / 1e12 if filt_ms > 0 else None
+            n_chunks = (K + 4 + 63) // 64
+            executed = ((NT * (NT + 1) / 2) / world * 256 * 256 * n_products * 64 * n_chunks * 2 / (filt_ms * 1e-3) / 1e12
+                        if filt_ms > 0 else None)
             extra = {"tc_slices": tc_slices, "executed_tflops": executed, "frac_executed": (executed / peak) if executed else None,
                      "peak_sustained": mp.get("bf16_tflops_sustained"),
                      "kernel": "k_filter_tc (K2 GEMM-form filter on tcgen05, split fp16, fp32 accumulate in TMEM)",
                      "peak_source": "of %s: MEASURED_PEAKS.json bf16_tflops (cuBLAS bf16 8192^3 burst); the kernel is timed "
                                     "alone per launch (CUDA events around it); sustained figure beside it" % src}
-            if tc_slices == 1:
+            if tc_slices == 1 and n_chunks == 1:
                 # what actually bounds the one-slice kernel: every pair's fp32 accumulator has to come out of tensor
                 # memory once (tcgen05.ld moves 128 B/clk/SM = 32 pairs/clk/SM; ncu: tensor pipe 48 % busy)
                 mhz = (clocks or {}).get("sm_max_mhz") or 1965.0

@@ -40,10 +40,11 @@ extern "C" {
  * kind::f16 with fp32 accumulators in tensor memory, row norms and threshold folded into spare operand
  * columns so that the sign of the accumulator decides; survivors (edges + a guard band covering the
  * slicing and accumulation error) take the same exact FP64 recompute. Same edge list, same distance
- * bits. Needs 6 * spline_points <= 60; wider rows silently take SCEMA_PAIRS_DMMA. The filter starts
- * with the hi slices alone (a third of the tensor work, guard band 2^-9 of the squared norms) and
- * repeats with both slices (2^-13) when the survivors overflow the candidate queue;
- * SCEMA_TC_SLICES=1|2 in the environment pins the choice. */
+ * bits. Rows of up to 60 columns (10 spline points) start with the hi slices alone (a third of the
+ * tensor work, guard band 2^-9 of the squared norms) and repeat with both slices (2^-13) when the
+ * survivors overflow the candidate queue; SCEMA_TC_SLICES=1|2 in the environment pins the choice. Wider
+ * rows (up to 636 columns = 106 spline points) are cut into 64-column chunks and run with the hi slices,
+ * falling back to SCEMA_PAIRS_DMMA on overflow; beyond that SCEMA_PAIRS_DMMA is taken straight away. */
 #define SCEMA_PAIRS_TC 3
 
 typedef struct scema_ctx scema_ctx;

@@ -18,7 +18,8 @@ class ScemaError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libscema_hist.so")
+    # SCEMA_LIB: another build of the same library (A/B measurements of kernel changes on one box)
+    return os.environ.get("SCEMA_LIB") or os.path.join(_HERE, "libscema_hist.so")
 
 
 def lib():

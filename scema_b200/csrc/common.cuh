@@ -175,6 +175,7 @@ bool pipeline_wanted(uint64_t n);
 int cluster_pipelined(scema_ctx *ctx, const double *steps_host, uint32_t P, double thr, bool *done);
 // pairs_tc.cu
 bool tc_supported(const scema_ctx *ctx);
+bool tc_two_slices_possible(const scema_ctx *ctx);
 int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices);
 int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices);
 int tc_stats_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1, bool into_scale);

@@ -1007,6 +1007,17 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
             if (rc) return rc;
             continue;
         }
+        if (*variant == SCEMA_PAIRS_TC && ctx->tc_mode == 2 && n_cand > ctx->cand_cap) {
+            // wide rows have no two-slice kernel: the FP64 DMMA filter takes over (its guard band is 2^-40 of the norms)
+            *variant = SCEMA_PAIRS_DMMA;
+            rc = prepare_filter(ctx, SCEMA_PAIRS_DMMA);
+            if (rc) return rc;
+            SCEMA_CUDA(ctx, ctx->d_panel_start.reserve(sc.ps.size() * sizeof(uint64_t)));
+            SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_panel_start.p, sc.ps.data(), sc.ps.size() * sizeof(uint64_t),
+                                            cudaMemcpyHostToDevice, ctx->stream));
+            SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            continue;
+        }
         if (*variant != SCEMA_PAIRS_EXACT && n_cand > ctx->cand_cap) {
             SCEMA_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
             const uint64_t want = n_cand + n_cand / 4;
@@ -1059,7 +1070,7 @@ static int compare_begin(scema_ctx *ctx, double thr, int &variant, uint32_t shar
     if (!ctx->have_spline) return fail(ctx, SCEMA_ERR_STATE, "Spline is not up to date.");
     if (n_shards == 0 || shard >= n_shards) return fail(ctx, SCEMA_ERR_INVALID, "compare: bad shard");
     if (variant < 0 || variant > 3) return fail(ctx, SCEMA_ERR_INVALID, "compare: bad variant");
-    // the tcgen05 filter holds one 64-column fp16 slice per operand row (K <= 60); wider rows take the DMMA filter
+    // the tcgen05 filter takes rows of up to 10 chunks of 64 columns (K <= 636); wider rows take the DMMA filter
     if (variant == SCEMA_PAIRS_TC && (ctx->have_spline && !tc_supported(ctx))) variant = SCEMA_PAIRS_DMMA;
     if (ctx->n >= (1ull << 32)) return fail(ctx, SCEMA_ERR_INVALID, "compare: more than 2^32-1 histories");
     for (int i = 0; i < 8; i++) ctx->counters[i] = 0;
@@ -1089,6 +1100,7 @@ static int compare_begin(scema_ctx *ctx, double thr, int &variant, uint32_t shar
             ctx->tc_n == n && ctx->tc_K == ctx->K)
             slices = ctx->tc_slices;
         ctx->tc_mode = (pin == 1 || pin == 2) ? 0u : 1u;  // 1: may fall back to two slices
+        if (!tc_two_slices_possible(ctx)) { slices = 1; ctx->tc_mode = 2; }  // K > 60: hi slices only, falls back to the DMMA filter
         rc = tc_prepare(ctx, thr, slices);
         if (rc) return rc;
         if (ctx->cand_cap == 0) ctx->cand_cap = std::max<uint64_t>(1ull << 20, 32 * n);

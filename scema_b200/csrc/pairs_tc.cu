@@ -199,6 +199,9 @@ struct Args {
     uint32_t strip_len;
     uint32_t shard, n_shards;
     uint32_t slices;   // 2: a_hi.b_hi + a_lo.b_hi + a_hi.b_lo; 1: a_hi.b_hi only (coarser guard band, a third of the MMAs)
+    uint32_t nc;       // 64-column chunks per row (K <= 60: 1); a 128-row block holds nc x [hi | lo]
+    // shared-memory plan (tc_launch): A buffers of a_bytes each, then a ring of 2^lg_nst B stages
+    uint32_t a_bytes, n_abuf, lg_nst, stage_bytes, data_bytes;
     float *dbg;        // debug: every accumulator of every tile, dbg[row * dbg_ld + col]
     uint64_t dbg_ld;
 };
@@ -239,20 +242,18 @@ struct Sched {
 
 template <int CG>
 struct Smem {
-    static constexpr uint32_t NST = CG == 2 ? 4 : 2;              // B stages
     static constexpr uint32_t B_ROWS = COLT / CG;                 // B rows held by one CTA
-    static constexpr uint32_t B_SLICE = B_ROWS * 128;             // bytes of one slice of a B stage
+    static constexpr uint32_t B_SLICE = B_ROWS * 128;             // bytes of one slice of a B stage (one chunk)
     static constexpr uint32_t B_STAGE = 2 * B_SLICE;
-    static constexpr uint32_t off_A = 0;                          // 2 x BLOCK_BYTES (A double-buffered over items)
-    static constexpr uint32_t off_B = 2 * BLOCK_BYTES;
-    static constexpr uint32_t off_bar = off_B + NST * B_STAGE;
-    static constexpr uint32_t MAXST = 2 * NST;                    // one-slice mode: twice as many half-size stages
+    static constexpr uint32_t DATA_MAX = 224 * 1024;              // operand tiles: A buffers, then the B ring
+    static constexpr uint32_t MAXST = 8;
     static constexpr uint32_t n_bars = 3 * MAXST + 6;             // full, pfull, empty | a_empty[2] tfull[2] tempty[2]
-    static constexpr uint32_t off_tmem = off_bar + n_bars * 8;
-    static constexpr uint32_t bytes = off_tmem + 16 + 1024;       // + slack to align the base to 1024
+    static constexpr uint32_t tail = n_bars * 8 + 16 + 1024;      // barriers, TMEM address, slack to align the base to 1024
 };
 
-template <int CG, bool DBG>
+// WIDE = false: rows of one chunk (K <= 60) with a compile-time shared-memory plan (A double-buffered at a 32 KB
+// stride, B ring behind it); WIDE = true: several chunks per row, plan from tc_launch.
+template <int CG, bool DBG, bool WIDE>
 __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
 {
     using SM = Smem<CG>;
@@ -260,19 +261,23 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
-    const uint32_t sA = base + SM::off_A, sB = base + SM::off_B, sBar = base + SM::off_bar;
+    const uint32_t k_nc = WIDE ? a.nc : 1u;                               // chunks per row
+    const uint32_t k_nabuf = WIDE ? a.n_abuf : 2u;                        // A buffers
+    const uint32_t k_abytes = WIDE ? a.a_bytes : BLOCK_BYTES;             // bytes per A buffer
+    const uint32_t sA = base, sB = base + k_nabuf * k_abytes, sBar = base + a.data_bytes;
     auto bar_full = [&](uint32_t i) { return sBar + 8 * i; };
     auto bar_pfull = [&](uint32_t i) { return sBar + 8 * (MAXST + i); };
     auto bar_empty = [&](uint32_t i) { return sBar + 8 * (2 * MAXST + i); };
     auto bar_aempty = [&](uint32_t i) { return sBar + 8 * (3 * MAXST + i); };
     auto bar_tfull = [&](uint32_t i) { return sBar + 8 * (3 * MAXST + 2 + i); };
     auto bar_tempty = [&](uint32_t i) { return sBar + 8 * (3 * MAXST + 4 + i); };
-    // B ring: with one slice a stage only holds the hi rows, so the same memory gives twice the stages
-    // (the TMA round trip is then hidden behind 7 instead of 3 tiles of a third of the MMA work each)
-    const uint32_t lg_nst = a.slices == 1 ? (CG == 2 ? 3u : 2u) : (CG == 2 ? 2u : 1u);
-    const uint32_t nst_mask = (1u << lg_nst) - 1u;
-    const uint32_t stage_bytes = a.slices == 1 ? SM::B_SLICE : SM::B_STAGE;
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_raw + (base - raw) + SM::off_tmem);
+    // B ring: one stage = one 64-column chunk of a column tile (its hi rows alone with one slice, which gives
+    // twice the stages in the same memory); A: all chunks of the row tile, double-buffered over items when it fits
+    const uint32_t lg_nst = a.lg_nst, nst_mask = (1u << lg_nst) - 1u, stage_bytes = a.stage_bytes;
+    const uint32_t a_chunk = a.slices == 1 ? SLICE_BYTES : BLOCK_BYTES;  // bytes of one chunk of an A tile in shared memory
+    const uint64_t gblk = (uint64_t)k_nc * BLOCK_BYTES;                  // bytes of a 128-row block in global memory
+    const uint32_t off_tmem = a.data_bytes + SM::n_bars * 8;
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_raw + (base - raw) + off_tmem);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
         for (uint32_t i = 0; i < 2; i++) { mbar_init(bar_aempty(i), 1); mbar_init(bar_tfull(i), 1); mbar_init(bar_tempty(i), 8 * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) tmem_alloc<CG>(base + SM::off_tmem, 512);
+    if (warp == 2) tmem_alloc<CG>(base + off_tmem, 512);
     fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     fence_after();
@@ -295,31 +300,35 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
             Sched<CG> sc;
             sc.init(a, unit, n_units);
             uint32_t I, J0, J1, t = 0, item = 0;
+            const uint32_t nc = k_nc, n_abuf = k_nabuf, a_bytes = k_abytes, slices = a.slices;
+            const unsigned char *const HA = a.HA, *const HB = a.HB;
             while (sc.next(I, J0, J1)) {
-                const uint32_t ab = item & 1u;
-                mbar_wait(bar_aempty(ab), ((item >> 1) & 1u) ^ 1u, 1);
-                for (uint32_t J = J0; J < J1; J++, t++) {
-                    const uint32_t st = t & nst_mask;
-                    mbar_wait(bar_empty(st), ((t >> lg_nst) & 1u) ^ 1u, 2);
-                    const bool first = J == J0;
-                    // one slice (hi) or both (hi | lo, contiguous in a block)
-                    const uint32_t blk_bytes = a.slices == 1 ? SLICE_BYTES : BLOCK_BYTES;
-                    mbar_expect_tx(bar_full(st), (COLT / CG / ROWS) * blk_bytes + (first ? blk_bytes : 0u));
-                    if (first) bulk_g2s(sA + ab * BLOCK_BYTES, a.HA + (uint64_t)(I * CG + rank) * BLOCK_BYTES, blk_bytes, bar_full(st));
-                    const uint32_t dst = sB + st * stage_bytes;
-                    if (CG == 2) {
-                        bulk_g2s(dst, a.HB + (uint64_t)(J * 2 + rank) * BLOCK_BYTES, blk_bytes, bar_full(st));
-                    } else {
-                        // 256 B rows of one CTA: the hi slices of both 128-row blocks, then both lo slices
-                        const unsigned char *b0 = a.HB + (uint64_t)(J * 2) * BLOCK_BYTES;
-                        bulk_g2s(dst, b0, SLICE_BYTES, bar_full(st));
-                        bulk_g2s(dst + SLICE_BYTES, b0 + BLOCK_BYTES, SLICE_BYTES, bar_full(st));
-                        if (a.slices != 1) {
-                            bulk_g2s(dst + 2 * SLICE_BYTES, b0 + SLICE_BYTES, SLICE_BYTES, bar_full(st));
-                            bulk_g2s(dst + 3 * SLICE_BYTES, b0 + BLOCK_BYTES + SLICE_BYTES, SLICE_BYTES, bar_full(st));
+                const uint32_t ab = n_abuf == 2 ? (item & 1u) : 0u;
+                mbar_wait(bar_aempty(ab), ((n_abuf == 2 ? (item >> 1) : item) & 1u) ^ 1u, 1);
+                for (uint32_t J = J0; J < J1; J++)
+                    for (uint32_t c = 0; c < nc; c++, t++) {
+                        const uint32_t st = t & nst_mask;
+                        mbar_wait(bar_empty(st), ((t >> lg_nst) & 1u) ^ 1u, 2);
+                        const bool first = J == J0 && c == 0;  // the item's A tile (all chunks) rides on its first stage
+                        mbar_expect_tx(bar_full(st), (COLT / CG / ROWS) * a_chunk + (first ? nc * a_chunk : 0u));
+                        if (first)
+                            for (uint32_t ca = 0; ca < nc; ca++)
+                                bulk_g2s(sA + ab * a_bytes + ca * a_chunk, HA + (uint64_t)(I * CG + rank) * gblk + (uint64_t)ca * BLOCK_BYTES,
+                                         a_chunk, bar_full(st));
+                        const uint32_t dst = sB + st * stage_bytes;
+                        if (CG == 2) {
+                            bulk_g2s(dst, HB + (uint64_t)(J * 2 + rank) * gblk + (uint64_t)c * BLOCK_BYTES, a_chunk, bar_full(st));
+                        } else {
+                            // 256 B rows of one CTA: the hi slices of both 128-row blocks, then both lo slices
+                            const unsigned char *b0 = HB + (uint64_t)(J * 2) * gblk + (uint64_t)c * BLOCK_BYTES;
+                            bulk_g2s(dst, b0, SLICE_BYTES, bar_full(st));
+                            bulk_g2s(dst + SLICE_BYTES, b0 + gblk, SLICE_BYTES, bar_full(st));
+                            if (slices != 1) {
+                                bulk_g2s(dst + 2 * SLICE_BYTES, b0 + SLICE_BYTES, SLICE_BYTES, bar_full(st));
+                                bulk_g2s(dst + 3 * SLICE_BYTES, b0 + gblk + SLICE_BYTES, SLICE_BYTES, bar_full(st));
+                            }
                         }
                     }
-                }
                 item++;
             }
         }
@@ -332,29 +341,37 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
             Sched<CG> sc;
             sc.init(a, unit, n_units);
             uint32_t I, J0, J1, t = 0, item = 0, tile = 0;
+            // everything the loop needs sits in registers: the asm statements clobber memory, and a kernel parameter
+            // re-read from the constant bank on the way from "accumulator free" to the first MMA is latency on the
+            // critical path of every tile
+            const uint32_t n_terms = a.slices == 1 ? 1u : 3u, nc = k_nc, n_abuf = k_nabuf, a_bytes = k_abytes;
             while (sc.next(I, J0, J1)) {
-                const uint32_t ab = item & 1u;
-                const uint64_t adesc = make_desc(sA + ab * BLOCK_BYTES);
-                for (uint32_t J = J0; J < J1; J++, t++, tile++) {
+                const uint32_t ab = n_abuf == 2 ? (item & 1u) : 0u;
+                const uint32_t a_tile = sA + ab * a_bytes;
+                for (uint32_t J = J0; J < J1; J++, tile++) {
                     const uint32_t as = tile & 1u;
-                    mbar_wait(bar_tempty(as), ((tile >> 1) & 1u) ^ 1u, 3);
-                    const uint32_t st = t & nst_mask, ph = (t >> lg_nst) & 1u;
-                    mbar_wait(bar_full(st), ph, 4);
-                    if (CG == 2) mbar_wait(bar_pfull(st), ph, 5);
-                    fence_after();
-                    const uint64_t bdesc = make_desc(sB + st * stage_bytes);
                     const uint32_t d_tmem = tmem_base + as * COLT;
-                    const uint32_t n_terms = a.slices == 1 ? 1u : 3u;
+                    for (uint32_t c = 0; c < nc; c++, t++) {
+                        // operands first (they were prefetched: the barrier is normally complete already), the
+                        // accumulator stage last, so that nothing but the MMA issue follows the epilogue's release
+                        const uint32_t st = t & nst_mask, ph = (t >> lg_nst) & 1u;
+                        mbar_wait(bar_full(st), ph, 4);
+                        if (CG == 2) mbar_wait(bar_pfull(st), ph, 5);
+                        const uint64_t adesc = make_desc(a_tile + c * a_chunk);
+                        const uint64_t bdesc = make_desc(sB + st * stage_bytes);
+                        if (c == 0) mbar_wait(bar_tempty(as), ((tile >> 1) & 1u) ^ 1u, 3);
+                        fence_after();
 #pragma unroll 1
-                    for (uint32_t term = 0; term < n_terms; term++) {
-                        // a_hi.b_hi, a_lo.b_hi, a_hi.b_lo
-                        const uint32_t a_off = (term == 1 ? SLICE_BYTES : 0u) >> 4;
-                        const uint32_t b_off = (term == 2 ? SM::B_SLICE : 0u) >> 4;
+                        for (uint32_t term = 0; term < n_terms; term++) {
+                            // a_hi.b_hi, a_lo.b_hi, a_hi.b_lo
+                            const uint32_t a_off = (term == 1 ? SLICE_BYTES : 0u) >> 4;
+                            const uint32_t b_off = (term == 2 ? SM::B_SLICE : 0u) >> 4;
 #pragma unroll
-                        for (uint32_t kk = 0; kk < 4; kk++)
-                            umma_f16<CG>(d_tmem, adesc + a_off + 2 * kk, bdesc + b_off + 2 * kk, idesc, (term | kk) != 0 ? 1u : 0u);
+                            for (uint32_t kk = 0; kk < 4; kk++)
+                                umma_f16<CG>(d_tmem, adesc + a_off + 2 * kk, bdesc + b_off + 2 * kk, idesc, (c | term | kk) != 0 ? 1u : 0u);
+                        }
+                        umma_commit<CG>(bar_empty(st));
                     }
-                    umma_commit<CG>(bar_empty(st));
                     umma_commit<CG>(bar_tfull(as));
                     if (J == J1 - 1) umma_commit<CG>(bar_aempty(ab));
                 }
@@ -365,8 +382,9 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
             Sched<CG> sc;
             sc.init(a, unit, n_units);
             uint32_t I, J0, J1, t = 0;
+            const uint32_t nc_fw = k_nc;
             while (sc.next(I, J0, J1))
-                for (uint32_t J = J0; J < J1; J++, t++) {
+                for (uint32_t q = (J1 - J0) * nc_fw; q > 0; q--, t++) {
                     const uint32_t st = t & nst_mask;
                     mbar_wait(bar_full(st), (t >> lg_nst) & 1u, 6);
                     mbar_arrive_cluster(bar_pfull(st), 0);
@@ -495,16 +513,17 @@ __device__ __forceinline__ double h16z(double v)
     return fabsf(f) < 6.103515625e-05f ? 0.0 : (double)f;
 }
 
-// pass 2: one warp per row. Writes the row's hi and lo fp16 slices (60 data columns + 4 columns
-// carrying the row term -h_i, split three ways against the constants P = 2^15 and Q = 2^3 on the other
-// operand) into the A-flavoured and the B-flavoured copy, already in the swizzled shared-memory image.
+// pass 2: one warp per row. Writes the row's hi and lo fp16 slices, chunk by chunk (64 columns each; the last
+// chunk has at most 60 data columns and 4 columns carrying the row term -h_i, split three ways against the
+// constants P = 2^15 and Q = 2^3 on the other operand), into the A-flavoured and the B-flavoured copy, already in
+// the swizzled shared-memory image.
 //   A hi: [x0 x1 P Q]   A lo: [0 x2 0 0]        B hi: [P Q x0 x1]   B lo: [0 0 0 x2]
 // so that  A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  adds  (P x0 + Q x1 + Q x2)_i + (P x0 + Q x1 + Q x2)_j = -h_i - h_j
 // (to 2^-33 |h| + 2^-11; with the hi slices alone the x2 terms drop out: 2^-22 |h| + 2^-11).
 __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, uint64_t n, uint64_t r0, uint64_t r1, uint32_t K,
-                                                 const double *__restrict__ NRM, unsigned long long *__restrict__ misc,
-                                                 double T0, double cguard, unsigned char *__restrict__ HA,
-                                                 unsigned char *__restrict__ HB)
+                                                 uint32_t nc, double vmax, const double *__restrict__ NRM,
+                                                 unsigned long long *__restrict__ misc, double T0, double cguard,
+                                                 unsigned char *__restrict__ HA, unsigned char *__restrict__ HB)
 {
     const uint64_t row = r0 + (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -512,22 +531,23 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
     const double s = __longlong_as_double((long long)misc[1]);
     const bool real = row < n;
     const bool wild = real && !isfinite(NRM[row]);
-    double v[2] = {0.0, 0.0};
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-        const uint32_t k = lane + 32 * e;
-        if (real && !wild && k < K) v[e] = S[row * K + k] * s;
-    }
-    // a row beyond the range the scale was chosen for (possible only when the scale was fixed before every
-    // row had been seen): no fp16 image; it survives against everybody like a row with a non-finite norm
-    const bool too_big = __any_sync(0xffffffffu, fabs(v[0]) >= 4096.0 || fabs(v[1]) >= 4096.0);
-    if (too_big) {
-        v[0] = v[1] = 0.0;
-        if (lane == 0) atomicAdd(misc + 2, 1ull);
-    }
-    double nrm = fma(v[1], v[1], v[0] * v[0]);
+    const bool data = real && !wild;
+    // norm of the scaled row; a row beyond the range the scale was chosen for (possible only when the scale was
+    // fixed before every row had been seen) gets no fp16 image and survives against everybody, like a row with
+    // a non-finite norm
+    double nrm = 0.0;
+    bool big = false;
+    if (data)
+        for (uint32_t k = lane; k < K; k += 32) {
+            const double v = S[row * K + k] * s;
+            nrm = fma(v, v, nrm);
+            big |= fabs(v) >= vmax;
+        }
+    const bool too_big = __any_sync(0xffffffffu, big);
+    if (too_big && lane == 0) atomicAdd(misc + 2, 1ull);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    if (too_big) nrm = 0.0;
     // row term
     const double P = 32768.0, Q = 8.0;
     const double T0s = (T0 * s) * s;
@@ -535,7 +555,7 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
     const double h = 0.5 * (nrm * (1.0 - cguard) - T0s * (0.5 + 2.0 * cguard) - e0);
     double x0, x1, x2;
     if (!real) { x0 = -65504.0; x1 = x2 = 0.0; }                              // padding row: never a survivor
-    else if (wild || too_big || !(-h <= 32768.0 * P)) { x0 = 65504.0; x1 = x2 = 0.0; }   // NaN/inf row, or threshold beyond every distance: always
+    else if (wild || too_big || !(-h <= 32768.0 * P)) { x0 = 65504.0; x1 = x2 = 0.0; }  // always a survivor
     else {
         x0 = h16z(-h / P);
         x1 = h16z((-h - P * x0) / Q);
@@ -543,26 +563,32 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
     }
     const uint64_t blk = row / ROWS;
     const uint32_t r = (uint32_t)(row % ROWS);
-    unsigned char *a_hi = HA + blk * BLOCK_BYTES + (uint64_t)r * 128, *a_lo = a_hi + SLICE_BYTES;
-    unsigned char *b_hi = HB + blk * BLOCK_BYTES + (uint64_t)r * 128, *b_lo = b_hi + SLICE_BYTES;
+    for (uint32_t c = 0; c < nc; c++) {
+        const uint64_t base = (blk * nc + c) * BLOCK_BYTES + (uint64_t)r * 128;
+        unsigned char *a_hi = HA + base, *a_lo = a_hi + SLICE_BYTES;
+        unsigned char *b_hi = HB + base, *b_lo = b_hi + SLICE_BYTES;
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-        const uint32_t k = lane + 32 * e;  // column 0..63 of the slice
-        const double hi = h16z(v[e]);
-        const double lo = h16z(v[e] - hi);
-        double ahi = hi, alo = lo, bhi = hi, blo = lo;
-        if (k >= KMAX) {
-            const uint32_t c = k - KMAX;
-            ahi = c == 0 ? x0 : c == 1 ? x1 : c == 2 ? P : Q;
-            alo = c == 1 ? x2 : 0.0;
-            bhi = c == 0 ? P : c == 1 ? Q : c == 2 ? x0 : x1;
-            blo = c == 3 ? x2 : 0.0;
+        for (int e = 0; e < 2; e++) {
+            const uint32_t k = lane + 32 * e;  // column 0..63 of the chunk
+            const uint32_t kd = c * 64 + k;    // data column
+            double v = 0.0;
+            if (data && !too_big && kd < K) v = S[row * K + kd] * s;
+            const double hi = h16z(v);
+            const double lo = h16z(v - hi);
+            double ahi = hi, alo = lo, bhi = hi, blo = lo;
+            if (c == nc - 1 && k >= KMAX) {
+                const uint32_t f = k - KMAX;
+                ahi = f == 0 ? x0 : f == 1 ? x1 : f == 2 ? P : Q;
+                alo = f == 1 ? x2 : 0.0;
+                bhi = f == 0 ? P : f == 1 ? Q : f == 2 ? x0 : x1;
+                blo = f == 3 ? x2 : 0.0;
+            }
+            const uint32_t off = ((((k >> 3) ^ (r & 7u)) << 4) | ((k & 7u) << 1));  // swizzled 16-byte chunk, element in chunk
+            *reinterpret_cast<__half *>(a_hi + off) = __double2half(ahi);
+            *reinterpret_cast<__half *>(a_lo + off) = __double2half(alo);
+            *reinterpret_cast<__half *>(b_hi + off) = __double2half(bhi);
+            *reinterpret_cast<__half *>(b_lo + off) = __double2half(blo);
         }
-        const uint32_t off = ((((k >> 3) ^ (r & 7u)) << 4) | ((k & 7u) << 1));  // swizzled 16-byte chunk, element in chunk
-        *reinterpret_cast<__half *>(a_hi + off) = __double2half(ahi);
-        *reinterpret_cast<__half *>(a_lo + off) = __double2half(alo);
-        *reinterpret_cast<__half *>(b_hi + off) = __double2half(bhi);
-        *reinterpret_cast<__half *>(b_lo + off) = __double2half(blo);
     }
 }
 
@@ -571,7 +597,14 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-bool tc_supported(const scema_ctx *ctx) { return ctx->K >= 1 && ctx->K <= tc::KMAX; }
+// 64-column chunks of a K-column row: the last one keeps 4 columns for the row term
+static uint32_t tc_chunks(uint32_t K) { return (K + 4 + 63) / 64; }
+// binades the scale gives up so that |row|^2 stays below 2^30 (the fold columns hold h / 2^15 in fp16)
+static int tc_k_headroom(uint32_t K) { return K <= 64 ? 0 : K <= 256 ? 1 : 2; }
+// up to 10 chunks (K <= 636): the one-slice A tile of a row block (160 KB) plus two B stages still fit one SM
+bool tc_supported(const scema_ctx *ctx) { return ctx->K >= 1 && tc_chunks(ctx->K) <= 10; }
+// more than one chunk: hi slices only (the two-slice A tile would not fit next to a B ring)
+bool tc_two_slices_possible(const scema_ctx *ctx) { return tc_chunks(ctx->K) == 1; }
 
 // Operand preparation in three steps so that the host-buffer pipeline can run it range by range:
 //   tc_prepare_begin : buffers, threshold constants, guard band of the slice count
@@ -584,8 +617,10 @@ int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices)
     const uint32_t K = ctx->K;
     const uint64_t n_pad = (n + tc::COLT - 1) / tc::COLT * tc::COLT;
     ctx->tc_valid = false;
-    SCEMA_CUDA(ctx, ctx->d_tc_a.reserve(n_pad * 256));
-    SCEMA_CUDA(ctx, ctx->d_tc_b.reserve(n_pad * 256));
+    const uint32_t nc = tc_chunks(K);
+    if (nc > 1 && slices != 1) return fail(ctx, SCEMA_ERR_INVALID, "tensor-core filter: rows wider than 60 columns run with one slice");
+    SCEMA_CUDA(ctx, ctx->d_tc_a.reserve(n_pad * 256 * nc));
+    SCEMA_CUDA(ctx, ctx->d_tc_b.reserve(n_pad * 256 * nc));
     SCEMA_CUDA(ctx, ctx->d_tc_nrm.reserve(n_pad * sizeof(double)));
     SCEMA_CUDA(ctx, ctx->d_tc_misc.reserve(64));
     SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_tc_misc.p, 0, 64, ctx->stream));
@@ -596,7 +631,8 @@ int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices)
     ctx->tc_T0 = thr * thr * (1.0 + (2.0 * K + 16.0) * eps) * (1.0 + 4.0 * eps) + (2.0 * K + 4.0) * 4.9406564584124654e-324;
     // Guard band (DESIGN.md "K2-TC"): relative to |a_i|^2 + |a_j|^2 the computed accumulator is off by at most
     //   two slices: 3.1 2^-22 (slicing) + 13 2^-18 (12 MMA steps, fp32 accumulate)          < 2^-14
-    //   one slice : 2^-11 (dropping a_lo, b_lo) + 5 2^-18 (4 steps) + 2^-23 (two-slice fold)  < 2^-10.9
+    //   one slice : 2^-11 (dropping a_lo, b_lo) + (4 nc + 1) 2^-18 (4 steps per chunk, nc <= 10) + 2^-23 (two-slice fold)
+    //               < 2^-10.6
     // and the band must be twice that.
     ctx->tc_cguard = slices == 1 ? 0.001953125 : 0.0001220703125;  // 2^-9, 2^-13
     ctx->tc_thr = thr;
@@ -619,7 +655,7 @@ int tc_stats_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1, bool into_scale)
 
 int tc_fix_scale(scema_ctx *ctx, int headroom)
 {
-    tc::k_tc_fix_scale<<<1, 1, 0, ctx->stream>>>(ctx->d_tc_misc.as<unsigned long long>(), headroom);
+    tc::k_tc_fix_scale<<<1, 1, 0, ctx->stream>>>(ctx->d_tc_misc.as<unsigned long long>(), headroom + tc_k_headroom(ctx->K));
     ctx->launches++;
     SCEMA_CUDA(ctx, cudaGetLastError());
     return SCEMA_OK;
@@ -629,8 +665,9 @@ int tc_prep_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1)
 {
     if (r1 <= r0) return SCEMA_OK;
     tc::k_tc_prep<<<(unsigned)((r1 - r0 + 7) / 8), 256, 0, ctx->stream>>>(
-        ctx->d_spline, ctx->n, r0, r1, ctx->K, ctx->d_tc_nrm.as<double>(), ctx->d_tc_misc.as<unsigned long long>(), ctx->tc_T0,
-        ctx->tc_cguard, ctx->d_tc_a.as<unsigned char>(), ctx->d_tc_b.as<unsigned char>());
+        ctx->d_spline, ctx->n, r0, r1, ctx->K, tc_chunks(ctx->K), ldexp(1.0, 12 - tc_k_headroom(ctx->K)), ctx->d_tc_nrm.as<double>(),
+        ctx->d_tc_misc.as<unsigned long long>(), ctx->tc_T0, ctx->tc_cguard, ctx->d_tc_a.as<unsigned char>(),
+        ctx->d_tc_b.as<unsigned char>());
     ctx->launches++;
     SCEMA_CUDA(ctx, cudaGetLastError());
     return SCEMA_OK;
@@ -653,11 +690,11 @@ int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices)
     return SCEMA_OK;
 }
 
-template <int CG, bool DBG>
+template <int CG, bool DBG, bool WIDE>
 static int tc_launch_t(scema_ctx *ctx, const tc::Args &a, uint64_t items)
 {
-    auto kern = tc::k_filter_tc<CG, DBG>;
-    const size_t smem = tc::Smem<CG>::bytes;
+    auto kern = tc::k_filter_tc<CG, DBG, WIDE>;
+    const size_t smem = (size_t)a.data_bytes + tc::Smem<CG>::tail;
     if (smem > ctx->smem_optin) return fail(ctx, SCEMA_ERR_CUDA, "tensor-core filter: shared memory exceeds device limit");
     SCEMA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint64_t units = std::min<uint64_t>((uint64_t)ctx->sm_count / CG, std::max<uint64_t>(items, 1));
@@ -700,11 +737,12 @@ int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t C0, uint32_t C1
     a.slices = ctx->tc_slices;
     a.dbg = dbg;
     a.dbg_ld = dbg_ld;
+    a.nc = tc_chunks(ctx->K);
     static const char *cg_env = getenv("SCEMA_TC_CG");
     // cta_group::2 pairs halve the B traffic and the shared-memory reads per SM, but neither bounds this kernel
     // (the TMEM read-out resp. the tensor pipe do) and the pair pays a forwarder hop per stage: measured 61.0 ms
     // against 56.4 ms for one CTA per tile at 1M histories, so single CTAs are the default.
-    const int cg = (cg_env && atoi(cg_env) == 2) ? 2 : 1;
+    const int cg = cg_env && atoi(cg_env) == 2 ? 2 : 1;
     // strips: long enough to amortise the A tile, short enough to leave every cluster many items
     const uint64_t rows = a.I1 > a.I0 ? a.I1 - a.I0 : 0;
     const uint64_t cols = a.C1 > a.C0 ? a.C1 - a.C0 : 0;
@@ -715,8 +753,35 @@ int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t C0, uint32_t C1
     // items of this shard (upper bound is enough to size the grid)
     const uint64_t n_strips = (cols + a.strip_len - 1) / a.strip_len + 1;
     const uint64_t items = std::max<uint64_t>(1, rows * (2 / cg) * n_strips / std::max<uint32_t>(n_shards, 1));
-    if (cg == 1) return dbg ? tc_launch_t<1, true>(ctx, a, items) : tc_launch_t<1, false>(ctx, a, items);
-    return dbg ? tc_launch_t<2, true>(ctx, a, items) : tc_launch_t<2, false>(ctx, a, items);
+    // shared-memory plan: A = all chunks of the row tile (double-buffered over items if two copies and two B
+    // stages fit), B ring = as many power-of-two stages of one chunk as the rest holds
+    {
+        const uint32_t b_rows = tc::COLT / (uint32_t)cg;
+        a.stage_bytes = (a.slices == 1 ? 1u : 2u) * b_rows * 128u;
+        a.a_bytes = a.nc * (a.slices == 1 ? tc::SLICE_BYTES : tc::BLOCK_BYTES);
+        const uint32_t data = 224u * 1024u;
+        if (a.nc == 1) {
+            // one chunk: two A buffers at a 32 KB stride, the B ring in what the 192 KB budget leaves
+            a.a_bytes = tc::BLOCK_BYTES;
+            a.n_abuf = 2;
+            a.lg_nst = a.slices == 1 ? (cg == 2 ? 3u : 2u) : (cg == 2 ? 2u : 1u);
+        } else {
+            auto lg_stages = [&](uint32_t n_abuf) -> int {  // log2 of the B stages left next to n_abuf A buffers, -1: does not fit
+                if (n_abuf * a.a_bytes + 2u * a.stage_bytes > data) return -1;
+                const uint32_t room = (data - n_abuf * a.a_bytes) / a.stage_bytes;
+                return room >= 8 ? 3 : room >= 4 ? 2 : 1;
+            };
+            const int lg2 = lg_stages(2), lg1 = lg_stages(1);
+            if (lg1 < 0) return fail(ctx, SCEMA_ERR_INVALID, "tensor-core filter: row tile does not fit shared memory");
+            // a deep B ring hides the TMA round trip on every tile, a second A buffer only the reload at item boundaries
+            a.n_abuf = (lg2 < 0 || (lg2 < 3 && lg1 > lg2)) ? 1u : 2u;
+            a.lg_nst = (uint32_t)(a.n_abuf == 2 ? lg2 : lg1);
+        }
+        a.data_bytes = a.n_abuf * a.a_bytes + (a.stage_bytes << a.lg_nst);  // only what is used: the rest of the SM stays L1
+    }
+    if (a.nc > 1) return cg == 1 ? tc_launch_t<1, false, true>(ctx, a, items) : tc_launch_t<2, false, true>(ctx, a, items);
+    if (cg == 1) return dbg ? tc_launch_t<1, true, false>(ctx, a, items) : tc_launch_t<1, false, false>(ctx, a, items);
+    return dbg ? tc_launch_t<2, true, false>(ctx, a, items) : tc_launch_t<2, false, false>(ctx, a, items);
 }
 
 // Debug / validation entry (scema_tc_debug): runs the instrumented kernel over the whole pair matrix
@@ -728,7 +793,7 @@ int tc_debug_run(scema_ctx *ctx, double thr, uint32_t slices, float *acc_host, u
 {
     if (slices != 1 && slices != 2) return fail(ctx, SCEMA_ERR_INVALID, "tc_debug: slices must be 1 or 2");
     if (!ctx->have_spline) return fail(ctx, SCEMA_ERR_STATE, "Spline is not up to date.");
-    if (!tc_supported(ctx)) return fail(ctx, SCEMA_ERR_INVALID, "tensor-core filter needs 1 <= K <= 60");
+    if (!tc_supported(ctx) || !tc_two_slices_possible(ctx)) return fail(ctx, SCEMA_ERR_INVALID, "tc_debug needs 1 <= K <= 60");
     const uint64_t n_pad = (ctx->n + tc::COLT - 1) / tc::COLT * tc::COLT;
     if (ld < n_pad) return fail(ctx, SCEMA_ERR_INVALID, "tc_debug: ld < padded n");
     if (n_pad > 8192) return fail(ctx, SCEMA_ERR_INVALID, "tc_debug: at most 8192 rows");

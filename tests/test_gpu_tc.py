@@ -193,15 +193,40 @@ def test_tc_threshold_beyond_all_distances(hc, oracle):
     assert edges_equal(hc.get_edges(), want)
 
 
-def test_tc_wide_rows_fall_back(hc, oracle):
-    """K > 60 does not fit the 64-column fp16 slice: the variant silently takes the DMMA filter."""
-    rows = synth.rows(5, 1500, 16, 50, 5e-3, synth.default_pert(THR, 50))
+@pytest.mark.parametrize("P", [11, 32, 50, 64, 106, 107])
+def test_tc_wide_rows(hc, oracle, P):
+    """K > 60: the row is cut into 64-column chunks (hi slices only, the fold columns in the last chunk, scale one or
+    two binades lower so the norms still fit); up to 10 chunks (P <= 106), beyond that the DMMA filter runs."""
+    n = 1500
+    rows = synth.rows(5, n, 16, P, 5e-3, synth.default_pert(THR, P))
+    rng = np.random.default_rng(P)
+    for q in range(150):
+        a = int(rng.integers(0, n)); b = (a + n // 2) % n
+        u = rng.standard_normal(6 * P); u /= np.linalg.norm(u)
+        rows[b] = rows[a] + u * THR * (1 + (q - 75) * 3e-16)
+    rows[7] = np.nan
+    rows[9, 5] = 1e200
     want = oracle.all_pairs(rows, THR)
     hc.set_spline(rows)
     assert hc.compare(THR, PAIRS_TC) == len(want[0])
     assert edges_equal(hc.get_edges(), want)
+    assert hc.counters()["tc_slices"] == (1 if P <= 106 else 0)
+    assert len(want[0]) > n
     with pytest.raises(scema_b200.ScemaError):
-        hc.tc_debug(THR, 1500)
+        hc.tc_debug(THR, n)
+
+
+def test_tc_wide_rows_dense_fall_back_to_dmma(oracle):
+    """Wide rows have no two-slice kernel: when the one-slice survivors overflow the queue the DMMA filter takes over."""
+    n = 2200
+    rows = 1e-3 + 1e-9 * np.random.default_rng(0).standard_normal((n, 300))
+    h = scema_b200.HistCluster(0)
+    h.set_spline(rows)
+    assert h.compare(THR, PAIRS_TC) == n * (n - 1) // 2
+    assert h.counters()["passes"] >= 2 and h.counters()["tc_slices"] == 0
+    want = oracle.all_pairs(rows, THR)
+    assert edges_equal(h.get_edges(), want)
+    h.close()
 
 
 def test_tc_threshold_change_rebuilds_operands(hc, oracle):
