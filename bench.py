@@ -359,6 +359,9 @@ def run_ours(args, wl, wl_name):
                 extra["limiter"] = {"what": "TMEM read-out of the accumulators (tcgen05.ld, 4 bytes per pair, 128 B/clk/SM)",
                                     "ceiling_pairs_per_s": ceiling,
                                     "frac_of_ceiling": (pairs_this_rank / (filt_ms * 1e-3)) / ceiling if filt_ms > 0 else None}
+            elif tc_slices == 1:
+                extra["limiter"] = {"what": "wide rows (%d chunks of 64 columns per tile): tensor pipe 62 %% busy in the ncu capture, "
+                                            "the 4-stage B ring does not quite hide the TMA round trip" % n_chunks}
             else:
                 extra["limiter"] = {"what": "tensor pipe (ncu: 90 % busy, SM clock pulled to 1.70 GHz by the power cap)"}
             fp64 = max(hc.fp64_peak()["dmma_tflops"] for _ in range(2))
