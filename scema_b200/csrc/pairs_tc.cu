@@ -21,6 +21,7 @@
 // global memory exactly as the 128-byte-swizzled K-major image tcgen05 wants in shared memory, so one
 // block = one contiguous 1-D bulk copy of the TMA engine (no tensor map).
 #include "common.cuh"
+#include "tc_sched.h"
 #include <cuda_fp16.h>
 #include <algorithm>
 
@@ -206,40 +207,6 @@ struct Args {
     uint64_t dbg_ld;
 };
 
-// Static schedule, identical in every role: work item = (row tile I of 128*CG rows, the column tiles of
-// one strip at or right of the diagonal). Items are numbered strip by strip so that the clusters
-// working at the same time walk the same strip of B (shared through L2); item g belongs to shard
-// g % n_shards, and inside a shard cluster u takes the items u, u + n_units, ...
-template <int CG>
-struct Sched {
-    static constexpr uint32_t RPC = 2 / CG;  // row tiles per column tile
-    uint32_t S, NT, C0, R0, R1, ns, s, shard, n_shards;  // NT: end of the column range
-    uint64_t cum, k, stride;
-    __device__ void init(const Args &a, uint32_t unit, uint32_t n_units)
-    {
-        S = a.strip_len; NT = min(a.NT, a.C1); C0 = a.C0; R0 = a.I0 * RPC; R1 = a.I1 * RPC;
-        ns = (NT + S - 1) / S; s = max(a.I0, a.C0) / S; cum = 0; k = unit; stride = n_units;
-        shard = a.shard; n_shards = a.n_shards;
-    }
-    __device__ uint32_t count(uint32_t strip) const
-    {
-        const uint32_t ce = min((strip + 1) * S, NT) * RPC;
-        const uint32_t e = min(R1, ce);
-        return e > R0 ? e - R0 : 0u;
-    }
-    __device__ bool next(uint32_t &I, uint32_t &J0, uint32_t &J1)
-    {
-        const uint64_t g = k * n_shards + shard;
-        while (s < ns && g >= cum + count(s)) { cum += count(s); s++; }
-        if (s >= ns) return false;
-        I = R0 + (uint32_t)(g - cum);
-        J1 = min((s + 1) * S, NT);
-        J0 = max(max(I / RPC, s * S), C0);
-        k += stride;
-        return true;
-    }
-};
-
 template <int CG>
 struct Smem {
     static constexpr uint32_t B_ROWS = COLT / CG;                 // B rows held by one CTA
@@ -281,6 +248,7 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
+    const SchedArgs sa = {a.NT, a.I0, a.I1, a.C0, a.C1, a.strip_len, a.shard, a.n_shards};
     const uint32_t unit = blockIdx.x / CG, n_units = gridDim.x / CG;
 
     if (tid == 0) {
@@ -298,7 +266,7 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
         // ------------------------------------------------------------------ producer: TMA bulk copies
         if (lane == 0) {
             Sched<CG> sc;
-            sc.init(a, unit, n_units);
+            sc.init(sa, unit, n_units);
             uint32_t I, J0, J1, t = 0, item = 0;
             const uint32_t nc = k_nc, n_abuf = k_nabuf, a_bytes = k_abytes, slices = a.slices;
             const unsigned char *const HA = a.HA, *const HB = a.HB;
@@ -339,7 +307,7 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
             // instruction descriptor: D fp32, A/B fp16, both K-major, N = 256, M = 128 * CG
             const uint32_t idesc = (1u << 4) | ((COLT >> 3) << 17) | (((128u * CG) >> 4) << 24);
             Sched<CG> sc;
-            sc.init(a, unit, n_units);
+            sc.init(sa, unit, n_units);
             uint32_t I, J0, J1, t = 0, item = 0, tile = 0;
             // everything the loop needs sits in registers: the asm statements clobber memory, and a kernel parameter
             // re-read from the constant bank on the way from "accumulator free" to the first MMA is latency on the
@@ -380,7 +348,7 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
         } else if (CG == 2 && lane == 0 && rank == 1) {
             // ---------------------------- peer CTA: tell the leader when this CTA's half of a stage landed
             Sched<CG> sc;
-            sc.init(a, unit, n_units);
+            sc.init(sa, unit, n_units);
             uint32_t I, J0, J1, t = 0;
             const uint32_t nc_fw = k_nc;
             while (sc.next(I, J0, J1))
@@ -396,7 +364,7 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
         // warp -> (TMEM lane quarter it may read, column half of the tile)
         const uint32_t q = warp & 3u, half = (warp - 4u) >> 2;
         Sched<CG> sc;
-        sc.init(a, unit, n_units);
+        sc.init(sa, unit, n_units);
         uint32_t I, J0, J1, tile = 0;
         while (sc.next(I, J0, J1)) {
             const uint64_t row = (uint64_t)(I * CG + rank) * ROWS + q * 32 + lane;
