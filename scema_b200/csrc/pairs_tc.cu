@@ -33,7 +33,7 @@ constexpr uint32_t SLICE_BYTES = ROWS * 128;       // 128 rows x 64 fp16, SW128 
 constexpr uint32_t BLOCK_BYTES = 2 * SLICE_BYTES;  // hi | lo
 constexpr uint32_t COLT = 256;                     // B rows (= pair-matrix columns) per tile
 constexpr uint32_t KMAX = 60;                      // data columns per slice (4 more carry the row terms)
-constexpr long long WAIT_TIMEOUT = 4000000000ll;   // cycles; a wait this long is a bug, trap instead of hanging
+constexpr long long WAIT_TIMEOUT = 20000000000ll;  // cycles (~10 s); a wait this long is a bug, trap instead of hanging
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
