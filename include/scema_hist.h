@@ -44,7 +44,10 @@ extern "C" {
  * tensor work, guard band 2^-9 of the squared norms) and repeat with both slices (2^-13) when the
  * survivors overflow the candidate queue; SCEMA_TC_SLICES=1|2 in the environment pins the choice. Wider
  * rows (up to 636 columns = 106 spline points) are cut into 64-column chunks and run with the hi slices,
- * falling back to SCEMA_PAIRS_DMMA on overflow; beyond that SCEMA_PAIRS_DMMA is taken straight away. */
+ * falling back to SCEMA_PAIRS_DMMA on overflow; beyond that SCEMA_PAIRS_DMMA is taken straight away.
+ * SCEMA_NORM_BAND=1 (opt-in, scema_compare only, rows of up to 60 columns, all norms finite) additionally sorts
+ * the rows by norm and skips every tile whose norm intervals lie farther apart than the threshold
+ * (| |a| - |b| | <= d(a, b)): an exact shortcut whose gain depends entirely on how spread the norms are. */
 #define SCEMA_PAIRS_TC 3
 
 typedef struct scema_ctx scema_ctx;
@@ -178,7 +181,8 @@ int scema_last_timings(scema_ctx *ctx, float ms[SCEMA_T_COUNT]);
 /* Counters of the last compare: [0] pairs evaluated by the filter, [1] survivors recomputed
  * exactly, [2] edges, [3] passes (>1 when a buffer had to grow), [4] tiles, [5] fp16 slices the
  * tcgen05 filter ended up using (SCEMA_PAIRS_TC only), [6] ranges of the host-buffer pipeline of
- * scema_cluster (0: the batch was not pipelined). */
+ * scema_cluster (0: the batch was not pipelined), [7] tiles (128 x 256 pairs; 256 x 256 with SCEMA_TC_CG=2) walked by the norm-band schedule
+ * (0: dense schedule). */
 int scema_last_counters(scema_ctx *ctx, uint64_t counters[8]);
 /* Total kernels launched by this context so far. */
 uint64_t scema_kernel_launches(const scema_ctx *ctx);

@@ -371,7 +371,7 @@ class HistCluster:
         c = (C.c_uint64 * 8)()
         self._ck(self._L.scema_last_counters(self._h, c))
         return {"pairs": int(c[0]), "survivors": int(c[1]), "edges": int(c[2]), "passes": int(c[3]), "tiles": int(c[4]),
-                "tc_slices": int(c[5]), "pipeline_ranges": int(c[6])}
+                "tc_slices": int(c[5]), "pipeline_ranges": int(c[6]), "band_tiles": int(c[7])}
 
     def kernel_launches(self):
         return int(self._L.scema_kernel_launches(self._h))

@@ -49,6 +49,7 @@ void scema_destroy(scema_ctx *c)
     for (int b = 0; b < 2; b++) { c->d_edge_key[b].release(); c->d_edge_val[b].release(); }
     c->d_sort_tmp.release();
     c->d_tc_a.release(); c->d_tc_b.release(); c->d_tc_nrm.release(); c->d_tc_misc.release();
+    c->d_tc_perm.release(); c->d_tc_iota.release(); c->d_tc_snrm.release(); c->d_tc_band.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (int k = 0; k < 2; k++) {
         if (c->h_stage_key[k]) cudaFreeHost(c->h_stage_key[k]);

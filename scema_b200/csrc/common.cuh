@@ -106,6 +106,8 @@ struct scema_ctx {
 
     // ---- K2 tensor-core filter (SCEMA_PAIRS_TC): fp16 split operands, A- and B-flavoured
     scema::DevBuf d_tc_a, d_tc_b, d_tc_nrm, d_tc_misc;
+    scema::DevBuf d_tc_perm, d_tc_iota, d_tc_snrm, d_tc_band;  // norm-band mode: permutation, sorted squared norms, band plan
+    bool tc_band = false, tc_band_wanted = false, tc_band_allowed = false;
     uint64_t tc_for_version = 0, tc_n = 0;
     uint32_t tc_K = 0, tc_slices = 0;
     uint32_t tc_mode = 0;  // slices the next compare starts with (auto: 1, falling back to 2 when survivors overflow)
@@ -176,7 +178,7 @@ int cluster_pipelined(scema_ctx *ctx, const double *steps_host, uint32_t P, doub
 // pairs_tc.cu
 bool tc_supported(const scema_ctx *ctx);
 bool tc_two_slices_possible(const scema_ctx *ctx);
-int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices);
+int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices, bool want_band);
 int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices);
 int tc_stats_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1, bool into_scale);
 int tc_fix_scale(scema_ctx *ctx, int headroom);

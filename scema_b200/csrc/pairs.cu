@@ -1003,7 +1003,7 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
         const uint64_t n_cand = ctx->h_counters[0], n_edge = ctx->h_counters[1];
         if (*variant == SCEMA_PAIRS_TC && ctx->tc_slices == 1 && ctx->tc_mode == 1 && n_cand > ctx->cand_cap) {
             // the one-slice guard band keeps too much of this data: filter with both slices before growing the queue
-            rc = tc_prepare(ctx, thr, 2);
+            rc = tc_prepare(ctx, thr, 2, ctx->tc_band_wanted);
             if (rc) return rc;
             continue;
         }
@@ -1035,7 +1035,14 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
         }
         ctx->counters[1] += n_cand;
         ctx->counters[3] += passes;
-        if (*variant == SCEMA_PAIRS_TC) ctx->counters[5] = ctx->tc_slices;
+        if (*variant == SCEMA_PAIRS_TC) {
+            ctx->counters[5] = ctx->tc_slices;
+            if (ctx->tc_band) {  // tiles the band schedule actually walked (k_tc_band_plan)
+                unsigned long long misc[4];
+                SCEMA_CUDA(ctx, cudaMemcpy(misc, ctx->d_tc_misc.p, sizeof(misc), cudaMemcpyDeviceToHost));
+                ctx->counters[7] = misc[3];
+            }
+        }
         ctx->n_edges = n_edge;
         break;
     }
@@ -1101,7 +1108,10 @@ static int compare_begin(scema_ctx *ctx, double thr, int &variant, uint32_t shar
             slices = ctx->tc_slices;
         ctx->tc_mode = (pin == 1 || pin == 2) ? 0u : 1u;  // 1: may fall back to two slices
         if (!tc_two_slices_possible(ctx)) { slices = 1; ctx->tc_mode = 2; }  // K > 60: hi slices only, falls back to the DMMA filter
-        rc = tc_prepare(ctx, thr, slices);
+        // SCEMA_NORM_BAND=1 (one-shot compares only): rows in norm order, tiles beyond the threshold's reach skipped
+        const char *band_env = getenv("SCEMA_NORM_BAND");
+        const bool want_band = ctx->tc_band_allowed && band_env && atoi(band_env) == 1;
+        rc = tc_prepare(ctx, thr, slices, want_band);
         if (rc) return rc;
         if (ctx->cand_cap == 0) ctx->cand_cap = std::max<uint64_t>(1ull << 20, 32 * n);
         t_end(ctx, SCEMA_T_PREP);
@@ -1122,7 +1132,9 @@ static int compare_begin(scema_ctx *ctx, double thr, int &variant, uint32_t shar
 int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards)
 {
     Schedule sc;
+    ctx->tc_band_allowed = true;   // the whole pair matrix in one launch: the norm-band schedule applies
     int rc = compare_begin(ctx, thr, variant, shard, n_shards, sc);
+    ctx->tc_band_allowed = false;
     if (rc < 0) return SCEMA_OK;
     if (rc) return rc;
     rc = compare_panels(ctx, thr, &variant, shard, n_shards, sc, 0, sc.n_panels);

@@ -23,6 +23,8 @@
 #include "common.cuh"
 #include "tc_sched.h"
 #include <cuda_fp16.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <type_traits>
 #include <algorithm>
 
 namespace scema {
@@ -203,9 +205,23 @@ struct Args {
     uint32_t nc;       // 64-column chunks per row (K <= 60: 1); a 128-row block holds nc x [hi | lo]
     // shared-memory plan (tc_launch): A buffers of a_bytes each, then a ring of 2^lg_nst B stages
     uint32_t a_bytes, n_abuf, lg_nst, stage_bytes, data_bytes;
+    // norm-band mode (rows sorted by norm): band schedule + map from sorted position to row index
+    const uint32_t *band_item_start, *band_jend, *perm;
+    uint32_t band_row_tiles;
     float *dbg;        // debug: every accumulator of every tile, dbg[row * dbg_ld + col]
     uint64_t dbg_ld;
 };
+
+template <int CG>
+__device__ __forceinline__ void sched_init(Sched<CG> &sc, const Args &, const SchedArgs &sa, uint32_t unit, uint32_t n_units)
+{
+    sc.init(sa, unit, n_units);
+}
+template <int CG>
+__device__ __forceinline__ void sched_init(BandSched<CG> &sc, const Args &a, const SchedArgs &sa, uint32_t unit, uint32_t n_units)
+{
+    sc.init(a.band_item_start, a.band_jend, a.band_row_tiles, sa.strip_len, sa.shard, sa.n_shards, unit, n_units);
+}
 
 template <int CG>
 struct Smem {
@@ -220,9 +236,11 @@ struct Smem {
 
 // WIDE = false: rows of one chunk (K <= 60) with a compile-time shared-memory plan (A double-buffered at a 32 KB
 // stride, B ring behind it); WIDE = true: several chunks per row, plan from tc_launch.
-template <int CG, bool DBG, bool WIDE>
+// BAND = true: rows are sorted by norm and only the band of tiles the triangle inequality cannot rule out is walked.
+template <int CG, bool DBG, bool WIDE, bool BAND>
 __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
 {
+    using SchedT = typename std::conditional<BAND, BandSched<CG>, Sched<CG>>::type;
     using SM = Smem<CG>;
     constexpr uint32_t MAXST = SM::MAXST;
     extern __shared__ unsigned char smem_raw[];
@@ -265,8 +283,8 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
     if (warp == 0) {
         // ------------------------------------------------------------------ producer: TMA bulk copies
         if (lane == 0) {
-            Sched<CG> sc;
-            sc.init(sa, unit, n_units);
+            SchedT sc;
+            sched_init(sc, a, sa, unit, n_units);
             uint32_t I, J0, J1, t = 0, item = 0;
             const uint32_t nc = k_nc, n_abuf = k_nabuf, a_bytes = k_abytes, slices = a.slices;
             const unsigned char *const HA = a.HA, *const HB = a.HB;
@@ -306,8 +324,8 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
             // -------------------------------------------------------------- MMA issuer (leader CTA)
             // instruction descriptor: D fp32, A/B fp16, both K-major, N = 256, M = 128 * CG
             const uint32_t idesc = (1u << 4) | ((COLT >> 3) << 17) | (((128u * CG) >> 4) << 24);
-            Sched<CG> sc;
-            sc.init(sa, unit, n_units);
+            SchedT sc;
+            sched_init(sc, a, sa, unit, n_units);
             uint32_t I, J0, J1, t = 0, item = 0, tile = 0;
             // everything the loop needs sits in registers: the asm statements clobber memory, and a kernel parameter
             // re-read from the constant bank on the way from "accumulator free" to the first MMA is latency on the
@@ -347,8 +365,8 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
             }
         } else if (CG == 2 && lane == 0 && rank == 1) {
             // ---------------------------- peer CTA: tell the leader when this CTA's half of a stage landed
-            Sched<CG> sc;
-            sc.init(sa, unit, n_units);
+            SchedT sc;
+            sched_init(sc, a, sa, unit, n_units);
             uint32_t I, J0, J1, t = 0;
             const uint32_t nc_fw = k_nc;
             while (sc.next(I, J0, J1))
@@ -363,8 +381,8 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
         // ---------------------------------------------------------------------- epilogue (8 warps)
         // warp -> (TMEM lane quarter it may read, column half of the tile)
         const uint32_t q = warp & 3u, half = (warp - 4u) >> 2;
-        Sched<CG> sc;
-        sc.init(sa, unit, n_units);
+        SchedT sc;
+        sched_init(sc, a, sa, unit, n_units);
         uint32_t I, J0, J1, tile = 0;
         while (sc.next(I, J0, J1)) {
             const uint64_t row = (uint64_t)(I * CG + rank) * ROWS + q * 32 + lane;
@@ -397,18 +415,45 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
                     }
                 }
                 if (__any_sync(0xffffffffu, (all_neg >> 31) == 0u)) {
+                    // survivors of this warp's 32 x 128 accumulators: one bit mask per lane, one atomic per warp
+                    // (a queue counter hit once per column serialises in L2 when many tiles carry survivors)
+                    uint32_t km[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                     for (int c = 0; c < 128; c++) {
                         const uint64_t col = col0 + c;
                         const uint32_t bitsv = c < 64 ? v0[c & 63] : v1[c & 63];
                         const bool keep = (bitsv >> 31) == 0u && row < col && col < a.n;
-                        const unsigned m = __ballot_sync(0xffffffffu, keep);
-                        if (m) {
-                            const int leader = __ffs(m) - 1;
-                            unsigned long long pos = 0;
-                            if ((int)lane == leader) pos = atomicAdd(a.cand_count, (unsigned long long)__popc(m));
-                            pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(m & ((1u << lane) - 1u));
-                            if (keep && pos < a.cand_cap) a.cand[pos] = (row << 32) | col;
+                        km[c >> 5] |= (keep ? 1u : 0u) << (c & 31);
+                    }
+                    const uint32_t mine = __popc(km[0]) + __popc(km[1]) + __popc(km[2]) + __popc(km[3]);
+                    uint32_t incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                        if ((int)lane >= o) incl += up;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total) {
+                        unsigned long long base = 0;
+                        if (lane == 31) base = atomicAdd(a.cand_count, (unsigned long long)total);
+                        unsigned long long pos = __shfl_sync(0xffffffffu, base, 31) + (incl - mine);
+#pragma unroll
+                        for (int w = 0; w < 4; w++) {
+                            uint32_t m = km[w];
+                            while (m) {
+                                const uint32_t b = __ffs(m) - 1;
+                                m &= m - 1;
+                                if (pos < a.cand_cap) {
+                                    uint64_t ri = row, ci = col0 + 32u * w + b;
+                                    if (BAND) {  // sorted positions -> row indices, smaller one first
+                                        const uint32_t pr = a.perm[ri], pc = a.perm[ci];
+                                        ri = pr < pc ? pr : pc;
+                                        ci = pr < pc ? pc : pr;
+                                    }
+                                    a.cand[pos] = (ri << 32) | ci;
+                                }
+                                pos++;
+                            }
                         }
                     }
                 }
@@ -448,6 +493,7 @@ __global__ void __launch_bounds__(256) k_tc_rowstats(const double *__restrict__ 
     if (lane == 0) {
         if (row < r1) NRM[row] = nrm;
         s_max[warp] = (row < r1 && isfinite(nrm)) ? m : 0.0;  // rows with a non-finite norm take no part in the scale
+        if (gmax && row < r1 && !isfinite(nrm)) atomicAdd(gmax + 4, 1ull);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -491,14 +537,16 @@ __device__ __forceinline__ double h16z(double v)
 __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, uint64_t n, uint64_t r0, uint64_t r1, uint32_t K,
                                                  uint32_t nc, double vmax, const double *__restrict__ NRM,
                                                  unsigned long long *__restrict__ misc, double T0, double cguard,
-                                                 unsigned char *__restrict__ HA, unsigned char *__restrict__ HB)
+                                                 const uint32_t *__restrict__ perm, unsigned char *__restrict__ HA,
+                                                 unsigned char *__restrict__ HB)
 {
-    const uint64_t row = r0 + (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint64_t row = r0 + (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);  // position in the operand copies
     const int lane = threadIdx.x & 31;
     if (row >= r1) return;
     const double s = __longlong_as_double((long long)misc[1]);
     const bool real = row < n;
-    const bool wild = real && !isfinite(NRM[row]);
+    const uint64_t src = real && perm ? perm[row] : row;                     // row of S (norm-band mode: sorted order)
+    const bool wild = real && !isfinite(NRM[src]);
     const bool data = real && !wild;
     // norm of the scaled row; a row beyond the range the scale was chosen for (possible only when the scale was
     // fixed before every row had been seen) gets no fp16 image and survives against everybody, like a row with
@@ -507,7 +555,7 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
     bool big = false;
     if (data)
         for (uint32_t k = lane; k < K; k += 32) {
-            const double v = S[row * K + k] * s;
+            const double v = S[src * K + k] * s;
             nrm = fma(v, v, nrm);
             big |= fabs(v) >= vmax;
         }
@@ -540,7 +588,7 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
             const uint32_t k = lane + 32 * e;  // column 0..63 of the chunk
             const uint32_t kd = c * 64 + k;    // data column
             double v = 0.0;
-            if (data && !too_big && kd < K) v = S[row * K + kd] * s;
+            if (data && !too_big && kd < K) v = S[src * K + kd] * s;
             const double hi = h16z(v);
             const double lo = h16z(v - hi);
             double ahi = hi, alo = lo, bhi = hi, blo = lo;
@@ -557,6 +605,75 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
             *reinterpret_cast<__half *>(b_hi + off) = __double2half(bhi);
             *reinterpret_cast<__half *>(b_lo + off) = __double2half(blo);
         }
+    }
+}
+
+// ---- norm-band mode -------------------------------------------------------------------------------
+__global__ void k_tc_iota(uint32_t *v, uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (uint32_t)i;
+}
+
+// One block. snrm2: squared norms in ascending order (non-finite ones last). For every row tile I (rows_per_tile rows)
+// the first column tile (256 rows) that no pair of the two can share an edge with: all its norms exceed the
+// row tile's largest norm by more than the threshold plus the rounding of the norms themselves. Then the
+// exclusive scan of the strips per row tile. misc[3] receives the number of tiles in the band.
+__global__ void __launch_bounds__(1024) k_tc_band_plan(const double *__restrict__ snrm2, uint64_t n, uint32_t rows_per_tile,
+                                                       uint32_t n_row_tiles, uint32_t n_col_tiles, double thr, double keps,
+                                                       uint32_t S, uint32_t *__restrict__ jend, uint32_t *__restrict__ item_start,
+                                                       unsigned long long *__restrict__ misc)
+{
+    __shared__ unsigned long long s_sum[1024];
+    const uint32_t rpc = 256 / rows_per_tile;
+    unsigned long long tiles = 0;
+    for (uint32_t I = threadIdx.x; I < n_row_tiles; I += blockDim.x) {
+        const uint64_t last = min((uint64_t)(I + 1) * rows_per_tile, n) - 1;
+        const double hi2 = snrm2[last];
+        uint32_t je = n_col_tiles;
+        if (isfinite(hi2)) {
+            const double hi = sqrt(hi2);
+            // smallest J > I / rpc whose first (= smallest) norm is out of reach; norms ascend, so bisect
+            uint32_t lo_j = I / rpc, hi_j = n_col_tiles;  // tile lo_j is always in the band
+            while (hi_j - lo_j > 1) {
+                const uint32_t mid = (lo_j + hi_j) >> 1;
+                const double l2 = snrm2[(uint64_t)mid * 256];
+                const double l = sqrt(l2);
+                const bool out = isfinite(l2) && (l - hi > thr * (1.0 + 4.0 * keps) + 4.0 * keps * l + 1e-150);
+                if (out) hi_j = mid; else lo_j = mid;
+            }
+            je = hi_j;
+        }
+        jend[I] = je;
+        tiles += je - I / rpc;
+    }
+    // strips per row tile -> exclusive prefix: every thread scans a contiguous run of row tiles, thread 0 the 1024 run sums
+    __shared__ unsigned int s_items[1024];
+    const uint32_t per = (n_row_tiles + blockDim.x - 1) / blockDim.x;
+    const uint32_t i0 = min(threadIdx.x * per, n_row_tiles), i1 = min(i0 + per, n_row_tiles);
+    __syncthreads();  // jend[] of the whole block is visible
+    unsigned int run = 0;
+    for (uint32_t I = i0; I < i1; I++) run += (jend[I] - I / rpc + S - 1) / S;
+    s_items[threadIdx.x] = run;
+    s_sum[threadIdx.x] = tiles;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        unsigned int acc = 0;
+        for (uint32_t q = 0; q < blockDim.x; q++) {
+            t += s_sum[q];
+            const unsigned int r = s_items[q];
+            s_items[q] = acc;
+            acc += r;
+        }
+        misc[3] = t;
+        item_start[n_row_tiles] = acc;
+    }
+    __syncthreads();
+    unsigned int acc = s_items[threadIdx.x];
+    for (uint32_t I = i0; I < i1; I++) {
+        item_start[I] = acc;
+        acc += (jend[I] - I / rpc + S - 1) / S;
     }
 }
 
@@ -585,6 +702,7 @@ int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices)
     const uint32_t K = ctx->K;
     const uint64_t n_pad = (n + tc::COLT - 1) / tc::COLT * tc::COLT;
     ctx->tc_valid = false;
+    ctx->tc_band = false;  // row order unless tc_prepare sorts by norm afterwards
     const uint32_t nc = tc_chunks(K);
     if (nc > 1 && slices != 1) return fail(ctx, SCEMA_ERR_INVALID, "tensor-core filter: rows wider than 60 columns run with one slice");
     SCEMA_CUDA(ctx, ctx->d_tc_a.reserve(n_pad * 256 * nc));
@@ -634,34 +752,62 @@ int tc_prep_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1)
     if (r1 <= r0) return SCEMA_OK;
     tc::k_tc_prep<<<(unsigned)((r1 - r0 + 7) / 8), 256, 0, ctx->stream>>>(
         ctx->d_spline, ctx->n, r0, r1, ctx->K, tc_chunks(ctx->K), ldexp(1.0, 12 - tc_k_headroom(ctx->K)), ctx->d_tc_nrm.as<double>(),
-        ctx->d_tc_misc.as<unsigned long long>(), ctx->tc_T0, ctx->tc_cguard, ctx->d_tc_a.as<unsigned char>(),
-        ctx->d_tc_b.as<unsigned char>());
+        ctx->d_tc_misc.as<unsigned long long>(), ctx->tc_T0, ctx->tc_cguard, ctx->tc_band ? ctx->d_tc_perm.as<uint32_t>() : nullptr,
+        ctx->d_tc_a.as<unsigned char>(), ctx->d_tc_b.as<unsigned char>());
     ctx->launches++;
     SCEMA_CUDA(ctx, cudaGetLastError());
     return SCEMA_OK;
 }
 
-// Builds (or reuses) the fp16 operand copies for the current spline matrix and threshold.
-int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices)
+// Builds (or reuses) the fp16 operand copies for the current spline matrix and threshold. want_band: sort the rows by
+// norm first (operand copies in sorted order, ctx->d_tc_perm maps a position back to its row) so that the launch can
+// restrict itself to the band of tiles the triangle inequality cannot rule out; refused (dense order instead) when a
+// row has a non-finite norm or the rows are wider than one chunk.
+int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices, bool want_band)
 {
     const uint64_t n = ctx->n;
     const uint64_t n_pad = (n + tc::COLT - 1) / tc::COLT * tc::COLT;
     if (ctx->tc_for_version == ctx->spline_version && ctx->tc_thr == thr && ctx->tc_n == n && ctx->tc_K == ctx->K &&
-        ctx->tc_slices == slices && ctx->tc_valid)
+        ctx->tc_slices == slices && ctx->tc_valid && ctx->tc_band_wanted == want_band)
         return SCEMA_OK;
     int rc = tc_prepare_begin(ctx, thr, slices);
+    ctx->tc_band = false;
+    ctx->tc_band_wanted = want_band;
     if (!rc) rc = tc_stats_rows(ctx, 0, n, true);
-    if (!rc) rc = tc_fix_scale(ctx, 0);
+    if (rc) return rc;
+    if (want_band && tc_chunks(ctx->K) == 1) {
+        unsigned long long misc[8];
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(misc, ctx->d_tc_misc.p, sizeof(misc), cudaMemcpyDeviceToHost, ctx->stream));
+        SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (misc[4] == 0) {
+            // ascending squared norms (non-negative doubles order as unsigned integers) and the permutation
+            SCEMA_CUDA(ctx, ctx->d_tc_perm.reserve(n_pad * sizeof(uint32_t)));
+            SCEMA_CUDA(ctx, ctx->d_tc_iota.reserve(n_pad * sizeof(uint32_t)));
+            SCEMA_CUDA(ctx, ctx->d_tc_snrm.reserve(n_pad * sizeof(double)));
+            tc::k_tc_iota<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_tc_iota.as<uint32_t>(), n);
+            size_t tmp = 0;
+            SCEMA_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_tc_nrm.as<uint64_t>(), ctx->d_tc_snrm.as<uint64_t>(),
+                                                            ctx->d_tc_iota.as<uint32_t>(), ctx->d_tc_perm.as<uint32_t>(), (int64_t)n, 0, 64,
+                                                            ctx->stream));
+            SCEMA_CUDA(ctx, ctx->d_sort_tmp.reserve(tmp));
+            SCEMA_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp.p, tmp, ctx->d_tc_nrm.as<uint64_t>(),
+                                                            ctx->d_tc_snrm.as<uint64_t>(), ctx->d_tc_iota.as<uint32_t>(),
+                                                            ctx->d_tc_perm.as<uint32_t>(), (int64_t)n, 0, 64, ctx->stream));
+            ctx->launches += 10;
+            ctx->tc_band = true;
+        }
+    }
+    rc = tc_fix_scale(ctx, 0);
     if (!rc) rc = tc_prep_rows(ctx, 0, n_pad);
     if (rc) return rc;
     ctx->tc_valid = true;
     return SCEMA_OK;
 }
 
-template <int CG, bool DBG, bool WIDE>
+template <int CG, bool DBG, bool WIDE, bool BAND>
 static int tc_launch_t(scema_ctx *ctx, const tc::Args &a, uint64_t items)
 {
-    auto kern = tc::k_filter_tc<CG, DBG, WIDE>;
+    auto kern = tc::k_filter_tc<CG, DBG, WIDE, BAND>;
     const size_t smem = (size_t)a.data_bytes + tc::Smem<CG>::tail;
     if (smem > ctx->smem_optin) return fail(ctx, SCEMA_ERR_CUDA, "tensor-core filter: shared memory exceeds device limit");
     SCEMA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -706,6 +852,8 @@ int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t C0, uint32_t C1
     a.dbg = dbg;
     a.dbg_ld = dbg_ld;
     a.nc = tc_chunks(ctx->K);
+    a.band_item_start = a.band_jend = a.perm = nullptr;
+    a.band_row_tiles = 0;
     static const char *cg_env = getenv("SCEMA_TC_CG");
     // cta_group::2 pairs halve the B traffic and the shared-memory reads per SM, but neither bounds this kernel
     // (the TMEM read-out resp. the tensor pipe do) and the pair pays a forwarder hop per stage: measured 61.0 ms
@@ -747,9 +895,28 @@ int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t C0, uint32_t C1
         }
         a.data_bytes = a.n_abuf * a.a_bytes + (a.stage_bytes << a.lg_nst);  // only what is used: the rest of the SM stays L1
     }
-    if (a.nc > 1) return cg == 1 ? tc_launch_t<1, false, true>(ctx, a, items) : tc_launch_t<2, false, true>(ctx, a, items);
-    if (cg == 1) return dbg ? tc_launch_t<1, true, false>(ctx, a, items) : tc_launch_t<1, false, false>(ctx, a, items);
-    return dbg ? tc_launch_t<2, true, false>(ctx, a, items) : tc_launch_t<2, false, false>(ctx, a, items);
+    if (ctx->tc_band && !dbg && a.nc == 1) {
+        // band plan for this kernel flavour: last column tile per row tile, strips per row tile, their prefix
+        const uint32_t rpt = 128u * (uint32_t)cg;
+        const uint64_t n_pad = (uint64_t)a.NT * tc::COLT;
+        a.band_row_tiles = (uint32_t)(n_pad / rpt);
+        a.strip_len = 8;
+        SCEMA_CUDA(ctx, ctx->d_tc_band.reserve((2ull * a.band_row_tiles + 2) * sizeof(uint32_t)));
+        uint32_t *jend = ctx->d_tc_band.as<uint32_t>(), *item_start = jend + a.band_row_tiles;
+        const double keps = (ctx->K + 8.0) * 2.220446049250313e-16;
+        tc::k_tc_band_plan<<<1, 1024, 0, ctx->stream>>>(ctx->d_tc_snrm.as<double>(), ctx->n, rpt, a.band_row_tiles, a.NT, ctx->tc_thr, keps,
+                                                      a.strip_len, jend, item_start, ctx->d_tc_misc.as<unsigned long long>());
+        ctx->launches++;
+        a.band_item_start = item_start;
+        a.band_jend = jend;
+        a.perm = ctx->d_tc_perm.as<uint32_t>();
+        a.I0 = 0; a.I1 = a.NT; a.C0 = 0; a.C1 = a.NT;
+        return cg == 1 ? tc_launch_t<1, false, false, true>(ctx, a, ctx->sm_count) : tc_launch_t<2, false, false, true>(ctx, a, ctx->sm_count);
+    }
+    if (ctx->tc_band) return fail(ctx, SCEMA_ERR_STATE, "tensor-core filter: operands are in norm order, this launch needs row order");
+    if (a.nc > 1) return cg == 1 ? tc_launch_t<1, false, true, false>(ctx, a, items) : tc_launch_t<2, false, true, false>(ctx, a, items);
+    if (cg == 1) return dbg ? tc_launch_t<1, true, false, false>(ctx, a, items) : tc_launch_t<1, false, false, false>(ctx, a, items);
+    return dbg ? tc_launch_t<2, true, false, false>(ctx, a, items) : tc_launch_t<2, false, false, false>(ctx, a, items);
 }
 
 // Debug / validation entry (scema_tc_debug): runs the instrumented kernel over the whole pair matrix
@@ -765,7 +932,7 @@ int tc_debug_run(scema_ctx *ctx, double thr, uint32_t slices, float *acc_host, u
     const uint64_t n_pad = (ctx->n + tc::COLT - 1) / tc::COLT * tc::COLT;
     if (ld < n_pad) return fail(ctx, SCEMA_ERR_INVALID, "tc_debug: ld < padded n");
     if (n_pad > 8192) return fail(ctx, SCEMA_ERR_INVALID, "tc_debug: at most 8192 rows");
-    int rc = tc_prepare(ctx, thr, slices);
+    int rc = tc_prepare(ctx, thr, slices, false);
     if (rc) return rc;
     SCEMA_CUDA(ctx, ctx->d_counters.reserve(8 * sizeof(uint64_t)));
     SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(uint64_t), ctx->stream));

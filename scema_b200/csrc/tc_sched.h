@@ -56,5 +56,38 @@ struct Sched {
     }
 };
 
+// Band schedule (rows sorted by norm, SCEMA_NORM_BAND): row tile I only meets the column tiles
+// [I / RPC, jend[I]) — beyond that every pair is farther apart than the threshold by the triangle
+// inequality | |a| - |b| | <= d(a, b). item_start[I] = number of items (strips of <= S tiles) of the
+// row tiles before I; item g = (row tile found by bisection, strip g - item_start[I] of it).
+template <int CG>
+struct BandSched {
+    static constexpr uint32_t RPC = 2 / CG;
+    const uint32_t *item_start, *jend;
+    uint32_t S, n_row_tiles, shard, n_shards;
+    uint64_t k, stride;
+    SCEMA_TC_HD void init(const uint32_t *item_start_, const uint32_t *jend_, uint32_t n_row_tiles_, uint32_t strip_len,
+                          uint32_t shard_, uint32_t n_shards_, uint32_t unit, uint32_t n_units)
+    {
+        item_start = item_start_; jend = jend_; n_row_tiles = n_row_tiles_; S = strip_len;
+        shard = shard_; n_shards = n_shards_; k = unit; stride = n_units;
+    }
+    SCEMA_TC_HD bool next(uint32_t &I, uint32_t &J0, uint32_t &J1)
+    {
+        const uint64_t g = k * n_shards + shard;
+        if (g >= item_start[n_row_tiles]) return false;
+        uint32_t lo = 0, hi = n_row_tiles;  // item_start[lo] <= g < item_start[hi]
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (item_start[mid] <= g) lo = mid; else hi = mid;
+        }
+        I = lo;
+        J0 = I / RPC + (uint32_t)(g - item_start[I]) * S;
+        J1 = J0 + S < jend[I] ? J0 + S : jend[I];
+        k += stride;
+        return true;
+    }
+};
+
 }  // namespace tc
 }  // namespace scema

@@ -300,3 +300,68 @@ def test_cluster_from_host_buffers_is_pipelined_and_identical(oracle, monkeypatc
     h = scema_b200.HistCluster(0)
     assert h.cluster(steps, off, None, P, THR) > 0 and h.counters()["pipeline_ranges"] == 0
     h.close()
+
+
+def test_norm_band_mode(oracle, monkeypatch):
+    """SCEMA_NORM_BAND=1: rows sorted by norm, tiles out of the threshold's reach skipped (triangle inequality). Same
+    edge list as always — on clustered rows (norms spread: nearly everything skipped), on rows of equal norm (nothing
+    can be skipped), with pairs a few ulp either side of the threshold, sharded, and with a NaN row (dense order)."""
+    monkeypatch.setenv("SCEMA_NORM_BAND", "1")
+    rng = np.random.default_rng(12)
+    n = 20000
+    clustered = synth.rows(41, n, 16, 10, 5e-3, synth.default_pert(THR, 10))
+    for q in range(400):
+        a = int(rng.integers(0, n)); b = (a + n // 2) % n
+        u = rng.standard_normal(60); u /= np.linalg.norm(u)
+        clustered[b] = clustered[a] + u * THR * (1 + (q - 200) * 3e-16)
+    sphere = rng.standard_normal((6000, 60))
+    sphere *= 5e-3 / np.linalg.norm(sphere, axis=1)[:, None]        # equal norms
+    sphere[1::2] = sphere[::2] + 2e-7 * rng.standard_normal((3000, 60)) / np.sqrt(60)
+    for name, rows in (("clustered", clustered), ("sphere", sphere)):
+        want = oracle.all_pairs(rows, THR)
+        h = scema_b200.HistCluster(0)
+        h.set_spline(rows)
+        assert h.compare(THR, PAIRS_TC) == len(want[0]), name
+        assert edges_equal(h.get_edges(), want), name
+        c = h.counters()
+        nt = (len(rows) + 255) // 256
+        assert c["band_tiles"] > 0
+        if name == "clustered":
+            assert c["band_tiles"] < nt * (nt + 1) // 2 // 5      # most of the triangle is out of reach
+        else:
+            assert c["band_tiles"] >= nt * (nt + 1) // 2           # nothing can be ruled out
+        # sharded: union of the shards
+        parts = []
+        for r in range(3):
+            h.compare(THR, PAIRS_TC, shard=r, n_shards=3)
+            parts.append(h.get_edges())
+        a = np.concatenate([p[0] for p in parts]); b = np.concatenate([p[1] for p in parts]); d = np.concatenate([p[2] for p in parts])
+        o = np.lexsort((b, a))
+        assert edges_equal((a[o], b[o], d[o]), want), name
+        # the streamed compare needs row order: the operand copies are rebuilt, same list
+        chunks = []
+        h.compare_stream(THR, lambda x, y, z: chunks.append((x, y, z)), PAIRS_TC, panels_per_chunk=2)
+        assert edges_equal(tuple(np.concatenate([ch[k] for ch in chunks]) for k in range(3)), want), name
+        h.close()
+    # a pipelined scema_cluster on a context whose last compare ran in norm order must not inherit that order
+    monkeypatch.setenv("SCEMA_PIPELINE_MIN_N", "4096")
+    off = synth.offsets(13, 9000, 16, 6, 60)
+    steps = synth.histories(13, 9000, 16, 5e-3, synth.default_pert(THR, 10), off)
+    h = scema_b200.HistCluster(0)
+    h.set_histories(steps, off)
+    h.resample(10)
+    ne = h.compare(THR, PAIRS_TC)
+    ref = h.get_edges()
+    assert h.counters()["band_tiles"] > 0
+    assert h.cluster(steps, off, None, 10, THR) == ne and edges_equal(h.get_edges(), ref)
+    assert h.counters()["pipeline_ranges"] >= 2 and h.counters()["band_tiles"] == 0
+    assert h.compare(THR, PAIRS_TC) == ne and edges_equal(h.get_edges(), ref) and h.counters()["band_tiles"] > 0
+    h.close()
+    bad = clustered[:5000].copy()
+    bad[17] = np.nan
+    want = oracle.all_pairs(bad, THR)
+    h = scema_b200.HistCluster(0)
+    h.set_spline(bad)
+    assert h.compare(THR, PAIRS_TC) == len(want[0]) and edges_equal(h.get_edges(), want)
+    assert h.counters()["band_tiles"] == 0
+    h.close()
