@@ -50,6 +50,8 @@ def datasets():
     yield "cancel", alt * np.where(rng.random((n, 1)) < 0.5, 1.0, -1.0), 1e-5   # a.b = +-|a||b|: worst cancellation
     yield "ranges", rng.standard_normal((n, 60)) * 10.0 ** rng.integers(-12, -2, size=(n, 1)), 1e-7
     yield "k18", rng.standard_normal((n, 18)) * 1e-2, 1e-2
+    # ten decades INSIDE every row and a larger matrix (16.8M accumulators): most products are far below the running sum
+    yield "inrow", rng.standard_normal((4096, 60)) * 10.0 ** rng.uniform(-10, 0, size=(4096, 60)), 1e-4
 
 
 @pytest.mark.parametrize("slices", [2, 1])
@@ -107,10 +109,10 @@ def test_tc_accumulators_match_sliced_fp64(hc, name, rows, thr, slices):
     assert np.all(alo[:, 60] == 0) and np.all(alo[:, 62:] == 0) and np.all(blo[:, 60:63] == 0)
     assert np.all(ahi[n:, 60] == -65504.0)  # padding rows can never survive
     # soundness on this data: every true edge (FP64 direct differences) has a non-negative accumulator
-    for r0 in range(0, n, 256):
-        d2 = ((rows[r0:r0 + 256, None, :] - rows[None, :, :]) ** 2).sum(-1)
-        edge = (np.sqrt(d2) < thr) & (np.arange(r0, min(r0 + 256, n))[:, None] < np.arange(n)[None, :])
-        a_blk = acc[r0:r0 + 256, :n][: edge.shape[0]]
+    for r0 in range(0, n, 64):
+        d2 = ((rows[r0:r0 + 64, None, :] - rows[None, :, :]) ** 2).sum(-1)
+        edge = (np.sqrt(d2) < thr) & (np.arange(r0, min(r0 + 64, n))[:, None] < np.arange(n)[None, :])
+        a_blk = acc[r0:r0 + 64, :n][: edge.shape[0]]
         assert not np.any(edge & (np.signbit(a_blk))), "a true edge was rejected by the filter"
 
 
