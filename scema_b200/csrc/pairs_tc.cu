@@ -535,7 +535,7 @@ __device__ __forceinline__ double h16z(double v)
 // so that  A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  adds  (P x0 + Q x1 + Q x2)_i + (P x0 + Q x1 + Q x2)_j = -h_i - h_j
 // (to 2^-33 |h| + 2^-11; with the hi slices alone the x2 terms drop out: 2^-22 |h| + 2^-11).
 __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, uint64_t n, uint64_t r0, uint64_t r1, uint32_t K,
-                                                 uint32_t nc, double vmax, const double *__restrict__ NRM,
+                                                 uint32_t nc, uint32_t slices, double vmax, const double *__restrict__ NRM,
                                                  unsigned long long *__restrict__ misc, double T0, double cguard,
                                                  const uint32_t *__restrict__ perm, unsigned char *__restrict__ HA,
                                                  unsigned char *__restrict__ HB)
@@ -601,9 +601,11 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
             }
             const uint32_t off = ((((k >> 3) ^ (r & 7u)) << 4) | ((k & 7u) << 1));  // swizzled 16-byte chunk, element in chunk
             *reinterpret_cast<__half *>(a_hi + off) = __double2half(ahi);
-            *reinterpret_cast<__half *>(a_lo + off) = __double2half(alo);
             *reinterpret_cast<__half *>(b_hi + off) = __double2half(bhi);
-            *reinterpret_cast<__half *>(b_lo + off) = __double2half(blo);
+            if (slices != 1) {  // the one-slice kernel never reads the lo halves
+                *reinterpret_cast<__half *>(a_lo + off) = __double2half(alo);
+                *reinterpret_cast<__half *>(b_lo + off) = __double2half(blo);
+            }
         }
     }
 }
@@ -751,7 +753,8 @@ int tc_prep_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1)
 {
     if (r1 <= r0) return SCEMA_OK;
     tc::k_tc_prep<<<(unsigned)((r1 - r0 + 7) / 8), 256, 0, ctx->stream>>>(
-        ctx->d_spline, ctx->n, r0, r1, ctx->K, tc_chunks(ctx->K), ldexp(1.0, 12 - tc_k_headroom(ctx->K)), ctx->d_tc_nrm.as<double>(),
+        ctx->d_spline, ctx->n, r0, r1, ctx->K, tc_chunks(ctx->K), ctx->tc_slices, ldexp(1.0, 12 - tc_k_headroom(ctx->K)),
+        ctx->d_tc_nrm.as<double>(),
         ctx->d_tc_misc.as<unsigned long long>(), ctx->tc_T0, ctx->tc_cguard, ctx->tc_band ? ctx->d_tc_perm.as<uint32_t>() : nullptr,
         ctx->d_tc_a.as<unsigned char>(), ctx->d_tc_b.as<unsigned char>());
     ctx->launches++;

@@ -86,27 +86,36 @@ def test_tc_accumulators_match_sliced_fp64(hc, name, rows, thr, slices):
     s = 2.0 ** (11 - int(np.floor(np.log2(M))))
     a_s = np.zeros((n_pad, 64))
     a_s[:n, :K] = rows * s
-    rec = (ahi + alo)[:, :60]
-    assert np.all(np.abs(rec[:n] - a_s[:n, :60]) <= 2.0 ** -22 * np.abs(a_s[:n, :60]) + 2.0 ** -13)
-    assert np.array_equal(ahi[:, :60], bhi[:, :60]) and np.array_equal(alo[:, :60], blo[:, :60])
+    if slices == 2:
+        rec = (ahi + alo)[:, :60]
+        assert np.all(np.abs(rec[:n] - a_s[:n, :60]) <= 2.0 ** -22 * np.abs(a_s[:n, :60]) + 2.0 ** -13)
+        assert np.array_equal(alo[:, :60], blo[:, :60])
+    else:  # the lo halves are neither written nor read with one slice
+        assert np.all(np.abs(ahi[:n, :60] - a_s[:n, :60]) <= 2.0 ** -11 * np.abs(a_s[:n, :60]) + 2.0 ** -13)
+    assert np.array_equal(ahi[:, :60], bhi[:, :60])
     assert np.abs(ahi[:n, :60]).max() < 4096
     # no fp16 subnormal anywhere in the operands (the prep flushes them; the bound budgets for that)
-    for arr in (ahi, alo, bhi, blo):
+    for arr in ((ahi, alo, bhi, blo) if slices == 2 else (ahi, bhi)):
         nz = np.abs(arr[arr != 0])
         assert nz.size == 0 or nz.min() >= 2.0 ** -14
-    # fold columns: P x0 + Q x1 + Q x2 == -h_i to 2^-30 relative, h_i as documented (guard 2^-13 / 2^-9)
+    # fold columns: P x0 + Q x1 (+ Q x2) == -h_i, h_i as documented (guard 2^-13 / 2^-9)
     P, Q = 32768.0, 8.0
     cg = 2.0 ** -13 if slices == 2 else 2.0 ** -9
     nrm = (a_s[:n] ** 2).sum(1)
     T0 = thr * thr * (1 + (2 * K + 16) * 2.0 ** -53) * (1 + 4 * 2.0 ** -53) * s * s
     h = 0.5 * (nrm * (1 - cg) - T0 * (0.5 + 2 * cg) - K * 2.0 ** -7)
-    fold_a = P * ahi[:n, 60] + Q * ahi[:n, 61] + Q * alo[:n, 61]
-    fold_b = P * bhi[:n, 62] + Q * bhi[:n, 63] + Q * blo[:n, 63]
+    fold_a = P * ahi[:n, 60] + Q * ahi[:n, 61]
+    fold_b = P * bhi[:n, 62] + Q * bhi[:n, 63]
+    if slices == 2:
+        fold_a = fold_a + Q * alo[:n, 61]
+        fold_b = fold_b + Q * blo[:n, 63]
     normal = -h <= 32768.0 * P
-    assert np.all(np.abs(fold_a[normal] + h[normal]) <= 2.0 ** -30 * np.abs(h[normal]) + 2.0 ** -10)
+    rel = 2.0 ** -30 if slices == 2 else 2.0 ** -21
+    assert np.all(np.abs(fold_a[normal] + h[normal]) <= rel * np.abs(h[normal]) + 2.0 ** -10)
     assert np.array_equal(fold_a, fold_b)
     assert np.all(ahi[:n, 62] == P) and np.all(ahi[:n, 63] == Q) and np.all(bhi[:n, 60] == P) and np.all(bhi[:n, 61] == Q)
-    assert np.all(alo[:, 60] == 0) and np.all(alo[:, 62:] == 0) and np.all(blo[:, 60:63] == 0)
+    if slices == 2:
+        assert np.all(alo[:, 60] == 0) and np.all(alo[:, 62:] == 0) and np.all(blo[:, 60:63] == 0)
     assert np.all(ahi[n:, 60] == -65504.0)  # padding rows can never survive
     # soundness on this data: every true edge (FP64 direct differences) has a non-negative accumulator
     for r0 in range(0, n, 64):
