@@ -74,6 +74,7 @@ struct scema_ctx {
     std::map<uint32_t, uint64_t> table_off;  // L -> offset (doubles) in d_tables
     scema::DevBuf d_tables, d_table_index;   // d_table_index: int64 [max_len+1] -> offset or -1
     uint64_t tables_used = 0;                // doubles
+    uint64_t tables_for_version = ~0ull;     // histories_version the tables were last checked against
     uint32_t table_index_len = 0;
     scema::DevBuf zscratch, d_order, d_chunks, d_chunk_counters;  // K1 work plan: padded group order, chunk list
     std::vector<uint32_t> plan_chunk_begin;                        // [classes+1] into d_chunks

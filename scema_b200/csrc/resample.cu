@@ -469,10 +469,15 @@ static int ensure_tables_present(scema_ctx *ctx, uint32_t P, const std::vector<u
 
 static int ensure_tables(scema_ctx *ctx, uint32_t P)
 {
+    // nothing to do when these histories already have their tables for this P (the scan below is O(n) on the host,
+    // with the GPU idle: a re-fit of unchanged histories should not pay it)
+    if (ctx->tables_for_version == ctx->histories_version && ctx->table_P == P && ctx->tables_used) return SCEMA_OK;
     // distinct lengths of the current batch
     std::vector<uint8_t> present((size_t)ctx->max_len + 1, 0);
     for (uint64_t i = 0; i < ctx->hn; i++) present[ctx->h_offsets[i + 1] - ctx->h_offsets[i]] = 1;
-    return ensure_tables_present(ctx, P, present, ctx->max_len);
+    const int rc = ensure_tables_present(ctx, P, present, ctx->max_len);
+    if (!rc) ctx->tables_for_version = ctx->histories_version;
+    return rc;
 }
 
 static int ensure_tables_present(scema_ctx *ctx, uint32_t P, const std::vector<uint8_t> &present, uint32_t max_len)
