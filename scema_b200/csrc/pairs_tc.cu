@@ -504,15 +504,65 @@ __global__ void __launch_bounds__(256) k_tc_rowstats(const double *__restrict__ 
     }
 }
 
+constexpr uint32_t HIST_BINS = 2112;   // exponent of a squared norm + 1075 (0: zero norm)
+constexpr uint32_t MISC_WORDS = 8 + HIST_BINS;
+constexpr uint32_t MAX_OUTLIERS = 16;  // rows the scale may leave behind (they survive against everybody)
+
+// histogram of the exponents of the finite squared norms of rows [r0, r1) into misc[8 ..]
+__global__ void __launch_bounds__(256) k_tc_nrm_hist(const double *__restrict__ NRM, uint64_t r0, uint64_t r1,
+                                                     unsigned long long *__restrict__ misc)
+{
+    __shared__ unsigned int h[HIST_BINS];
+    for (uint32_t b = threadIdx.x; b < HIST_BINS; b += blockDim.x) h[b] = 0;
+    __syncthreads();
+    for (uint64_t i = r0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += (uint64_t)gridDim.x * blockDim.x) {
+        const double v = NRM[i];
+        if (isfinite(v)) atomicAdd(&h[v > 0.0 ? (uint32_t)(ilogb(v) + 1075) : 0u], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < HIST_BINS; b += blockDim.x)
+        if (h[b]) atomicAdd(misc + 8 + b, (unsigned long long)h[b]);
+}
+
 // Power-of-two scale that brings the largest finite magnitude into [2^(11-headroom), 2^(12-headroom)).
 // misc[0] = largest magnitude seen (bits), misc[1] = the scale (double bits), misc[2] = rows whose scaled
-// magnitude reached 2^12 (only possible when the scale was fixed before all rows were seen).
-__global__ void k_tc_fix_scale(unsigned long long *misc, int headroom)
+// magnitude reached the limit, misc[3] = tiles of the norm band, misc[4] = rows with a non-finite norm,
+// misc[8 ..] = histogram of the squared-norm exponents.
+// A handful of rows many decades above the rest would push everybody else into the flushed range of fp16 (every
+// pair a survivor). If at most MAX_OUTLIERS rows sit at least 12 binades of squared norm (6 of magnitude) above all
+// others, the scale is taken from the others instead: |v| <= |row| < 2^((E+1)/2) for a row whose squared norm has
+// exponent E; the rows left behind exceed the limit in k_tc_prep and are treated like rows with a non-finite norm.
+__global__ void __launch_bounds__(256) k_tc_fix_scale(unsigned long long *misc, int headroom)
 {
+    __shared__ int s_hi;
+    if (threadIdx.x == 0) s_hi = -1;
+    __syncthreads();
+    for (int b = threadIdx.x + 1; b < (int)HIST_BINS; b += blockDim.x)   // highest populated bin, all threads
+        if (misc[8 + b]) atomicMax(&s_hi, b);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     const double maxabs = __longlong_as_double((long long)misc[0]);
     double s = 1.0;
     if (maxabs > 0.0) {
-        int se = 11 - headroom - ilogb(maxabs);
+        int top = ilogb(maxabs);  // exponent the scale is built on
+        const int e_hi = s_hi;
+        if (e_hi > 0) {
+            unsigned long long above = 0;
+            for (int b = e_hi; b > 0; b--) {
+                above += misc[8 + b];
+                if (above > MAX_OUTLIERS) break;
+                int nb = b - 1;  // next populated bin below
+                while (nb > 0 && !misc[8 + nb]) nb--;
+                if (nb > 0 && b - nb >= 12) {
+                    // rows in bins >= b are left behind; everybody else has |v| < 2^((E+1)/2), E = nb - 1075
+                    const int E = nb - 1075;
+                    const int cap = (E + 1 + (E + 1 >= 0 ? 1 : 0)) / 2;  // ceil((E + 1) / 2)
+                    if (cap - 1 < top) top = cap - 1;                     // as if the largest magnitude were just below 2^cap
+                    break;
+                }
+            }
+        }
+        int se = 11 - headroom - top;
         se = max(-1000, min(1000, se));
         s = scalbn(1.0, se);
     }
@@ -710,8 +760,8 @@ int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices)
     SCEMA_CUDA(ctx, ctx->d_tc_a.reserve(n_pad * 256 * nc));
     SCEMA_CUDA(ctx, ctx->d_tc_b.reserve(n_pad * 256 * nc));
     SCEMA_CUDA(ctx, ctx->d_tc_nrm.reserve(n_pad * sizeof(double)));
-    SCEMA_CUDA(ctx, ctx->d_tc_misc.reserve(64));
-    SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_tc_misc.p, 0, 64, ctx->stream));
+    SCEMA_CUDA(ctx, ctx->d_tc_misc.reserve(tc::MISC_WORDS * sizeof(unsigned long long)));
+    SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_tc_misc.p, 0, tc::MISC_WORDS * sizeof(unsigned long long), ctx->stream));
     const double eps = 1.1102230246251565e-16;  // 2^-53
     // The operands are rescaled, so the reference's underflow must be budgeted explicitly: each squared
     // difference of compare_L2_norm may lose up to half a subnormal ulp, i.e. the reference's sum can sit
@@ -737,13 +787,18 @@ int tc_stats_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1, bool into_scale)
     tc::k_tc_rowstats<<<(unsigned)((r1 - r0 + 7) / 8), 256, 0, ctx->stream>>>(
         ctx->d_spline, r0, r1, ctx->K, ctx->d_tc_nrm.as<double>(), into_scale ? ctx->d_tc_misc.as<unsigned long long>() : nullptr);
     ctx->launches++;
+    if (into_scale) {
+        const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count * 4, (r1 - r0 + 255) / 256);
+        tc::k_tc_nrm_hist<<<grid, 256, 0, ctx->stream>>>(ctx->d_tc_nrm.as<double>(), r0, r1, ctx->d_tc_misc.as<unsigned long long>());
+        ctx->launches++;
+    }
     SCEMA_CUDA(ctx, cudaGetLastError());
     return SCEMA_OK;
 }
 
 int tc_fix_scale(scema_ctx *ctx, int headroom)
 {
-    tc::k_tc_fix_scale<<<1, 1, 0, ctx->stream>>>(ctx->d_tc_misc.as<unsigned long long>(), headroom + tc_k_headroom(ctx->K));
+    tc::k_tc_fix_scale<<<1, 256, 0, ctx->stream>>>(ctx->d_tc_misc.as<unsigned long long>(), headroom + tc_k_headroom(ctx->K));
     ctx->launches++;
     SCEMA_CUDA(ctx, cudaGetLastError());
     return SCEMA_OK;

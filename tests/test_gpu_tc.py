@@ -376,3 +376,24 @@ def test_norm_band_mode(oracle, monkeypatch):
     assert h.compare(THR, PAIRS_TC) == len(want[0]) and edges_equal(h.get_edges(), want)
     assert h.counters()["band_tiles"] == 0
     h.close()
+
+
+def test_tc_scale_ignores_a_few_outlier_rows(oracle):
+    """Five rows nine decades above the rest must not push everybody else into the flushed range of fp16 (where every
+    pair would survive and the compare would end on the filter-free kernel): the scale is taken from the rest and the
+    outliers are handled like rows with a non-finite norm. Also with the outliers only moderately larger (no gap: the
+    largest magnitude rules as before)."""
+    n = 3000
+    for factor, few_passes in ((1e9, True), (40.0, True)):
+        rows = synth.rows(33, n, 16, 10, 5e-3, synth.default_pert(THR, 10))
+        rows[[5, 700, 701, 1500, 2999]] *= factor
+        rows[701] = rows[700] * (1 + 1e-12)          # two of the large rows nearly equal (the oracle decides whether that is an edge)
+        want = oracle.all_pairs(rows, THR)
+        h = scema_b200.HistCluster(0)
+        h.set_spline(rows)
+        assert h.compare(THR, PAIRS_TC) == len(want[0])
+        assert edges_equal(h.get_edges(), want)
+        c = h.counters()
+        assert c["passes"] == 1 and c["survivors"] < 40 * n, (factor, c)
+        assert len(want[0]) > n
+        h.close()
