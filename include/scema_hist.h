@@ -195,6 +195,10 @@ uint64_t scema_kernel_launches(const scema_ctx *ctx);
  * stored at chunk c ^ (r & 7). */
 int scema_tc_debug(scema_ctx *ctx, double threshold, uint32_t slices, float *acc_host, uint64_t ld,
                    void *operand_a_host, void *operand_b_host);
+/* Shared-memory plan the tcgen05 filter would use for rows of k columns (host logic only, no device needed):
+ * plan = {chunks of 64 columns, bytes per A buffer, A buffers, log2(B stages), bytes per B stage, bytes used}.
+ * SCEMA_ERR_INVALID when the variant does not take such rows (more than 10 chunks, or two slices on wide rows). */
+int scema_tc_plan(uint32_t k, uint32_t slices, uint32_t cta_group, uint32_t plan[6]);
 /* Measured FP64 issue rates on the context's device (TFLOP/s): out[0] DFMA, out[1] DMMA m8n8k4. */
 int scema_fp64_peak(scema_ctx *ctx, double out[2]);
 

@@ -402,6 +402,14 @@ int scema_fp64_peak(scema_ctx *c, double out[2])
     return fp64_peak_run(c, out);
 }
 
+int scema_tc_plan(uint32_t k, uint32_t slices, uint32_t cta_group, uint32_t plan[6])
+{
+    if (!plan || k == 0 || (slices != 1 && slices != 2) || (cta_group != 1 && cta_group != 2)) return SCEMA_ERR_INVALID;
+    plan[0] = tc_chunks_for(k);
+    if (plan[0] > 10 || (plan[0] > 1 && slices != 1)) return SCEMA_ERR_INVALID;
+    return tc_smem_plan(plan[0], slices, cta_group, &plan[1], &plan[2], &plan[3], &plan[4], &plan[5]) ? SCEMA_OK : SCEMA_ERR_INVALID;
+}
+
 int scema_tc_debug(scema_ctx *c, double threshold, uint32_t slices, float *acc_host, uint64_t ld, void *operand_a_host,
                    void *operand_b_host)
 {

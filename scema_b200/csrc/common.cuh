@@ -179,6 +179,9 @@ int cluster_pipelined(scema_ctx *ctx, const double *steps_host, uint32_t P, doub
 // pairs_tc.cu
 bool tc_supported(const scema_ctx *ctx);
 bool tc_two_slices_possible(const scema_ctx *ctx);
+bool tc_smem_plan(uint32_t nc, uint32_t slices, uint32_t cg, uint32_t *a_bytes, uint32_t *n_abuf, uint32_t *lg_nst,
+                  uint32_t *stage_bytes, uint32_t *data_bytes);
+uint32_t tc_chunks_for(uint32_t K);
 int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices, bool want_band);
 int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices);
 int tc_stats_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1, bool into_scale);

@@ -887,6 +887,41 @@ static int tc_launch_t(scema_ctx *ctx, const tc::Args &a, uint64_t items)
     return SCEMA_OK;
 }
 
+// Shared-memory plan of k_filter_tc (pure host logic, also reachable through scema_tc_plan for the CPU tests):
+// A = all chunks of the row tile, double-buffered over items when that still leaves a deep B ring; B ring = a
+// power-of-two number of stages of one chunk of a column tile; data_bytes = what is actually used (the rest of the
+// SM stays L1). False when even one A buffer and two B stages do not fit 224 KB.
+bool tc_smem_plan(uint32_t nc, uint32_t slices, uint32_t cg, uint32_t *a_bytes, uint32_t *n_abuf, uint32_t *lg_nst,
+                  uint32_t *stage_bytes, uint32_t *data_bytes)
+{
+    const uint32_t b_rows = tc::COLT / cg;
+    *stage_bytes = (slices == 1 ? 1u : 2u) * b_rows * 128u;
+    *a_bytes = nc * (slices == 1 ? tc::SLICE_BYTES : tc::BLOCK_BYTES);
+    const uint32_t data = 224u * 1024u;
+    if (nc == 1) {
+        // one chunk: two A buffers at a 32 KB stride, the B ring in what the 192 KB budget leaves (compile-time plan
+        // of the WIDE = false kernel)
+        *a_bytes = tc::BLOCK_BYTES;
+        *n_abuf = 2;
+        *lg_nst = slices == 1 ? (cg == 2 ? 3u : 2u) : (cg == 2 ? 2u : 1u);
+    } else {
+        auto lg_stages = [&](uint32_t nb) -> int {  // log2 of the B stages left next to nb A buffers, -1: does not fit
+            if (nb * *a_bytes + 2u * *stage_bytes > data) return -1;
+            const uint32_t room = (data - nb * *a_bytes) / *stage_bytes;
+            return room >= 8 ? 3 : room >= 4 ? 2 : 1;
+        };
+        const int lg2 = lg_stages(2), lg1 = lg_stages(1);
+        if (lg1 < 0) return false;
+        // a deep B ring hides the TMA round trip on every tile, a second A buffer only the reload at item boundaries
+        *n_abuf = (lg2 < 0 || (lg2 < 3 && lg1 > lg2)) ? 1u : 2u;
+        *lg_nst = (uint32_t)(*n_abuf == 2 ? lg2 : lg1);
+    }
+    *data_bytes = *n_abuf * *a_bytes + (*stage_bytes << *lg_nst);
+    return true;
+}
+
+uint32_t tc_chunks_for(uint32_t K) { return tc_chunks(K); }
+
 // Filter the pairs of the row tiles [I0, I1) (256-row units) that belong to this shard; survivors go
 // to the candidate queue (cand_count is d_counters[0]). dbg != nullptr selects the instrumented kernel.
 int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t C0, uint32_t C1, uint32_t shard, uint32_t n_shards,
@@ -927,32 +962,8 @@ int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t C0, uint32_t C1
     // items of this shard (upper bound is enough to size the grid)
     const uint64_t n_strips = (cols + a.strip_len - 1) / a.strip_len + 1;
     const uint64_t items = std::max<uint64_t>(1, rows * (2 / cg) * n_strips / std::max<uint32_t>(n_shards, 1));
-    // shared-memory plan: A = all chunks of the row tile (double-buffered over items if two copies and two B
-    // stages fit), B ring = as many power-of-two stages of one chunk as the rest holds
-    {
-        const uint32_t b_rows = tc::COLT / (uint32_t)cg;
-        a.stage_bytes = (a.slices == 1 ? 1u : 2u) * b_rows * 128u;
-        a.a_bytes = a.nc * (a.slices == 1 ? tc::SLICE_BYTES : tc::BLOCK_BYTES);
-        const uint32_t data = 224u * 1024u;
-        if (a.nc == 1) {
-            // one chunk: two A buffers at a 32 KB stride, the B ring in what the 192 KB budget leaves
-            a.a_bytes = tc::BLOCK_BYTES;
-            a.n_abuf = 2;
-            a.lg_nst = a.slices == 1 ? (cg == 2 ? 3u : 2u) : (cg == 2 ? 2u : 1u);
-        } else {
-            auto lg_stages = [&](uint32_t n_abuf) -> int {  // log2 of the B stages left next to n_abuf A buffers, -1: does not fit
-                if (n_abuf * a.a_bytes + 2u * a.stage_bytes > data) return -1;
-                const uint32_t room = (data - n_abuf * a.a_bytes) / a.stage_bytes;
-                return room >= 8 ? 3 : room >= 4 ? 2 : 1;
-            };
-            const int lg2 = lg_stages(2), lg1 = lg_stages(1);
-            if (lg1 < 0) return fail(ctx, SCEMA_ERR_INVALID, "tensor-core filter: row tile does not fit shared memory");
-            // a deep B ring hides the TMA round trip on every tile, a second A buffer only the reload at item boundaries
-            a.n_abuf = (lg2 < 0 || (lg2 < 3 && lg1 > lg2)) ? 1u : 2u;
-            a.lg_nst = (uint32_t)(a.n_abuf == 2 ? lg2 : lg1);
-        }
-        a.data_bytes = a.n_abuf * a.a_bytes + (a.stage_bytes << a.lg_nst);  // only what is used: the rest of the SM stays L1
-    }
+    if (!tc_smem_plan(a.nc, a.slices, (uint32_t)cg, &a.a_bytes, &a.n_abuf, &a.lg_nst, &a.stage_bytes, &a.data_bytes))
+        return fail(ctx, SCEMA_ERR_INVALID, "tensor-core filter: row tile does not fit shared memory");
     if (ctx->tc_band && !dbg && a.nc == 1) {
         // band plan for this kernel flavour: last column tile per row tile, strips per row tile, their prefix
         const uint32_t rpt = 128u * (uint32_t)cg;

@@ -388,7 +388,7 @@ inline void compare_batch(std::vector<Strain6D *> &hist, double threshold, const
     // carries its deferred splinify(P) with the same P. The raw histories then go to the GPU once,
     // K1 writes the spline matrix where K2 reads it, and nothing comes back but the edges; an object's
     // own spline vector is only materialised if somebody asks for it (get_spline, print, ...).
-    bool direct = true;
+    bool direct = true, clustered = false;
     const uint32_t P0 = hist[0]->get_num_spline_points_per_component();
     for (size_t i = 0; i < n; i++) direct = direct && hist[i]->b200_pending() && hist[i]->get_num_spline_points_per_component() == P0;
     if (direct && P0 > 0) {
@@ -398,8 +398,14 @@ inline void compare_batch(std::vector<Strain6D *> &hist, double threshold, const
             flat.insert(flat.end(), hist[i]->b200_steps().begin(), hist[i]->b200_steps().end());
             offsets.push_back(offsets.back() + hist[i]->b200_num_steps());
         }
-        check(scema_set_histories(ctx, flat.data(), 0, offsets.data(), ids.data(), n), "compare_histories_with_all_ranks");
-        check(scema_resample(ctx, P0), "compare_histories_with_all_ranks");
+        // one call: for large batches the library pipelines copy, resample and compare range by range (scema_cluster)
+        const bool dense0 = keep_all_similar();
+        uint64_t m0 = 0;
+        check(scema_cluster(ctx, flat.data(), offsets.data(), ids.data(), n, P0,
+                            dense0 ? std::numeric_limits<double>::infinity() : threshold,
+                            dense0 ? SCEMA_PAIRS_EXACT : SCEMA_PAIRS_TC, &m0),
+              "compare_histories_with_all_ranks");
+        clustered = true;
     } else {
         resolve_splines(hist);
         const uint32_t K = (uint32_t)hist[0]->get_spline()->size();
@@ -417,8 +423,10 @@ inline void compare_batch(std::vector<Strain6D *> &hist, double threshold, const
     }
     const bool dense = keep_all_similar();
     uint64_t m = 0;
-    check(scema_compare(ctx, dense ? std::numeric_limits<double>::infinity() : threshold, dense ? SCEMA_PAIRS_EXACT : SCEMA_PAIRS_TC, 0, 1, &m),
-          "compare_histories_with_all_ranks");
+    if (!clustered)
+        check(scema_compare(ctx, dense ? std::numeric_limits<double>::infinity() : threshold, dense ? SCEMA_PAIRS_EXACT : SCEMA_PAIRS_TC, 0, 1, &m),
+              "compare_histories_with_all_ranks");
+    check(scema_edges_device(ctx, NULL, NULL, NULL, &m), "compare_histories_with_all_ranks");
     std::vector<uint32_t> a(m), b(m);
     std::vector<double> d(m);
     check(scema_get_edges(ctx, a.data(), b.data(), d.data(), m), "compare_histories_with_all_ranks");

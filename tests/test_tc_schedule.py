@@ -13,3 +13,36 @@ def test_schedule_covers_every_tile_once(tmp_path):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(HERE, "helpers", "tc_sched_check.cc")])
     r = subprocess.run([exe, "4000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout[-2000:]
+
+
+def test_shared_memory_plan_fits_for_every_supported_row_width():
+    """Host logic of the tcgen05 launch (scema_tc_plan): for every K the variant accepts, both kernel flavours and both
+    slice counts, the A buffers plus a power-of-two B ring of at least two stages fit the 224 KB the kernel may use;
+    single-chunk rows keep the compile-time plan (two A buffers at 32 KB, 192 KB in all)."""
+    import ctypes as C
+    import numpy as np
+    from scema_b200 import binding
+    L = binding.lib()
+    plan = np.zeros(6, dtype=np.uint32)
+    seen_wide = 0
+    for K in range(1, 700):
+        for slices in (1, 2):
+            for cg in (1, 2):
+                rc = L.scema_tc_plan(K, slices, cg, plan.ctypes.data)
+                nc = (K + 4 + 63) // 64
+                if nc > 10 or (nc > 1 and slices == 2):
+                    assert rc != 0, (K, slices, cg)
+                    continue
+                assert rc == 0, (K, slices, cg)
+                chunks, a_bytes, n_abuf, lg_nst, stage, used = (int(x) for x in plan)
+                assert chunks == nc and n_abuf in (1, 2) and 1 <= lg_nst <= 3
+                assert stage == (1 if slices == 1 else 2) * (256 // cg) * 128
+                assert used == n_abuf * a_bytes + (stage << lg_nst) <= 224 * 1024
+                assert a_bytes % 1024 == 0 and stage % 1024 == 0          # swizzle atoms stay 1024-byte aligned
+                if nc == 1:
+                    assert a_bytes == 32768 and n_abuf == 2 and used == 192 * 1024
+                else:
+                    assert a_bytes == nc * 16384
+                    seen_wide += 1
+    assert seen_wide > 1000
+    assert L.scema_tc_plan(0, 1, 1, plan.ctypes.data) != 0 and L.scema_tc_plan(60, 3, 1, plan.ctypes.data) != 0
