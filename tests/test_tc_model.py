@@ -1,0 +1,132 @@
+"""Model-level check of the tcgen05 filter's guard band, on the CPU.
+
+The operand preparation of scema_b200/csrc/pairs_tc.cu (k_tc_prep: power-of-two scale, fp16 slices with flushed
+subnormals, fold columns carrying -h_i) is restated in numpy; the three sliced products are summed exactly (float64)
+and then pushed DOWN by the largest error the design budgets for the tensor core's fp32 accumulation
+((steps + 1) * 2^-18 * sum |terms|). Even then no pair the reference would call an edge may come out negative — for
+both slice counts, on clustered rows, pairs planted a hair inside the threshold, rows of mixed magnitude, tiny and
+huge thresholds. This pins the ARITHMETIC of the bound (constants c, e0, T', fold split); that the hardware stays
+inside the budget is what tests/test_gpu_tc.py::test_tc_accumulators_match_sliced_fp64 measures on the GPU.
+"""
+import numpy as np
+import pytest
+
+P_, Q_ = 32768.0, 8.0
+
+
+def h16z(v):
+    """fp16 rounding (nearest even) with subnormal results flushed to zero, as the prep kernel does"""
+    with np.errstate(over="ignore"):
+        f = np.asarray(v, dtype=np.float64).astype(np.float16).astype(np.float64)
+    return np.where(np.abs(f) < 2.0 ** -14, 0.0, f)
+
+
+def prepare(rows, thr, slices):
+    n, K = rows.shape
+    assert K <= 60
+    nrm_raw = (rows ** 2).sum(1)
+    finite = np.isfinite(nrm_raw)
+    M = np.abs(rows[finite]).max() if finite.any() else 0.0
+    s = 2.0 ** (11 - int(np.floor(np.log2(M)))) if M > 0 else 1.0
+    a = np.zeros((n, 60))
+    a[:, :K] = np.where(finite[:, None], rows * s, 0.0)
+    hi = h16z(a)
+    lo = h16z(a - hi)
+    cg = 2.0 ** -9 if slices == 1 else 2.0 ** -13
+    eps = 2.0 ** -53
+    T0 = thr * thr * (1 + (2 * K + 16) * eps) * (1 + 4 * eps) + (2 * K + 4) * 4.9406564584124654e-324
+    T0s = (T0 * s) * s
+    nrm = (a ** 2).sum(1)
+    h = 0.5 * (nrm * (1 - cg) - T0s * (0.5 + 2 * cg) - K * 2.0 ** -7)
+    force = (~finite) | ~(-h <= 32768.0 * P_)
+    with np.errstate(invalid="ignore", over="ignore"):
+        x0 = h16z(-h / P_)
+        x1 = h16z((-h - P_ * x0) / Q_)
+        x2 = h16z((-h - P_ * x0 - Q_ * x1) / Q_)
+    x0 = np.where(force, 65504.0, x0)
+    x1 = np.where(force, 0.0, x1)
+    x2 = np.where(force, 0.0, x2)
+    z = np.zeros(n)
+    one = np.ones(n)
+    a_hi = np.concatenate([hi, np.stack([x0, x1, P_ * one, Q_ * one], 1)], 1)
+    a_lo = np.concatenate([lo, np.stack([z, x2, z, z], 1)], 1)
+    b_hi = np.concatenate([hi, np.stack([P_ * one, Q_ * one, x0, x1], 1)], 1)
+    b_lo = np.concatenate([lo, np.stack([z, z, z, x2], 1)], 1)
+    return a_hi, a_lo, b_hi, b_lo
+
+
+def worst_case_acc(rows, thr, slices):
+    a_hi, a_lo, b_hi, b_lo = prepare(rows, thr, slices)
+    acc = a_hi @ b_hi.T
+    absum = np.abs(a_hi) @ np.abs(b_hi).T
+    steps = 4
+    if slices == 2:
+        acc = acc + a_lo @ b_hi.T + a_hi @ b_lo.T
+        absum = absum + np.abs(a_lo) @ np.abs(b_hi).T + np.abs(a_hi) @ np.abs(b_lo).T
+        steps = 12
+    return acc - (steps + 1) * 2.0 ** -18 * absum
+
+
+def reference_edges(rows, thr):
+    """compare_L2_norm in the reference's order (sequential k, separate multiply and add), strict threshold"""
+    n, K = rows.shape
+    s = np.zeros((n, n))
+    for k in range(K):
+        d = rows[:, None, k] - rows[None, :, k]
+        s = s + d * d
+    with np.errstate(invalid="ignore"):
+        return np.sqrt(s) < thr
+
+
+def cases():
+    rng = np.random.default_rng(7)
+    n = 400
+    t = np.linspace(0, 1, 10)
+    centres = rng.uniform(-5e-3, 5e-3, size=(n // 8, 6))
+    base = (centres[:, None, :] * t[None, :, None]).reshape(n // 8, 60)
+    clustered = np.repeat(base, 8, axis=0) + 3e-7 * rng.standard_normal((n, 60)) / np.sqrt(60)
+    yield "clustered", clustered, 1e-6
+    planted = clustered.copy()
+    for q in range(0, n - 1, 2):  # partner a hair inside / outside the threshold
+        u = rng.standard_normal(60)
+        u /= np.linalg.norm(u)
+        planted[q + 1] = planted[q] + u * 1e-6 * (1 + (q % 7 - 3) * 1e-13)
+    yield "planted", planted, 1e-6
+    mixed = rng.standard_normal((n, 60)) * 10.0 ** rng.integers(-7, 0, size=(n, 1))
+    mixed[1::2] = mixed[::2] * (1 + 1e-9 * rng.standard_normal((n // 2, 60)))
+    yield "mixed_magnitudes", mixed, 1e-7
+    yield "tiny_threshold", clustered * 1e-6, 1e-12
+    yield "large_threshold", clustered, 3e-3
+    yield "k18", rng.standard_normal((n, 18)) * 1e-2 + 1.0, 6e-2
+    zero = clustered.copy()
+    zero[:40] = 0.0
+    zero[40:60] = 1e-30 * rng.standard_normal((20, 60))
+    yield "zero_rows", zero, 1e-6
+
+
+@pytest.mark.parametrize("slices", [1, 2])
+@pytest.mark.parametrize("name,rows,thr", list(cases()), ids=[c[0] for c in cases()])
+def test_no_edge_is_rejected_under_the_worst_budgeted_error(name, rows, thr, slices):
+    edge = reference_edges(rows, thr)
+    acc = worst_case_acc(rows, thr, slices)
+    off_diag = ~np.eye(len(rows), dtype=bool)
+    bad = edge & off_diag & (acc < 0)
+    assert not bad.any(), (name, slices, int(bad.sum()), np.argwhere(bad)[:3])
+    assert (edge & off_diag).sum() > 0
+    # and the filter does reject most of what is far away (it is a filter, after all), except where the threshold
+    # is of the order of the spread of the data
+    if name in ("clustered", "planted", "tiny_threshold"):
+        assert (acc < 0).mean() > 0.9
+
+
+def test_fold_columns_carry_minus_h():
+    rng = np.random.default_rng(1)
+    rows = rng.standard_normal((200, 60)) * 10.0 ** rng.integers(-5, 0, size=(200, 1))
+    for slices in (1, 2):
+        a_hi, a_lo, b_hi, b_lo = prepare(rows, 1e-6, slices)
+        fold_a = P_ * a_hi[:, 60] + Q_ * a_hi[:, 61] + (Q_ * a_lo[:, 61] if slices == 2 else 0.0)
+        fold_b = P_ * b_hi[:, 62] + Q_ * b_hi[:, 63] + (Q_ * b_lo[:, 63] if slices == 2 else 0.0)
+        assert np.array_equal(fold_a, fold_b)
+        for arr in (a_hi, a_lo):
+            nz = np.abs(arr[arr != 0])
+            assert nz.min() >= 2.0 ** -14 and nz.max() <= 65504
