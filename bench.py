@@ -396,6 +396,18 @@ def run_ours(args, wl, wl_name):
                     "other_kernels_ms": {k: acc[k] / max(acc["steps"], 1)
                                          for k in ("resample", "prep", "exact", "sort") + (("allgather",) if world > 1 else ())}}
         roofline.update(extra)
+        # K1 (ragged spline resample) is the HBM-bound kernel of the step: 48 bytes per raw step read + 8 K bytes per history written
+        res_ms = acc["resample"] / max(acc["steps"], 1)
+        try:
+            hbm_peak, hbm_src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback"
+        k1_bytes = steps_bytes + n_local * K * 8
+        roofline_resample = {"bound": "hbm", "achieved": k1_bytes / (res_ms * 1e-3) / 1e9 if res_ms > 0 else None, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": (k1_bytes / (res_ms * 1e-3) / 1e9 / hbm_peak) if res_ms > 0 else None,
+                             "launch_ms": res_ms, "kernel": "k_resample_stream (K1), launches per length class summed",
+                             "peak_source": "of %s: MEASURED_PEAKS.json hbm_gbs" % hbm_src,
+                             "note": "instruction-bound, not bandwidth-bound: bit-exact division sequences in two dependent sweeps per history"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             m = min(n, 65536)
@@ -435,6 +447,7 @@ def run_ours(args, wl, wl_name):
                     "pipeline_ranges": hc.counters().get("pipeline_ranges", 0) if world == 1 else 0},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "roofline_resample": roofline_resample,
             "cpu_baseline": cpu,
         }
         emit(line)
