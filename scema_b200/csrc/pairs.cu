@@ -1113,7 +1113,7 @@ static int compare_begin(scema_ctx *ctx, double thr, int &variant, uint32_t shar
         const bool want_band = ctx->tc_band_allowed && band_env && atoi(band_env) == 1;
         rc = tc_prepare(ctx, thr, slices, want_band);
         if (rc) return rc;
-        if (ctx->cand_cap == 0) ctx->cand_cap = std::max<uint64_t>(1ull << 20, 32 * n);
+        ctx->cand_cap = std::max<uint64_t>(ctx->cand_cap, std::max<uint64_t>(1ull << 20, 32 * n));  // grows with the batch: a context that started small must not mistake a full queue for a wide guard band
         t_end(ctx, SCEMA_T_PREP);
     } else if (variant != SCEMA_PAIRS_EXACT) {
         t_begin(ctx, SCEMA_T_PREP);
@@ -1123,7 +1123,7 @@ static int compare_begin(scema_ctx *ctx, double thr, int &variant, uint32_t shar
         SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_panel_start.p, sc.ps.data(), sc.ps.size() * sizeof(uint64_t),
                                         cudaMemcpyHostToDevice, ctx->stream));
         SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // sc.ps may not outlive the copy otherwise
-        if (ctx->cand_cap == 0) ctx->cand_cap = std::max<uint64_t>(1ull << 20, 32 * n);
+        ctx->cand_cap = std::max<uint64_t>(ctx->cand_cap, std::max<uint64_t>(1ull << 20, 32 * n));  // grows with the batch: a context that started small must not mistake a full queue for a wide guard band
         t_end(ctx, SCEMA_T_PREP);
     }
     return SCEMA_OK;
@@ -1210,7 +1210,7 @@ static int cluster_pipelined_impl(scema_ctx *ctx, const double *steps_host, uint
     if (!ctx->h_counters) SCEMA_CUDA(ctx, cudaMallocHost(&ctx->h_counters, 8 * sizeof(uint64_t)));
     rc = ensure_edge_buffers(ctx, std::max<uint64_t>(1ull << 20, 16 * n));
     if (rc) return rc;
-    if (ctx->cand_cap == 0) ctx->cand_cap = std::max<uint64_t>(1ull << 20, 32 * n);
+    ctx->cand_cap = std::max<uint64_t>(ctx->cand_cap, std::max<uint64_t>(1ull << 20, 32 * n));  // grows with the batch: a context that started small must not mistake a full queue for a wide guard band
     SCEMA_CUDA(ctx, ctx->d_cand.reserve(ctx->cand_cap * sizeof(uint64_t)));
     rc = tc_prepare_begin(ctx, thr, 1);
     if (rc) return rc;

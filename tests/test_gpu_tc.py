@@ -397,3 +397,21 @@ def test_tc_scale_ignores_a_few_outlier_rows(oracle):
         assert c["passes"] == 1 and c["survivors"] < 40 * n, (factor, c)
         assert len(want[0]) > n
         h.close()
+
+
+def test_queue_capacity_follows_the_batch_size():
+    """A context that started on a small batch must not read the overflow of its small survivor queue on a later, larger
+    batch as 'the one-slice band keeps too much' (and fall back to two slices at half the speed): the capacity is 32
+    survivors per history of the CURRENT batch."""
+    h = scema_b200.HistCluster(0)
+    small = synth.rows(3, 1000, 16, 10, 5e-3, synth.default_pert(THR, 10))
+    h.set_spline(small)
+    h.compare(THR, PAIRS_TC)
+    n = 200000
+    d_rows = synth.device_rows(4, n, 16, 10, 5e-3, synth.default_pert(THR, 10))
+    h.set_spline(device_ptr=d_rows.data_ptr(), n=n, k=60)
+    ne = h.compare(THR, PAIRS_TC)
+    c = h.counters()
+    assert c["survivors"] > (1 << 20) and c["tc_slices"] == 1 and c["passes"] == 1, c
+    assert ne > n
+    h.close()
