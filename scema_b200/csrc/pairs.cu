@@ -1178,7 +1178,7 @@ static int cluster_pipelined_impl(scema_ctx *ctx, const double *steps_host, uint
     while (bounds.back() < n) bounds.push_back(std::min<uint64_t>(n, bounds.back() + per));
     n_ranges = bounds.size() - 1;
 
-    // ---- the first two ranges start travelling at once; the host-side preparation below (factor tables, K1 plan:
+    // ---- the first four ranges start travelling at once; the host-side preparation below (factor tables, K1 plan:
     //      a few ms of host work with small host->device copies of its own, which queue behind what is already on
     //      the copy engine) runs meanwhile, and only then are the remaining ranges queued
     if (!ctx->copy_stream) SCEMA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -1195,7 +1195,7 @@ static int cluster_pipelined_impl(scema_ctx *ctx, const double *steps_host, uint
         SCEMA_CUDA(ctx, cudaEventRecord(ctx->copy_events[r], ctx->copy_stream));
         return SCEMA_OK;
     };
-    const uint64_t early = std::min<uint64_t>(2, n_ranges);
+    const uint64_t early = std::min<uint64_t>(4, n_ranges);  // ~17 ms of copies at config 4: covers the host-side planning below
     int rc;
     for (uint64_t r = 0; r < early; r++)
         if ((rc = queue_copy(r))) return rc;
