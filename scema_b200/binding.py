@@ -324,13 +324,21 @@ class HistCluster:
         self.n_edges = 0
         return int(tot.value)
 
-    def get_edges(self):
+    def get_edges(self, out=None):
+        """-> (index_a, index_b, diff). out = (a, b, d): caller-owned arrays of at least n_edges entries (uint32, uint32,
+        float64; e.g. views of pinned memory that a caller reuses from call to call) that receive the edges; views
+        of their first n_edges entries are returned."""
         m = self.n_edges
-        a = np.empty(m, dtype=np.uint32)
-        b = np.empty(m, dtype=np.uint32)
-        d = np.empty(m, dtype=np.float64)
+        if out is None:
+            a = np.empty(m, dtype=np.uint32)
+            b = np.empty(m, dtype=np.uint32)
+            d = np.empty(m, dtype=np.float64)
+        else:
+            a, b, d = out
+            if min(len(a), len(b), len(d)) < m or a.dtype != np.uint32 or b.dtype != np.uint32 or d.dtype != np.float64:
+                raise ValueError("get_edges: out arrays too small or of the wrong type")
         self._ck(self._L.scema_get_edges(self._h, _ptr(a), _ptr(b), _ptr(d), m))
-        return a, b, d
+        return a[:m], b[:m], d[:m]
 
     def edges_device(self):
         keys, diff, sh, ne = C.c_void_p(None), C.c_void_p(None), C.c_uint32(0), C.c_uint64(0)

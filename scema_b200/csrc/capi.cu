@@ -257,6 +257,22 @@ int scema_compare_stream(scema_ctx *c, double threshold, int variant, uint32_t s
     return rc;
 }
 
+}  // extern "C"
+
+// keys (a << shift | b) -> the two index arrays, on the device: the host then receives exactly the arrays it asked for
+// (a host-side unpack of 4M keys plus the page faults of a temporary costs more than the copy)
+static __global__ void k_unpack_keys(const uint64_t *__restrict__ keys, uint64_t m, uint32_t shift, uint32_t *__restrict__ a,
+                              uint32_t *__restrict__ b)
+{
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    const uint64_t k = keys[e];
+    a[e] = (uint32_t)(k >> shift);
+    b[e] = (uint32_t)(k & ((1ull << shift) - 1));
+}
+
+extern "C" {
+
 int scema_get_edges(scema_ctx *c, uint32_t *ia, uint32_t *ib, double *diff, uint64_t cap)
 {
     int rc = enter(c);
@@ -265,17 +281,16 @@ int scema_get_edges(scema_ctx *c, uint32_t *ia, uint32_t *ib, double *diff, uint
     const uint64_t m = std::min<uint64_t>(cap, c->n_edges);
     if (m == 0) return SCEMA_OK;
     if (diff) SCEMA_CUDA(c, cudaMemcpyAsync(diff, c->d_edge_val[c->edge_cur].p, m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    std::vector<uint64_t> keys;
     if (ia || ib) {
-        keys.resize(m);
-        SCEMA_CUDA(c, cudaMemcpyAsync(keys.data(), c->d_edge_key[c->edge_cur].p, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        // the other half of the sort's double buffer is free after the sort: unpack there
+        uint32_t *da = c->d_edge_key[c->edge_cur ^ 1].as<uint32_t>(), *db = da + m;
+        k_unpack_keys<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(c->d_edge_key[c->edge_cur].as<uint64_t>(), m, c->key_shift, da, db);
+        c->launches++;
+        SCEMA_CUDA(c, cudaGetLastError());
+        if (ia) SCEMA_CUDA(c, cudaMemcpyAsync(ia, da, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (ib) SCEMA_CUDA(c, cudaMemcpyAsync(ib, db, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     }
     SCEMA_CUDA(c, cudaStreamSynchronize(c->stream));
-    const uint64_t mask = (1ull << c->key_shift) - 1;
-    for (uint64_t e = 0; e < keys.size(); e++) {
-        if (ia) ia[e] = (uint32_t)(keys[e] >> c->key_shift);
-        if (ib) ib[e] = (uint32_t)(keys[e] & mask);
-    }
     return SCEMA_OK;
 }
 

@@ -552,14 +552,18 @@ static int build_plan(scema_ctx *ctx, const std::vector<uint64_t> &bounds)
     if (ctx->order_version == ctx->histories_version && ctx->plan_bounds == bounds) return SCEMA_OK;
     const size_t n_ranges = bounds.size() - 1;
     auto cls_of = [&](uint32_t L) { int k = 0; while (k < K1_NCLS - 1 && L > K1_CAPS[k]) k++; return k; };
-    std::vector<uint32_t> order;
-    std::vector<K1Chunk> chunks;
+    // scratch kept between calls (per thread; a context is driven by one thread at a time): a fresh 4 MB vector per
+    // call costs more in page faults than the plan costs to compute
+    static thread_local std::vector<uint32_t> order;
+    static thread_local std::vector<K1Chunk> chunks;
+    static thread_local std::vector<uint64_t> len_count, group_first, fill;
+    order.clear();
+    chunks.clear();
     ctx->plan_chunk_begin.assign(n_ranges * (K1_NCLS + 1), 0);
     ctx->plan_groups.assign(n_ranges * K1_NCLS, 0);
     ctx->plan_first_slot.assign(n_ranges * K1_NCLS, 0);
     ctx->plan_max_len.assign(n_ranges, 0);
     ctx->plan_steps.assign(n_ranges, 0);
-    std::vector<uint64_t> len_count, group_first, fill;
     for (size_t r = 0; r < n_ranges; r++) {
         const uint64_t h0 = bounds[r], h1 = bounds[r + 1];
         uint32_t max_len = 0;
