@@ -327,8 +327,14 @@ int scema_cluster(scema_ctx *c, const double *steps, const uint64_t *offsets, co
     // is still on the bus (cluster_pipelined, pairs.cu). Same spline matrix, same edge list.
     if (c && steps && offsets && variant == SCEMA_PAIRS_TC && spline_points >= 1 && spline_points <= 10 && threshold > 0.0 &&
         pipeline_wanted(n)) {
-        int rc = set_histories_impl(c, steps, 2, offsets, ids, n);
+        int rc = enter(c);
         if (rc) return rc;
+        rc = pipeline_begin(c, steps, offsets, n);       // the first ranges are on the bus before anything else happens
+        if (!rc) rc = set_histories_impl(c, steps, 2, offsets, ids, n);
+        if (rc) {
+            if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);  // the caller's buffer is the caller's again on return
+            return rc;
+        }
         bool done = false;
         rc = cluster_pipelined(c, steps, spline_points, threshold, &done);
         if (rc) { c->have_edges = false; return rc; }

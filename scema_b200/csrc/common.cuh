@@ -133,6 +133,8 @@ struct scema_ctx {
     // ---- host-buffer pipeline of scema_cluster: copy stream + one event per range
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> copy_events;
+    std::vector<uint64_t> pipe_bounds;  // history ranges of the current pipelined batch
+    uint64_t pipe_early = 0;            // ranges whose copy was queued by pipeline_begin
 
     // ---- instrumentation
     cudaEvent_t ev[2 * SCEMA_T_COUNT] = {};
@@ -175,6 +177,7 @@ int compare_stream_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, 
                        scema_edge_sink sink, void *user, uint64_t *n_total);
 int fp64_peak_run(scema_ctx *ctx, double out[2]);
 bool pipeline_wanted(uint64_t n);
+int pipeline_begin(scema_ctx *ctx, const double *steps_host, const uint64_t *offsets, uint64_t n);
 int cluster_pipelined(scema_ctx *ctx, const double *steps_host, uint32_t P, double thr, bool *done);
 // pairs_tc.cu
 bool tc_supported(const scema_ctx *ctx);

@@ -1167,38 +1167,64 @@ bool pipeline_wanted(uint64_t n)
     return n >= min_n && n >= 4096;
 }
 
-static int cluster_pipelined_impl(scema_ctx *ctx, const double *steps_host, uint32_t P, double thr, bool *done)
+// Ranges of the pipeline: up to 16, whole panels (2048 rows, hence whole 256-row tiles) each.
+static void pipeline_bounds(uint64_t n, std::vector<uint64_t> &bounds)
 {
-    *done = false;
-    const uint64_t n = ctx->hn;
-    const uint64_t panel_rows = (uint64_t)PANEL_ROWBLOCKS * TILE;  // 2048: range boundaries are whole panels (and 256-row tiles)
-    uint64_t n_ranges = std::min<uint64_t>(16, std::max<uint64_t>(2, n / 65536));
-    uint64_t per = ((n + n_ranges - 1) / n_ranges + panel_rows - 1) / panel_rows * panel_rows;
-    std::vector<uint64_t> bounds(1, 0);
+    const uint64_t panel_rows = (uint64_t)PANEL_ROWBLOCKS * TILE;
+    const uint64_t n_ranges = std::min<uint64_t>(16, std::max<uint64_t>(2, n / 65536));
+    const uint64_t per = ((n + n_ranges - 1) / n_ranges + panel_rows - 1) / panel_rows * panel_rows;
+    bounds.assign(1, 0);
     while (bounds.back() < n) bounds.push_back(std::min<uint64_t>(n, bounds.back() + per));
-    n_ranges = bounds.size() - 1;
+}
 
-    // ---- the first four ranges start travelling at once; the host-side preparation below (factor tables, K1 plan:
-    //      a few ms of host work with small host->device copies of its own, which queue behind what is already on
-    //      the copy engine) runs meanwhile, and only then are the remaining ranges queued
+static int pipeline_queue_copy(scema_ctx *ctx, const double *steps_host, const uint64_t *offsets, uint64_t r)
+{
+    const uint64_t s0 = offsets[ctx->pipe_bounds[r]], s1 = offsets[ctx->pipe_bounds[r + 1]];
+    if (s1 > s0)
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->steps_own.as<double>() + s0 * 6, steps_host + s0 * 6, (s1 - s0) * 6 * sizeof(double),
+                                        cudaMemcpyHostToDevice, ctx->copy_stream));
+    SCEMA_CUDA(ctx, cudaEventRecord(ctx->copy_events[r], ctx->copy_stream));
+    return SCEMA_OK;
+}
+
+// First act of the pipeline, before anything else touches the batch: the first four ranges start travelling at once
+// (~17 ms of copies at config 4); the host-side work that follows — validation of the offsets, factor tables, K1 plan,
+// a few ms with small host->device copies of its own, which queue behind what is already on the copy engine — runs
+// meanwhile, and only then are the remaining ranges queued. Only the five offsets that delimit these ranges are
+// looked at here (they must be ordered and inside the batch); everything else is validated by set_histories.
+int pipeline_begin(scema_ctx *ctx, const double *steps_host, const uint64_t *offsets, uint64_t n)
+{
+    pipeline_bounds(n, ctx->pipe_bounds);
+    const uint64_t n_ranges = ctx->pipe_bounds.size() - 1;
+    ctx->pipe_early = 0;
     if (!ctx->copy_stream) SCEMA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     while (ctx->copy_events.size() < n_ranges) {
         cudaEvent_t e;
         SCEMA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->copy_events.push_back(e);
     }
-    auto queue_copy = [&](uint64_t r) -> int {
-        const uint64_t s0 = ctx->h_offsets[bounds[r]], s1 = ctx->h_offsets[bounds[r + 1]];
-        if (s1 > s0)
-            SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->steps_own.as<double>() + s0 * 6, steps_host + s0 * 6, (s1 - s0) * 6 * sizeof(double),
-                                            cudaMemcpyHostToDevice, ctx->copy_stream));
-        SCEMA_CUDA(ctx, cudaEventRecord(ctx->copy_events[r], ctx->copy_stream));
-        return SCEMA_OK;
-    };
-    const uint64_t early = std::min<uint64_t>(4, n_ranges);  // ~17 ms of copies at config 4: covers the host-side planning below
-    int rc;
+    const uint64_t early = std::min<uint64_t>(4, n_ranges);
     for (uint64_t r = 0; r < early; r++)
-        if ((rc = queue_copy(r))) return rc;
+        if (offsets[ctx->pipe_bounds[r]] > offsets[ctx->pipe_bounds[r + 1]] || offsets[ctx->pipe_bounds[r + 1]] > offsets[n]) return SCEMA_OK;
+    // the previous batch's kernels may still read the buffer the copies are about to overwrite
+    SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SCEMA_CUDA(ctx, ctx->steps_own.reserve(std::max<uint64_t>(offsets[n], 1) * 6 * sizeof(double)));
+    for (uint64_t r = 0; r < early; r++) {
+        const int rc = pipeline_queue_copy(ctx, steps_host, offsets, r);
+        if (rc) return rc;
+        ctx->pipe_early = r + 1;
+    }
+    return SCEMA_OK;
+}
+
+static int cluster_pipelined_impl(scema_ctx *ctx, const double *steps_host, uint32_t P, double thr, bool *done)
+{
+    *done = false;
+    const uint64_t n = ctx->hn;
+    const std::vector<uint64_t> &bounds = ctx->pipe_bounds;
+    const uint64_t n_ranges = bounds.size() - 1;
+    const uint64_t early = ctx->pipe_early;
+    int rc;
     rc = resample_prepare(ctx, P, bounds);
     if (rc) return rc;
     for (int i = 0; i < 8; i++) ctx->counters[i] = 0;
@@ -1220,7 +1246,7 @@ static int cluster_pipelined_impl(scema_ctx *ctx, const double *steps_host, uint
 
     // ---- queue the remaining copies, then the per-range work
     for (uint64_t r = early; r < n_ranges; r++)
-        if ((rc = queue_copy(r))) return rc;
+        if ((rc = pipeline_queue_copy(ctx, steps_host, ctx->h_offsets.data(), r))) return rc;
     const uint64_t n_pad = (n + 255) / 256 * 256;
     t_begin(ctx, SCEMA_T_FILTER);  // in this mode "filter" spans the whole overlapped region (K1, operand prep and filter of every range)
     for (uint64_t r = 0; r < n_ranges; r++) {
