@@ -122,13 +122,22 @@ def cpu_reference_rows(wl, m, timed):
     off = synth.offsets(SEED, m, CLUSTER, wl["lmin"], wl["lmax"])
     steps = synth.histories(SEED, m, CLUSTER, AMP, synth.default_pert(THR, wl["P"]), off)
     t0 = time.perf_counter()
-    rows = lib.splinify_batch(steps, off, wl["P"])
+    rows = lib.splinify_batch(steps, off, wl["P"], host_threads())
     return rows, lib, kind, time.perf_counter() - t0
+
+
+def host_threads():
+    """All host cores this process may use. Asked for explicitly: torch.distributed.run exports OMP_NUM_THREADS=1
+    to every rank, which would silently turn the CPU arm into a single-core run."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def cpu_pairs_step(lib, rows, r0, r1):
     t0 = time.perf_counter()
-    edges, pairs = lib.all_pairs(rows, THR, r0, r1, 0, count_only=True)
+    edges, pairs = lib.all_pairs(rows, THR, r0, r1, host_threads(), count_only=True)
     return pairs, time.perf_counter() - t0, edges
 
 
@@ -144,7 +153,7 @@ def run_reference(args, wl, wl_name):
         return  # the CPU reference runs once, on rank 0
     m = min(wl["n"], 65536)
     rows, lib, kind, t_spl = cpu_reference_rows(wl, m, True)
-    cores = lib.max_threads()
+    cores = host_threads()
     # calibrate the per-step sample: whole run ~ 100 s at most
     pairs, dt, _ = cpu_pairs_step(lib, rows, 0, 64)
     rate = pairs / dt
@@ -429,7 +438,7 @@ def run_ours(args, wl, wl_name):
             pairs, dt, _ = cpu_pairs_step(lib, rows, 0, 64)
             rps = int(max(64, min(m // 2, (pairs / dt) * 12.0 / m)))
             pairs, dt, _ = cpu_pairs_step(lib, rows, 0, rps)
-            cpu = {"value": pairs / dt, "unit": "pairs/s", "cores": lib.max_threads(), "kind": kind,
+            cpu = {"value": pairs / dt, "unit": "pairs/s", "cores": host_threads(), "kind": kind,
                    "sample": f"first {m} of {n} histories; rows [0,{rps}) x all later rows = {pairs} pairs in {dt:.1f} s; "
                              f"reference splinify {m / t_spl:.0f} histories/s"}
             # one core, for scale: the -O2 build and the as-shipped build (clustering/Makefile has no -O)
