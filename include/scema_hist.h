@@ -195,6 +195,9 @@ uint64_t scema_kernel_launches(const scema_ctx *ctx);
  * stored at chunk c ^ (r & 7). */
 int scema_tc_debug(scema_ctx *ctx, double threshold, uint32_t slices, float *acc_host, uint64_t ld,
                    void *operand_a_host, void *operand_b_host);
+/* Ranges of histories the host-buffer pipeline of scema_cluster would use for a batch of n (host logic only):
+ * bounds[0] = 0 < ... < bounds[*n_ranges] = n, at most 16 ranges, every inner boundary a multiple of 2048. */
+int scema_pipeline_plan(uint64_t n, uint64_t *bounds, uint32_t cap, uint32_t *n_ranges);
 /* Shared-memory plan the tcgen05 filter would use for rows of k columns (host logic only, no device needed):
  * plan = {chunks of 64 columns, bytes per A buffer, A buffers, log2(B stages), bytes per B stage, bytes used}.
  * SCEMA_ERR_INVALID when the variant does not take such rows (more than 10 chunks, or two slices on wide rows). */

@@ -66,6 +66,7 @@ def lib():
         "scema_fp64_peak": (i32, [vp, P(dbl)]),
         "scema_tc_debug": (i32, [vp, dbl, u32, vp, u64, vp, vp]),
         "scema_tc_plan": (i32, [u32, u32, u32, vp]),
+        "scema_pipeline_plan": (i32, [u64, vp, u32, P(u32)]),
         "scema_ingest_last_error": (C.c_char_p, []),
         "scema_batch_read_dir": (i32, [C.c_char_p, u32, P(vp)]),
         "scema_batch_read_files": (i32, [P(C.c_char_p), vp, u64, u32, P(vp)]),
@@ -96,7 +97,7 @@ EXPORTED = (
     "scema_store_reset scema_store_append scema_store_info scema_store_resample scema_select_rows "
     "scema_set_spline scema_get_spline scema_spline_info scema_compare scema_compare_stream scema_get_edges scema_edges_device "
     "scema_get_degrees scema_cluster scema_write_similar_hist scema_reduce_edges scema_reduce_calls scema_reduce_dir "
-    "scema_last_timings scema_last_counters scema_kernel_launches scema_fp64_peak scema_tc_debug scema_tc_plan scema_synth_offsets "
+    "scema_last_timings scema_last_counters scema_kernel_launches scema_fp64_peak scema_tc_debug scema_tc_plan scema_pipeline_plan scema_synth_offsets "
     "scema_synth_histories_device scema_synth_rows_device scema_ingest_last_error scema_batch_read_dir "
     "scema_batch_read_files scema_batch_from_lhistory scema_batch_count scema_batch_total_steps scema_batch_steps "
     "scema_batch_offsets scema_batch_ids scema_batch_name scema_batch_write_strain_files "

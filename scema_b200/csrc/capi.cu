@@ -423,6 +423,17 @@ int scema_fp64_peak(scema_ctx *c, double out[2])
     return fp64_peak_run(c, out);
 }
 
+int scema_pipeline_plan(uint64_t n, uint64_t *bounds, uint32_t cap, uint32_t *n_ranges)
+{
+    if (!bounds || !n_ranges || n < 2) return SCEMA_ERR_INVALID;
+    std::vector<uint64_t> b;
+    pipeline_bounds(n, b);
+    *n_ranges = (uint32_t)(b.size() - 1);
+    if (b.size() > cap) return SCEMA_ERR_INVALID;
+    std::copy(b.begin(), b.end(), bounds);
+    return SCEMA_OK;
+}
+
 int scema_tc_plan(uint32_t k, uint32_t slices, uint32_t cta_group, uint32_t plan[6])
 {
     if (!plan || k == 0 || (slices != 1 && slices != 2) || (cta_group != 1 && cta_group != 2)) return SCEMA_ERR_INVALID;

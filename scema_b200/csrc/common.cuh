@@ -177,6 +177,7 @@ int compare_stream_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, 
                        scema_edge_sink sink, void *user, uint64_t *n_total);
 int fp64_peak_run(scema_ctx *ctx, double out[2]);
 bool pipeline_wanted(uint64_t n);
+void pipeline_bounds(uint64_t n, std::vector<uint64_t> &bounds);
 int pipeline_begin(scema_ctx *ctx, const double *steps_host, const uint64_t *offsets, uint64_t n);
 int cluster_pipelined(scema_ctx *ctx, const double *steps_host, uint32_t P, double thr, bool *done);
 // pairs_tc.cu

@@ -1168,7 +1168,7 @@ bool pipeline_wanted(uint64_t n)
 }
 
 // Ranges of the pipeline: up to 16, whole panels (2048 rows, hence whole 256-row tiles) each.
-static void pipeline_bounds(uint64_t n, std::vector<uint64_t> &bounds)
+void pipeline_bounds(uint64_t n, std::vector<uint64_t> &bounds)
 {
     const uint64_t panel_rows = (uint64_t)PANEL_ROWBLOCKS * TILE;
     const uint64_t n_ranges = std::min<uint64_t>(16, std::max<uint64_t>(2, n / 65536));

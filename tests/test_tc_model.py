@@ -130,3 +130,58 @@ def test_fold_columns_carry_minus_h():
         for arr in (a_hi, a_lo):
             nz = np.abs(arr[arr != 0])
             assert nz.min() >= 2.0 ** -14 and nz.max() <= 65504
+
+
+def band_plan(rows, thr, rows_per_tile):
+    """numpy restatement of k_tc_band_plan (pairs_tc.cu): rows sorted by squared norm; for every row tile the first
+    256-row column tile whose smallest norm is out of reach of the row tile's largest one."""
+    n, K = rows.shape
+    nrm2 = (rows ** 2).sum(1)
+    perm = np.argsort(nrm2, kind="stable")
+    s2 = nrm2[perm]
+    n_pad = (n + 255) // 256 * 256
+    n_col = n_pad // 256
+    rpc = 256 // rows_per_tile
+    keps = (K + 8.0) * 2.0 ** -52
+    jend = []
+    for I in range(n_pad // rows_per_tile):
+        last = min((I + 1) * rows_per_tile, n) - 1
+        hi = np.sqrt(s2[last])
+        je = n_col
+        for J in range(I // rpc + 1, n_col):
+            l = np.sqrt(s2[J * 256])
+            if l - hi > thr * (1 + 4 * keps) + 4 * keps * l + 1e-150:
+                je = J
+                break
+        jend.append(je)
+    return perm, jend
+
+
+@pytest.mark.parametrize("rows_per_tile", [128, 256])
+def test_norm_band_never_cuts_an_edge(rows_per_tile):
+    """Every pair the reference calls an edge lies inside the band of tiles the norm-band schedule walks."""
+    rng = np.random.default_rng(5)
+    n = 1500
+    for name, rows, thr in (
+        ("spread", rng.standard_normal((n, 60)) * 10.0 ** rng.uniform(-4, -2, size=(n, 1)), 1e-6),
+        ("near", 1e-3 * (1 + 1e-4 * rng.standard_normal((n, 60))), 3e-6),       # many edges, norms within a few thr
+        ("tiny", 1e-160 * rng.standard_normal((n, 60)), 1e-159),               # squares underflow in the norms
+        ("equal", np.tile(rng.standard_normal((1, 60)), (n, 1)) * 1e-2, 1e-6),   # all distances 0
+    ):
+        if name == "spread":
+            rows[1::2] = rows[::2] + thr * 0.9 * rng.standard_normal((n // 2, 60)) / np.sqrt(60)
+        edge = reference_edges(rows, thr)
+        perm, jend = band_plan(rows, thr, rows_per_tile)
+        pos = np.empty(n, dtype=np.int64)
+        pos[perm] = np.arange(n)
+        ii, jj = np.nonzero(np.triu(edge, 1))
+        assert len(ii) > 0, name
+        a = np.minimum(pos[ii], pos[jj])
+        b = np.maximum(pos[ii], pos[jj])
+        row_tile = a // rows_per_tile
+        col_tile = b // 256
+        limit = np.asarray(jend)[row_tile]
+        assert np.all(col_tile < limit), (name, int(np.sum(col_tile >= limit)))
+        if name == "spread":
+            full = sum(len(jend) * 0 + (len(jend) // (256 // rows_per_tile)) for _ in [0])
+            assert sum(je - I // (256 // rows_per_tile) for I, je in enumerate(jend)) < 0.6 * len(jend) * full  # it does prune

@@ -46,3 +46,23 @@ def test_shared_memory_plan_fits_for_every_supported_row_width():
                     seen_wide += 1
     assert seen_wide > 1000
     assert L.scema_tc_plan(0, 1, 1, plan.ctypes.data) != 0 and L.scema_tc_plan(60, 3, 1, plan.ctypes.data) != 0
+
+
+def test_pipeline_ranges_are_whole_panels():
+    """Host logic of the host-buffer pipeline (scema_pipeline_plan): at most 16 ranges that tile [0, n), every inner
+    boundary a whole panel (2048 rows, so column panels start on 256-row tiles), no empty range."""
+    import ctypes as C
+    import numpy as np
+    from scema_b200 import binding
+    L = binding.lib()
+    b = np.zeros(32, dtype=np.uint64)
+    k = C.c_uint32(0)
+    for n in [4096, 4097, 6000, 21000, 65535, 65536, 100000, 131072, 999999, 1000000, 1048576, 4000000, 4000001, (1 << 32) - 2]:
+        assert L.scema_pipeline_plan(n, b.ctypes.data, 32, C.byref(k)) == 0
+        r = int(k.value)
+        bounds = [int(x) for x in b[: r + 1]]
+        assert 1 <= r <= 16 and bounds[0] == 0 and bounds[-1] == n
+        assert all(x < y for x, y in zip(bounds, bounds[1:]))
+        assert all(x % 2048 == 0 for x in bounds[:-1])
+        if n >= 2 * 65536:
+            assert r >= 2
