@@ -480,3 +480,31 @@ def test_config4_1M_properties(hc, oracle):
     tot = hc.compare_stream(THR, lambda x, y, z: chunks.append((x, y, z)), PAIRS_TC)
     assert tot == ne and edges_equal(tuple(np.concatenate([c[k] for c in chunks]) for k in range(3)), (a, b, d))
     del d_steps
+
+
+def test_config5_shape_properties(hc, oracle):
+    """BASELINE configs[4] shape (K = 300) at 60k histories (1.8e9 pairs): the chunked tcgen05 filter, the streamed
+    compare and the filter-free exact kernel emit the same edge list; every edge re-derived on the CPU; 100 complete
+    rows recomputed on the CPU."""
+    import torch
+    n, P = 60000, 50
+    d_rows = synth.device_rows(5, n, 16, P, 5e-3, synth.default_pert(THR, P), device="cuda:0")
+    torch.cuda.synchronize()
+    hc.set_spline(device_ptr=d_rows.data_ptr(), n=n, k=6 * P)
+    ne = hc.compare(THR, PAIRS_TC)
+    a, b, d = hc.get_edges()
+    assert hc.counters()["tc_slices"] == 1                      # the tcgen05 path really ran (5 chunks of 64 columns)
+    assert ne > n and np.all(a < b) and np.all(np.diff(a.astype(np.int64) * n + b) > 0)
+    sp = d_rows.cpu().numpy()
+    assert oracle.check_edges(sp, THR, a, b, d) == 0
+    for r in np.random.default_rng(3).choice(n - 1, size=100, replace=False).tolist():
+        ei, ej, ed, _ = oracle.all_pairs(sp, THR, r, r + 1)
+        lo, hi = np.searchsorted(a, r), np.searchsorted(a, r + 1)
+        assert np.array_equal(b[lo:hi], ej) and same_bits(d[lo:hi], ed), r
+    chunks = []
+    tot = hc.compare_stream(THR, lambda x, y, z: chunks.append((x, y, z)), PAIRS_TC, panels_per_chunk=8)
+    assert tot == ne and len(chunks) >= 3
+    assert edges_equal(tuple(np.concatenate([c[k] for c in chunks]) for k in range(3)), (a, b, d))
+    hc.compare(THR, PAIRS_EXACT)
+    assert edges_equal(hc.get_edges(), (a, b, d))
+    del d_rows
