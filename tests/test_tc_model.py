@@ -185,3 +185,55 @@ def test_norm_band_never_cuts_an_edge(rows_per_tile):
         if name == "spread":
             full = sum(len(jend) * 0 + (len(jend) // (256 // rows_per_tile)) for _ in [0])
             assert sum(je - I // (256 // rows_per_tile) for I, je in enumerate(jend)) < 0.6 * len(jend) * full  # it does prune
+
+
+def prepare_wide(rows, thr):
+    """k_tc_prep for rows of several 64-column chunks (hi slices only): scale one binade lower for K > 64, two for
+    K > 256; the fold columns sit in the last four columns of the last chunk."""
+    n, K = rows.shape
+    nc = (K + 4 + 63) // 64
+    assert 1 < nc <= 10
+    hb = 0 if K <= 64 else (1 if K <= 256 else 2)
+    M = np.abs(rows).max()
+    s = 2.0 ** (11 - hb - int(np.floor(np.log2(M))))
+    a = np.zeros((n, nc * 64))
+    a[:, :K] = rows * s
+    assert np.abs(a).max() < 2.0 ** (12 - hb)
+    hi = h16z(a)
+    cg = 2.0 ** -9
+    eps = 2.0 ** -53
+    T0 = thr * thr * (1 + (2 * K + 16) * eps) * (1 + 4 * eps) + (2 * K + 4) * 4.9406564584124654e-324
+    nrm = (a ** 2).sum(1)
+    assert nrm.max() < 2.0 ** 30
+    h = 0.5 * (nrm * (1 - cg) - (T0 * s) * s * (0.5 + 2 * cg) - K * 2.0 ** -7)
+    force = ~(-h <= 32768.0 * P_)
+    x0 = np.where(force, 65504.0, h16z(-h / P_))
+    x1 = np.where(force, 0.0, h16z((-h - P_ * x0) / Q_))
+    one = np.ones(n)
+    a_hi, b_hi = hi.copy(), hi.copy()
+    a_hi[:, -4:] = np.stack([x0, x1, P_ * one, Q_ * one], 1)
+    b_hi[:, -4:] = np.stack([P_ * one, Q_ * one, x0, x1], 1)
+    return a_hi, b_hi, nc
+
+
+@pytest.mark.parametrize("K", [66, 300, 636])
+def test_wide_rows_no_edge_is_rejected_under_the_worst_budgeted_error(K):
+    rng = np.random.default_rng(K)
+    n = 300
+    t = np.linspace(0, 1, K // 6)
+    centres = rng.uniform(-5e-3, 5e-3, size=(n // 6, 6))
+    base = (centres[:, None, :] * t[None, :, None]).reshape(n // 6, K)
+    rows = np.repeat(base, 6, axis=0) + 3e-7 * rng.standard_normal((n, K)) / np.sqrt(K)
+    for q in range(0, n - 1, 3):  # partners a hair inside the threshold
+        u = rng.standard_normal(K)
+        u /= np.linalg.norm(u)
+        rows[q + 1] = rows[q] + u * 1e-6 * (1 - 1e-13)
+    thr = 1e-6
+    edge = reference_edges(rows, thr)
+    a_hi, b_hi, nc = prepare_wide(rows, thr)
+    assert K > 60 and a_hi.shape[1] - 4 >= K                     # the data never reaches into the fold columns
+    acc = a_hi @ b_hi.T - (4 * nc + 1) * 2.0 ** -18 * (np.abs(a_hi) @ np.abs(b_hi).T)
+    off_diag = ~np.eye(n, dtype=bool)
+    assert (edge & off_diag).sum() > n // 3
+    assert not (edge & off_diag & (acc < 0)).any()
+    assert (acc < 0).mean() > 0.9
