@@ -1,4 +1,4 @@
-// Exhaustive host-side check of the tcgen05 filter's static schedule (scema_b200/csrc/tc_sched.h): over all
+// Exhaustive host-side check of the tcgen05 filter's schedules (scema_b200/csrc/tc_sched.h; dense and norm-band): over all
 // shards and units, every (row tile, column tile) of the launch's row and column range at or right of the diagonal
 // is visited exactly once, nothing else is, and every item is non-empty. Prints "ok <cases>" or the first failure.
 #include "../../scema_b200/csrc/tc_sched.h"
@@ -42,6 +42,43 @@ static int check(const SchedArgs &a, uint32_t n_units)
     return 0;
 }
 
+// BandSched: row tile I meets the column tiles [I / RPC, jend[I]); strips of S tiles, exclusive prefix in item_start
+template <int CG>
+static int check_band(uint32_t n_col, uint32_t S, uint32_t n_shards, uint32_t n_units)
+{
+    const uint32_t RPC = 2 / CG, rows = n_col * RPC;
+    std::vector<uint32_t> jend(rows), item_start(rows + 1);
+    uint32_t acc = 0;
+    for (uint32_t I = 0; I < rows; I++) {
+        jend[I] = I / RPC + 1 + rnd(n_col - I / RPC);  // at least the diagonal tile, at most everything to the right
+        if (I && jend[I] < jend[I - 1]) jend[I] = jend[I - 1] > I / RPC ? jend[I - 1] : jend[I];  // bands of sorted norms never shrink
+        item_start[I] = acc;
+        acc += (jend[I] - I / RPC + S - 1) / S;
+    }
+    item_start[rows] = acc;
+    std::vector<int> seen((size_t)rows * n_col, 0);
+    for (uint32_t shard = 0; shard < n_shards; shard++)
+        for (uint32_t u = 0; u < n_units; u++) {
+            BandSched<CG> sc;
+            sc.init(item_start.data(), jend.data(), rows, S, shard, n_shards, u, n_units);
+            uint32_t I, J0, J1;
+            while (sc.next(I, J0, J1)) {
+                if (J0 >= J1 || I >= rows || J1 > n_col || J1 - J0 > S) { printf("band: bad item I=%u J=[%u,%u)\n", I, J0, J1); return 1; }
+                for (uint32_t J = J0; J < J1; J++) seen[(size_t)I * n_col + J]++;
+            }
+        }
+    for (uint32_t I = 0; I < rows; I++)
+        for (uint32_t J = 0; J < n_col; J++) {
+            const int want = J >= I / RPC && J < jend[I] ? 1 : 0;
+            if (seen[(size_t)I * n_col + J] != want) {
+                printf("band CG=%d cols=%u S=%u shards=%u units=%u: tile (%u,%u) visited %d times, want %d\n", CG, n_col, S, n_shards,
+                       n_units, I, J, seen[(size_t)I * n_col + J], want);
+                return 1;
+            }
+        }
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     const int cases = argc > 1 ? atoi(argv[1]) : 3000;
@@ -58,6 +95,7 @@ int main(int argc, char **argv)
         a.shard = 0;
         const uint32_t n_units = 1 + rnd(t % 4 == 0 ? 148 : 5);
         if (check<1>(a, n_units) || check<2>(a, n_units)) return 1;
+        if (t % 4 == 0 && (check_band<1>(a.NT, a.strip_len, a.n_shards, n_units) || check_band<2>(a.NT, a.strip_len, a.n_shards, n_units))) return 1;
     }
     printf("ok %d\n", cases);
     return 0;
