@@ -55,8 +55,9 @@ def main():
     real = must & written & (np.arange(n_pad)[:, None] < n) & (np.arange(n_pad)[None, :] < n)
     err = np.abs(acc.astype(np.float64) - want)
     rel = np.where(real, err / np.maximum(absum, 1e-300), 0.0)
-    print("max |acc - fp64(sliced)| / sum|terms| = %.3e (2^%.1f); model allows 13*2^-18 = %.3e" %
-          (rel.max(), np.log2(max(rel.max(), 1e-300)), 13 * 2.0 ** -18))
+    steps = 12 if slices == 2 else 4
+    print("max |acc - fp64(sliced)| / sum|terms| = %.3e (2^%.1f); the guard band budgets %d*2^-18 = %.3e" %
+          (rel.max(), np.log2(max(rel.max(), 1e-300)), steps + 1, (steps + 1) * 2.0 ** -18))
     i, j = np.unravel_index(np.argmax(rel), rel.shape)
     print("  worst at", (i, j), "acc", acc[i, j], "want", want[i, j], "absum", absum[i, j])
     for (i, j) in [(0, 1), (0, 17), (5, 300 % n), (n - 2, n - 1)]:
