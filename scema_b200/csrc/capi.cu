@@ -44,7 +44,7 @@ void scema_destroy(scema_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->steps_own.release(); c->d_offsets.release(); c->d_tables.release(); c->d_table_index.release();
-    c->zscratch.release(); c->d_order.release(); c->d_chunks.release(); c->d_chunk_counters.release(); c->spline_own.release(); c->spline_sel.release(); c->d_select.release(); c->d_store.release(); c->d_filter.release(); c->d_halfnorm.release();
+    c->zscratch.release(); c->d_order.release(); c->d_chunks.release(); c->d_chunk_counters.release(); c->spline_own.release(); c->spline_sel[0].release(); c->spline_sel[1].release(); c->d_select.release(); c->d_store.release(); c->d_filter.release(); c->d_halfnorm.release();
     c->d_blockmax.release(); c->d_panel_start.release(); c->d_cand.release(); c->d_counters.release();
     for (int b = 0; b < 2; b++) { c->d_edge_key[b].release(); c->d_edge_val[b].release(); }
     c->d_sort_tmp.release();

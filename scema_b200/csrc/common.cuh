@@ -90,7 +90,8 @@ struct scema_ctx {
     const double *d_spline = nullptr;  // borrowed or = spline_own
     scema::DevBuf spline_own;
     bool have_spline = false;
-    scema::DevBuf spline_sel, d_select;  // scema_select_rows: compacted subset of the rows
+    scema::DevBuf spline_sel[2], d_select;  // scema_select_rows: compacted subset of the rows (ping-pong: a second
+                                            // selection gathers out of the first one's buffer)
 
     // ---- incremental history store, time-major [step][store_n][6]
     scema::DevBuf d_store;

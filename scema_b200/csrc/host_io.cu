@@ -21,6 +21,17 @@ namespace scema {
 int write_similar_hist(scema_ctx *c, const char *pattern)
 {
     const uint64_t m = c->n_edges, n = c->n;
+    // the pattern goes to snprintf as the format: exactly one conversion, and that one %u ("%%" is a literal percent sign)
+    {
+        int n_u = 0;
+        for (const char *q = pattern; *q; q++) {
+            if (*q != '%') continue;
+            if (q[1] == '%') { q++; continue; }
+            if (q[1] == 'u') { n_u++; q++; continue; }
+            return fail(c, SCEMA_ERR_INVALID, "write_similar_hist: the file name pattern may only contain one %u");
+        }
+        if (n_u != 1) return fail(c, SCEMA_ERR_INVALID, "write_similar_hist: the file name pattern needs exactly one %u");
+    }
     std::vector<uint32_t> a(m), b(m);
     std::vector<double> d(m);
     int rc = scema_get_edges(c, a.data(), b.data(), d.data(), m);

@@ -921,16 +921,17 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
         SCEMA_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 8 * sizeof(uint64_t), ctx->stream));
         if (*variant == SCEMA_PAIRS_EXACT) {
             const uint32_t nbx = (uint32_t)((n + XT - 1) / XT);
-            if (nbx > 65535) return fail(ctx, SCEMA_ERR_INVALID, "exact all-pairs variant supports n <= 4194240");
             const uint32_t per_panel = PANEL_ROWBLOCKS * (TILE / XT);
-            const uint32_t i_first = p0 * per_panel;
-            const uint32_t i_end = std::min<uint64_t>((uint64_t)p1 * per_panel, nbx);
+            const uint32_t i_first = (uint32_t)std::min<uint64_t>((uint64_t)p0 * per_panel, nbx);
+            const uint32_t i_end = (uint32_t)std::min<uint64_t>((uint64_t)p1 * per_panel, nbx);
             t_begin(ctx, SCEMA_T_FILTER);
-            if (i_end > i_first)
-                k_exact_all<<<dim3(nbx, i_end - i_first), 256, 0, ctx->stream>>>(
-                    ctx->d_spline, n, K, thr, ctx->key_shift, shard, n_shards, i_first, d_cnt + 1, ctx->edge_cap,
+            // gridDim.y stops at 65535: row slabs of that many 64-row blocks, so any n < 2^32 works
+            for (uint32_t i0 = i_first; i0 < i_end; i0 += 65535u) {
+                k_exact_all<<<dim3(nbx, std::min<uint32_t>(65535u, i_end - i0)), 256, 0, ctx->stream>>>(
+                    ctx->d_spline, n, K, thr, ctx->key_shift, shard, n_shards, i0, d_cnt + 1, ctx->edge_cap,
                     ctx->d_edge_key[0].as<uint64_t>(), ctx->d_edge_val[0].as<double>());
-            ctx->launches++;
+                ctx->launches++;
+            }
             t_end(ctx, SCEMA_T_FILTER);
             SCEMA_CUDA(ctx, cudaGetLastError());
         } else if (*variant == SCEMA_PAIRS_TC) {
@@ -1190,8 +1191,8 @@ static int pipeline_queue_copy(scema_ctx *ctx, const double *steps_host, const u
 // First act of the pipeline, before anything else touches the batch: the first four ranges start travelling at once
 // (~17 ms of copies at config 4); the host-side work that follows — validation of the offsets, factor tables, K1 plan,
 // a few ms with small host->device copies of its own, which queue behind what is already on the copy engine — runs
-// meanwhile, and only then are the remaining ranges queued. Only the five offsets that delimit these ranges are
-// looked at here (they must be ordered and inside the batch); everything else is validated by set_histories.
+// meanwhile, and only then are the remaining ranges queued. The offsets are scanned once here (monotone, no history
+// beyond the length limit) because they size the device buffer; set_histories reports what is wrong with a bad array.
 int pipeline_begin(scema_ctx *ctx, const double *steps_host, const uint64_t *offsets, uint64_t n)
 {
     pipeline_bounds(n, ctx->pipe_bounds);
@@ -1204,8 +1205,10 @@ int pipeline_begin(scema_ctx *ctx, const double *steps_host, const uint64_t *off
         ctx->copy_events.push_back(e);
     }
     const uint64_t early = std::min<uint64_t>(4, n_ranges);
-    for (uint64_t r = 0; r < early; r++)
-        if (offsets[ctx->pipe_bounds[r]] > offsets[ctx->pipe_bounds[r + 1]] || offsets[ctx->pipe_bounds[r + 1]] > offsets[n]) return SCEMA_OK;
+    // the offsets size the device buffer below: a bad array must come back as SCEMA_ERR_INVALID from set_histories
+    // (which repeats this scan), not as an out-of-memory error from here (~0.3 ms for 10^6 histories)
+    for (uint64_t i = 0; i < n; i++)
+        if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0x7fffffffull / 64) return SCEMA_OK;
     // the previous batch's kernels may still read the buffer the copies are about to overwrite
     SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     SCEMA_CUDA(ctx, ctx->steps_own.reserve(std::max<uint64_t>(offsets[n], 1) * 6 * sizeof(double)));

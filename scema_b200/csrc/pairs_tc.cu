@@ -96,6 +96,24 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// One lane of a converged warp. The single-thread roles (TMA producer, MMA issuer) run their loops with the WHOLE warp
+// converged and only the issuing instructions under this predicate: addresses, descriptors and barrier phases are then
+// warp-uniform for the compiler and live in uniform registers. (Round 1 ran these loops inside `if (lane == 0)`: in
+// divergent code every UTCHMMA / UBLKCP / UTCBAR is wrapped in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop, and the
+// issuer needed ~1000 cycles of instruction latency per tile for 512 cycles of tensor work — ncu source page,
+// profiles/r02_k2_issue_loop.txt.)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_rank()
@@ -264,7 +282,8 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
     const uint32_t off_tmem = a.data_bytes + SM::n_bars * 8;
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_raw + (base - raw) + off_tmem);
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
     const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
     const SchedArgs sa = {a.NT, a.I0, a.I1, a.C0, a.C1, a.strip_len, a.shard, a.n_shards};
     const uint32_t unit = blockIdx.x / CG, n_units = gridDim.x / CG;
@@ -282,26 +301,27 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
 
     if (warp == 0) {
         // ------------------------------------------------------------------ producer: TMA bulk copies
-        if (lane == 0) {
-            SchedT sc;
-            sched_init(sc, a, sa, unit, n_units);
-            uint32_t I, J0, J1, t = 0, item = 0;
-            const uint32_t nc = k_nc, n_abuf = k_nabuf, a_bytes = k_abytes, slices = a.slices;
-            const unsigned char *const HA = a.HA, *const HB = a.HB;
-            while (sc.next(I, J0, J1)) {
-                const uint32_t ab = n_abuf == 2 ? (item & 1u) : 0u;
-                mbar_wait(bar_aempty(ab), ((n_abuf == 2 ? (item >> 1) : item) & 1u) ^ 1u, 1);
-                for (uint32_t J = J0; J < J1; J++)
-                    for (uint32_t c = 0; c < nc; c++, t++) {
-                        const uint32_t st = t & nst_mask;
-                        mbar_wait(bar_empty(st), ((t >> lg_nst) & 1u) ^ 1u, 2);
-                        const bool first = J == J0 && c == 0;  // the item's A tile (all chunks) rides on its first stage
+        // (whole warp converged; one elected lane arms the barrier and issues the copies)
+        SchedT sc;
+        sched_init(sc, a, sa, unit, n_units);
+        uint32_t I, J0, J1, t = 0, item = 0;
+        const uint32_t nc = k_nc, n_abuf = k_nabuf, a_bytes = k_abytes, slices = a.slices;
+        const unsigned char *const HA = a.HA, *const HB = a.HB;
+        while (sc.next(I, J0, J1)) {
+            const uint32_t ab = n_abuf == 2 ? (item & 1u) : 0u;
+            mbar_wait(bar_aempty(ab), ((n_abuf == 2 ? (item >> 1) : item) & 1u) ^ 1u, 1);
+            for (uint32_t J = J0; J < J1; J++)
+                for (uint32_t c = 0; c < nc; c++, t++) {
+                    const uint32_t st = t & nst_mask;
+                    mbar_wait(bar_empty(st), ((t >> lg_nst) & 1u) ^ 1u, 2);
+                    const bool first = J == J0 && c == 0;  // the item's A tile (all chunks) rides on its first stage
+                    const uint32_t dst = sB + st * stage_bytes;
+                    if (elect_one()) {
                         mbar_expect_tx(bar_full(st), (COLT / CG / ROWS) * a_chunk + (first ? nc * a_chunk : 0u));
                         if (first)
                             for (uint32_t ca = 0; ca < nc; ca++)
                                 bulk_g2s(sA + ab * a_bytes + ca * a_chunk, HA + (uint64_t)(I * CG + rank) * gblk + (uint64_t)ca * BLOCK_BYTES,
                                          a_chunk, bar_full(st));
-                        const uint32_t dst = sB + st * stage_bytes;
                         if (CG == 2) {
                             bulk_g2s(dst, HB + (uint64_t)(J * 2 + rank) * gblk + (uint64_t)c * BLOCK_BYTES, a_chunk, bar_full(st));
                         } else {
@@ -315,21 +335,19 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
                             }
                         }
                     }
-                item++;
-            }
+                    __syncwarp();
+                }
+            item++;
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             // -------------------------------------------------------------- MMA issuer (leader CTA)
+            // whole warp converged, the MMAs and their commits issued by one elected lane (always the same one)
             // instruction descriptor: D fp32, A/B fp16, both K-major, N = 256, M = 128 * CG
             const uint32_t idesc = (1u << 4) | ((COLT >> 3) << 17) | (((128u * CG) >> 4) << 24);
             SchedT sc;
             sched_init(sc, a, sa, unit, n_units);
             uint32_t I, J0, J1, t = 0, item = 0, tile = 0;
-            // everything the loop needs sits in registers: the asm statements clobber memory, and a kernel parameter
-            // re-read from the constant bank on the way from "accumulator free" to the first MMA is latency on the
-            // critical path of every tile
             const uint32_t n_terms = a.slices == 1 ? 1u : 3u, nc = k_nc, n_abuf = k_nabuf, a_bytes = k_abytes;
             while (sc.next(I, J0, J1)) {
                 const uint32_t ab = n_abuf == 2 ? (item & 1u) : 0u;
@@ -347,23 +365,28 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
                         const uint64_t bdesc = make_desc(sB + st * stage_bytes);
                         if (c == 0) mbar_wait(bar_tempty(as), ((tile >> 1) & 1u) ^ 1u, 3);
                         fence_after();
+                        if (elect_one()) {
 #pragma unroll 1
-                        for (uint32_t term = 0; term < n_terms; term++) {
-                            // a_hi.b_hi, a_lo.b_hi, a_hi.b_lo
-                            const uint32_t a_off = (term == 1 ? SLICE_BYTES : 0u) >> 4;
-                            const uint32_t b_off = (term == 2 ? SM::B_SLICE : 0u) >> 4;
+                            for (uint32_t term = 0; term < n_terms; term++) {
+                                // a_hi.b_hi, a_lo.b_hi, a_hi.b_lo
+                                const uint32_t a_off = (term == 1 ? SLICE_BYTES : 0u) >> 4;
+                                const uint32_t b_off = (term == 2 ? SM::B_SLICE : 0u) >> 4;
 #pragma unroll
-                            for (uint32_t kk = 0; kk < 4; kk++)
-                                umma_f16<CG>(d_tmem, adesc + a_off + 2 * kk, bdesc + b_off + 2 * kk, idesc, (c | term | kk) != 0 ? 1u : 0u);
+                                for (uint32_t kk = 0; kk < 4; kk++)
+                                    umma_f16<CG>(d_tmem, adesc + a_off + 2 * kk, bdesc + b_off + 2 * kk, idesc, (c | term | kk) != 0 ? 1u : 0u);
+                            }
+                            umma_commit<CG>(bar_empty(st));
+                            if (c == nc - 1) {
+                                umma_commit<CG>(bar_tfull(as));
+                                if (J == J1 - 1) umma_commit<CG>(bar_aempty(ab));
+                            }
                         }
-                        umma_commit<CG>(bar_empty(st));
+                        __syncwarp();
                     }
-                    umma_commit<CG>(bar_tfull(as));
-                    if (J == J1 - 1) umma_commit<CG>(bar_aempty(ab));
                 }
                 item++;
             }
-        } else if (CG == 2 && lane == 0 && rank == 1) {
+        } else if (CG == 2) {
             // ---------------------------- peer CTA: tell the leader when this CTA's half of a stage landed
             SchedT sc;
             sched_init(sc, a, sa, unit, n_units);
@@ -373,10 +396,10 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
                 for (uint32_t q = (J1 - J0) * nc_fw; q > 0; q--, t++) {
                     const uint32_t st = t & nst_mask;
                     mbar_wait(bar_full(st), (t >> lg_nst) & 1u, 6);
-                    mbar_arrive_cluster(bar_pfull(st), 0);
+                    if (elect_one()) mbar_arrive_cluster(bar_pfull(st), 0);
+                    __syncwarp();
                 }
         }
-        __syncwarp();
     } else if (warp >= 4) {
         // ---------------------------------------------------------------------- epilogue (8 warps)
         // warp -> (TMEM lane quarter it may read, column half of the tile)
@@ -403,9 +426,13 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
                     else mbar_arrive_local(bar_tempty(as));
                 }
                 // acc < 0 for every pair <=> the AND of the bit patterns keeps the sign bit
-                uint32_t all_neg = v0[0] & v1[0];
+                // (four independent chains: one chain of 64 dependent LOP3s costs ~350 cycles per tile)
+                uint32_t an[4];
 #pragma unroll
-                for (int c = 1; c < 64; c++) all_neg &= v0[c] & v1[c];
+                for (int c = 0; c < 4; c++) an[c] = v0[c] & v1[c];
+#pragma unroll
+                for (int c = 4; c < 64; c++) an[c & 3] &= v0[c] & v1[c];
+                const uint32_t all_neg = (an[0] & an[1]) & (an[2] & an[3]);
                 const uint64_t col0 = (uint64_t)J * COLT + half * 128u;
                 if (DBG && a.dbg) {
 #pragma unroll

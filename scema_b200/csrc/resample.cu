@@ -828,13 +828,15 @@ int select_rows(scema_ctx *ctx, const uint32_t *rows, uint64_t m)
         if (rows[i] >= ctx->n) return fail(ctx, SCEMA_ERR_INVALID, "select_rows: row index out of range");
     const uint32_t K = ctx->K;
     SCEMA_CUDA(ctx, ctx->d_select.reserve(std::max<uint64_t>(m, 1) * sizeof(uint32_t)));
-    SCEMA_CUDA(ctx, ctx->spline_sel.reserve(std::max<uint64_t>(m * K, 1) * sizeof(double)));
+    // never gather in place, never grow the buffer that is being read: a selection of a selection (rows of the
+    // current matrix, duplicates allowed, so m may exceed n) goes to the other of two buffers
+    scema::DevBuf &dst = ctx->spline_sel[ctx->d_spline == ctx->spline_sel[0].as<double>() ? 1 : 0];
+    SCEMA_CUDA(ctx, dst.reserve(std::max<uint64_t>(m * K, 1) * sizeof(double)));
     if (m) {
         SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_select.p, rows, m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         if (K) {
             const unsigned grid = (unsigned)std::min<uint64_t>((m * K + 255) / 256, (uint64_t)ctx->sm_count * 16);
-            k_gather_rows<<<grid, 256, 0, ctx->stream>>>(ctx->d_spline, ctx->d_select.as<uint32_t>(), m, K,
-                                                         ctx->spline_sel.as<double>());
+            k_gather_rows<<<grid, 256, 0, ctx->stream>>>(ctx->d_spline, ctx->d_select.as<uint32_t>(), m, K, dst.as<double>());
             ctx->launches++;
             SCEMA_CUDA(ctx, cudaGetLastError());
         }
@@ -843,7 +845,7 @@ int select_rows(scema_ctx *ctx, const uint32_t *rows, uint64_t m)
     std::vector<uint32_t> ids(m);
     for (uint64_t i = 0; i < m; i++) ids[i] = ctx->ids[rows[i]];
     ctx->ids.swap(ids);
-    ctx->d_spline = ctx->spline_sel.as<double>();
+    ctx->d_spline = dst.as<double>();
     ctx->n = m;
     ctx->spline_version++;
     ctx->have_edges = false;
