@@ -35,7 +35,6 @@ constexpr uint32_t SLICE_BYTES = ROWS * 128;       // 128 rows x 64 fp16, SW128 
 constexpr uint32_t BLOCK_BYTES = 2 * SLICE_BYTES;  // hi | lo
 constexpr uint32_t COLT = 256;                     // B rows (= pair-matrix columns) per tile
 constexpr uint32_t KMAX = 60;                      // data columns per slice (4 more carry the row terms)
-constexpr long long WAIT_TIMEOUT = 20000000000ll;  // cycles (~10 s); a wait this long is a bug, trap instead of hanging
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -61,18 +60,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
-__device__ __noinline__ void wait_timeout(uint32_t bar, uint32_t parity, int tag)
+// Wait for a barrier phase. The whole loop is one PTX block (no compiler-visible divergence, hence no BSSY/BSYNC and
+// no reconvergence code around it: the single-thread roles execute three of these per tile and their instruction
+// count IS the critical path). Bounded: after WAIT_SPINS failed polls (each poll itself blocks for a hardware time
+// slice; seconds in total) the thread traps, so a protocol bug ends the kernel instead of hanging the GPU.
+constexpr uint32_t WAIT_SPINS = 1u << 26;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int /*tag*/)
 {
-    printf("scema k_filter_tc: barrier wait timed out (block %d thread %d tag %d bar 0x%x parity %u)\n", (int)blockIdx.x,
-           (int)threadIdx.x, tag, bar, parity);
-    __trap();
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag)
-{
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity))
-        if (clock64() - t0 > WAIT_TIMEOUT) wait_timeout(bar, parity, tag);
+    asm volatile(
+        "{\n"
+        ".reg .pred P1, P2;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 P2, n, %2;\n"
+        "@P2 bra LAB_WAIT;\n"
+        "trap;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity), "r"(WAIT_SPINS)
+        : "memory");
 }
 // arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta)
@@ -113,6 +123,12 @@ __device__ __forceinline__ bool elect_one()
         "}\n"
         : "=r"(pred));
     return pred != 0;
+}
+__device__ __forceinline__ uint32_t and3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -366,14 +382,17 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
                         if (c == 0) mbar_wait(bar_tempty(as), ((tile >> 1) & 1u) ^ 1u, 3);
                         fence_after();
                         if (elect_one()) {
-#pragma unroll 1
-                            for (uint32_t term = 0; term < n_terms; term++) {
-                                // a_hi.b_hi, a_lo.b_hi, a_hi.b_lo
-                                const uint32_t a_off = (term == 1 ? SLICE_BYTES : 0u) >> 4;
-                                const uint32_t b_off = (term == 2 ? SM::B_SLICE : 0u) >> 4;
+                            // a_hi.b_hi (one slice), then a_lo.b_hi and a_hi.b_lo (two slices)
+#pragma unroll
+                            for (uint32_t kk = 0; kk < 4; kk++)
+                                umma_f16<CG>(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (c | kk) != 0 ? 1u : 0u);
+                            if (n_terms != 1) {
 #pragma unroll
                                 for (uint32_t kk = 0; kk < 4; kk++)
-                                    umma_f16<CG>(d_tmem, adesc + a_off + 2 * kk, bdesc + b_off + 2 * kk, idesc, (c | term | kk) != 0 ? 1u : 0u);
+                                    umma_f16<CG>(d_tmem, adesc + (SLICE_BYTES >> 4) + 2 * kk, bdesc + 2 * kk, idesc, 1u);
+#pragma unroll
+                                for (uint32_t kk = 0; kk < 4; kk++)
+                                    umma_f16<CG>(d_tmem, adesc + 2 * kk, bdesc + (SM::B_SLICE >> 4) + 2 * kk, idesc, 1u);
                             }
                             umma_commit<CG>(bar_empty(st));
                             if (c == nc - 1) {
@@ -426,13 +445,15 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
                     else mbar_arrive_local(bar_tempty(as));
                 }
                 // acc < 0 for every pair <=> the AND of the bit patterns keeps the sign bit
-                // (four independent chains: one chain of 64 dependent LOP3s costs ~350 cycles per tile)
-                uint32_t an[4];
+                // Eight independent chains of three-input ANDs, spelled in PTX: left to the compiler, the 128 values are
+                // re-associated into ONE chain of 64 dependent LOP3s (~5 cycles each = 310 of the warp's ~710 cycles per
+                // tile, profiles/r02_ncu_filter_tc_roles.txt)
+                uint32_t an[8];
 #pragma unroll
-                for (int c = 0; c < 4; c++) an[c] = v0[c] & v1[c];
+                for (int c = 0; c < 8; c++) an[c] = v0[c] & v1[c];
 #pragma unroll
-                for (int c = 4; c < 64; c++) an[c & 3] &= v0[c] & v1[c];
-                const uint32_t all_neg = (an[0] & an[1]) & (an[2] & an[3]);
+                for (int c = 8; c < 64; c++) an[c & 7] = and3(an[c & 7], v0[c], v1[c]);
+                const uint32_t all_neg = and3(and3(an[0], an[1], an[2]), and3(an[3], an[4], an[5]), an[6] & an[7]);
                 const uint64_t col0 = (uint64_t)J * COLT + half * 128u;
                 if (DBG && a.dbg) {
 #pragma unroll
