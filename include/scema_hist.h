@@ -29,6 +29,10 @@ extern "C" {
 #define SCEMA_ERR_IO 4      /* file could not be opened (strain2spline.h:117-120, :303-307) */
 #define SCEMA_ERR_STATE 5   /* call order: e.g. compare before any spline matrix exists (strain2spline.h:214-221) */
 #define SCEMA_ERR_MAPPING 6 /* graph reduction: ID >= num_gps or dist == 0 (coarsegrain_dependency_network.py:57,73) */
+#define SCEMA_ERR_DENSE 7   /* sharded compare (n_shards > 1) only: this shard's survivors are too dense for its queue and the
+                             * remedy — another filter — would change how the pair matrix is split between the shards; EVERY
+                             * shard must repeat the compare with SCEMA_PAIRS_DMMA (and, if that fails too, SCEMA_PAIRS_EXACT).
+                             * scema_cluster_multi and scema_b200/distributed.py do this; a single-shard compare switches by itself. */
 
 /* Which kernel evaluates the all-pairs distance (north star: DMMA tensor path, CUDA-core FMA
  * variant kept for comparison, exact direct-difference kernel as the anchor). All three emit
@@ -181,7 +185,7 @@ int scema_last_timings(scema_ctx *ctx, float ms[SCEMA_T_COUNT]);
 /* Counters of the last compare: [0] pairs evaluated by the filter, [1] survivors recomputed
  * exactly, [2] edges, [3] passes (>1 when a buffer had to grow), [4] tiles, [5] fp16 slices the
  * tcgen05 filter ended up using (SCEMA_PAIRS_TC only), [6] ranges of the host-buffer pipeline of
- * scema_cluster (0: the batch was not pipelined), [7] tiles (128 x 256 pairs; 256 x 256 with SCEMA_TC_CG=2) walked by the norm-band schedule
+ * scema_cluster (0: the batch was not pipelined), [7] tiles (256 x 256 pairs; 128 x 256 with SCEMA_TC_CG=1) walked by the norm-band schedule
  * (0: dense schedule). */
 int scema_last_counters(scema_ctx *ctx, uint64_t counters[8]);
 /* Total kernels launched by this context so far. */
@@ -195,6 +199,18 @@ uint64_t scema_kernel_launches(const scema_ctx *ctx);
  * stored at chunk c ^ (r & 7). */
 int scema_tc_debug(scema_ctx *ctx, double threshold, uint32_t slices, float *acc_host, uint64_t ld,
                    void *operand_a_host, void *operand_b_host);
+/* The column means the tcgen05 filter subtracted from its operand copies (centre_host[k], k = columns of the rows;
+ * the exact recompute never sees them). Valid after a compare / scema_tc_debug that built the copies. */
+int scema_tc_centre(scema_ctx *ctx, double *centre_host);
+/* Survivor-density sample behind the last automatic choice of the filter: plan = {pairs of the sample that would
+ * survive the one-slice filter, the two-slice filter (centred copies), the same two with raw copies, the DMMA filter,
+ * sample size}. */
+int scema_tc_last_plan(scema_ctx *ctx, uint64_t plan[6]);
+/* The choice itself as host logic (no device needed): given those five counts for `pairs` pairs of rows of k columns and
+ * the bytes a survivor queue may take, *choice = 1 / 2 (tcgen05 filter with that many fp16 slices), 0 (SCEMA_PAIRS_DMMA)
+ * or -1 (SCEMA_PAIRS_EXACT), *centred = whether the tcgen05 copies are centred, *est_survivors = queue entries expected. */
+int scema_tc_choose(uint64_t pairs, uint32_t k, const uint64_t counts[5], uint64_t sample, uint64_t mem_budget, int *choice,
+                    int *centred, uint64_t *est_survivors);
 /* Ranges of histories the host-buffer pipeline of scema_cluster would use for a batch of n (host logic only):
  * bounds[0] = 0 < ... < bounds[*n_ranges] = n, at most 16 ranges, every inner boundary a multiple of 2048. */
 int scema_pipeline_plan(uint64_t n, uint64_t *bounds, uint32_t cap, uint32_t *n_ranges);

@@ -31,6 +31,18 @@ int scema_synth_histories_device(uint64_t seed, uint64_t first, uint64_t n, uint
 int scema_synth_rows_device(uint64_t seed, uint64_t first, uint64_t n, uint32_t cluster_size, uint32_t spline_points, double amp,
                             double pert, double *d_rows, void *stream);
 
+
+/* Same with a choice of population model. model 0: the cluster model above (spread unused). model 1, "smooth"
+ * (emulation of the reference's dogbone stretch, input_configurations/inputs_dogbone_cuboid.json:
+ * every quadrature point follows nearly the same path): zz(t) = amp t (1 + delta_q), xx = yy = -0.3 zz,
+ * shear_c = zz sigma_qc, delta_q in spread (-1,1) and sigma_qc in 0.01 (-1,1) per group q of cluster_size symmetric
+ * points, members jittered by pert (-1,1) t per component as in model 0. All row norms are ~ 2 amp, group
+ * distances ~ spread amp. */
+int scema_synth_histories_model_device(int model, double spread, uint64_t seed, uint64_t first, uint64_t n, uint32_t cluster_size,
+                                       double amp, double pert, const uint64_t *d_offsets, double *d_steps, void *stream);
+int scema_synth_rows_model_device(int model, double spread, uint64_t seed, uint64_t first, uint64_t n, uint32_t cluster_size,
+                                  uint32_t spline_points, double amp, double pert, double *d_rows, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,9 @@ def lib():
         "scema_fp64_peak": (i32, [vp, P(dbl)]),
         "scema_tc_debug": (i32, [vp, dbl, u32, vp, u64, vp, vp]),
         "scema_tc_plan": (i32, [u32, u32, u32, vp]),
+        "scema_tc_centre": (i32, [vp, vp]),
+        "scema_tc_last_plan": (i32, [vp, vp]),
+        "scema_tc_choose": (i32, [u64, u32, vp, u64, u64, P(i32), P(i32), P(u64)]),
         "scema_pipeline_plan": (i32, [u64, vp, u32, P(u32)]),
         "scema_ingest_last_error": (C.c_char_p, []),
         "scema_batch_read_dir": (i32, [C.c_char_p, u32, P(vp)]),
@@ -83,6 +86,8 @@ def lib():
         "scema_synth_offsets": (i32, [u64, u64, u64, u32, u32, u32, vp]),
         "scema_synth_histories_device": (i32, [u64, u64, u64, u32, dbl, dbl, vp, vp, vp]),
         "scema_synth_rows_device": (i32, [u64, u64, u64, u32, u32, dbl, dbl, vp, vp]),
+        "scema_synth_histories_model_device": (i32, [i32, dbl, u64, u64, u64, u32, dbl, dbl, vp, vp, vp]),
+        "scema_synth_rows_model_device": (i32, [i32, dbl, u64, u64, u64, u32, u32, dbl, dbl, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -97,8 +102,8 @@ EXPORTED = (
     "scema_store_reset scema_store_append scema_store_info scema_store_resample scema_select_rows "
     "scema_set_spline scema_get_spline scema_spline_info scema_compare scema_compare_stream scema_get_edges scema_edges_device "
     "scema_get_degrees scema_cluster scema_write_similar_hist scema_reduce_edges scema_reduce_calls scema_reduce_dir "
-    "scema_last_timings scema_last_counters scema_kernel_launches scema_fp64_peak scema_tc_debug scema_tc_plan scema_pipeline_plan scema_synth_offsets "
-    "scema_synth_histories_device scema_synth_rows_device scema_ingest_last_error scema_batch_read_dir "
+    "scema_last_timings scema_last_counters scema_kernel_launches scema_fp64_peak scema_tc_debug scema_tc_plan scema_tc_centre scema_tc_last_plan scema_tc_choose scema_pipeline_plan scema_synth_offsets "
+    "scema_synth_histories_device scema_synth_rows_device scema_synth_histories_model_device scema_synth_rows_model_device scema_ingest_last_error scema_batch_read_dir "
     "scema_batch_read_files scema_batch_from_lhistory scema_batch_count scema_batch_total_steps scema_batch_steps "
     "scema_batch_offsets scema_batch_ids scema_batch_name scema_batch_write_strain_files "
     "scema_set_histories_from_batch scema_batch_free").split()
@@ -194,6 +199,17 @@ class Batch:
             self.close()
         except Exception:
             pass
+
+
+def tc_choose(pairs, k, counts, sample, mem_budget):
+    """Host logic of the filter choice (scema_tc_choose); counts = survivors of the sample for (one slice, two slices)
+    centred, (one slice, two slices) raw, DMMA. -> (choice, centred, estimated survivors)."""
+    cnt = (C.c_uint64 * 5)(*[int(x) for x in counts])
+    ch, cen, est = C.c_int(0), C.c_int(0), C.c_uint64(0)
+    rc = lib().scema_tc_choose(int(pairs), int(k), cnt, int(sample), int(mem_budget), C.byref(ch), C.byref(cen), C.byref(est))
+    if rc:
+        raise ScemaError(rc, "tc_choose")
+    return int(ch.value), int(cen.value), int(est.value)
 
 
 class HistCluster:
@@ -395,6 +411,20 @@ class HistCluster:
         hb = np.empty(n_pad * 256, dtype=np.uint8)
         self._ck(self._L.scema_tc_debug(self._h, float(threshold), int(slices), _ptr(acc), n_pad, _ptr(ha), _ptr(hb)))
         return acc, ha, hb
+
+    def tc_centre(self):
+        """Column means the tcgen05 filter subtracted from its operand copies."""
+        _, k, _ = self.spline_info()
+        out = np.empty(k, dtype=np.float64)
+        self._ck(self._L.scema_tc_centre(self._h, _ptr(out)))
+        return out
+
+    def tc_last_plan(self):
+        """-> dict: pairs of the last survivor-density sample that would survive 1 slice / 2 slices / DMMA, sample size."""
+        p = (C.c_uint64 * 6)()
+        self._ck(self._L.scema_tc_last_plan(self._h, p))
+        return {"one_slice": int(p[0]), "two_slices": int(p[1]), "one_slice_raw": int(p[2]), "two_slices_raw": int(p[3]),
+                "dmma": int(p[4]), "sample": int(p[5])}
 
     def fp64_peak(self):
         out = (C.c_double * 2)()

@@ -48,7 +48,7 @@ void scema_destroy(scema_ctx *c)
     c->d_blockmax.release(); c->d_panel_start.release(); c->d_cand.release(); c->d_counters.release();
     for (int b = 0; b < 2; b++) { c->d_edge_key[b].release(); c->d_edge_val[b].release(); }
     c->d_sort_tmp.release();
-    c->d_tc_a.release(); c->d_tc_b.release(); c->d_tc_nrm.release(); c->d_tc_misc.release();
+    c->d_tc_a.release(); c->d_tc_b.release(); c->d_tc_nrm.release(); c->d_tc_misc.release(); c->d_tc_centre.release();
     c->d_tc_perm.release(); c->d_tc_iota.release(); c->d_tc_snrm.release(); c->d_tc_band.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     for (int k = 0; k < 2; k++) {
@@ -440,6 +440,32 @@ int scema_tc_plan(uint32_t k, uint32_t slices, uint32_t cta_group, uint32_t plan
     plan[0] = tc_chunks_for(k);
     if (plan[0] > 10 || (plan[0] > 1 && slices != 1)) return SCEMA_ERR_INVALID;
     return tc_smem_plan(plan[0], slices, cta_group, &plan[1], &plan[2], &plan[3], &plan[4], &plan[5]) ? SCEMA_OK : SCEMA_ERR_INVALID;
+}
+
+int scema_tc_choose(uint64_t pairs, uint32_t k, const uint64_t counts[5], uint64_t sample, uint64_t mem_budget, int *choice,
+                    int *centred, uint64_t *est_survivors)
+{
+    if (!counts || !choice || !centred || !est_survivors || sample == 0 || k == 0) return SCEMA_ERR_INVALID;
+    tc_choose(pairs, k, counts, sample, mem_budget, tc_chunks_for(k) <= 10, choice, centred, est_survivors);
+    return SCEMA_OK;
+}
+
+int scema_tc_last_plan(scema_ctx *c, uint64_t plan[6])
+{
+    if (!c || !plan) return SCEMA_ERR_INVALID;
+    for (int i = 0; i < 5; i++) plan[i] = c->tc_plan_counts[i];
+    plan[5] = tc_plan_sample_size();
+    return SCEMA_OK;
+}
+
+int scema_tc_centre(scema_ctx *c, double *centre_host)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    if (!c->tc_valid || !centre_host) return fail(c, SCEMA_ERR_STATE, "tc_centre: no tensor-core operand copies");
+    SCEMA_CUDA(c, cudaMemcpyAsync(centre_host, c->d_tc_centre.p, (size_t)c->tc_K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SCEMA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SCEMA_OK;
 }
 
 int scema_tc_debug(scema_ctx *c, double threshold, uint32_t slices, float *acc_host, uint64_t ld, void *operand_a_host,

@@ -14,6 +14,10 @@
 namespace scema {
 
 constexpr int TILE = 128;         // rows per pair-matrix tile side (K2)
+// Measured rates on one B200 behind the up-front choice of the filter and the overflow
+// decisions: pairs per second of the one-slice / two-slice tcgen05 filter (one chunk of 64 columns), the DMMA filter
+// and the filter-free kernel at K = 60, survivors per second of the exact recompute.
+constexpr double RATE_TC1 = 1.4e13, RATE_TC2 = 4.6e12, RATE_DMMA = 2.9e11, RATE_EXACT = 7.0e10, RATE_QUEUE = 1.0e10;
 constexpr int PANEL_ROWBLOCKS = 16;  // row blocks per scheduling panel (L2 reuse of the B tiles)
 
 // Growable device buffer.
@@ -107,12 +111,13 @@ struct scema_ctx {
     int filter_variant = -1;
 
     // ---- K2 tensor-core filter (SCEMA_PAIRS_TC): fp16 split operands, A- and B-flavoured
-    scema::DevBuf d_tc_a, d_tc_b, d_tc_nrm, d_tc_misc;
+    scema::DevBuf d_tc_a, d_tc_b, d_tc_nrm, d_tc_misc, d_tc_centre;  // centre: [K] column means subtracted in the filter copies only
+    uint64_t tc_plan_counts[5] = {0, 0, 0, 0, 0};  // last survivor-density sample (of tc::PLAN_SAMPLE pairs): one / two slices centred, one / two slices raw, DMMA
     scema::DevBuf d_tc_perm, d_tc_iota, d_tc_snrm, d_tc_band;  // norm-band mode: permutation, sorted squared norms, band plan
     bool tc_band = false, tc_band_wanted = false, tc_band_allowed = false;
     uint64_t tc_for_version = 0, tc_n = 0;
     uint32_t tc_K = 0, tc_slices = 0;
-    uint32_t tc_mode = 0;  // slices the next compare starts with (auto: 1, falling back to 2 when survivors overflow)
+    uint32_t tc_mode = 0;  // 1: the filter was chosen automatically and compare_panels may change it on overflow; 0: SCEMA_TC_SLICES pins it
     double tc_thr = 0.0, tc_T0 = 0.0, tc_cguard = 0.0;
     bool tc_valid = false;
 
@@ -187,7 +192,12 @@ bool tc_two_slices_possible(const scema_ctx *ctx);
 bool tc_smem_plan(uint32_t nc, uint32_t slices, uint32_t cg, uint32_t *a_bytes, uint32_t *n_abuf, uint32_t *lg_nst,
                   uint32_t *stage_bytes, uint32_t *data_bytes);
 uint32_t tc_chunks_for(uint32_t K);
-int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices, bool want_band);
+int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices, bool want_band, uint64_t pairs, int *choice, uint64_t *est_survivors);
+void tc_choose(uint64_t pairs, uint32_t K, const uint64_t counts[5], uint64_t sample, uint64_t mem_budget, bool tc_ok, int *choice,
+               int *centred, uint64_t *est_survivors);
+int tc_centre_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1);
+int tc_plan_rows(scema_ctx *ctx, uint64_t r1, uint64_t counts[5]);
+uint32_t tc_plan_sample_size();
 int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices);
 int tc_stats_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1, bool into_scale);
 int tc_fix_scale(scema_ctx *ctx, int headroom);

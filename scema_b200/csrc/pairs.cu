@@ -915,6 +915,13 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
     int rc;
     ctx->n_edges = 0;
     ctx->edge_cur = 0;
+    // pairs this call evaluates: the rows of panels [p0, p1) against everything to their right, this shard's share
+    double pairs_call = 0.0;
+    {
+        const double panel_rows = (double)PANEL_ROWBLOCKS * TILE;
+        const double r0 = std::min<double>((double)n, p0 * panel_rows), r1 = std::min<double>((double)n, p1 * panel_rows);
+        pairs_call = ((r1 - r0) * (double)n - 0.5 * (r1 * r1 - r0 * r0)) / (double)n_shards;
+    }
     while (true) {
         passes++;
         if (passes > 8) return fail(ctx, SCEMA_ERR_NOMEM, "compare: buffers kept overflowing");
@@ -1002,31 +1009,42 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
         }
         SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         const uint64_t n_cand = ctx->h_counters[0], n_edge = ctx->h_counters[1];
-        if (*variant == SCEMA_PAIRS_TC && ctx->tc_slices == 1 && ctx->tc_mode == 1 && n_cand > ctx->cand_cap) {
-            // the one-slice guard band keeps too much of this data: filter with both slices before growing the queue
-            rc = tc_prepare(ctx, thr, 2, ctx->tc_band_wanted);
-            if (rc) return rc;
-            continue;
-        }
-        if (*variant == SCEMA_PAIRS_TC && ctx->tc_mode == 2 && n_cand > ctx->cand_cap) {
-            // wide rows have no two-slice kernel: the FP64 DMMA filter takes over (its guard band is 2^-40 of the norms)
-            *variant = SCEMA_PAIRS_DMMA;
-            rc = prepare_filter(ctx, SCEMA_PAIRS_DMMA);
-            if (rc) return rc;
-            SCEMA_CUDA(ctx, ctx->d_panel_start.reserve(sc.ps.size() * sizeof(uint64_t)));
-            SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_panel_start.p, sc.ps.data(), sc.ps.size() * sizeof(uint64_t),
-                                            cudaMemcpyHostToDevice, ctx->stream));
-            SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            continue;
-        }
         if (*variant != SCEMA_PAIRS_EXACT && n_cand > ctx->cand_cap) {
+            // The survivors did not fit (the up-front estimate of compare_begin was too low, or the filter was pinned).
+            // Cheapest way on, by the same cost model: repeat with a larger queue, with both fp16 slices, with the FP64
+            // DMMA filter, or without a filter. Filters split the pair matrix between shards differently, so a sharded
+            // compare never changes filter on its own (every shard would have to): it reports SCEMA_ERR_DENSE instead.
             SCEMA_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
             const uint64_t want = n_cand + n_cand / 4;
-            if (want * sizeof(uint64_t) > (free_b + ctx->d_cand.bytes) / 2) {
-                *variant = SCEMA_PAIRS_EXACT;  // survivors too dense for a queue: filter-free kernel
-            } else {
-                ctx->cand_cap = want;
+            const bool can_grow = want * sizeof(uint64_t) <= (free_b + ctx->d_cand.bytes) / 2;
+            const double kf = 60.0 / (double)std::max<uint32_t>(K, 1);
+            const double Pc = pairs_call, requeue = (double)n_cand / (RATE_QUEUE * kf);
+            if (*variant == SCEMA_PAIRS_TC) {
+                const uint32_t nc = tc_chunks_for(K);
+                if (ctx->tc_mode == 1 && ctx->tc_slices == 1 && nc == 1) {
+                    if (can_grow && requeue <= Pc * (1.0 / RATE_TC2 - 1.0 / RATE_TC1)) { ctx->cand_cap = want; continue; }
+                    rc = tc_prepare(ctx, thr, 2, ctx->tc_band_wanted, 0, nullptr, nullptr);  // same tiles, same shards
+                    if (rc) return rc;
+                    continue;
+                }
+                if (can_grow && (requeue <= Pc / (RATE_DMMA * kf) || ctx->tc_mode == 0)) { ctx->cand_cap = want; continue; }
+                if (n_shards > 1) {
+                    if (can_grow) { ctx->cand_cap = want; continue; }
+                    return fail(ctx, SCEMA_ERR_DENSE, "compare: survivors too dense for this shard's queue; repeat on every shard with SCEMA_PAIRS_DMMA");
+                }
+                *variant = SCEMA_PAIRS_DMMA;  // guard band 2^-40 of the norms instead of 2^-9 / 2^-13
+                rc = prepare_filter(ctx, SCEMA_PAIRS_DMMA);
+                if (rc) return rc;
+                SCEMA_CUDA(ctx, ctx->d_panel_start.reserve(sc.ps.size() * sizeof(uint64_t)));
+                SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_panel_start.p, sc.ps.data(), sc.ps.size() * sizeof(uint64_t),
+                                                cudaMemcpyHostToDevice, ctx->stream));
+                SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                continue;
             }
+            if (can_grow) { ctx->cand_cap = want; continue; }
+            if (n_shards > 1)
+                return fail(ctx, SCEMA_ERR_DENSE, "compare: survivors too dense for this shard's queue; repeat on every shard with SCEMA_PAIRS_EXACT");
+            *variant = SCEMA_PAIRS_EXACT;  // survivors too dense for a queue: filter-free kernel
             continue;
         }
         if (n_edge > ctx->edge_cap) {
@@ -1097,36 +1115,38 @@ static int compare_begin(scema_ctx *ctx, double thr, int &variant, uint32_t shar
     if (rc) return rc;
     make_schedule(ctx, n, sc);
     ctx->counters[4] = sc.tiles;
+    const uint64_t queue_floor = std::max<uint64_t>(1ull << 20, 32 * n);  // grows with the batch: a context that started small must not mistake a full queue for a wide guard band
+    if (variant != SCEMA_PAIRS_EXACT) t_begin(ctx, SCEMA_T_PREP);
     if (variant == SCEMA_PAIRS_TC) {
-        t_begin(ctx, SCEMA_T_PREP);
-        // Start with the hi slices alone unless the environment pins the choice or these very rows and
-        // threshold already needed both slices (compare_panels falls back when the survivors overflow).
+        // How many fp16 slices, or another filter altogether? Pinned by SCEMA_TC_SLICES=1|2, otherwise decided from a
+        // sample of the pairs (tc_prepare / tc_choose; the same rows and threshold keep their earlier decision):
+        // survivors of every option estimated in FP64 BEFORE the first launch, so the common case is one pass.
         static const char *sl_env = getenv("SCEMA_TC_SLICES");
         const int pin = sl_env ? atoi(sl_env) : 0;
-        uint32_t slices = pin == 2 ? 2u : 1u;
-        if (pin != 1 && pin != 2 && ctx->tc_valid && ctx->tc_for_version == ctx->spline_version && ctx->tc_thr == thr &&
-            ctx->tc_n == n && ctx->tc_K == ctx->K)
-            slices = ctx->tc_slices;
-        ctx->tc_mode = (pin == 1 || pin == 2) ? 0u : 1u;  // 1: may fall back to two slices
-        if (!tc_two_slices_possible(ctx)) { slices = 1; ctx->tc_mode = 2; }  // K > 60: hi slices only, falls back to the DMMA filter
+        uint32_t slices = (pin == 1 || pin == 2) ? (uint32_t)pin : 0u;
+        if (slices == 2 && !tc_two_slices_possible(ctx)) slices = 1;  // K > 60: hi slices only
+        ctx->tc_mode = slices ? 0u : 1u;                              // 1: automatic (compare_panels may change it on overflow)
         // SCEMA_NORM_BAND=1 (one-shot compares only): rows in norm order, tiles beyond the threshold's reach skipped
         const char *band_env = getenv("SCEMA_NORM_BAND");
         const bool want_band = ctx->tc_band_allowed && band_env && atoi(band_env) == 1;
-        rc = tc_prepare(ctx, thr, slices, want_band);
+        int choice = 1;
+        uint64_t est = 0;
+        rc = tc_prepare(ctx, thr, slices, want_band, n * (n - 1) / 2 / n_shards, &choice, &est);
         if (rc) return rc;
-        ctx->cand_cap = std::max<uint64_t>(ctx->cand_cap, std::max<uint64_t>(1ull << 20, 32 * n));  // grows with the batch: a context that started small must not mistake a full queue for a wide guard band
-        t_end(ctx, SCEMA_T_PREP);
-    } else if (variant != SCEMA_PAIRS_EXACT) {
-        t_begin(ctx, SCEMA_T_PREP);
+        if (choice == 0) variant = SCEMA_PAIRS_DMMA;
+        else if (choice < 0) variant = SCEMA_PAIRS_EXACT;
+        else ctx->cand_cap = std::max<uint64_t>(ctx->cand_cap, std::max<uint64_t>(queue_floor, est + est / 4));
+    }
+    if (variant == SCEMA_PAIRS_DMMA || variant == SCEMA_PAIRS_FMA) {
         rc = prepare_filter(ctx, variant);
         if (rc) return rc;
         SCEMA_CUDA(ctx, ctx->d_panel_start.reserve(sc.ps.size() * sizeof(uint64_t)));
         SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_panel_start.p, sc.ps.data(), sc.ps.size() * sizeof(uint64_t),
                                         cudaMemcpyHostToDevice, ctx->stream));
         SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // sc.ps may not outlive the copy otherwise
-        ctx->cand_cap = std::max<uint64_t>(ctx->cand_cap, std::max<uint64_t>(1ull << 20, 32 * n));  // grows with the batch: a context that started small must not mistake a full queue for a wide guard band
-        t_end(ctx, SCEMA_T_PREP);
+        ctx->cand_cap = std::max<uint64_t>(ctx->cand_cap, queue_floor);
     }
+    if (ctx->ev_used[SCEMA_T_PREP]) t_end(ctx, SCEMA_T_PREP);
     return SCEMA_OK;
 }
 
@@ -1258,8 +1278,24 @@ static int cluster_pipelined_impl(scema_ctx *ctx, const double *steps_host, uint
         if (rc) return rc;
         const uint64_t r0 = bounds[r], r1 = bounds[r + 1];
         const uint64_t r1p = r + 1 == n_ranges ? n_pad : r1;  // the last range also writes the padding rows
-        rc = tc_stats_rows(ctx, r0, r1, r == 0);
+        rc = r == 0 ? tc_centre_rows(ctx, r0, r1) : SCEMA_OK;  // centre and scale come from the first range
+        if (!rc) rc = tc_stats_rows(ctx, r0, r1, r == 0);
         if (!rc && r == 0) rc = tc_fix_scale(ctx, 6);
+        if (!rc && r == 0) {
+            // is the one-slice filter the right one for this data? (sample of the first range; the host waits for
+            // range 0 here, the later copies keep travelling) If not, the ordinary path decides with all rows in hand.
+            uint64_t counts[5];
+            rc = tc_plan_rows(ctx, r1, counts);
+            int choice = 1, centred = 1;
+            uint64_t est = 0;
+            if (!rc) {
+                size_t free_b = 0, total_b = 0;
+                SCEMA_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+                tc_choose(n * (n - 1) / 2, ctx->K, counts, tc_plan_sample_size(), (uint64_t)((free_b + ctx->d_cand.bytes) / 2), true, &choice,
+                          &centred, &est);
+                if (choice != 1 || !centred || est + est / 4 > ctx->cand_cap) { t_end(ctx, SCEMA_T_FILTER); return SCEMA_OK; }
+            }
+        }
         if (!rc) rc = tc_prep_rows(ctx, r0, r1p);
         if (!rc) rc = tc_launch(ctx, 0, (uint32_t)(r1p / 256), (uint32_t)(r0 / 256), (uint32_t)(r1p / 256), 0, 1, d_cnt + 0, nullptr, 0);
         if (rc) return rc;

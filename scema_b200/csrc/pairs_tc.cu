@@ -520,8 +520,52 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
 // operand preparation
 // ------------------------------------------------------------------------------------------------
 // pass 1: row norms (FP64) and the largest finite magnitude of the rows [r0, r1)
-__global__ void __launch_bounds__(256) k_tc_rowstats(const double *__restrict__ S, uint64_t r0, uint64_t r1, uint32_t K,
-                                                     double *__restrict__ NRM, unsigned long long *__restrict__ gmax)
+// ---- centre of the filter copies. d(a, b) = d(a - m, b - m) for ANY vector m, and the guard band of the filter scales
+// with |a - m|^2 + |b - m|^2: on production-shaped data (every quadrature point on nearly the same stretch path,
+// FE_problem.h:1091-1103; rows differ by ~1 % of their norm) the band of the un-centred rows keeps every pair, that of
+// the centred rows only real neighbours. m = column MEDIANS over a fixed sample of <= 4096 rows (non-finite entries
+// skipped): a mean is dragged away from the bulk by one row at 1e200 or by a minority cloud far from everybody else,
+// a median is not; and it is deterministic, so every rank of a sharded compare derives the same m from the same rows.
+// One block per column, bitonic sort in shared memory. The exact recompute never sees m: k_exact_queue reads the
+// original rows.
+constexpr uint32_t CENTRE_SAMPLE = 4096;
+__global__ void __launch_bounds__(256) k_tc_centre_median(const double *__restrict__ S, uint64_t r0, uint64_t r1, uint32_t K,
+                                                          double *__restrict__ centre)
+{
+    __shared__ double v[CENTRE_SAMPLE];
+    __shared__ unsigned int s_cnt;
+    const uint32_t k = blockIdx.x;
+    const uint64_t n = r1 - r0;
+    const uint64_t ns = n < CENTRE_SAMPLE ? n : CENTRE_SAMPLE;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    unsigned int mine = 0;
+    for (uint32_t j = threadIdx.x; j < CENTRE_SAMPLE; j += blockDim.x) {
+        double x = INFINITY;  // padding and non-finite entries sort to the end
+        if (j < ns) {
+            const double y = S[(r0 + j * (n / ns)) * K + k];
+            if (isfinite(y)) { x = y; mine++; }
+        }
+        v[j] = x;
+    }
+    atomicAdd(&s_cnt, mine);
+    __syncthreads();
+    for (uint32_t size = 2; size <= CENTRE_SAMPLE; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < CENTRE_SAMPLE / 2; t += blockDim.x) {
+                const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const double a = v[lo], b = v[hi];
+                if ((a > b) == up) { v[lo] = b; v[hi] = a; }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) centre[k] = s_cnt ? v[(s_cnt - 1) / 2] : 0.0;
+}
+
+__global__ void __launch_bounds__(256) k_tc_rowstats(const double *__restrict__ S, const double *__restrict__ centre, uint64_t r0,
+                                                     uint64_t r1, uint32_t K, double *__restrict__ NRM,
+                                                     unsigned long long *__restrict__ gmax)
 {
     __shared__ double s_max[8];
     const uint64_t row = r0 + (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -529,7 +573,7 @@ __global__ void __launch_bounds__(256) k_tc_rowstats(const double *__restrict__ 
     double nrm = 0.0, m = 0.0;
     if (row < r1)
         for (uint32_t k = lane; k < K; k += 32) {
-            const double v = S[row * K + k];
+            const double v = __dsub_rn(S[row * K + k], centre[k]);
             nrm = fma(v, v, nrm);
             m = fmax(m, fabs(v));
         }
@@ -553,7 +597,8 @@ __global__ void __launch_bounds__(256) k_tc_rowstats(const double *__restrict__ 
 }
 
 constexpr uint32_t HIST_BINS = 2112;   // exponent of a squared norm + 1075 (0: zero norm)
-constexpr uint32_t MISC_WORDS = 8 + HIST_BINS;
+constexpr uint32_t PLAN_WORD = 8 + HIST_BINS;  // five counters of the survivor-density sample behind the histogram
+constexpr uint32_t MISC_WORDS = 8 + HIST_BINS + 8;
 constexpr uint32_t MAX_OUTLIERS = 16;  // rows the scale may leave behind (they survive against everybody)
 
 // histogram of the exponents of the finite squared norms of rows [r0, r1) into misc[8 ..]
@@ -635,8 +680,8 @@ __device__ __forceinline__ double h16z(double v)
 __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, uint64_t n, uint64_t r0, uint64_t r1, uint32_t K,
                                                  uint32_t nc, uint32_t slices, double vmax, const double *__restrict__ NRM,
                                                  unsigned long long *__restrict__ misc, double T0, double cguard,
-                                                 const uint32_t *__restrict__ perm, unsigned char *__restrict__ HA,
-                                                 unsigned char *__restrict__ HB)
+                                                 const uint32_t *__restrict__ perm, const double *__restrict__ centre,
+                                                 unsigned char *__restrict__ HA, unsigned char *__restrict__ HB)
 {
     const uint64_t row = r0 + (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);  // position in the operand copies
     const int lane = threadIdx.x & 31;
@@ -653,7 +698,7 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
     bool big = false;
     if (data)
         for (uint32_t k = lane; k < K; k += 32) {
-            const double v = S[src * K + k] * s;
+            const double v = __dsub_rn(S[src * K + k], centre[k]) * s;
             nrm = fma(v, v, nrm);
             big |= fabs(v) >= vmax;
         }
@@ -686,7 +731,7 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
             const uint32_t k = lane + 32 * e;  // column 0..63 of the chunk
             const uint32_t kd = c * 64 + k;    // data column
             double v = 0.0;
-            if (data && !too_big && kd < K) v = S[src * K + kd] * s;
+            if (data && !too_big && kd < K) v = __dsub_rn(S[src * K + kd], centre[kd]) * s;
             const double hi = h16z(v);
             const double lo = h16z(v - hi);
             double ahi = hi, alo = lo, bhi = hi, blo = lo;
@@ -706,6 +751,55 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
             }
         }
     }
+}
+
+// ---- survivor-density estimate ---------------------------------------------------------------------
+// PLAN_SAMPLE pseudo-random pairs, one warp each, in FP64: would the pair survive the one-slice filter, the two-slice
+// filter — each with centred and with raw operand copies — and the FP64 DMMA filter? plan[0..4] receive the five
+// counts; the host turns them into survivor estimates and picks the variant BEFORE the first launch (tc_choose),
+// instead of finding out by overflowing the queue.
+// Criterion (DESIGN.md "K2-TC"): acc >= 0  <=>  d^2 <= c (|a'|^2 + |b'|^2) + T0 (1 + 4c) + 2 e0 / s^2, a' = a - m.
+constexpr uint32_t PLAN_SAMPLE = 8192;
+__device__ __forceinline__ uint64_t plan_mix(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) k_tc_plan_sample(const double *__restrict__ S, const double *__restrict__ NRM, uint64_t n,
+                                                        uint32_t K, double T0, unsigned long long *__restrict__ misc)
+{
+    const uint32_t t = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= PLAN_SAMPLE) return;
+    const uint64_t i = plan_mix(0x5ce3a0000ull + 2 * t) % n, j = plan_mix(0x5ce3a0001ull + 2 * t) % n;
+    if (i == j) return;
+    double d2 = 0.0, ua = 0.0, ub = 0.0;
+    for (uint32_t k = lane; k < K; k += 32) {
+        const double a = S[i * K + k], b = S[j * K + k];
+        const double d = a - b;
+        d2 = fma(d, d, d2);
+        ua = fma(a, a, ua);
+        ub = fma(b, b, ub);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        ua += __shfl_xor_sync(0xffffffffu, ua, o);
+        ub += __shfl_xor_sync(0xffffffffu, ub, o);
+    }
+    if (lane != 0) return;
+    const double s = __longlong_as_double((long long)misc[1]);
+    const double nn = NRM[i] + NRM[j];            // centred squared norms (raw ones: ua + ub)
+    const double e0 = 2.0 * (double)K * 0.0078125 / (s * s);
+    const double c1 = 0.001953125, c2 = 0.0001220703125;
+    unsigned long long *plan = misc + PLAN_WORD;
+    // anything non-finite survives every filter
+    if (!(d2 > c1 * nn + T0 * (1.0 + 4.0 * c1) + e0)) atomicAdd(plan + 0, 1ull);
+    if (!(d2 > c2 * nn + T0 * (1.0 + 4.0 * c2) + e0)) atomicAdd(plan + 1, 1ull);
+    if (!(d2 > c1 * (ua + ub) + T0 * (1.0 + 4.0 * c1) + e0)) atomicAdd(plan + 2, 1ull);
+    if (!(d2 > c2 * (ua + ub) + T0 * (1.0 + 4.0 * c2) + e0)) atomicAdd(plan + 3, 1ull);
+    if (!(d2 > T0 + (4.0 * K + 64.0) * 1.1102230246251565e-16 * 4.0 * (ua + ub))) atomicAdd(plan + 4, 1ull);
 }
 
 // ---- norm-band mode -------------------------------------------------------------------------------
@@ -810,6 +904,9 @@ int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices)
     SCEMA_CUDA(ctx, ctx->d_tc_nrm.reserve(n_pad * sizeof(double)));
     SCEMA_CUDA(ctx, ctx->d_tc_misc.reserve(tc::MISC_WORDS * sizeof(unsigned long long)));
     SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_tc_misc.p, 0, tc::MISC_WORDS * sizeof(unsigned long long), ctx->stream));
+    // centre vector [K]; all zero until tc_centre_rows has run
+    SCEMA_CUDA(ctx, ctx->d_tc_centre.reserve((size_t)std::max<uint32_t>(K, 1) * sizeof(double)));
+    SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_tc_centre.p, 0, (size_t)std::max<uint32_t>(K, 1) * sizeof(double), ctx->stream));
     const double eps = 1.1102230246251565e-16;  // 2^-53
     // The operands are rescaled, so the reference's underflow must be budgeted explicitly: each squared
     // difference of compare_L2_norm may lose up to half a subnormal ulp, i.e. the reference's sum can sit
@@ -819,7 +916,9 @@ int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices)
     //   two slices: 3.1 2^-22 (slicing) + 13 2^-18 (12 MMA steps, fp32 accumulate)          < 2^-14
     //   one slice : 2^-11 (dropping a_lo, b_lo) + (4 nc + 1) 2^-18 (4 steps per chunk, nc <= 10) + 2^-23 (two-slice fold)
     //               < 2^-10.6
-    // and the band must be twice that.
+    // and the band must be twice that. Centring (a' = fl(a - m), relative error 2^-53 per element) moves d^2 by at most
+    // 2 d 2^-53 (|a'| + |b'|) <= 2^-53 d^2 + 2^-52 (|a'|^2 + |b'|^2): the first term sits in the slack of T0 (the
+    // reference needs (K + 4) eps of its (2K + 16) eps), the second is 2^-39 of the band.
     ctx->tc_cguard = slices == 1 ? 0.001953125 : 0.0001220703125;  // 2^-9, 2^-13
     ctx->tc_thr = thr;
     ctx->tc_n = n;
@@ -829,11 +928,23 @@ int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices)
     return SCEMA_OK;
 }
 
+// Centre of the filter copies from a sample of the rows [r0, r1) (SCEMA_TC_CENTRE=0 leaves it at zero).
+int tc_centre_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1)
+{
+    static const char *env = getenv("SCEMA_TC_CENTRE");
+    if (r1 <= r0 || ctx->K == 0 || (env && atoi(env) == 0)) return SCEMA_OK;
+    tc::k_tc_centre_median<<<ctx->K, 256, 0, ctx->stream>>>(ctx->d_spline, r0, r1, ctx->K, ctx->d_tc_centre.as<double>());
+    ctx->launches++;
+    SCEMA_CUDA(ctx, cudaGetLastError());
+    return SCEMA_OK;
+}
+
 int tc_stats_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1, bool into_scale)
 {
     if (r1 <= r0) return SCEMA_OK;
     tc::k_tc_rowstats<<<(unsigned)((r1 - r0 + 7) / 8), 256, 0, ctx->stream>>>(
-        ctx->d_spline, r0, r1, ctx->K, ctx->d_tc_nrm.as<double>(), into_scale ? ctx->d_tc_misc.as<unsigned long long>() : nullptr);
+        ctx->d_spline, ctx->d_tc_centre.as<double>(), r0, r1, ctx->K, ctx->d_tc_nrm.as<double>(),
+        into_scale ? ctx->d_tc_misc.as<unsigned long long>() : nullptr);
     ctx->launches++;
     if (into_scale) {
         const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count * 4, (r1 - r0 + 255) / 256);
@@ -859,32 +970,105 @@ int tc_prep_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1)
         ctx->d_spline, ctx->n, r0, r1, ctx->K, tc_chunks(ctx->K), ctx->tc_slices, ldexp(1.0, 12 - tc_k_headroom(ctx->K)),
         ctx->d_tc_nrm.as<double>(),
         ctx->d_tc_misc.as<unsigned long long>(), ctx->tc_T0, ctx->tc_cguard, ctx->tc_band ? ctx->d_tc_perm.as<uint32_t>() : nullptr,
-        ctx->d_tc_a.as<unsigned char>(), ctx->d_tc_b.as<unsigned char>());
+        ctx->d_tc_centre.as<double>(), ctx->d_tc_a.as<unsigned char>(), ctx->d_tc_b.as<unsigned char>());
     ctx->launches++;
     SCEMA_CUDA(ctx, cudaGetLastError());
     return SCEMA_OK;
 }
 
-// Builds (or reuses) the fp16 operand copies for the current spline matrix and threshold. want_band: sort the rows by
-// norm first (operand copies in sorted order, ctx->d_tc_perm maps a position back to its row) so that the launch can
-// restrict itself to the band of tiles the triangle inequality cannot rule out; refused (dense order instead) when a
-// row has a non-finite norm or the rows are wider than one chunk.
-int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices, bool want_band)
+// Which filter should evaluate `pairs` pairs of rows of K columns, given how many of `sample` random pairs would survive
+// the one-slice / two-slice tcgen05 filter with centred copies (counts[0], [1]), with raw copies (counts[2], [3]) and the
+// DMMA filter (counts[4])? Cost model in seconds on one B200 (measured rates): filter time + exact
+// recompute of the estimated survivors; a queue that would not fit `mem_budget` bytes rules an option out; raw copies
+// must beat the centred ones by 20 % to be taken. Fewer than four hits in the sample are noise as far as SIZING a queue
+// goes (one hit in 8192 stands for 6e7 survivors at 1M rows). Pure host logic (scema_tc_choose: CPU tests).
+//   -> choice: 1 / 2 = tcgen05 with that many slices, 0 = SCEMA_PAIRS_DMMA, -1 = SCEMA_PAIRS_EXACT; centred: which copies;
+//      est_survivors: queue entries to expect for the choice.
+void tc_choose(uint64_t pairs, uint32_t K, const uint64_t counts[5], uint64_t sample, uint64_t mem_budget, bool tc_ok,
+               int *choice, int *centred, uint64_t *est_survivors)
+{
+    const uint32_t nc = tc_chunks(K);
+    const double P = (double)pairs, kf = 60.0 / (double)std::max<uint32_t>(K, 1);
+    const double R1 = RATE_TC1 / nc, R2 = RATE_TC2, RD = RATE_DMMA * kf, RE = RATE_EXACT * kf, RQ = RATE_QUEUE * kf;
+    double best = P / RE;
+    *choice = -1;
+    *centred = 1;
+    *est_survivors = 0;
+    auto consider = [&](int ch, int cen, double rate, uint64_t count) {
+        const double surv = (double)count / (double)sample * P;
+        const double sized = count >= 4 ? surv : 0.0;
+        if (sized * 8.0 > (double)mem_budget) return;
+        const double t = (P / rate + surv / RQ) * (cen || ch == 0 ? 1.0 : 1.25);
+        if (t < best) { best = t; *choice = ch; *centred = cen; *est_survivors = (uint64_t)sized; }
+    };
+    consider(0, 1, RD, counts[4]);
+    if (tc_ok && nc == 1) consider(2, 0, R2, counts[3]);
+    if (tc_ok) consider(1, 0, R1, counts[2]);
+    if (tc_ok && nc == 1) consider(2, 1, R2, counts[1]);
+    if (tc_ok) consider(1, 1, R1, counts[0]);
+}
+
+// Builds (or reuses) the fp16 operand copies for the current spline matrix and threshold.
+// slices: 1 or 2 pins the number of fp16 slices; 0 = decide from a sample of the pairs (k_tc_plan_sample, tc_choose):
+// *choice then returns what was decided (1 / 2 slices, 0: the caller should take SCEMA_PAIRS_DMMA, -1: SCEMA_PAIRS_EXACT —
+// no operand copies are built in those two cases) and *est_survivors the estimate behind it. `pairs` = pairs this
+// context will evaluate (its shard). want_band: sort the rows by norm first (operand copies in sorted order,
+// ctx->d_tc_perm maps a position back to its row) so that the launch can restrict itself to the band of tiles the
+// triangle inequality cannot rule out; refused (dense order instead) when a row has a non-finite norm or the rows
+// are wider than one chunk.
+int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices, bool want_band, uint64_t pairs, int *choice, uint64_t *est_survivors)
 {
     const uint64_t n = ctx->n;
     const uint64_t n_pad = (n + tc::COLT - 1) / tc::COLT * tc::COLT;
+    if (choice) *choice = (int)slices;
+    if (est_survivors) *est_survivors = 0;
     if (ctx->tc_for_version == ctx->spline_version && ctx->tc_thr == thr && ctx->tc_n == n && ctx->tc_K == ctx->K &&
-        ctx->tc_slices == slices && ctx->tc_valid && ctx->tc_band_wanted == want_band)
+        (slices == 0 || ctx->tc_slices == slices) && ctx->tc_valid && ctx->tc_band_wanted == want_band) {
+        if (choice) *choice = (int)ctx->tc_slices;   // the same rows and threshold: the earlier decision stands
         return SCEMA_OK;
-    int rc = tc_prepare_begin(ctx, thr, slices);
+    }
+    const bool two_ok = tc_two_slices_possible(ctx);
+    int rc = tc_prepare_begin(ctx, thr, slices ? slices : 1);
     ctx->tc_band = false;
     ctx->tc_band_wanted = want_band;
+    if (!rc) rc = tc_centre_rows(ctx, 0, n);
     if (!rc) rc = tc_stats_rows(ctx, 0, n, true);
+    if (!rc) rc = tc_fix_scale(ctx, 0);
     if (rc) return rc;
+    unsigned long long misc[8] = {};
+    bool have_misc = false;
+    if (slices == 0 && n >= 2) {
+        uint64_t counts[5];
+        rc = tc_plan_rows(ctx, n, counts);
+        if (rc) return rc;
+        size_t free_b = 0, total_b = 0;
+        SCEMA_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+        int ch = 1, centred = 1;
+        uint64_t est = 0;
+        tc_choose(pairs, ctx->K, counts, tc::PLAN_SAMPLE, (uint64_t)((free_b + ctx->d_cand.bytes) / 2), true, &ch, &centred, &est);
+        if (ch == 2 && !two_ok) ch = 1;
+        if (choice) *choice = ch;
+        if (est_survivors) *est_survivors = est;
+        if (ch <= 0) return SCEMA_OK;  // the caller takes the DMMA / the filter-free kernel
+        slices = (uint32_t)ch;
+        ctx->tc_slices = slices;
+        ctx->tc_cguard = slices == 1 ? 0.001953125 : 0.0001220703125;
+        if (!centred) {
+            // the raw rows filter better than the centred ones (a centre far from most rows): statistics and scale again
+            SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_tc_centre.p, 0, (size_t)ctx->K * sizeof(double), ctx->stream));
+            SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_tc_misc.p, 0, tc::MISC_WORDS * sizeof(unsigned long long), ctx->stream));
+            rc = tc_stats_rows(ctx, 0, n, true);
+            if (!rc) rc = tc_fix_scale(ctx, 0);
+            if (rc) return rc;
+        }
+    } else if (slices == 0) {
+        slices = 1;
+    }
     if (want_band && tc_chunks(ctx->K) == 1) {
-        unsigned long long misc[8];
-        SCEMA_CUDA(ctx, cudaMemcpyAsync(misc, ctx->d_tc_misc.p, sizeof(misc), cudaMemcpyDeviceToHost, ctx->stream));
-        SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!have_misc) {
+            SCEMA_CUDA(ctx, cudaMemcpyAsync(misc, ctx->d_tc_misc.p, sizeof(misc), cudaMemcpyDeviceToHost, ctx->stream));
+            SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
         if (misc[4] == 0) {
             // ascending squared norms (non-negative doubles order as unsigned integers) and the permutation
             SCEMA_CUDA(ctx, ctx->d_tc_perm.reserve(n_pad * sizeof(uint32_t)));
@@ -903,12 +1087,30 @@ int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices, bool want_band)
             ctx->tc_band = true;
         }
     }
-    rc = tc_fix_scale(ctx, 0);
-    if (!rc) rc = tc_prep_rows(ctx, 0, n_pad);
+    rc = tc_prep_rows(ctx, 0, n_pad);
     if (rc) return rc;
     ctx->tc_valid = true;
     return SCEMA_OK;
 }
+
+// Survivor-density sample over the rows [0, r1) (all rows; host-buffer pipeline: the first range, after its statistics
+// and scale). counts = pairs of tc::PLAN_SAMPLE that would survive one slice / two slices with centred copies, the same
+// with raw copies, the DMMA filter. One host synchronisation.
+int tc_plan_rows(scema_ctx *ctx, uint64_t r1, uint64_t counts[5])
+{
+    for (int i = 0; i < 5; i++) counts[i] = 0;
+    if (r1 < 2) return SCEMA_OK;
+    unsigned long long *d_plan = ctx->d_tc_misc.as<unsigned long long>() + tc::PLAN_WORD, plan[8];
+    SCEMA_CUDA(ctx, cudaMemsetAsync(d_plan, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    tc::k_tc_plan_sample<<<tc::PLAN_SAMPLE / 8, 256, 0, ctx->stream>>>(ctx->d_spline, ctx->d_tc_nrm.as<double>(), r1, ctx->K, ctx->tc_T0,
+                                                                     ctx->d_tc_misc.as<unsigned long long>());
+    ctx->launches++;
+    SCEMA_CUDA(ctx, cudaMemcpyAsync(plan, d_plan, sizeof(plan), cudaMemcpyDeviceToHost, ctx->stream));
+    SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 5; i++) ctx->tc_plan_counts[i] = counts[i] = plan[i];
+    return SCEMA_OK;
+}
+uint32_t tc_plan_sample_size() { return tc::PLAN_SAMPLE; }
 
 template <int CG, bool DBG, bool WIDE, bool BAND>
 static int tc_launch_t(scema_ctx *ctx, const tc::Args &a, uint64_t items)
@@ -996,10 +1198,11 @@ int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t C0, uint32_t C1
     a.band_item_start = a.band_jend = a.perm = nullptr;
     a.band_row_tiles = 0;
     static const char *cg_env = getenv("SCEMA_TC_CG");
-    // cta_group::2 pairs halve the B traffic and the shared-memory reads per SM, but neither bounds this kernel
-    // (the TMEM read-out resp. the tensor pipe do) and the pair pays a forwarder hop per stage: measured 61.0 ms
-    // against 56.4 ms for one CTA per tile at 1M histories, so single CTAs are the default.
-    const int cg = cg_env && atoi(cg_env) == 2 ? 2 : 1;
+    // cta_group::2 pairs (the default): each SM of a pair fetches half of every B tile, which halves the L2 -> SM traffic
+    // and the shared-memory reads per SM. With the issue loops out of the way (round 2) the single-CTA kernel sits on
+    // the L2 -> SM rate for wide rows (config-5 shape 14.6 vs 13.6 ms) and draws more power for the same work at
+    // config 4 (37.0 vs 36.7 ms, both power-capped); SCEMA_TC_CG=1 selects it.
+    const int cg = cg_env && atoi(cg_env) == 1 ? 1 : 2;
     // strips: long enough to amortise the A tile, short enough to leave every cluster many items
     const uint64_t rows = a.I1 > a.I0 ? a.I1 - a.I0 : 0;
     const uint64_t cols = a.C1 > a.C0 ? a.C1 - a.C0 : 0;
@@ -1049,7 +1252,7 @@ int tc_debug_run(scema_ctx *ctx, double thr, uint32_t slices, float *acc_host, u
     const uint64_t n_pad = (ctx->n + tc::COLT - 1) / tc::COLT * tc::COLT;
     if (ld < n_pad) return fail(ctx, SCEMA_ERR_INVALID, "tc_debug: ld < padded n");
     if (n_pad > 8192) return fail(ctx, SCEMA_ERR_INVALID, "tc_debug: at most 8192 rows");
-    int rc = tc_prepare(ctx, thr, slices, false);
+    int rc = tc_prepare(ctx, thr, slices, false, 0, nullptr, nullptr);
     if (rc) return rc;
     SCEMA_CUDA(ctx, ctx->d_counters.reserve(8 * sizeof(uint64_t)));
     SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, 8 * sizeof(uint64_t), ctx->stream));

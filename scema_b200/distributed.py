@@ -49,15 +49,16 @@ def gather_rows(local_rows, n, world, group=None):
     return torch.cat([buf[r * h_max: r * h_max + (e - b)] for r, (b, e) in enumerate(bounds)], dim=0)
 
 
-def gather_counts(local_count, device, group=None):
-    """All-gather of the per-rank edge counts -> (counts list, exclusive offsets list)."""
+def gather_counts(local_count, device, group=None, flag=0):
+    """All-gather of the per-rank (edge count, flag) pairs -> (counts list, exclusive offsets list, max flag)."""
     world = dist.get_world_size(group)
-    mine = torch.tensor([int(local_count)], dtype=torch.int64, device=device)
-    allc = torch.empty(world, dtype=torch.int64, device=device)
+    mine = torch.tensor([int(local_count), int(flag)], dtype=torch.int64, device=device)
+    allc = torch.empty(2 * world, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(allc, mine, group=group)
-    counts = allc.cpu().tolist()
+    both = allc.cpu().view(world, 2)
+    counts = both[:, 0].tolist()
     offs = np.concatenate([[0], np.cumsum(counts)[:-1]]).tolist()
-    return counts, offs
+    return counts, offs, int(both[:, 1].max())
 
 
 class ShardedCluster:
@@ -94,9 +95,33 @@ class ShardedCluster:
             ev1.record()
             self.gather_events = (ev0, ev1)  # ev0.elapsed_time(ev1) after a synchronize = the all-gather alone
             hc.set_spline(device_ptr=full.data_ptr(), n=n, k=K)
-            if sink is not None:
-                ne = hc.compare_stream(threshold, sink, variant, shard=self.rank, n_shards=self.world)
-            else:
-                ne = hc.compare(threshold, variant, shard=self.rank, n_shards=self.world)
-            counts, offs = gather_counts(ne, full.device, self.group)
+            ne, counts, offs = self.compare_all_ranks(threshold, variant, sink, full.device)
         return ne, counts, offs, full
+
+    def compare_all_ranks(self, threshold, variant, sink, device):
+        """This rank's share of the pair matrix, then ONE all-gather of (edge count, flag) per rank. The filters split
+        the matrix between the shards differently, so a shard whose survivors are too dense for its queue does not
+        change filter by itself (SCEMA_ERR_DENSE): it raises the flag and ALL ranks repeat with the next filter —
+        tcgen05 -> DMMA -> filter-free kernel. -> (local edge count, counts, offsets)."""
+        from .binding import ScemaError, PAIRS_DMMA, PAIRS_EXACT, PAIRS_TC, PAIRS_FMA
+        ERR_DENSE = 7
+        hc = self.hc
+        chain = {PAIRS_TC: PAIRS_DMMA, PAIRS_DMMA: PAIRS_EXACT, PAIRS_FMA: PAIRS_EXACT}
+        self.variant_used = variant
+        while True:
+            dense, ne = 0, 0
+            try:
+                if sink is not None:
+                    ne = hc.compare_stream(threshold, sink, self.variant_used, shard=self.rank, n_shards=self.world)
+                else:
+                    ne = hc.compare(threshold, self.variant_used, shard=self.rank, n_shards=self.world)
+            except ScemaError as e:
+                if e.code != ERR_DENSE or self.variant_used not in chain:
+                    raise
+                dense = 1
+            counts, offs, any_dense = gather_counts(ne, device, self.group, flag=dense)
+            if not any_dense:
+                return ne, counts, offs
+            if sink is not None:
+                raise ScemaError(ERR_DENSE, "a streamed shard ran out of queue after chunks had been delivered; rerun with variant DMMA")
+            self.variant_used = chain[self.variant_used]

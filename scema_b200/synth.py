@@ -47,7 +47,25 @@ def _value(seed, i, q, c, t, amp, pert):
     return centre + delta * t
 
 
-def histories(seed, n, cluster_size, amp, pert, off, first=0):
+def _value_smooth(seed, i, q, c, t, amp, pert, spread):
+    """model 1 of include/scema_synth.h (dogbone emulation), operation for operation as synth_value_smooth."""
+    dq = spread * (2.0 * u01(hash4(seed, q, 0, 11)) - 1.0)
+    zz = (amp * t) * (1.0 + dq)
+    if c == 2:
+        centre = zz
+    elif c < 2:
+        centre = -0.3 * zz
+    else:
+        centre = zz * (0.01 * (2.0 * u01(hash4(seed, q, c, 12)) - 1.0))
+    delta = pert * (2.0 * u01(hash4(seed, i, c, 3)) - 1.0)
+    return centre + delta * t
+
+
+def _any(model, spread, seed, i, q, c, t, amp, pert):
+    return _value_smooth(seed, i, q, c, t, amp, pert, spread) if model == 1 else _value(seed, i, q, c, t, amp, pert)
+
+
+def histories(seed, n, cluster_size, amp, pert, off, first=0, model=0, spread=0.0):
     """-> steps [off[n], 6] float64 for the given (shard-relative) offsets."""
     off = np.asarray(off, dtype=np.uint64)
     lens = (off[1:] - off[:-1]).astype(np.int64)
@@ -59,11 +77,11 @@ def histories(seed, n, cluster_size, amp, pert, off, first=0):
     q = i // np.uint64(cluster_size)
     out = np.empty((total, 6), dtype=np.float64)
     for c in range(6):
-        out[:, c] = _value(seed, i, q, c, t, amp, pert)
+        out[:, c] = _any(model, spread, seed, i, q, c, t, amp, pert)
     return out
 
 
-def rows(seed, n, cluster_size, spline_points, amp, pert, first=0):
+def rows(seed, n, cluster_size, spline_points, amp, pert, first=0, model=0, spread=0.0):
     """-> already-resampled rows [n, 6*P] in the reference's p*6+c order."""
     P = spline_points
     i = (np.arange(n, dtype=np.uint64) + np.uint64(first))[:, None]
@@ -71,7 +89,7 @@ def rows(seed, n, cluster_size, spline_points, amp, pert, first=0):
     t = (np.arange(P, dtype=np.float64) / float(P - 1))[None, :]
     out = np.empty((n, P, 6), dtype=np.float64)
     for c in range(6):
-        out[:, :, c] = _value(seed, i, q, c, t, amp, pert)
+        out[:, :, c] = _any(model, spread, seed, i, q, c, t, amp, pert)
     return out.reshape(n, 6 * P)
 
 
@@ -93,26 +111,26 @@ def device_offsets(seed, n, cluster_size, len_min, len_max, first=0):
     return off
 
 
-def device_histories(seed, n, cluster_size, amp, pert, off, first=0, device="cuda"):
+def device_histories(seed, n, cluster_size, amp, pert, off, first=0, device="cuda", model=0, spread=0.0):
     """-> torch float64 tensor [off[n], 6] generated on the device (bit-identical to histories())."""
     import torch
     from . import binding
     d_off = torch.from_numpy(off.astype(np.int64)).to(device)
     steps = torch.empty((int(off[-1]), 6), dtype=torch.float64, device=device)
-    rc = binding.lib().scema_synth_histories_device(seed, first, n, cluster_size, amp, pert, d_off.data_ptr(),
-                                                    steps.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    rc = binding.lib().scema_synth_histories_model_device(model, spread, seed, first, n, cluster_size, amp, pert, d_off.data_ptr(),
+                                                          steps.data_ptr(), torch.cuda.current_stream().cuda_stream)
     if rc:
         raise binding.ScemaError(rc, "synth_histories_device")
     torch.cuda.current_stream().synchronize()
     return steps
 
 
-def device_rows(seed, n, cluster_size, spline_points, amp, pert, first=0, device="cuda"):
+def device_rows(seed, n, cluster_size, spline_points, amp, pert, first=0, device="cuda", model=0, spread=0.0):
     import torch
     from . import binding
     rows_t = torch.empty((n, 6 * spline_points), dtype=torch.float64, device=device)
-    rc = binding.lib().scema_synth_rows_device(seed, first, n, cluster_size, spline_points, amp, pert,
-                                               rows_t.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    rc = binding.lib().scema_synth_rows_model_device(model, spread, seed, first, n, cluster_size, spline_points, amp, pert,
+                                                     rows_t.data_ptr(), torch.cuda.current_stream().cuda_stream)
     if rc:
         raise binding.ScemaError(rc, "synth_rows_device")
     torch.cuda.current_stream().synchronize()

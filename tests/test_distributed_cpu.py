@@ -29,9 +29,29 @@ def _worker(rank, world, port, n, k, out_dir):
         b, e = shard_bounds(n, world)[rank]
         full = gather_rows(full_ref[b:e].clone(), n, world)
         assert torch.equal(full, full_ref)
-        counts, offs = gather_counts(10 * rank + 3, torch.device("cpu"))
+        counts, offs, flag = gather_counts(10 * rank + 3, torch.device("cpu"), flag=int(rank == world - 1))
         assert counts == [10 * r + 3 for r in range(world)]
         assert offs == [sum(counts[:r]) for r in range(world)]
+        assert flag == 1 and gather_counts(1, torch.device("cpu"))[2] == 0
+        # one shard reports "survivors too dense" (SCEMA_ERR_DENSE) for the tcgen05 filter: every rank repeats with the
+        # DMMA filter, and, when that is too dense on another rank, with the filter-free kernel
+        from scema_b200.binding import ScemaError
+        from scema_b200.distributed import ShardedCluster
+
+        class FakeContext:
+            calls = []
+
+            def compare(self, thr, variant, shard=0, n_shards=1):
+                self.calls.append(variant)
+                if (variant == 3 and shard == 1) or (variant == 0 and shard == 0):
+                    raise ScemaError(7, "dense")
+                return 100 * variant + shard
+
+        fake = FakeContext()
+        sc = ShardedCluster(fake)
+        ne, counts, offs = sc.compare_all_ranks(1e-6, 3, None, torch.device("cpu"))
+        assert fake.calls == [3, 0, 2] and sc.variant_used == 2
+        assert ne == 200 + rank and counts == [200 + r for r in range(world)]
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

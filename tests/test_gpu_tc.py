@@ -61,6 +61,7 @@ def test_tc_accumulators_match_sliced_fp64(hc, name, rows, thr, slices):
     operand copies, within a quarter of the error the guard band budgets for; the operand copies
     reproduce s*a to 2^-22 and fold -h_i-h_j as documented; and no true edge has a negative accumulator."""
     n, K = rows.shape
+    rows0 = rows
     hc.set_spline(rows)
     acc, ha, hb = hc.tc_debug(thr, n, slices)
     n_pad = acc.shape[0]
@@ -80,7 +81,11 @@ def test_tc_accumulators_match_sliced_fp64(hc, name, rows, thr, slices):
     err = np.abs(acc.astype(np.float64) - want)
     budget = (steps + 1) * 2.0 ** -18 * absum
     assert np.all(err[must] <= 0.25 * budget[must] + 1e-30), float(np.max(err[must] / np.maximum(budget[must], 1e-300)))
-    # data columns: hi + lo == s * a to 2^-22 relative (+ the fp16 subnormal floor), same in both copies
+    # data columns: hi + lo == s * (a - m) to 2^-22 relative (+ the fp16 subnormal floor), same in both copies;
+    # m = the column means of the (sampled) rows
+    m = hc.tc_centre()
+    assert m.shape == (K,) and np.array_equal(m, np.sort(rows, axis=0)[(n - 1) // 2])   # all n <= 4096 rows are sampled
+    rows = rows - m[None, :]
     finite = np.isfinite((rows ** 2).sum(1))
     M = np.abs(rows[finite]).max()
     s = 2.0 ** (11 - int(np.floor(np.log2(M))))
@@ -119,32 +124,96 @@ def test_tc_accumulators_match_sliced_fp64(hc, name, rows, thr, slices):
     assert np.all(ahi[n:, 60] == -65504.0)  # padding rows can never survive
     # soundness on this data: every true edge (FP64 direct differences) has a non-negative accumulator
     for r0 in range(0, n, 64):
-        d2 = ((rows[r0:r0 + 64, None, :] - rows[None, :, :]) ** 2).sum(-1)
+        d2 = ((rows0[r0:r0 + 64, None, :] - rows0[None, :, :]) ** 2).sum(-1)
         edge = (np.sqrt(d2) < thr) & (np.arange(r0, min(r0 + 64, n))[:, None] < np.arange(n)[None, :])
         a_blk = acc[r0:r0 + 64, :n][: edge.shape[0]]
         assert not np.any(edge & (np.signbit(a_blk))), "a true edge was rejected by the filter"
 
 
-def test_tc_falls_back_to_two_slices_when_one_slice_keeps_too_much():
-    """A cloud whose pairwise distances are ~3 % of the norms sits inside the one-slice guard band (6 %) but
-    outside the two-slice band (1.6 %): the survivors overflow the queue and the compare repeats with both slices."""
-    from oracle.pyoracle import Oracle
-    rng = np.random.default_rng(2)
-    n = 2600
+def two_blobs(n, spread, seed=2):
+    """Two tight blobs at +-base (so the mean is ~0 and centring changes nothing): pairs inside a blob lie `spread`
+    of the norm apart, i.e. inside a guard band wider than that and outside a narrower one."""
+    rng = np.random.default_rng(seed)
     base = 5e-3 * rng.standard_normal(60)
-    rows = base[None, :] * (1 + 0.03 / np.sqrt(2) * rng.standard_normal((n, 60)))
-    rows[::50] = rows[1::50][: len(rows[::50])] + 1e-8 * rng.standard_normal((len(rows[::50]), 60))  # a few true edges
-    want = Oracle().all_pairs(rows, THR)
-    h = scema_b200.HistCluster(0)  # fresh context: default queue capacity
+    rows = base[None, :] * (1 + spread / np.sqrt(2) * rng.standard_normal((n, 60)))
+    rows[1::2] *= -1.0
+    rows[::50] = rows[2::50][: len(rows[::50])] + 1e-8 * rng.standard_normal((len(rows[::50]), 60))  # a few true edges
+    return rows
+
+
+def test_tc_filter_is_chosen_up_front_from_a_sample():
+    """The survivor-density sample decides BEFORE the first launch (one pass, no overflow-and-retry): blobs 3 % of
+    their norm wide sit inside the one-slice band (6 %) and outside the two-slice band (1.6 %) -> two slices;
+    blobs 0.1 % wide defeat both -> the FP64 DMMA filter; clustered rows -> one slice. Same edge list every time."""
+    from oracle.pyoracle import Oracle
+    o = Oracle()
+    n = 2600
+    for name, rows, slices_want in (("3pct", two_blobs(n, 0.03), 2), ("0.1pct", two_blobs(n, 0.001), 0),
+                                    ("clusters", synth.rows(3, n, 16, 10, 5e-3, synth.default_pert(THR, 10)), 1)):
+        want = o.all_pairs(rows, THR)
+        h = scema_b200.HistCluster(0)  # fresh context: default queue capacity
+        h.set_spline(rows)
+        assert h.compare(THR, PAIRS_TC) == len(want[0]), name
+        assert edges_equal(h.get_edges(), want), name
+        c, plan = h.counters(), h.tc_last_plan()
+        assert c["tc_slices"] == slices_want and c["passes"] == 1 and len(want[0]) >= 40, (name, c, plan)
+        assert plan["sample"] == 8192
+        if name == "3pct":
+            assert plan["one_slice"] > 3000 and plan["two_slices"] < 300 and c["survivors"] < n * 40, plan
+            # the same rows and threshold again keep the decision without sampling again
+            assert h.compare(THR, PAIRS_TC) == len(want[0]) and h.counters()["passes"] == 1 and h.counters()["tc_slices"] == 2
+        if name == "0.1pct":
+            assert plan["two_slices"] > 3000 and plan["two_slices_raw"] > 3000 and plan["dmma"] < 50, plan
+        h.close()
+
+
+def test_tc_production_shaped_rows_keep_the_one_slice_filter(oracle):
+    """SURVEY 8d C1 / FE_problem.h:1091-1103: every quadrature point follows nearly the same stretch path (model 1 of
+    the generator: groups 0.5 % of the norm apart). The guard band of the raw rows would keep every pair; the centred
+    filter copies keep only group mates. Edge list identical to the oracle, one pass, one slice; with the centring
+    switched off (SCEMA_TC_CENTRE=0 in a child process) the sample sends the same rows to the DMMA filter."""
+    n, P = 20000, 10
+    rows = synth.rows(7, n, 16, P, 2e-2, synth.default_pert(THR, P), model=1, spread=5e-3)
+    nrm = np.linalg.norm(rows, axis=1)
+    assert nrm.min() > 0.9 * nrm.max()                       # all on the same path
+    want = oracle.all_pairs(rows, THR)
+    h = scema_b200.HistCluster(0)
     h.set_spline(rows)
-    assert h.compare(THR, PAIRS_TC) == len(want[0])
+    assert h.compare(THR, PAIRS_TC) == len(want[0]) and len(want[0]) > n
     assert edges_equal(h.get_edges(), want)
     c = h.counters()
-    assert c["tc_slices"] == 2 and c["passes"] >= 2 and len(want[0]) >= 40
-    assert c["survivors"] < n * 8
-    # the same rows and threshold again start with both slices straight away
-    assert h.compare(THR, PAIRS_TC) == len(want[0]) and h.counters()["passes"] == 1
+    assert c["tc_slices"] == 1 and c["passes"] == 1 and c["survivors"] < 40 * n, c
     h.close()
+    code = (
+        "import numpy as np, scema_b200\n"
+        "from scema_b200 import synth, PAIRS_TC, PAIRS_EXACT\n"
+        "rows = synth.rows(7, 6000, 16, 10, 2e-2, synth.default_pert(1e-6, 10), model=1, spread=5e-3)\n"
+        "hc = scema_b200.HistCluster(0); hc.set_spline(rows)\n"
+        "n1 = hc.compare(1e-6, PAIRS_TC); e1 = hc.get_edges(); c = hc.counters(); plan = hc.tc_last_plan()\n"
+        "assert c['tc_slices'] == 0 and c['passes'] == 1 and plan['one_slice'] > 8000 and plan['one_slice_raw'] > 8000 and plan['dmma'] < 50, (c, plan)\n"
+        "n2 = hc.compare(1e-6, PAIRS_EXACT); e2 = hc.get_edges()\n"
+        "assert n1 == n2 and all(np.array_equal(x.view(np.uint64) if x.dtype == np.float64 else x, y.view(np.uint64) if y.dtype == np.float64 else y) for x, y in zip(e1, e2))\n"
+        "print('ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SCEMA_TC_CENTRE="0", PYTHONPATH=ROOT), capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.stdout, r.stderr)
+
+
+def test_tc_pinned_one_slice_grows_the_queue():
+    """SCEMA_TC_SLICES=1 pins the hi-slice filter: survivors that overflow the queue make it grow (second pass), the
+    edge list stays the oracle's."""
+    code = (
+        "import numpy as np, scema_b200, sys, importlib.util\n"
+        "spec = importlib.util.spec_from_file_location('t', %r); t = importlib.util.module_from_spec(spec); spec.loader.exec_module(t)\n"
+        "from oracle.pyoracle import Oracle\n"
+        "rows = t.two_blobs(2600, 0.03); want = Oracle().all_pairs(rows, 1e-6)\n"
+        "h = scema_b200.HistCluster(0); h.set_spline(rows)\n"
+        "assert h.compare(1e-6, scema_b200.PAIRS_TC) == len(want[0]) and t.edges_equal(h.get_edges(), want)\n"
+        "c = h.counters(); assert c['tc_slices'] == 1 and c['passes'] == 2 and c['survivors'] >= 1300 * 1299, c\n"
+        "print('ok')\n") % os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SCEMA_TC_SLICES="1", PYTHONPATH=ROOT), capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.stdout, r.stderr)
 
 
 @pytest.mark.parametrize("scale", [1.0, 1e-150, 1e140, 1e-300])
@@ -174,7 +243,7 @@ def test_tc_mixed_norm_scales_and_dense_neighbourhoods(hc, oracle):
     rows whose fp16 image is zero, and a dense cloud well inside the guard band but outside the threshold."""
     rng = np.random.default_rng(8)
     n = 4000
-    rows = rng.standard_normal((n, 60)) * 10.0 ** rng.integers(-9, -1, size=(n, 1))
+    rows = rng.standard_normal((n, 60)) * 10.0 ** rng.integers(-5, -1, size=(n, 1))
     rows[:600] = 0.3 + 2e-6 * rng.standard_normal((600, 60))        # |a| ~ 2.3, distances ~ 2e-5: all inside the guard band
     rows[600:900] = 1e-14 * rng.standard_normal((300, 60))          # vanish in fp16 next to the 0.3 rows; all mutual edges
     rows[900] = rows[901] = 0.0
@@ -189,7 +258,9 @@ def test_tc_mixed_norm_scales_and_dense_neighbourhoods(hc, oracle):
     assert hc.compare(THR, PAIRS_TC) == len(want[0])
     assert edges_equal(hc.get_edges(), want)
     c = hc.counters()
-    assert c["survivors"] >= 600 * 599 // 2          # the cloud really went through the exact path
+    # the cloud goes through the exact path whenever a tcgen05 filter runs (the up-front sample may prefer the DMMA
+    # filter on rows like these: its band separates the cloud)
+    assert c["tc_slices"] == 0 or c["survivors"] >= 600 * 599 // 2
     assert len(want[0]) >= 300 * 299 // 2 + 150
 
 
@@ -227,14 +298,14 @@ def test_tc_wide_rows(hc, oracle, P):
         hc.tc_debug(THR, n)
 
 
-def test_tc_wide_rows_dense_fall_back_to_dmma(oracle):
-    """Wide rows have no two-slice kernel: when the one-slice survivors overflow the queue the DMMA filter takes over."""
+def test_tc_wide_rows_dense_take_the_filter_free_kernel(oracle):
+    """Every pair an edge (wide rows): the sample sees that no filter can help and the filter-free kernel runs at once."""
     n = 2200
     rows = 1e-3 + 1e-9 * np.random.default_rng(0).standard_normal((n, 300))
     h = scema_b200.HistCluster(0)
     h.set_spline(rows)
     assert h.compare(THR, PAIRS_TC) == n * (n - 1) // 2
-    assert h.counters()["passes"] >= 2 and h.counters()["tc_slices"] == 0
+    assert h.counters()["tc_slices"] == 0 and h.tc_last_plan()["dmma"] > 8000
     want = oracle.all_pairs(rows, THR)
     assert edges_equal(h.get_edges(), want)
     h.close()
@@ -252,8 +323,8 @@ def test_tc_threshold_change_rebuilds_operands(hc, oracle):
 
 
 def test_tc_single_cta_kernel_and_pinned_slices_match(tmp_path):
-    """SCEMA_TC_CG=2 selects the cta_group::2 kernel (an SM pair per 256 x 256 tile), SCEMA_TC_SLICES pins the
-    number of fp16 slices; every combination emits the exact kernel's edge list."""
+    """SCEMA_TC_CG=1 selects the single-CTA kernel (128 x 256 tile per SM; the default is cta_group::2, an SM pair per
+    256 x 256 tile), SCEMA_TC_SLICES pins the number of fp16 slices; every combination emits the exact kernel's edge list."""
     code = (
         "import numpy as np, scema_b200\n"
         "from scema_b200 import synth, PAIRS_TC, PAIRS_EXACT\n"
@@ -268,6 +339,31 @@ def test_tc_single_cta_kernel_and_pinned_slices_match(tmp_path):
         env = dict(os.environ, SCEMA_TC_CG=cg, SCEMA_TC_SLICES=sl, PYTHONPATH=ROOT)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and r.stdout.startswith("ok"), (cg, sl, r.stdout, r.stderr)
+
+
+def test_tc_single_cta_kernel_on_the_other_paths():
+    """The non-default single-CTA kernel (SCEMA_TC_CG=1) through the wide-row, host-buffer-pipeline and norm-band
+    paths: same edge list as the filter-free kernel."""
+    code = (
+        "import os, numpy as np, scema_b200\n"
+        "from scema_b200 import synth, PAIRS_TC, PAIRS_EXACT\n"
+        "def same(e1, e2):\n"
+        "    return all(np.array_equal(x.view(np.uint64) if x.dtype == np.float64 else x, y.view(np.uint64) if y.dtype == np.float64 else y) for x, y in zip(e1, e2))\n"
+        "hc = scema_b200.HistCluster(0)\n"
+        "rows = synth.rows(32, 5000, 16, 50, 5e-3, synth.default_pert(1e-6, 50))\n"   # K = 300: five chunks
+        "hc.set_spline(rows); n1 = hc.compare(1e-6, PAIRS_TC); e1 = hc.get_edges(); n2 = hc.compare(1e-6, PAIRS_EXACT)\n"
+        "assert n1 == n2 and n1 > 5000 and same(e1, hc.get_edges()), 'wide'\n"
+        "off = synth.offsets(13, 21000, 16, 6, 90); st = synth.histories(13, 21000, 16, 5e-3, synth.default_pert(1e-6, 10), off)\n"
+        "n1 = hc.cluster(st, off, None, 10, 1e-6); e1 = hc.get_edges(); assert hc.counters()['pipeline_ranges'] == 2\n"
+        "n2 = hc.compare(1e-6, PAIRS_EXACT); assert n1 == n2 and same(e1, hc.get_edges()), 'pipeline'\n"
+        "os.environ['SCEMA_NORM_BAND'] = '1'\n"
+        "rows = synth.rows(33, 9000, 16, 10, 5e-3, synth.default_pert(1e-6, 10)); hc.set_spline(rows)\n"
+        "n1 = hc.compare(1e-6, PAIRS_TC); e1 = hc.get_edges(); assert hc.counters()['band_tiles'] > 0\n"
+        "n2 = hc.compare(1e-6, PAIRS_EXACT); assert n1 == n2 and same(e1, hc.get_edges()), 'band'\n"
+        "print('ok')\n")
+    env = dict(os.environ, SCEMA_TC_CG="1", SCEMA_PIPELINE_MIN_N="4096", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.stdout, r.stderr)
 
 
 def test_cluster_from_host_buffers_is_pipelined_and_identical(oracle, monkeypatch):
@@ -339,8 +435,8 @@ def test_norm_band_mode(oracle, monkeypatch):
         assert c["band_tiles"] > 0
         if name == "clustered":
             assert c["band_tiles"] < nt * (nt + 1) // 2 // 5      # most of the triangle is out of reach
-        else:
-            assert c["band_tiles"] >= nt * (nt + 1) // 2           # nothing can be ruled out
+        # (rows of equal norm: the filter copies are centred, so their norms differ a little and part of the triangle
+        # may still go; what matters is the edge list above)
         # sharded: union of the shards
         parts = []
         for r in range(3):

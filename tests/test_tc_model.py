@@ -21,10 +21,27 @@ def h16z(v):
     return np.where(np.abs(f) < 2.0 ** -14, 0.0, f)
 
 
-def prepare(rows, thr, slices):
+def centre_of(rows):
+    """k_tc_centre_partial / _final: column means over a strided sample of <= 4096 rows, non-finite entries skipped
+    (any vector would do for correctness: d(a, b) = d(a - m, b - m); the mean makes the centred norms small)"""
+    n = len(rows)
+    ns = min(n, 4096)
+    sample = rows[(np.arange(ns) * (n // ns))]
+    ok = np.isfinite(sample)
+    cnt = ok.sum(0)
+    with np.errstate(invalid="ignore", over="ignore"):
+        m = np.where(cnt > 0, np.where(ok, sample, 0.0).sum(0) / np.maximum(cnt, 1), 0.0)
+    return np.where(np.isfinite(m), m, 0.0)
+
+
+def prepare(rows, thr, slices, centred=True):
     n, K = rows.shape
     assert K <= 60
-    nrm_raw = (rows ** 2).sum(1)
+    if centred:
+        with np.errstate(invalid="ignore", over="ignore"):
+            rows = rows - centre_of(rows)[None, :]      # fl(a - m), one rounding per element
+    with np.errstate(over="ignore", invalid="ignore"):
+        nrm_raw = (rows ** 2).sum(1)
     finite = np.isfinite(nrm_raw)
     M = np.abs(rows[finite]).max() if finite.any() else 0.0
     s = 2.0 ** (11 - int(np.floor(np.log2(M)))) if M > 0 else 1.0
@@ -55,8 +72,8 @@ def prepare(rows, thr, slices):
     return a_hi, a_lo, b_hi, b_lo
 
 
-def worst_case_acc(rows, thr, slices):
-    a_hi, a_lo, b_hi, b_lo = prepare(rows, thr, slices)
+def worst_case_acc(rows, thr, slices, centred=True):
+    a_hi, a_lo, b_hi, b_lo = prepare(rows, thr, slices, centred)
     acc = a_hi @ b_hi.T
     absum = np.abs(a_hi) @ np.abs(b_hi).T
     steps = 4
@@ -98,6 +115,14 @@ def cases():
     yield "tiny_threshold", clustered * 1e-6, 1e-12
     yield "large_threshold", clustered, 3e-3
     yield "k18", rng.standard_normal((n, 18)) * 1e-2 + 1.0, 6e-2
+    # production shape: every history on nearly the same stretch path, groups ~1e-2 of the norm apart
+    dq = 5e-3 * rng.uniform(-1, 1, size=n // 8)
+    sig = 1e-2 * rng.uniform(-1, 1, size=(n // 8, 3))
+    zz = 2e-2 * t[None, :] * (1 + dq[:, None])
+    comp = np.stack([-0.3 * zz, -0.3 * zz, zz] + [zz * sig[:, c:c + 1] for c in range(3)], axis=2)   # [group, point, 6]
+    smooth = np.repeat(comp.reshape(n // 8, 60), 8, axis=0) + 3e-7 * rng.standard_normal((n, 60)) / np.sqrt(60)
+    yield "smooth", smooth, 1e-6
+    yield "smooth_offset", smooth + 0.3, 1e-6     # a large common offset on top: only the centred copies can filter
     zero = clustered.copy()
     zero[:40] = 0.0
     zero[40:60] = 1e-30 * rng.standard_normal((20, 60))
@@ -115,8 +140,13 @@ def test_no_edge_is_rejected_under_the_worst_budgeted_error(name, rows, thr, sli
     assert (edge & off_diag).sum() > 0
     # and the filter does reject most of what is far away (it is a filter, after all), except where the threshold
     # is of the order of the spread of the data
-    if name in ("clustered", "planted", "tiny_threshold"):
+    if name in ("clustered", "planted", "tiny_threshold", "smooth", "smooth_offset"):
         assert (acc < 0).mean() > 0.9
+    if name in ("smooth", "smooth_offset") and slices == 1:
+        # ... which on production-shaped rows is owed to the centring: the band of the raw rows keeps nearly everything
+        raw = worst_case_acc(rows, thr, slices, centred=False)
+        assert not (edge & off_diag & (raw < 0)).any()
+        assert (raw < 0).mean() < 0.2
 
 
 def test_fold_columns_carry_minus_h():
@@ -194,6 +224,7 @@ def prepare_wide(rows, thr):
     nc = (K + 4 + 63) // 64
     assert 1 < nc <= 10
     hb = 0 if K <= 64 else (1 if K <= 256 else 2)
+    rows = rows - centre_of(rows)[None, :]
     M = np.abs(rows).max()
     s = 2.0 ** (11 - hb - int(np.floor(np.log2(M))))
     a = np.zeros((n, nc * 64))

@@ -66,3 +66,27 @@ def test_pipeline_ranges_are_whole_panels():
         assert all(x % 2048 == 0 for x in bounds[:-1])
         if n >= 2 * 65536:
             assert r >= 2
+
+
+def test_filter_choice_cost_model():
+    """scema_tc_choose (host logic behind the up-front choice of the filter): counts of a FP64 sample of 8192 pairs
+    (one / two slices with centred copies, one / two slices with raw copies, DMMA) -> 1 / 2 slices, DMMA (0) or the
+    filter-free kernel (-1), centred or raw copies, and the queue entries expected for the choice."""
+    from scema_b200 import binding
+    P = 1000000 * 999999 // 2
+    big = 1 << 40
+    ch = binding.tc_choose
+    assert ch(P, 60, (0, 0, 0, 0, 0), 8192, big) == (1, 1, 0)                          # nothing survives: hi slices, centred
+    assert ch(P, 60, (2, 0, 8192, 8192, 0), 8192, big) == (1, 1, 0)                    # two hits are noise for sizing the queue
+    c, cen, est = ch(P, 60, (8, 0, 8192, 8192, 0), 8192, big)                          # 0.1 % survive one slice: still cheapest
+    assert (c, cen) == (1, 1) and abs(est - P * 8 / 8192) <= P // 10 ** 6
+    assert ch(P, 60, (4000, 3, 8192, 8192, 0), 8192, big)[:2] == (2, 1)                # half survive one slice, few two
+    assert ch(P, 60, (8192, 8192, 8192, 8192, 2), 8192, big)[0] == 0                   # only the FP64 band separates
+    assert ch(P, 60, (8192, 8192, 8192, 8192, 8192), 8192, big)[0] == -1               # everything is a neighbour
+    assert ch(P, 60, (4000, 300, 4000, 300, 0), 8192, 1 << 20)[0] == 0                 # no room for a queue: DMMA (no survivors)
+    assert ch(P, 300, (4000, 4000, 4000, 4000, 0), 8192, big)[0] == 0                  # wide rows have no two-slice kernel
+    assert ch(P, 3000, (0, 0, 0, 0, 0), 8192, big)[0] == 0                             # beyond 10 chunks: no tcgen05 filter at all
+    assert ch(45, 60, (0, 0, 0, 0, 0), 8192, big)[:2] == (1, 1)
+    assert ch(P, 60, (8192, 8192, 20, 10, 0), 8192, big)[:2] == (1, 0)                 # a centre far from most rows: raw copies
+    assert ch(P, 60, (8192, 8192, 180, 10, 0), 8192, big)[:2] == (2, 0)                # ... and two slices when they pay
+    assert ch(P, 60, (20, 10, 18, 10, 0), 8192, big)[:2] == (1, 1)                     # ... but only when clearly better
