@@ -38,12 +38,32 @@ AMP = 5e-3
 CLUSTER = 16
 SEED = 4
 WORKLOADS = {
-    # name: n, spline points, raw history length range
+    # name: n, spline points, raw history length range (model 0 = cluster population of include/scema_synth.h)
     "c2": dict(n=16384, P=10, lmin=8, lmax=64, desc="BASELINE configs[1]: 16k histories x 6 x 10"),
     "c3": dict(n=200000, P=10, lmin=6, lmax=200, desc="BASELINE configs[2]: 200k ragged histories (6..200 steps)"),
     "c4": dict(n=1000000, P=10, lmin=8, lmax=64, desc="BASELINE configs[3]: 1M histories x 6 x 10 spline points"),
     "c5": dict(n=4000000, P=50, lmin=8, lmax=64, desc="BASELINE configs[4]: 4M histories x 6 x 50 spline points"),
+    # production shape (reference input_configurations/inputs_dogbone_cuboid.json, FE_problem.h:1091-1103):
+    # every quadrature point on nearly the same stretch path (model 1: 2 % stretch, groups of 16 symmetric points
+    # 0.5 % of the norm apart), all histories equally long
+    "c4s": dict(n=1000000, P=10, lmin=36, lmax=36, model=1, amp=2e-2, spread=5e-3,
+                desc="production-shaped: 1M histories on one common stretch path (dogbone emulation), 36 steps each, x 6 x 10 spline points"),
 }
+
+
+def wl_model(wl):
+    return dict(model=wl.get("model", 0), spread=wl.get("spread", 0.0))
+
+
+def wl_amp(wl):
+    return wl.get("amp", AMP)
+
+
+def wl_config(wl, wl_name):
+    """The workload as both arms print it (identical keys and values: the driver compares the two config objects)."""
+    return {"workload": f"{wl_name}: {wl['desc']}", "histories": wl["n"], "spline_points": wl["P"], "threshold": THR,
+            "raw_steps_per_history": [wl["lmin"], wl["lmax"]], "cluster_size": CLUSTER, "population_model": wl.get("model", 0),
+            "l2": "inputs (raw histories + spline matrix) larger than L2"}
 
 
 def env_int(name, default):
@@ -120,7 +140,7 @@ def cpu_reference_rows(wl, m, timed):
     else:
         lib, kind = Oracle(), "port"
     off = synth.offsets(SEED, m, CLUSTER, wl["lmin"], wl["lmax"])
-    steps = synth.histories(SEED, m, CLUSTER, AMP, synth.default_pert(THR, wl["P"]), off)
+    steps = synth.histories(SEED, m, CLUSTER, wl_amp(wl), synth.default_pert(THR, wl["P"]), off, **wl_model(wl))
     t0 = time.perf_counter()
     rows = lib.splinify_batch(steps, off, wl["P"], host_threads())
     return rows, lib, kind, time.perf_counter() - t0
@@ -184,12 +204,137 @@ def run_reference(args, wl, wl_name):
         "impl": "reference", "metric": "history pair comparisons/sec", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{wl_name}: {wl['desc']}", "threshold": THR, "spline_points": wl["P"]},
+        "config": wl_config(wl, wl_name),
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# ------------------------------------------------------------------------------------------------
+# verification of the measured path (after the timed regions; the oracle is only ever the checker)
+# ------------------------------------------------------------------------------------------------
+def edge_checksums(a, b, d, n):
+    """Order-independent fingerprints of an edge list: the same for any number of shards iff the union is the same."""
+    keys = a.astype(np.uint64) * np.uint64(n) + b.astype(np.uint64)
+    with np.errstate(over="ignore"):
+        ck = int(np.sum(keys, dtype=np.uint64))
+    cd = int(np.bitwise_xor.reduce(np.ascontiguousarray(d, dtype=np.float64).view(np.uint64))) if len(d) else 0
+    return {"edges": int(len(a)), "sum_keys_mod_2_64": ck, "xor_distance_bits": cd}
+
+
+def verify_run(args, hc, sc, world, rank, dev, n, P, variant, stream_mode, level):
+    """One more, untimed, pass of exactly the path that was timed (same context, same variant, same sharding), then:
+      (i)   every rank's list sorted and unique; the union of the ranks' lists unique;
+      (ii)  EVERY emitted edge re-derived on the CPU by direct differences in the reference's order (oracle.check_edges:
+            distance bits and strict threshold);
+      (iii) completeness: `rows` random complete rows of the pair matrix recomputed on the CPU, no edge missing or extra;
+      (iv)  N > 1: the union of the shards == the list ONE GPU produces for the whole matrix (ids, order, distance bits);
+            N = 1: the FP64 DMMA filter on the first 200k histories == the same sub-matrix of the tcgen05 list;
+      (v)   level "full" (config 5): 64 random 1024 x 1024 tiles of the pair matrix recomputed on the CPU.
+    -> dict for the JSON line (rank 0), None elsewhere."""
+    import torch
+    import scema_b200
+    from scema_b200.distributed import gather_edges
+    from oracle.pyoracle import Oracle
+    t0 = time.perf_counter()
+    got = []
+
+    def vsink(a, b, d):
+        got.append((a, b, d))
+
+    if world > 1:
+        ne, counts, offs, full = sc.run(n, P, THR, variant, sink=vsink if stream_mode else None)
+    else:
+        hc.resample(P)
+        ne = hc.compare_stream(THR, vsink, variant) if stream_mode else hc.compare(THR, variant)
+        counts, full = [ne], None
+    if stream_mode:
+        a, b, d = (np.concatenate([g[k] for g in got]) if got else np.zeros(0, dtype=(np.uint32, np.uint32, np.float64)[k]) for k in range(3))
+    else:
+        a, b, d = hc.get_edges()
+    key = a.astype(np.int64) * n + b
+    local_ok = bool(len(a) == ne and np.all(a < b) and np.all(np.diff(key) > 0))
+    if world > 1:
+        flags = torch.tensor([int(local_ok)], dtype=torch.int64, device=dev)
+        torch.distributed.all_reduce(flags, op=torch.distributed.ReduceOp.MIN)
+        local_ok = bool(flags.item())
+        A, B, D = gather_edges(a, b, d, n, counts, dev)
+    else:
+        A, B, D = a, b, d
+    if rank != 0:
+        if world > 1:
+            torch.distributed.barrier()
+        return None
+    out = {"level": level, "per_rank_lists_sorted_unique": local_ok, "per_rank_edges": [int(c) for c in counts]}
+    out.update(edge_checksums(A, B, D, n))
+    ukey = A.astype(np.int64) * n + B
+    out["union_unique"] = bool(np.all(np.diff(ukey) > 0))
+    n_rows, K, ptr = hc.spline_info()
+    rows = full.cpu().numpy() if full is not None else hc.get_spline()
+    o = Oracle()
+    out["cpu_recheck_bad_edges"] = int(o.check_edges(rows, THR, A, B, D, host_threads()))
+    rng = np.random.default_rng(12345)
+    n_check = 200 if level != "full" else 1000
+    bad_rows = 0
+    for r in rng.choice(n - 1, size=min(n_check, n - 1), replace=False).tolist():
+        ei, ej, ed, _ = o.all_pairs(rows, THR, r, r + 1, host_threads())
+        lo, hi = np.searchsorted(A, r), np.searchsorted(A, r + 1)
+        if not (np.array_equal(B[lo:hi], ej) and np.array_equal(D[lo:hi].view(np.uint64), ed.view(np.uint64))):
+            bad_rows += 1
+    out["complete_rows_checked"] = int(min(n_check, n - 1))
+    out["complete_rows_bad"] = bad_rows
+    if level == "full":
+        bad_tiles, T = 0, 1024
+        nt = (n + T - 1) // T
+        for _ in range(64):
+            I = int(rng.integers(0, nt)); J = int(rng.integers(I, nt))
+            ri = np.arange(I * T, min(n, (I + 1) * T)); rj = np.arange(J * T, min(n, (J + 1) * T))
+            idx = ri if I == J else np.concatenate([ri, rj])
+            ei, ej, ed, _ = o.all_pairs(rows[idx], THR, 0, len(ri), host_threads())
+            if I != J:
+                keep = ej >= len(ri)
+                ei, ej, ed = ei[keep], ej[keep], ed[keep]
+            want = set(zip(idx[ei].tolist(), idx[ej].tolist(), ed.view(np.uint64).tolist()))
+            lo, hi = np.searchsorted(A, I * T), np.searchsorted(A, min(n, (I + 1) * T))
+            sel = (B[lo:hi] >= J * T) & (B[lo:hi] < min(n, (J + 1) * T))
+            have = set(zip(A[lo:hi][sel].tolist(), B[lo:hi][sel].tolist(), D[lo:hi][sel].view(np.uint64).tolist()))
+            bad_tiles += int(want != have)
+        out["tiles_1024_checked"] = 64
+        out["tiles_1024_bad"] = bad_tiles
+    # (iv) an independent GPU list
+    if world > 1:
+        hc.set_spline(device_ptr=full.data_ptr(), n=n, k=K)
+        got1 = []
+        if stream_mode:
+            hc.compare_stream(THR, lambda x, y, z: got1.append((x, y, z)), variant)
+            a1, b1, d1 = (np.concatenate([g[k] for g in got1]) for k in range(3))
+        else:
+            hc.compare(THR, variant)
+            a1, b1, d1 = hc.get_edges()
+        out["union_equals_single_gpu_list"] = bool(len(a1) == len(A) and np.array_equal(a1, A) and np.array_equal(b1, B) and
+                                                   np.array_equal(d1.view(np.uint64), D.view(np.uint64)))
+        out["single_gpu"] = edge_checksums(a1, b1, d1, n)
+    else:
+        m = min(n, 200000)
+        hc.set_spline(device_ptr=ptr, n=m, k=K)
+        hc.compare(THR, scema_b200.PAIRS_DMMA)
+        a1, b1, d1 = hc.get_edges()
+        t = hc.timings()
+        sel = B < m
+        hi = np.searchsorted(A, m)
+        sel[hi:] = False
+        out["fp64_dmma_list_equals_on_first_rows"] = bool(np.array_equal(a1, A[sel]) and np.array_equal(b1, B[sel]) and
+                                                          np.array_equal(d1.view(np.uint64), D[sel].view(np.uint64)))
+        out["_fp64"] = {"rows": m, "filter_ms": t["filter"], "K": K}
+    out["ok"] = bool(local_ok and out["union_unique"] and out["cpu_recheck_bad_edges"] == 0 and bad_rows == 0 and
+                     out.get("tiles_1024_bad", 0) == 0 and out.get("union_equals_single_gpu_list", True) and
+                     out.get("fp64_dmma_list_equals_on_first_rows", True))
+    out["seconds"] = time.perf_counter() - t0
+    if world > 1:
+        torch.distributed.barrier()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -227,7 +372,7 @@ def run_ours(args, wl, wl_name):
     hc = scema_b200.HistCluster(local_rank, stream.cuda_stream)
     assert hc.stream_ptr() == stream.cuda_stream
     off = synth.device_offsets(SEED, n_local, CLUSTER, wl["lmin"], wl["lmax"], first=b)
-    d_steps = synth.device_histories(SEED, n_local, CLUSTER, AMP, pert, off, first=b, device=dev)
+    d_steps = synth.device_histories(SEED, n_local, CLUSTER, wl_amp(wl), pert, off, first=b, device=dev, **wl_model(wl))
     steps_bytes = d_steps.numel() * 8
     h_steps = torch.empty(d_steps.shape, dtype=torch.float64, pin_memory=True)
     h_steps.copy_(d_steps)
@@ -268,8 +413,11 @@ def run_ours(args, wl, wl_name):
                 acc["allgather"] += sc.gather_events[0].elapsed_time(sc.gather_events[1])  # hc.timings() synchronised
             acc["steps"] += 1
             acc["edges"] = tot
-            acc["survivors"] = hc.counters()["survivors"]
-            acc["band_tiles"] = hc.counters().get("band_tiles", 0)
+            cn = hc.counters()
+            acc["survivors"] = cn["survivors"]
+            acc["passes"] = cn["passes"]
+            acc["band_tiles"] = cn.get("band_tiles", 0)
+            acc["plan"] = dict(hc.tc_last_plan(), slices=cn["tc_slices"])
         return tot
 
     # result buffers of the end-to-end path: pinned, allocated once and reused like a real caller would
@@ -348,6 +496,12 @@ def run_ours(args, wl, wl_name):
     h2d = steps_bytes + off.nbytes
     d2h = ne_local * 16
 
+    # ---- verification of what was just timed (untimed; CPU oracle as the checker)
+    verified = None
+    if args.verify != "off":
+        hc.set_histories(None, off, device_ptr=d_steps.data_ptr())
+        verified = verify_run(args, hc, sc, world, rank, dev, n, P, variant, bool(args.stream), args.verify)
+
     if rank == 0:
         # ---- roofline of the dominant kernel (K2 filter): algorithmic 2*K flops per unordered pair
         pairs_this_rank = total_pairs / world
@@ -356,7 +510,8 @@ def run_ours(args, wl, wl_name):
         if args.norm_band and acc.get("band_tiles", 0):
             # the roofline describes the kernel on the tiles it walked (128 x 256 pairs each), not the pairs the
             # norm bound dismissed beforehand
-            achieved = acc["band_tiles"] * 128 * 256 * 2 * K / (filt_ms * 1e-3) / 1e12 if filt_ms > 0 else None
+            tile_rows = 128 if os.environ.get("SCEMA_TC_CG") == "1" else 256
+            achieved = acc["band_tiles"] * tile_rows * 256 * 2 * K / (filt_ms * 1e-3) / 1e12 if filt_ms > 0 else None
         NT = (n + 255) // 256
         if eff_variant == "tc":
             # tensor roofline: the denominators are the driver-measured cuBLAS bf16 figures (fp16 runs at the
@@ -379,17 +534,10 @@ def run_ours(args, wl, wl_name):
                      "kernel": "k_filter_tc (K2 GEMM-form filter on tcgen05, split fp16, fp32 accumulate in TMEM)",
                      "peak_source": "of %s: MEASURED_PEAKS.json bf16_tflops (cuBLAS bf16 8192^3 burst); the kernel is timed "
                                     "alone per launch (CUDA events around it); sustained figure beside it" % src}
-            if tc_slices == 1 and n_chunks == 1:
-                # what actually bounds the one-slice kernel: every pair's fp32 accumulator has to come out of tensor
-                # memory once (tcgen05.ld moves 128 B/clk/SM = 32 pairs/clk/SM; ncu: tensor pipe 48 % busy)
-                mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
-                ceiling = 148 * 32 * mhz * 1e6
-                extra["limiter"] = {"what": "TMEM read-out of the accumulators (tcgen05.ld, 4 bytes per pair, 128 B/clk/SM)",
-                                    "ceiling_pairs_per_s": ceiling,
-                                    "frac_of_ceiling": (pairs_this_rank / (filt_ms * 1e-3)) / ceiling if filt_ms > 0 else None}
-            elif tc_slices == 1:
-                extra["limiter"] = {"what": "wide rows (%d chunks of 64 columns per tile): tensor pipe 62 %% busy in the ncu capture, "
-                                            "the 4-stage B ring does not quite hide the TMA round trip" % n_chunks}
+            if tc_slices == 1:
+                extra["limiter"] = {"what": "tensor pipe under the board's power cap: executed flops exceed the cuBLAS bf16 burst figure "
+                                            "(ncu: tensor pipe ~80 % active at the capped SM clock; round 1's 'TMEM read-out ceiling' was the "
+                                            "issue loop of the MMA warp, tools/tmem_probe.cu measures >= 860 B/clk/SM of read-out)"}
             else:
                 extra["limiter"] = {"what": "tensor pipe (ncu: 90 % busy, SM clock pulled to 1.70 GHz by the power cap)"}
             fp64 = max(hc.fp64_peak()["dmma_tflops"] for _ in range(2))
@@ -431,6 +579,19 @@ def run_ours(args, wl, wl_name):
                              "launch_ms": res_ms, "kernel": "k_resample_stream (K1), launches per length class summed",
                              "peak_source": "of %s: MEASURED_PEAKS.json hbm_gbs" % hbm_src,
                              "note": "instruction-bound, not bandwidth-bound: bit-exact division sequences in two dependent sweeps per history"}
+        # BASELINE's metric is quoted as a fraction of the FP64 peak: the true FP64 contraction (DMMA filter) on a bounded
+        # sample of the same rows, timed by its own CUDA events, against the DMMA issue-rate probe
+        roofline_fp64 = None
+        if verified and verified.get("_fp64"):
+            f = verified.pop("_fp64")
+            dm = max(hc.fp64_peak()["dmma_tflops"] for _ in range(2))
+            pr = f["rows"] * (f["rows"] - 1) / 2
+            ach = pr * 2 * f["K"] / (f["filter_ms"] * 1e-3) / 1e12 if f["filter_ms"] > 0 else None
+            roofline_fp64 = {"bound": "tensor", "achieved": ach, "peak": dm, "unit": "TFLOP/s", "frac": (ach / dm) if ach else None,
+                             "traffic": None, "launch_ms": f["filter_ms"],
+                             "kernel": "k_filter_ws (K2 GEMM-form filter on FP64 DMMA, --variant dmma), first %d histories of the workload "
+                                       "(%.3g pairs), after the timed region" % (f["rows"], pr),
+                             "peak_source": "measured live: FP64 DMMA m8n8k4 issue-rate probe (scema_fp64_peak)"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             m = min(n, 65536)
@@ -456,21 +617,23 @@ def run_ours(args, wl, wl_name):
             "metric": "history pair comparisons/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{wl_name}: {wl['desc']}", "histories": n,
-                       "filter_arithmetic": ("fp16 x2 split operands on tcgen05, fp32 accumulate; every survivor and every emitted "
-                                             "distance recomputed in f64 in the reference's operation order")
-                       if eff_variant == "tc" else "f64", "spline_points": P, "threshold": THR,
-                       "raw_steps_per_history": [wl["lmin"], wl["lmax"]], "cluster_size": CLUSTER, "variant": eff_variant,
-                       "parallelism": f"tile-shard x{world}", "l2": "inputs (raw histories + spline matrix) larger than L2",
-                       "edges": acc["edges"], "survivors_last_rank0": acc["survivors"],
-                       "norm_band": bool(args.norm_band), "band_tiles_last_rank0": acc.get("band_tiles", 0)},
+            "config": wl_config(wl, wl_name),
+            "run": {"variant": eff_variant, "parallelism": f"tile-shard x{world}",
+                    "filter_arithmetic": ("fp16 split operands (centred copies) on tcgen05, fp32 accumulate; every survivor and every "
+                                          "emitted distance recomputed in f64 in the reference's operation order")
+                    if eff_variant == "tc" else "f64",
+                    "edges": acc["edges"], "survivors_last_rank0": acc["survivors"], "passes_last_rank0": acc.get("passes", 0),
+                    "filter_plan_rank0": acc.get("plan"), "norm_band": bool(args.norm_band),
+                    "band_tiles_last_rank0": acc.get("band_tiles", 0)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                     "pipeline_ranges": hc.counters().get("pipeline_ranges", 0) if world == 1 else 0},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "roofline_fp64": roofline_fp64,
             "roofline_resample": roofline_resample,
+            "verified": verified,
             "cpu_baseline": cpu,
         }
         emit(line)
@@ -513,6 +676,9 @@ def main():
     ap.add_argument("--norm-band", action="store_true",
                     help="opt-in exact shortcut (SCEMA_NORM_BAND=1): rows sorted by norm, tiles out of the threshold's reach skipped; "
                          "NOT part of the default line")
+    ap.add_argument("--verify", default="on", choices=["off", "on", "full"],
+                    help="after the timed regions: CPU re-check of every edge, complete rows, union of the shards == one GPU's list "
+                         "(full: 1000 rows and 64 tiles of 1024 x 1024, the config-5 checks of SURVEY 8d)")
     ap.add_argument("--stream", type=int, default=-1,
                     help="1: edges leave the device chunk by chunk through scema_compare_stream (default for c5), 0: one-shot compare")
     args = ap.parse_args()

@@ -61,6 +61,27 @@ def gather_counts(local_count, device, group=None, flag=0):
     return counts, offs, int(both[:, 1].max())
 
 
+def gather_edges(a, b, d, n, counts, device, group=None):
+    """All ranks' edge lists on every rank: (a, b, d) numpy arrays of this rank (counts[rank] entries) -> the union
+    sorted by (a, b) as numpy arrays. Keys a * n + b travel as int64, distances as their bit patterns."""
+    world = dist.get_world_size(group)
+    m = max(max(counts), 1)
+    mine = len(a)
+    buf = torch.zeros((2, m), dtype=torch.int64)
+    if mine:
+        buf[0, :mine] = torch.from_numpy(a.astype(np.int64) * int(n) + b.astype(np.int64))
+        buf[1, :mine] = torch.from_numpy(np.ascontiguousarray(d, dtype=np.float64).view(np.int64).copy())
+    buf = buf.to(device)
+    allb = torch.empty((world, 2, m), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allb, buf, group=group)
+    allb = allb.cpu().numpy()
+    keys = np.concatenate([allb[r, 0, :counts[r]] for r in range(world)])
+    bits = np.concatenate([allb[r, 1, :counts[r]] for r in range(world)])
+    order = np.argsort(keys, kind="stable")
+    keys, bits = keys[order], bits[order]
+    return (keys // int(n)).astype(np.uint32), (keys % int(n)).astype(np.uint32), bits.view(np.float64)
+
+
 class ShardedCluster:
     """Tile-sharded all-pairs over the ranks of a process group (rank == GPU)."""
 

@@ -27,10 +27,19 @@ def main():
     hc = scema_b200.HistCluster(local, stream.cuda_stream)
     hc.set_histories(steps, off)
     sc = ShardedCluster(hc)
-    for variant in (0, 1):
-        ne, counts, offs, full = sc.run(n, P, thr, variant)
-        a, bb, d = hc.get_edges()
+    # DMMA, FMA, the tcgen05 filter (the bench default) one-shot and streamed
+    for variant, streamed in ((0, False), (1, False), (3, False), (3, True)):
+        if streamed:
+            got = []
+            ne, counts, offs, full = sc.run(n, P, thr, variant, sink=lambda x, y, z: got.append((x, y, z)))
+            a, bb, d = (np.concatenate([g[k] for g in got]) if got else np.zeros(0, dtype=(np.uint32, np.uint32, np.float64)[k])
+                        for k in range(3))
+        else:
+            ne, counts, offs, full = sc.run(n, P, thr, variant)
+            a, bb, d = hc.get_edges()
         assert ne == counts[rank] and len(a) == ne
+        if variant == 3:
+            assert hc.counters()["tc_slices"] == 1, hc.counters()   # the tcgen05 filter really ran on this shard
         # gather the edge lists on every rank (padded to the largest count)
         m = max(max(counts), 1)
         buf = torch.zeros((m, 3), dtype=torch.float64, device=dev)
@@ -56,7 +65,7 @@ def main():
             assert len(got) == len(wi), (len(got), len(wi))
             assert np.array_equal(got[:, 0].astype(np.uint32), wi) and np.array_equal(got[:, 1].astype(np.uint32), wj)
             assert np.array_equal(np.ascontiguousarray(got[:, 2]).view(np.uint64), wd.view(np.uint64))
-            print(f"multigpu_check ok: world={world} variant={variant} edges={len(wi)} per-rank={counts}", flush=True)
+            print(f"multigpu_check ok: world={world} variant={variant} streamed={streamed} edges={len(wi)} per-rank={counts}", flush=True)
     hc.close()
     dist.barrier()
     dist.destroy_process_group()
