@@ -354,8 +354,10 @@ def run_ours(args, wl, wl_name):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        gloo = dist.new_group(backend="gloo")   # host-side barrier while rank 0 drives all GPUs through the library
     n, P = wl["n"], wl["P"]
     K = 6 * P
     variant = {"dmma": 0, "fma": 1, "exact": 2, "tc": 3}[args.variant]
@@ -496,6 +498,48 @@ def run_ours(args, wl, wl_name):
     h2d = steps_bytes + off.nbytes
     d2h = ne_local * 16
 
+    # ---- N > 1, end to end through the LIBRARY's own multi-GPU entry point (scema_multi_cluster: one process, one host
+    # thread + context per GPU, NCCL inside the library, host buffers in, merged sorted edge list out to pinned host
+    # memory). Rank 0 drives all N GPUs; the other ranks keep their GPUs idle behind a host-side (gloo) barrier.
+    e2e_lib = None
+    if world > 1 and not args.stream and not args.no_library_e2e:
+        torch.cuda.synchronize()
+        dist.barrier(group=gloo)
+        if rank == 0:
+            off_all = synth.device_offsets(SEED, n, CLUSTER, wl["lmin"], wl["lmax"])
+            h_all = torch.empty((int(off_all[-1]), 6), dtype=torch.float64, pin_memory=True)
+            for (sb, se) in shard_bounds(n, world):
+                so = (off_all[sb:se + 1] - off_all[sb]).astype(np.uint64)
+                part = synth.device_histories(SEED, se - sb, CLUSTER, wl_amp(wl), pert, so, first=sb, device=dev, **wl_model(wl))
+                h_all[int(off_all[sb]):int(off_all[se])].copy_(part)
+                del part
+            torch.cuda.synchronize()
+            mc = scema_b200.MultiCluster(list(range(world)))
+            s0 = torch.cuda.ExternalStream(mc.first.stream_ptr(), device=dev)
+            h_all_np = h_all.numpy()
+            for _ in range(2):
+                ne_m = mc.cluster(h_all_np, off_all, None, P, THR, variant)
+                mc.first.get_edges(out=e2e_buffers(ne_m))
+            lev0, lev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_wall = time.perf_counter()
+            lev0.record(s0)
+            for _ in range(e2e_steps):
+                ne_m = mc.cluster(h_all_np, off_all, None, P, THR, variant)
+                ma, mb, md = mc.first.get_edges(out=e2e_buffers(ne_m))
+            lev1.record(s0)
+            lev1.synchronize()
+            wall_ms = (time.perf_counter() - t_wall) * 1e3
+            lib_ms = lev0.elapsed_time(lev1)
+            e2e_lib = {"value": total_pairs * e2e_steps / (lib_ms * 1e-3), "unit": "pairs/s", "ms_per_step": lib_ms / e2e_steps,
+                       "wall_ms_per_step": wall_ms / e2e_steps, "h2d_bytes_per_step": int(h_all.numel() * 8 + off_all.nbytes),
+                       "d2h_bytes_per_step": int(ne_m * 16), "steps": e2e_steps, "phases_ms": mc.last_ms(),
+                       "checksums": edge_checksums(ma, mb, md, n),
+                       "api": "scema_multi_cluster + scema_get_edges (C ABI, one process, %d host threads, NCCL inside the library); "
+                              "timed with CUDA events on the first GPU's stream, which also receives the other shards' edges last" % world}
+            mc.close()
+            del h_all
+        dist.barrier(group=gloo)
+
     # ---- verification of what was just timed (untimed; CPU oracle as the checker)
     verified = None
     if args.verify != "off":
@@ -626,9 +670,16 @@ def run_ours(args, wl, wl_name):
                     "filter_plan_rank0": acc.get("plan"), "norm_band": bool(args.norm_band),
                     "band_tiles_last_rank0": acc.get("band_tiles", 0)},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                    "pipeline_ranges": hc.counters().get("pipeline_ranges", 0) if world == 1 else 0},
+            "e2e": ({"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                     "pipeline_ranges": hc.counters().get("pipeline_ranges", 0) if world == 1 else 0,
+                     "api": "scema_cluster + scema_get_edges (C ABI)" if world == 1 and not args.stream else
+                            "scema_set_histories + resample + NCCL all-gather (torch.distributed) + sharded compare, one process per GPU"}
+                    if e2e_lib is None else e2e_lib),
+            "e2e_process_per_gpu": None if e2e_lib is None else
+            {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e / e2e_steps, "h2d_bytes_per_step": int(h2d) * world,
+             "d2h_bytes_per_step": int(d2h) * world,
+             "api": "scema_set_histories + resample + NCCL all-gather (torch.distributed) + sharded compare, one process per GPU"},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_fp64": roofline_fp64,
@@ -676,6 +727,7 @@ def main():
     ap.add_argument("--norm-band", action="store_true",
                     help="opt-in exact shortcut (SCEMA_NORM_BAND=1): rows sorted by norm, tiles out of the threshold's reach skipped; "
                          "NOT part of the default line")
+    ap.add_argument("--no-library-e2e", action="store_true", help="N > 1: skip the end-to-end figure through scema_multi_cluster")
     ap.add_argument("--verify", default="on", choices=["off", "on", "full"],
                     help="after the timed regions: CPU re-check of every edge, complete rows, union of the shards == one GPU's list "
                          "(full: 1000 rows and 64 tiles of 1024 x 1024, the config-5 checks of SURVEY 8d)")

@@ -152,6 +152,35 @@ int scema_get_degrees(scema_ctx *ctx, uint32_t *degree_host);
 int scema_cluster(scema_ctx *ctx, const double *steps, const uint64_t *offsets, const uint32_t *ids,
                   uint64_t n, uint32_t spline_points, double threshold, int variant, uint64_t *n_edges);
 
+/* ---- several GPUs of one box behind the same boundary: replaces the collective of compare_histories_with_all_ranks
+ *      (strain2spline.h:546-614: R - 1 ring steps of blocking messages per history, called at FE_problem.h:1229) with a
+ *      tile-sharded all-pairs driven from ONE process. scema_multi_create(devices[n_devices]; NULL = 0..n-1) makes one
+ *      context and one host thread per GPU and an NCCL communicator over them (NCCL is loaded at run time; one device
+ *      needs none). scema_multi_cluster: host buffers as scema_cluster; every GPU receives its contiguous share of the
+ *      histories over its own PCIe link and resamples it, ONE all-gather of the row blocks (NCCL over NVLink) gives every
+ *      GPU the whole spline matrix, every GPU evaluates shard r of n_devices of the pair matrix (all shards switch filter
+ *      together when one is too dense), an ncclAllGather of the edge counts yields the offsets at which the shards' lists
+ *      are collected on the first GPU and put in canonical order. scema_multi_compare_rows: the same from already-
+ *      resampled rows in host memory. Afterwards the FIRST context (scema_multi_context(m, 0)) serves the result through
+ *      scema_get_edges / scema_get_degrees / scema_write_similar_hist / scema_reduce_edges exactly as after a one-GPU
+ *      scema_compare (bit-identical list). The other contexts answer scema_last_timings / scema_last_counters for
+ *      their shard. */
+typedef struct scema_multi scema_multi;
+int scema_multi_create(scema_multi **out, const int *devices, int n_devices);
+void scema_multi_destroy(scema_multi *m);
+const char *scema_multi_last_error(const scema_multi *m);
+int scema_multi_devices(const scema_multi *m);
+scema_ctx *scema_multi_context(scema_multi *m, int rank);
+int scema_multi_cluster(scema_multi *m, const double *steps, const uint64_t *offsets, const uint32_t *ids, uint64_t n,
+                        uint32_t spline_points, double threshold, int variant, uint64_t *n_edges);
+int scema_multi_compare_rows(scema_multi *m, const double *rows, uint64_t n, uint32_t k, const uint32_t *ids, double threshold,
+                             int variant, uint64_t *n_edges);
+/* Edges every shard found and the offset of its block in the gathered list before the canonical sort (host arrays [n_devices]). */
+int scema_multi_shard_edges(scema_multi *m, uint64_t *counts, uint64_t *offsets);
+/* Wall-clock milliseconds of the last call's phases on the first GPU: {ingest + K1, all-gather of the rows, compare,
+ * gather + sort of the edges}; *variant_used = the filter all shards ended up with. */
+int scema_multi_last_ms(scema_multi *m, double ms[4], int *variant_used);
+
 /* ---- result files: replaces most_similar_histories_to_file (strain2spline.h:301-314) as driven
  *      by FE_problem.h:1232-1235 ("<dir>/last.%u.similar_hist") and mpi_comparison_test.cc:99-103
  *      ("__results/ID_%u.txt"). One file per history of the batch (created even when empty), one

@@ -11,6 +11,7 @@ without a GPU), but creating a :class:`HistCluster` without a CUDA device raises
 """
 from .binding import (  # noqa: F401
     HistCluster,
+    MultiCluster,
     ScemaError,
     PAIRS_DMMA,
     PAIRS_FMA,
@@ -21,5 +22,5 @@ from .binding import (  # noqa: F401
     reduce_dir,
 )
 
-__all__ = ["HistCluster", "ScemaError", "PAIRS_DMMA", "PAIRS_FMA", "PAIRS_EXACT", "PAIRS_TC", "lib", "lib_path",
+__all__ = ["HistCluster", "MultiCluster", "ScemaError", "PAIRS_DMMA", "PAIRS_FMA", "PAIRS_EXACT", "PAIRS_TC", "lib", "lib_path",
            "reduce_dir"]

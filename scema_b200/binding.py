@@ -70,6 +70,15 @@ def lib():
         "scema_tc_last_plan": (i32, [vp, vp]),
         "scema_tc_choose": (i32, [u64, u32, vp, u64, u64, P(i32), P(i32), P(u64)]),
         "scema_pipeline_plan": (i32, [u64, vp, u32, P(u32)]),
+        "scema_multi_create": (i32, [P(vp), vp, i32]),
+        "scema_multi_destroy": (None, [vp]),
+        "scema_multi_last_error": (C.c_char_p, [vp]),
+        "scema_multi_devices": (i32, [vp]),
+        "scema_multi_context": (vp, [vp, i32]),
+        "scema_multi_cluster": (i32, [vp, vp, vp, vp, u64, u32, dbl, i32, P(u64)]),
+        "scema_multi_compare_rows": (i32, [vp, vp, u64, u32, vp, dbl, i32, P(u64)]),
+        "scema_multi_shard_edges": (i32, [vp, vp, vp]),
+        "scema_multi_last_ms": (i32, [vp, P(dbl), P(i32)]),
         "scema_ingest_last_error": (C.c_char_p, []),
         "scema_batch_read_dir": (i32, [C.c_char_p, u32, P(vp)]),
         "scema_batch_read_files": (i32, [P(C.c_char_p), vp, u64, u32, P(vp)]),
@@ -103,6 +112,8 @@ EXPORTED = (
     "scema_set_spline scema_get_spline scema_spline_info scema_compare scema_compare_stream scema_get_edges scema_edges_device "
     "scema_get_degrees scema_cluster scema_write_similar_hist scema_reduce_edges scema_reduce_calls scema_reduce_dir "
     "scema_last_timings scema_last_counters scema_kernel_launches scema_fp64_peak scema_tc_debug scema_tc_plan scema_tc_centre scema_tc_last_plan scema_tc_choose scema_pipeline_plan scema_synth_offsets "
+    "scema_multi_create scema_multi_destroy scema_multi_last_error scema_multi_devices scema_multi_context scema_multi_cluster "
+    "scema_multi_compare_rows scema_multi_shard_edges scema_multi_last_ms "
     "scema_synth_histories_device scema_synth_rows_device scema_synth_histories_model_device scema_synth_rows_model_device scema_ingest_last_error scema_batch_read_dir "
     "scema_batch_read_files scema_batch_from_lhistory scema_batch_count scema_batch_total_steps scema_batch_steps "
     "scema_batch_offsets scema_batch_ids scema_batch_name scema_batch_write_strain_files "
@@ -215,18 +226,24 @@ def tc_choose(pairs, k, counts, sample, mem_budget):
 class HistCluster:
     """One context = one GPU + one stream. Methods map 1:1 onto include/scema_hist.h."""
 
-    def __init__(self, device=0, stream=None):
+    def __init__(self, device=0, stream=None, _borrowed=None):
         self._L = lib()
+        self._keep = []
+        if _borrowed is not None:   # a context owned by a MultiCluster
+            self._h = C.c_void_p(_borrowed)
+            self._owned = False
+            return
+        self._owned = True
         self._h = C.c_void_p(None)
         rc = self._L.scema_create(C.byref(self._h), int(device), _ptr(stream) if stream else None)
         if rc:
             self._h = None
             raise ScemaError(rc, "scema_create failed (no CUDA device? there is no CPU fallback)")
-        self._keep = []
 
     def close(self):
         if getattr(self, "_h", None):
-            self._L.scema_destroy(self._h)
+            if getattr(self, "_owned", True):
+                self._L.scema_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -430,3 +447,69 @@ class HistCluster:
         out = (C.c_double * 2)()
         self._ck(self._L.scema_fp64_peak(self._h, out))
         return {"dfma_tflops": float(out[0]), "dmma_tflops": float(out[1])}
+
+
+class MultiCluster:
+    """Several GPUs of one box from one process (scema_multi_*): one context and host thread per GPU, NCCL inside the
+    library. After cluster() / compare_rows() the result is served by .first (a HistCluster view of the first GPU's
+    context): get_edges, write_similar_hist, reduce_edges ..."""
+
+    def __init__(self, devices):
+        self._L = lib()
+        self._h = C.c_void_p(None)
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = self._L.scema_multi_create(C.byref(self._h), devs, len(devices))
+        if rc:
+            self._h = None
+            raise ScemaError(rc, "scema_multi_create failed (devices missing, listed twice, or NCCL unavailable)")
+        self.n_devices = len(devices)
+        self.contexts = [HistCluster(_borrowed=self._L.scema_multi_context(self._h, r)) for r in range(self.n_devices)]
+        self.first = self.contexts[0]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for c in self.contexts:
+                c._h = None
+            self._L.scema_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise ScemaError(rc, self._L.scema_multi_last_error(self._h).decode())
+
+    def cluster(self, steps, offsets, ids, spline_points, threshold, variant=PAIRS_TC):
+        steps = np.ascontiguousarray(steps, dtype=np.float64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)
+        ne = C.c_uint64(0)
+        self._ck(self._L.scema_multi_cluster(self._h, _ptr(steps), _ptr(offsets), _ptr(ids_a), len(offsets) - 1, int(spline_points),
+                                             float(threshold), int(variant), C.byref(ne)))
+        self.first.n_edges = int(ne.value)
+        return int(ne.value)
+
+    def compare_rows(self, rows, threshold, variant=PAIRS_TC, ids=None):
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)
+        ne = C.c_uint64(0)
+        self._ck(self._L.scema_multi_compare_rows(self._h, _ptr(rows), rows.shape[0], rows.shape[1], _ptr(ids_a), float(threshold),
+                                                  int(variant), C.byref(ne)))
+        self.first.n_edges = int(ne.value)
+        return int(ne.value)
+
+    def shard_edges(self):
+        cnt = np.zeros(self.n_devices, dtype=np.uint64)
+        off = np.zeros(self.n_devices, dtype=np.uint64)
+        self._ck(self._L.scema_multi_shard_edges(self._h, _ptr(cnt), _ptr(off)))
+        return cnt, off
+
+    def last_ms(self):
+        ms = (C.c_double * 4)()
+        v = C.c_int(0)
+        self._ck(self._L.scema_multi_last_ms(self._h, ms, C.byref(v)))
+        return {"ingest_resample": ms[0], "allgather": ms[1], "compare": ms[2], "gather_sort": ms[3], "variant_used": int(v.value)}

@@ -26,6 +26,11 @@ int scema_create(scema_ctx **out, int device, void *stream)
     if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { delete c; return SCEMA_ERR_CUDA; }
     c->sm_count = p.multiProcessorCount;
     c->smem_optin = p.sharedMemPerBlockOptin;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = p.totalGlobalMem / 2; }
+        c->mem_budget = free_b / 2;
+    }
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {

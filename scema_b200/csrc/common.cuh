@@ -58,6 +58,8 @@ struct scema_ctx {
     int device = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
+    size_t mem_budget = 0;  // half of the device memory that was free when the context was created: what a survivor queue may take
+                            // (cudaMemGetInfo costs ~10 ms per call in a process that drives several GPUs through NCCL)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
@@ -182,6 +184,7 @@ int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_
 int compare_stream_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards, uint32_t panels_per_chunk,
                        scema_edge_sink sink, void *user, uint64_t *n_total);
 int fp64_peak_run(scema_ctx *ctx, double out[2]);
+int edges_adopt(scema_ctx *ctx, const uint64_t *d_keys, const double *d_vals, uint64_t total);
 bool pipeline_wanted(uint64_t n);
 void pipeline_bounds(uint64_t n, std::vector<uint64_t> &bounds);
 int pipeline_begin(scema_ctx *ctx, const double *steps_host, const uint64_t *offsets, uint64_t n);

@@ -1089,6 +1089,23 @@ static int sort_edges(scema_ctx *ctx)
     return SCEMA_OK;
 }
 
+// Install an edge list computed elsewhere (the union of the shards' lists, multi.cu) as this context's result: copied
+// into the context's own buffers (grown as needed), put in canonical (a, b) order, served by scema_get_edges and friends.
+int edges_adopt(scema_ctx *ctx, const uint64_t *d_keys, const double *d_vals, uint64_t total)
+{
+    int rc = ensure_edge_buffers(ctx, std::max<uint64_t>(total, 1));
+    if (rc) return rc;
+    if (total) {
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_edge_key[0].p, d_keys, total * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_edge_val[0].p, d_vals, total * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    ctx->n_edges = total;
+    ctx->edge_cur = 0;
+    ctx->have_edges = true;
+    ctx->counters[2] = total;
+    return sort_edges(ctx);
+}
+
 // Common front end: argument checks, buffers, filter copy and schedule. Returns 1 when there is
 // nothing to compare (result: no edges).
 static int compare_begin(scema_ctx *ctx, double thr, int &variant, uint32_t shard, uint32_t n_shards, Schedule &sc)
@@ -1289,10 +1306,7 @@ static int cluster_pipelined_impl(scema_ctx *ctx, const double *steps_host, uint
             int choice = 1, centred = 1;
             uint64_t est = 0;
             if (!rc) {
-                size_t free_b = 0, total_b = 0;
-                SCEMA_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-                tc_choose(n * (n - 1) / 2, ctx->K, counts, tc_plan_sample_size(), (uint64_t)((free_b + ctx->d_cand.bytes) / 2), true, &choice,
-                          &centred, &est);
+                tc_choose(n * (n - 1) / 2, ctx->K, counts, tc_plan_sample_size(), (uint64_t)ctx->mem_budget, true, &choice, &centred, &est);
                 if (choice != 1 || !centred || est + est / 4 > ctx->cand_cap) { t_end(ctx, SCEMA_T_FILTER); return SCEMA_OK; }
             }
         }

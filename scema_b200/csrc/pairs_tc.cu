@@ -1041,11 +1041,9 @@ int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices, bool want_band, uint
         uint64_t counts[5];
         rc = tc_plan_rows(ctx, n, counts);
         if (rc) return rc;
-        size_t free_b = 0, total_b = 0;
-        SCEMA_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
         int ch = 1, centred = 1;
         uint64_t est = 0;
-        tc_choose(pairs, ctx->K, counts, tc::PLAN_SAMPLE, (uint64_t)((free_b + ctx->d_cand.bytes) / 2), true, &ch, &centred, &est);
+        tc_choose(pairs, ctx->K, counts, tc::PLAN_SAMPLE, (uint64_t)ctx->mem_budget, true, &ch, &centred, &est);
         if (ch == 2 && !two_ok) ch = 1;
         if (choice) *choice = ch;
         if (est_survivors) *est_survivors = est;

@@ -79,6 +79,17 @@ int main(int argc, char **argv)
     if (n) {
         scema_ctx *ctx = MatHistPredict::b200::context();
         uint64_t n_edges = 0;
+        if (MatHistPredict::b200::multi() && spline_points > 0) {
+            // SCEMA_B200_DEVICES lists several GPUs: the batch is sharded over them inside the library (scema_multi_cluster);
+            // the result files below come from the first context, which holds the merged list
+            MatHistPredict::b200::check_multi(scema_multi_cluster(MatHistPredict::b200::multi(), scema_batch_steps(batch), off,
+                                                                  scema_batch_ids(batch), n, spline_points, threshold, SCEMA_PAIRS_TC,
+                                                                  &n_edges),
+                                              "compare_histories_with_all_ranks");
+            if (scema_write_similar_hist(ctx, "__results/ID_%u.txt") != SCEMA_OK) die(scema_last_error(ctx));
+            scema_batch_free(batch);
+            return 0;
+        }
         MatHistPredict::b200::check(scema_set_histories_from_batch(ctx, batch), "from_file");
         if (spline_points == 0) {
             // the reference builds empty spline vectors, every distance is sqrt(0) = 0

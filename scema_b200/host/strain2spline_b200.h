@@ -61,14 +61,45 @@ inline void die(const std::string &msg)
     exit(1);
 }
 
-// One GPU context per process (device from $SCEMA_B200_DEVICE, default 0).
+// The GPUs of this process: $SCEMA_B200_DEVICES="0,1,2,3" shards every comparison over those GPUs (scema_multi_*: one
+// host thread per GPU and NCCL inside the library; the caller stays single-threaded), otherwise one GPU
+// ($SCEMA_B200_DEVICE, default 0). Returns NULL when a single device is configured.
+inline scema_multi *multi()
+{
+    static scema_multi *m = NULL;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char *e = getenv("SCEMA_B200_DEVICES");
+        std::vector<int> devs;
+        if (e)
+            for (const char *p = e; *p;) {
+                char *end = NULL;
+                long v = strtol(p, &end, 10);
+                if (end == p) break;
+                devs.push_back((int)v);
+                p = (*end == ',') ? end + 1 : end;
+            }
+        if (devs.size() > 1) {
+            int rc = scema_multi_create(&m, devs.data(), (int)devs.size());
+            if (rc != SCEMA_OK) die("scema_b200: cannot create contexts on the GPUs listed in SCEMA_B200_DEVICES");
+        }
+    }
+    return m;
+}
+
+// The context that holds the results (the only one, or the first of the device set).
 inline scema_ctx *context()
 {
     static scema_ctx *ctx = NULL;
     if (!ctx) {
-        const char *d = getenv("SCEMA_B200_DEVICE");
-        int rc = scema_create(&ctx, d ? atoi(d) : 0, NULL);
-        if (rc != SCEMA_OK) die("scema_b200: cannot create a GPU context (no CUDA device? there is no CPU fallback)");
+        if (multi()) {
+            ctx = scema_multi_context(multi(), 0);
+        } else {
+            const char *d = getenv("SCEMA_B200_DEVICE");
+            int rc = scema_create(&ctx, d ? atoi(d) : 0, NULL);
+            if (rc != SCEMA_OK) die("scema_b200: cannot create a GPU context (no CUDA device? there is no CPU fallback)");
+        }
     }
     return ctx;
 }
@@ -76,6 +107,11 @@ inline scema_ctx *context()
 inline void check(int rc, const char *what)
 {
     if (rc != SCEMA_OK) die(std::string(what) + ": " + scema_last_error(context()));
+}
+
+inline void check_multi(int rc, const char *what)
+{
+    if (rc != SCEMA_OK) die(std::string(what) + ": " + scema_multi_last_error(multi()));
 }
 
 // $SCEMA_B200_ALL_SIMILAR=1 also fills the reference's "theory-checking only" full comparison
@@ -401,10 +437,13 @@ inline void compare_batch(std::vector<Strain6D *> &hist, double threshold, const
         // one call: for large batches the library pipelines copy, resample and compare range by range (scema_cluster)
         const bool dense0 = keep_all_similar();
         uint64_t m0 = 0;
-        check(scema_cluster(ctx, flat.data(), offsets.data(), ids.data(), n, P0,
-                            dense0 ? std::numeric_limits<double>::infinity() : threshold,
-                            dense0 ? SCEMA_PAIRS_EXACT : SCEMA_PAIRS_TC, &m0),
-              "compare_histories_with_all_ranks");
+        const double thr0 = dense0 ? std::numeric_limits<double>::infinity() : threshold;
+        const int var0 = dense0 ? SCEMA_PAIRS_EXACT : SCEMA_PAIRS_TC;
+        if (multi())
+            check_multi(scema_multi_cluster(multi(), flat.data(), offsets.data(), ids.data(), n, P0, thr0, var0, &m0),
+                        "compare_histories_with_all_ranks");
+        else
+            check(scema_cluster(ctx, flat.data(), offsets.data(), ids.data(), n, P0, thr0, var0, &m0), "compare_histories_with_all_ranks");
         clustered = true;
     } else {
         resolve_splines(hist);
@@ -419,7 +458,17 @@ inline void compare_batch(std::vector<Strain6D *> &hist, double threshold, const
             }
             if (K) memcpy(rows.data() + i * (size_t)K, sp->data(), K * sizeof(double));
         }
-        check(scema_set_spline(ctx, rows.data(), 0, n, K, ids.data()), "compare_histories_with_all_ranks");
+        if (multi()) {
+            uint64_t m1 = 0;
+            const bool dense1 = keep_all_similar();
+            check_multi(scema_multi_compare_rows(multi(), rows.data(), n, K, ids.data(),
+                                                 dense1 ? std::numeric_limits<double>::infinity() : threshold,
+                                                 dense1 ? SCEMA_PAIRS_EXACT : SCEMA_PAIRS_TC, &m1),
+                        "compare_histories_with_all_ranks");
+            clustered = true;
+        } else {
+            check(scema_set_spline(ctx, rows.data(), 0, n, K, ids.data()), "compare_histories_with_all_ranks");
+        }
     }
     const bool dense = keep_all_similar();
     uint64_t m = 0;
