@@ -144,6 +144,14 @@ int scema_edges_device(scema_ctx *ctx, const uint64_t **keys, const double **dif
 /* Per-history number of partners (size of most_similar_histories, strain2spline.h:429). */
 int scema_get_degrees(scema_ctx *ctx, uint32_t *degree_host);
 
+/* Legacy single nearest neighbour of every history of the current spline matrix (the most_similar_history the
+ * reference keeps "for legacy reasons", strain2spline.h:277-289; get_most_similar_history_ID / _diff, :233-245): the
+ * smallest compare_L2_norm to ANY other history — not only those below a threshold —, ties to the lowest ID, NaN
+ * distances ignored; {UINT32_MAX, +inf} when there is no candidate. Every pair is evaluated exactly (two passes of the
+ * filter-free tiles), nothing of size O(N^2) is stored. The full comparison lists (all_similar_histories, :271) are
+ * what scema_compare(+inf, SCEMA_PAIRS_EXACT) returns. Host arrays [n]; either may be NULL. */
+int scema_nearest(scema_ctx *ctx, uint32_t *nearest_id_host, double *nearest_diff_host);
+
 /* One call for a host caller: set_histories + resample + compare. With SCEMA_PAIRS_TC, 6 * spline_points <= 60
  * and a large batch (>= 65536 histories; SCEMA_PIPELINE=0 disables, SCEMA_PIPELINE_MIN_N moves the limit) the three
  * steps are pipelined range by range behind the host->device copy of the raw steps: range c is resampled and compared
@@ -219,6 +227,11 @@ int scema_last_timings(scema_ctx *ctx, float ms[SCEMA_T_COUNT]);
 int scema_last_counters(scema_ctx *ctx, uint64_t counters[8]);
 /* Total kernels launched by this context so far. */
 uint64_t scema_kernel_launches(const scema_ctx *ctx);
+/* Run-time audit of the filters (environment SCEMA_AUDIT=<samples>, off by default; one-GPU compares): after the
+ * compare, <samples> pairs (half random, half between histories of nearby index) are recomputed exactly and every one
+ * the reference calls an edge must be in the emitted list, otherwise the compare fails with SCEMA_ERR_STATE.
+ * out = {sampled pairs that were edges, of those missing from the list} of the last audited compare. */
+int scema_last_audit(scema_ctx *ctx, uint64_t out[2]);
 /* Validation hook of SCEMA_PAIRS_TC (tests only; n padded to 256 must be <= 8192): runs the instrumented
  * tcgen05 kernel over the whole pair matrix of the current spline rows. acc_host[row * ld + col] receives
  * every fp32 accumulator (a.b - h_row - h_col in the scaled units of the operands; slices = 2: all three

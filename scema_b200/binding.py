@@ -56,6 +56,7 @@ def lib():
         "scema_edges_device": (i32, [vp, P(vp), P(vp), P(u32), P(u64)]),
         "scema_get_degrees": (i32, [vp, vp]),
         "scema_cluster": (i32, [vp, vp, vp, vp, u64, u32, dbl, i32, P(u64)]),
+        "scema_nearest": (i32, [vp, vp, vp]),
         "scema_write_similar_hist": (i32, [vp, C.c_char_p]),
         "scema_reduce_edges": (i32, [vp, u32, vp, P(u64), P(u64)]),
         "scema_reduce_calls": (i32, [vp, vp, u64, u32, vp, P(u64), P(u64)]),
@@ -63,6 +64,7 @@ def lib():
         "scema_last_timings": (i32, [vp, P(C.c_float)]),
         "scema_last_counters": (i32, [vp, P(u64)]),
         "scema_kernel_launches": (u64, [vp]),
+        "scema_last_audit": (i32, [vp, vp]),
         "scema_fp64_peak": (i32, [vp, P(dbl)]),
         "scema_tc_debug": (i32, [vp, dbl, u32, vp, u64, vp, vp]),
         "scema_tc_plan": (i32, [u32, u32, u32, vp]),
@@ -110,8 +112,8 @@ EXPORTED = (
     "scema_create scema_destroy scema_last_error scema_version scema_stream scema_set_histories scema_resample "
     "scema_store_reset scema_store_append scema_store_info scema_store_resample scema_select_rows "
     "scema_set_spline scema_get_spline scema_spline_info scema_compare scema_compare_stream scema_get_edges scema_edges_device "
-    "scema_get_degrees scema_cluster scema_write_similar_hist scema_reduce_edges scema_reduce_calls scema_reduce_dir "
-    "scema_last_timings scema_last_counters scema_kernel_launches scema_fp64_peak scema_tc_debug scema_tc_plan scema_tc_centre scema_tc_last_plan scema_tc_choose scema_pipeline_plan scema_synth_offsets "
+    "scema_get_degrees scema_cluster scema_nearest scema_write_similar_hist scema_reduce_edges scema_reduce_calls scema_reduce_dir "
+    "scema_last_timings scema_last_counters scema_kernel_launches scema_last_audit scema_fp64_peak scema_tc_debug scema_tc_plan scema_tc_centre scema_tc_last_plan scema_tc_choose scema_pipeline_plan scema_synth_offsets "
     "scema_multi_create scema_multi_destroy scema_multi_last_error scema_multi_devices scema_multi_context scema_multi_cluster "
     "scema_multi_compare_rows scema_multi_shard_edges scema_multi_last_ms "
     "scema_synth_histories_device scema_synth_rows_device scema_synth_histories_model_device scema_synth_rows_model_device scema_ingest_last_error scema_batch_read_dir "
@@ -384,6 +386,14 @@ class HistCluster:
         self._ck(self._L.scema_get_degrees(self._h, _ptr(out)))
         return out
 
+    def nearest(self):
+        """Legacy nearest neighbour of every history: (ids [n] uint32, diffs [n] float64)."""
+        n, _, _ = self.spline_info()
+        ids = np.empty(n, dtype=np.uint32)
+        d = np.empty(n, dtype=np.float64)
+        self._ck(self._L.scema_nearest(self._h, _ptr(ids), _ptr(d)))
+        return ids, d
+
     def cluster(self, steps, offsets, ids, spline_points, threshold, variant=PAIRS_TC):
         steps = np.ascontiguousarray(steps, dtype=np.float64)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
@@ -415,6 +425,12 @@ class HistCluster:
         self._ck(self._L.scema_last_counters(self._h, c))
         return {"pairs": int(c[0]), "survivors": int(c[1]), "edges": int(c[2]), "passes": int(c[3]), "tiles": int(c[4]),
                 "tc_slices": int(c[5]), "pipeline_ranges": int(c[6]), "band_tiles": int(c[7])}
+
+    def last_audit(self):
+        """(sampled pairs that were reference edges, of those missing from the list) of the last SCEMA_AUDIT run."""
+        out = (C.c_uint64 * 2)()
+        self._ck(self._L.scema_last_audit(self._h, out))
+        return int(out[0]), int(out[1])
 
     def kernel_launches(self):
         return int(self._L.scema_kernel_launches(self._h))

@@ -324,6 +324,13 @@ int scema_get_degrees(scema_ctx *c, uint32_t *degree_host)
     return SCEMA_OK;
 }
 
+int scema_nearest(scema_ctx *c, uint32_t *nearest_id_host, double *nearest_diff_host)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    return nearest_run(c, nearest_id_host, nearest_diff_host);
+}
+
 int scema_cluster(scema_ctx *c, const double *steps, const uint64_t *offsets, const uint32_t *ids, uint64_t n,
                   uint32_t spline_points, double threshold, int variant, uint64_t *n_edges)
 {
@@ -420,6 +427,14 @@ int scema_last_counters(scema_ctx *c, uint64_t counters[8])
 }
 
 uint64_t scema_kernel_launches(const scema_ctx *c) { return c ? c->launches : 0; }
+
+int scema_last_audit(scema_ctx *c, uint64_t out[2])
+{
+    if (!c || !out) return SCEMA_ERR_INVALID;
+    out[0] = c->audit_edges;
+    out[1] = c->audit_missing;
+    return SCEMA_OK;
+}
 
 int scema_fp64_peak(scema_ctx *c, double out[2])
 {

@@ -149,6 +149,7 @@ struct scema_ctx {
     bool ev_used[SCEMA_T_COUNT] = {};
     float acc_ms[SCEMA_T_COUNT] = {};  // phases already folded in by earlier chunks of a streamed compare
     uint64_t counters[8] = {};
+    uint64_t audit_edges = 0, audit_missing = 0;  // last SCEMA_AUDIT run: sampled pairs that are reference edges / of those, missing from the list
 };
 
 namespace scema {
@@ -184,6 +185,7 @@ int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_
 int compare_stream_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards, uint32_t panels_per_chunk,
                        scema_edge_sink sink, void *user, uint64_t *n_total);
 int fp64_peak_run(scema_ctx *ctx, double out[2]);
+int nearest_run(scema_ctx *ctx, uint32_t *nearest_id_host, double *nearest_diff_host);
 int edges_adopt(scema_ctx *ctx, const uint64_t *d_keys, const double *d_vals, uint64_t total);
 bool pipeline_wanted(uint64_t n);
 void pipeline_bounds(uint64_t n, std::vector<uint64_t> &bounds);

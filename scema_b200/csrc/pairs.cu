@@ -692,6 +692,112 @@ __global__ void __launch_bounds__(256) k_exact_all(const double *__restrict__ S,
         }
 }
 
+// Legacy nearest neighbour of every history (choose_most_similar_history, strain2spline.h:277-289: the smallest
+// distance to ANY other history, ties to the lowest ID, NaN distances ignored) without the O(N^2) lists: the tiles of
+// k_exact_all, PASS 1 keeps the smallest distance per row (non-negative doubles order as unsigned integers),
+// PASS 2 the lowest ID among the histories at exactly that distance.
+template <int PASS>
+__global__ void __launch_bounds__(256) k_nearest(const double *__restrict__ S, uint64_t n, uint32_t K, const uint32_t *__restrict__ ids,
+                                                 uint32_t I_first, unsigned long long *__restrict__ minbits,
+                                                 unsigned int *__restrict__ minid)
+{
+    const uint32_t I = I_first + blockIdx.y, J = blockIdx.x;
+    if (J < I) return;
+    __shared__ double As[XT][XKC + 1], Bs[XT][XKC + 1];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double sum[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) sum[p][q] = 0.0;
+    const uint64_t r0 = (uint64_t)I * XT, c0 = (uint64_t)J * XT;
+    for (uint32_t k0 = 0; k0 < K; k0 += XKC) {
+        const uint32_t kn = K - k0 < (uint32_t)XKC ? K - k0 : (uint32_t)XKC;
+        __syncthreads();
+        for (int e = tid; e < XT * XKC; e += 256) {
+            const int rr = e / XKC, kk = e - rr * XKC;
+            double va = 0.0, vb = 0.0;
+            if ((uint32_t)kk < kn) {
+                if (r0 + rr < n) va = S[(r0 + rr) * K + k0 + kk];
+                if (c0 + rr < n) vb = S[(c0 + rr) * K + k0 + kk];
+            }
+            As[rr][kk] = va;
+            Bs[rr][kk] = vb;
+        }
+        __syncthreads();
+        for (uint32_t kk = 0; kk < kn; kk++) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) av[p] = As[ty + 16 * p][kk];
+#pragma unroll
+            for (int q = 0; q < 4; q++) bv[q] = Bs[tx + 16 * q][kk];
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double diff = __dsub_rn(av[p], bv[q]);
+                    sum[p][q] = __dadd_rn(sum[p][q], __dmul_rn(diff, diff));
+                }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint64_t row = r0 + ty + 16 * p, col = c0 + tx + 16 * q;
+            const double d = __dsqrt_rn(sum[p][q]);
+            if (!(row < col && col < n) || d != d) continue;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+            if (PASS == 1) {
+                atomicMin(minbits + row, bits);
+                atomicMin(minbits + col, bits);
+            } else {
+                if (bits == minbits[row]) atomicMin(minid + row, ids[col]);
+                if (bits == minbits[col]) atomicMin(minid + col, ids[row]);
+            }
+        }
+}
+
+int nearest_run(scema_ctx *ctx, uint32_t *nearest_id_host, double *nearest_diff_host)
+{
+    if (!ctx->have_spline) return fail(ctx, SCEMA_ERR_STATE, "Spline is not up to date.");
+    const uint64_t n = ctx->n;
+    if (n == 0) return SCEMA_OK;
+    DevBuf d_ids, d_bits, d_minid;
+    std::vector<unsigned long long> bits(n, 0x7ff0000000000000ull);  // +inf: also what the reference starts from (:256)
+    int rc = SCEMA_OK;
+    auto run = [&]() -> int {
+        SCEMA_CUDA(ctx, d_ids.reserve(n * sizeof(uint32_t)));
+        SCEMA_CUDA(ctx, d_bits.reserve(n * sizeof(unsigned long long)));
+        SCEMA_CUDA(ctx, d_minid.reserve(n * sizeof(unsigned int)));
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(d_ids.p, ctx->ids.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(d_bits.p, bits.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+        SCEMA_CUDA(ctx, cudaMemsetAsync(d_minid.p, 0xff, n * sizeof(unsigned int), ctx->stream));
+        const uint32_t nbx = (uint32_t)((n + XT - 1) / XT);
+        for (int pass = 1; pass <= 2; pass++)
+            for (uint32_t i0 = 0; i0 < nbx; i0 += 65535u) {
+                const dim3 grid(nbx, std::min<uint32_t>(65535u, nbx - i0));
+                if (pass == 1)
+                    k_nearest<1><<<grid, 256, 0, ctx->stream>>>(ctx->d_spline, n, ctx->K, d_ids.as<uint32_t>(), i0,
+                                                               d_bits.as<unsigned long long>(), d_minid.as<unsigned int>());
+                else
+                    k_nearest<2><<<grid, 256, 0, ctx->stream>>>(ctx->d_spline, n, ctx->K, d_ids.as<uint32_t>(), i0,
+                                                               d_bits.as<unsigned long long>(), d_minid.as<unsigned int>());
+                ctx->launches++;
+            }
+        SCEMA_CUDA(ctx, cudaGetLastError());
+        if (nearest_diff_host)
+            SCEMA_CUDA(ctx, cudaMemcpyAsync(nearest_diff_host, d_bits.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (nearest_id_host)
+            SCEMA_CUDA(ctx, cudaMemcpyAsync(nearest_id_host, d_minid.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return SCEMA_OK;
+    };
+    rc = run();
+    d_ids.release(); d_bits.release(); d_minid.release();
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1167,6 +1273,62 @@ static int compare_begin(scema_ctx *ctx, double thr, int &variant, uint32_t shar
     return SCEMA_OK;
 }
 
+// Run-time audit (SCEMA_AUDIT=<samples>, off by default): the filters reject pairs on the strength of an error budget
+// that — for the tcgen05 filter — rests on one measured hardware property (fp32 accumulation of a kind::f16 step,
+// DESIGN.md "K2-TC"). The audit recomputes `samples` pairs exactly (half uniformly random, half between histories whose
+// indices are close, where similar histories concentrate) and requires every one that the reference calls an edge to BE
+// in the emitted list (binary search in the sorted keys). A miss fails the compare loudly.
+__global__ void __launch_bounds__(256) k_audit(const double *__restrict__ S, uint64_t n, uint32_t K, double thr, uint32_t key_shift,
+                                               const uint64_t *__restrict__ keys, uint64_t n_edges, uint64_t samples, uint64_t seed,
+                                               unsigned long long *__restrict__ out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= samples) return;
+    auto mix = [](uint64_t z) {
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        return z ^ (z >> 31);
+    };
+    uint64_t i = mix(seed + 2 * t) % n, j;
+    if (t & 1) j = (i + 1 + mix(seed + 2 * t + 1) % 32) % n;   // a near index
+    else j = mix(seed + 2 * t + 1) % n;
+    if (i == j) return;
+    if (i > j) { const uint64_t x = i; i = j; j = x; }
+    const double d = exact_l2(S + i * K, S + j * K, K);
+    if (!(d < thr)) return;
+    atomicAdd(out + 0, 1ull);  // sampled pairs that are edges
+    const uint64_t key = (i << key_shift) | j;
+    uint64_t lo = 0, hi = n_edges;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    if (!(lo < n_edges && keys[lo] == key)) atomicAdd(out + 1, 1ull);
+}
+
+static int audit_run(scema_ctx *ctx, double thr)
+{
+    const char *e = getenv("SCEMA_AUDIT");
+    const uint64_t samples = e ? (uint64_t)atoll(e) : 0;
+    if (!samples || ctx->n < 2) return SCEMA_OK;
+    unsigned long long *d_cnt = ctx->d_counters.as<unsigned long long>();
+    SCEMA_CUDA(ctx, cudaMemsetAsync(d_cnt + 4, 0, 2 * sizeof(uint64_t), ctx->stream));
+    if (const char *f = getenv("SCEMA_AUDIT_THR_FACTOR")) thr *= atof(f);  // test hook: audit against a larger threshold than the compare used
+    k_audit<<<(unsigned)((samples + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_spline, ctx->n, ctx->K, thr, ctx->key_shift,
+                                                                         ctx->d_edge_key[ctx->edge_cur].as<uint64_t>(), ctx->n_edges, samples,
+                                                                         0x5ca1ab1eull + ctx->spline_version, d_cnt + 4);
+    ctx->launches++;
+    SCEMA_CUDA(ctx, cudaGetLastError());
+    SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->h_counters, d_cnt, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->audit_edges = ctx->h_counters[4];
+    ctx->audit_missing = ctx->h_counters[5];
+    if (ctx->audit_missing)
+        return fail(ctx, SCEMA_ERR_STATE, "audit: " + std::to_string(ctx->audit_missing) + " of " + std::to_string(ctx->audit_edges) +
+                                              " sampled reference edges are missing from the emitted list (filter unsound on this device?)");
+    return SCEMA_OK;
+}
+
 int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards)
 {
     Schedule sc;
@@ -1179,6 +1341,7 @@ int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_
     if (rc) return rc;
     ctx->counters[2] = ctx->n_edges;
     if (n_shards == 1) ctx->counters[0] = ctx->n * (ctx->n - 1) / 2;
+    if (n_shards == 1 && variant != SCEMA_PAIRS_EXACT) return audit_run(ctx, thr);  // a shard's list only holds its own tiles
     return SCEMA_OK;
 }
 

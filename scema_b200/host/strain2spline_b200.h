@@ -12,6 +12,17 @@
 // (include/scema_hist.h): K1 resample, K2 all-pairs, K3 compaction on the GPU. Results land in
 // the same per-object lists, in the reference's order, with bit-identical doubles.
 //
+// Deliberate differences from strain2spline.h (everything else is byte-compatible, tests/test_dropin_header.py):
+//   * all_similar_histories (the O(N^2) "theory-checking only" lists behind all_similar_histories_to_file,
+//     strain2spline.h:271,316-330, written at FE_problem.h:1237-1238) stay EMPTY unless SCEMA_B200_ALL_SIMILAR=1
+//     (then a dense exact pass fills them, in the reference's order, single- and multi-rank);
+//   * get_most_similar_history_ID / _diff (the legacy nearest neighbour, :277-289) then report the nearest history
+//     among those BELOW the threshold ({UINT32_MAX, inf} if none) instead of the global nearest; SCEMA_B200_NEAREST=1
+//     (or SCEMA_B200_ALL_SIMILAR=1) restores the reference's global nearest neighbour with its lowest-ID tie-break
+//     (scema_nearest: exact distances to all other histories, no O(N^2) storage). Nothing in SCEMa reads either.
+//   * Strain6DReceiver / send_strain6D_mpi / receive_strain6D_mpi / modulo_neg exist for name compatibility; the
+//     collective below does not use them (no ring).
+//
 // MPI: when <mpi.h> has been included before this header (MPI_VERSION defined) the collective
 // gathers every rank's histories to rank 0 of `comm`, which owns the GPU, and scatters the
 // per-history results back in the reference's ring order (local partners first, then those of
@@ -124,7 +135,31 @@ inline bool keep_all_similar()
     return v == 1;
 }
 
+// $SCEMA_B200_NEAREST=1: the legacy global nearest neighbour without the O(N^2) lists (scema_nearest).
+inline bool keep_nearest()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SCEMA_B200_NEAREST"); v = (e && atoi(e) != 0) ? 1 : 0; }
+    return v == 1;
+}
+
 void resolve_splines(std::vector<Strain6D *> &pending);
+
+// Partner order of the reference's ring (strain2spline.h:571-599). `li` lists the partners of one history of rank
+// `my_rank` by batch index, ascending, where the batch is the rank-major concatenation of every rank's local vector
+// and ring_rank[j] is the rank history j lives on. The ring visits the own rank first (the local a < b loop: partners
+// in ascending local index), then the histories received from rank-1, rank-2, ... each in its sender's order — a
+// stable pass by ring step keeps exactly that. Pure host logic (tests/helpers/ring_order_check.cc).
+inline void ring_sort(std::vector<std::pair<uint32_t, double> > &li, int my_rank, const std::vector<int> &ring_rank, int n_ranks)
+{
+    if (n_ranks <= 1) return;
+    std::vector<std::pair<uint32_t, double> > sorted;
+    sorted.reserve(li.size());
+    for (int step = 0; step < n_ranks; step++)
+        for (size_t q = 0; q < li.size(); q++)
+            if (((my_rank - ring_rank[li[q].first]) % n_ranks + n_ranks) % n_ranks == step) sorted.push_back(li[q]);
+    li.swap(sorted);
+}
 
 }  // namespace b200
 
@@ -320,7 +355,16 @@ public:
         note_nearest(diff, other_id);
     }
     void b200_note_nearest(double diff, uint32_t other_id) { note_nearest(diff, other_id); }
+    void b200_set_nearest(uint32_t other_id, double diff) { most_similar_history.ID = other_id; most_similar_history.diff = diff; }
+    void b200_push_all_raw(uint32_t other_id, double diff)
+    {
+        HISTORY_ID_DIFF_PAIR hp;
+        hp.ID = other_id;
+        hp.diff = diff;
+        all_similar_histories.push_back(hp);
+    }
     const std::vector<HISTORY_ID_DIFF_PAIR> &b200_most_similar() const { return most_similar_histories; }
+    const std::vector<HISTORY_ID_DIFF_PAIR> &b200_all_similar() const { return all_similar_histories; }
 
 private:
     void materialise()
@@ -490,22 +534,20 @@ inline void compare_batch(std::vector<Strain6D *> &hist, double threshold, const
     }
     for (size_t i = 0; i < n; i++) {
         std::vector<std::pair<uint32_t, double> > &li = lists[i];
-        if (n_ranks > 1) {
-            // ring order: own rank first, then rank-1, rank-2, ... (strain2spline.h:571-599); within
-            // one sender ascending index. A stable counting pass by ring step keeps that.
-            std::vector<std::pair<uint32_t, double> > sorted;
-            sorted.reserve(li.size());
-            for (int step = 0; step < n_ranks; step++)
-                for (size_t q = 0; q < li.size(); q++)
-                    if (((ring_rank[i] - ring_rank[li[q].first]) % n_ranks + n_ranks) % n_ranks == step) sorted.push_back(li[q]);
-            li.swap(sorted);
-        }
+        if (n_ranks > 1) ring_sort(li, ring_rank[i], ring_rank, n_ranks);
         for (size_t q = 0; q < li.size(); q++) {
             const bool keep = li[q].second < threshold;
             if (dense) hist[i]->b200_push_all(ids[li[q].first], li[q].second);
             hist[i]->b200_push_partner(ids[li[q].first], li[q].second, keep);
             if (!dense && keep) hist[i]->b200_note_nearest(li[q].second, ids[li[q].first]);
         }
+    }
+    if (!dense && keep_nearest()) {
+        // the reference's global nearest neighbour (lowest ID on ties), from exact distances to ALL other histories
+        std::vector<uint32_t> nid(n);
+        std::vector<double> nd(n);
+        check(scema_nearest(ctx, nid.data(), nd.data()), "compare_histories_with_all_ranks");
+        for (size_t i = 0; i < n; i++) hist[i]->b200_set_nearest(nid[i], nd[i]);
     }
 }
 
@@ -539,6 +581,50 @@ inline double compare_L2_norm(Strain6D *a, Strain6D *b)
     std::vector<double> *sa = a->get_spline(), *sb = b->get_spline();
     return compare_L2_norm(sa->data(), sb->data(), (uint32_t)sa->size(), (uint32_t)sb->size());
 }
+
+// ---- names the reference header also exports (strain2spline.h:445-464, :499-539). The collective below gathers the
+// histories instead of passing them round a ring, so it uses none of these; they behave like the reference's.
+class Strain6DReceiver {
+public:
+    Strain6DReceiver(uint32_t in_max_buf_size)
+    {
+        max_buf_size = in_max_buf_size;
+        spline = new double[max_buf_size];
+        recv_count = 0;
+        ID = 0;
+    }
+    ~Strain6DReceiver() { delete[] spline; }
+    double *spline;
+    uint32_t recv_count, max_buf_size, ID;
+};
+
+inline double compare_L2_norm(Strain6D *a, Strain6DReceiver *b)
+{
+    std::vector<double> *sa = a->get_spline();
+    return compare_L2_norm(sa->data(), b->spline, (uint32_t)sa->size(), b->recv_count);
+}
+
+inline int32_t modulo_neg(int32_t x, int32_t n) { return ((x % n + n) % n); }
+
+#if !defined(SCEMA_B200_NO_MPI)
+inline void send_strain6D_mpi(Strain6D *in_s6D, int32_t target_rank, int32_t this_rank, MPI_Comm comm)
+{
+    std::vector<double> *strain = in_s6D->get_spline();
+    uint32_t ID = in_s6D->get_ID();
+    int32_t num_doubles_to_send = (int32_t)strain->size();
+    MPI_Send(&num_doubles_to_send, 1, MPI_UNSIGNED, target_rank, this_rank, comm);
+    MPI_Send(strain->data(), num_doubles_to_send, MPI_DOUBLE, target_rank, this_rank, comm);
+    MPI_Send(&ID, 1, MPI_UNSIGNED, target_rank, this_rank, comm);
+}
+
+inline void receive_strain6D_mpi(Strain6DReceiver *recv, int32_t from_rank, MPI_Comm comm)
+{
+    MPI_Status status;
+    MPI_Recv(&(recv->recv_count), 1, MPI_UNSIGNED, from_rank, from_rank, comm, &status);
+    MPI_Recv(recv->spline, (int)recv->max_buf_size, MPI_DOUBLE, from_rank, from_rank, comm, &status);
+    MPI_Recv(&(recv->ID), 1, MPI_UNSIGNED, from_rank, from_rank, comm, &status);
+}
+#endif
 
 // Collective over `comm` exactly like the reference: every rank passes its local histories and
 // returns with each of them holding the list of all other histories (on any rank) closer than
@@ -610,9 +696,15 @@ inline void compare_histories_with_all_ranks(std::vector<Strain6D *> &histories,
         for (int r = 0; r < n_ranks; r++) {
             rdispl[r] = (int)packed.size();
             for (int i = 0; i < counts[r]; i++, idx++) {
+                // per history: partners below the threshold, the full comparison list (dense mode), the nearest neighbour
                 const std::vector<HISTORY_ID_DIFF_PAIR> &ms = proxy[idx].b200_most_similar();
                 packed.push_back((double)ms.size());
                 for (size_t q = 0; q < ms.size(); q++) { packed.push_back((double)ms[q].ID); packed.push_back(ms[q].diff); }
+                const std::vector<HISTORY_ID_DIFF_PAIR> &as = proxy[idx].b200_all_similar();
+                packed.push_back((double)as.size());
+                for (size_t q = 0; q < as.size(); q++) { packed.push_back((double)as[q].ID); packed.push_back(as[q].diff); }
+                packed.push_back((double)proxy[idx].get_most_similar_history_ID());
+                packed.push_back(proxy[idx].get_most_similar_history_diff());
             }
             rcounts[r] = (int)packed.size() - rdispl[r];
         }
@@ -625,10 +717,11 @@ inline void compare_histories_with_all_ranks(std::vector<Strain6D *> &histories,
     for (int i = 0; i < n_local; i++) {
         histories[i]->clear_most_similar_history();
         const size_t cnt = (size_t)mine[c++];
-        for (size_t q = 0; q < cnt; q++, c += 2) {
-            histories[i]->b200_push_partner((uint32_t)mine[c], mine[c + 1], true);
-            histories[i]->b200_note_nearest(mine[c + 1], (uint32_t)mine[c]);
-        }
+        for (size_t q = 0; q < cnt; q++, c += 2) histories[i]->b200_push_partner((uint32_t)mine[c], mine[c + 1], true);
+        const size_t cnt_all = (size_t)mine[c++];
+        for (size_t q = 0; q < cnt_all; q++, c += 2) histories[i]->b200_push_all_raw((uint32_t)mine[c], mine[c + 1]);
+        histories[i]->b200_set_nearest((uint32_t)mine[c], mine[c + 1]);
+        c += 2;
     }
 #endif
 }

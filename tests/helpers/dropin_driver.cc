@@ -78,6 +78,19 @@ int main(int argc, char **argv)
             snprintf(name, sizeof name, "%s/t%u.last.%u.similar_hist", out.c_str(), t, flagged[i]->get_ID());
             flagged[i]->most_similar_histories_to_file(name);
             if (i < 5) flagged[i]->print_most_similar_histories();
+            // DROPIN_LEGACY=1: the "theory-checking" outputs too — the full comparison lists (FE_problem.h:1237-1238)
+            // and the legacy nearest neighbour; =2: the nearest neighbour only
+            const char *legacy = getenv("DROPIN_LEGACY");
+            if (legacy && atoi(legacy) == 1) {
+                snprintf(name, sizeof name, "%s/t%u.last.%u.all_similar_hist", out.c_str(), t, flagged[i]->get_ID());
+                flagged[i]->all_similar_histories_to_file(name);
+            }
+            if (legacy && atoi(legacy) >= 1 && i < 40) {
+                std::cout.precision(17);
+                std::cout << "nearest of " << flagged[i]->get_ID() << ": " << flagged[i]->get_most_similar_history_ID() << " at "
+                          << flagged[i]->get_most_similar_history_diff() << "\n";
+                std::cout.precision(6);
+            }
         }
         // a few splines and one direct distance, in full precision
         std::cout.precision(17);

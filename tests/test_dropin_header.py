@@ -44,6 +44,32 @@ def test_same_caller_same_bytes(tmp_path, n_qp, n_steps, P, thr, seed):
     assert any(os.path.getsize(tmp_path / "ref" / f) > 0 for f in files if f.endswith("similar_hist"))
 
 
+@pytest.mark.parametrize("legacy,env", [("1", {"SCEMA_B200_ALL_SIMILAR": "1"}), ("2", {"SCEMA_B200_NEAREST": "1"})])
+def test_legacy_outputs_on_request(tmp_path, legacy, env):
+    """The reference's "theory-checking" outputs: all_similar_histories_to_file (every comparison of every history,
+    FE_problem.h:1237-1238) with SCEMA_B200_ALL_SIMILAR=1, and the legacy global nearest neighbour
+    (get_most_similar_history_ID / _diff, lowest ID on ties) with either knob — byte-identical to the reference header."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref not built")
+    ours_exe = build_ours(tmp_path)
+    outs = {}
+    for name, exe, extra in (("ref", REF_BIN, {}), ("ours", ours_exe, env)):
+        d = tmp_path / name
+        d.mkdir()
+        r = subprocess.run([exe, str(d), "120", "12", "10", "1e-6", "4"], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, DROPIN_LEGACY=legacy, **extra))
+        assert r.returncode == 0, r.stderr
+        outs[name] = r.stdout
+    assert outs["ours"] == outs["ref"] and outs["ref"].count("nearest of") >= 40
+    files = sorted(os.listdir(tmp_path / "ref"))
+    assert files == sorted(os.listdir(tmp_path / "ours"))
+    match, mismatch, errors = filecmp.cmpfiles(tmp_path / "ref", tmp_path / "ours", files, shallow=False)
+    assert not mismatch and not errors
+    if legacy == "1":
+        full = [f for f in files if f.endswith("all_similar_hist")]
+        assert full and all(os.path.getsize(tmp_path / "ref" / f) > 1000 for f in full)
+
+
 def test_error_behaviour_matches(tmp_path):
     """< 3 samples: both print the reference's message and exit(1) (strain2spline.h:142-148)."""
     if not os.path.exists(REF_BIN):

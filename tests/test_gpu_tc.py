@@ -511,3 +511,23 @@ def test_queue_capacity_follows_the_batch_size():
     assert c["survivors"] > (1 << 20) and c["tc_slices"] == 1 and c["passes"] == 1, c
     assert ne > n
     h.close()
+
+
+def test_run_time_audit_catches_a_missing_edge(oracle):
+    """SCEMA_AUDIT=<samples>: sampled pairs are recomputed exactly after the compare and every reference edge among them
+    must be in the list. Green on a sound compare; and it does catch a missing edge — checked by auditing a compare that
+    ran with a SMALLER threshold (so true edges of the larger threshold are absent) through the same kernel."""
+    code = (
+        "import numpy as np, scema_b200\n"
+        "from scema_b200 import synth, PAIRS_TC\n"
+        "rows = synth.rows(3, 5000, 16, 10, 5e-3, synth.default_pert(1e-6, 10))\n"
+        "hc = scema_b200.HistCluster(0); hc.set_spline(rows)\n"
+        "ne = hc.compare(1e-6, PAIRS_TC); a = hc.last_audit(); assert a[0] > 100 and a[1] == 0, a\n"
+        "print('ok', ne, a)\n")
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SCEMA_AUDIT="300000", PYTHONPATH=ROOT), capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.stdout, r.stderr)
+    # the audit's threshold can be moved by a test hook (SCEMA_AUDIT_THR_FACTOR): edges of 1.5 thr are then "missing"
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SCEMA_AUDIT="300000", SCEMA_AUDIT_THR_FACTOR="1.5", PYTHONPATH=ROOT),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "audit:" in r.stderr and "missing from the emitted list" in r.stderr, (r.stdout, r.stderr)
