@@ -245,7 +245,10 @@ def verify_run(args, hc, sc, world, rank, dev, n, P, variant, stream_mode, level
         got.append((a, b, d))
 
     if world > 1:
-        ne, counts, offs, full = sc.run(n, P, THR, variant, sink=vsink if stream_mode else None)
+        if getattr(sc, "side_group", None) is not None and not stream_mode:
+            ne, counts, offs, full = sc.run_overlapped(n, P, THR)   # the path that was timed
+        else:
+            ne, counts, offs, full = sc.run(n, P, THR, variant, sink=vsink if stream_mode else None)
     else:
         hc.resample(P)
         ne = hc.compare_stream(THR, vsink, variant) if stream_mode else hc.compare(THR, variant)
@@ -362,7 +365,7 @@ def run_ours(args, wl, wl_name):
     import torch.distributed as dist
     import scema_b200
     from scema_b200 import synth
-    from scema_b200.distributed import ShardedCluster, shard_bounds
+    from scema_b200.distributed import ShardedCluster, aligned_shard_bounds, shard_bounds
 
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
@@ -381,7 +384,12 @@ def run_ours(args, wl, wl_name):
     # the tcgen05 filter takes rows of up to 10 chunks of 64 columns; wider rows take the DMMA filter
     eff_variant = "dmma" if (args.variant == "tc" and K > 636) else args.variant
     pert = synth.default_pert(THR, P)
-    b, e = shard_bounds(n, world)[rank]
+    # N > 1 with the tcgen05 filter: aligned equal shares and the overlapped exchange (ShardedCluster.run_overlapped);
+    # SCEMA_SHARD_OVERLAP=0 keeps the plain sequence (all-gather of the FP64 rows, then everything else)
+    overlapped = (world > 1 and args.variant == "tc" and K <= 636 and not args.stream and n >= 4096 * world and
+                  os.environ.get("SCEMA_SHARD_OVERLAP", "1") != "0" and not args.norm_band)
+    all_bounds = aligned_shard_bounds(n, world)[1] if overlapped else shard_bounds(n, world)
+    b, e = all_bounds[rank]
     n_local = e - b
 
     # one explicit (non-default) stream carries everything: the library's kernels, the NCCL
@@ -397,7 +405,7 @@ def run_ours(args, wl, wl_name):
     h_steps.copy_(d_steps)
     torch.cuda.synchronize()
     h_steps_np = h_steps.numpy()
-    sc = ShardedCluster(hc) if world > 1 else None
+    sc = ShardedCluster(hc, side_group=dist.new_group(backend="nccl") if overlapped else None, bounds=all_bounds) if world > 1 else None
     total_pairs = n * (n - 1) // 2
 
     def barrier():
@@ -416,7 +424,10 @@ def run_ours(args, wl, wl_name):
 
     def step_resident(record):
         if world > 1:
-            ne, counts, offs, _ = sc.run(n, P, THR, variant, sink=sink if args.stream else None)
+            if overlapped:
+                ne, counts, offs, _ = sc.run_overlapped(n, P, THR)
+            else:
+                ne, counts, offs, _ = sc.run(n, P, THR, variant, sink=sink if args.stream else None)
             tot = sum(counts)
         else:
             hc.resample(P)
@@ -461,7 +472,9 @@ def run_ours(args, wl, wl_name):
             hc.get_edges(out=e2e_buffers(ne))        # device -> host read of the result
             return ne
         hc.set_histories(h_steps_np, off)            # pinned host -> device inside the timed region
-        if world > 1:
+        if world > 1 and overlapped:
+            ne, counts, offs, _ = sc.run_overlapped(n, P, THR)
+        elif world > 1:
             ne, counts, offs, _ = sc.run(n, P, THR, variant, sink=sink if args.stream else None)
         else:
             hc.resample(P)
@@ -525,7 +538,7 @@ def run_ours(args, wl, wl_name):
         if rank == 0:
             off_all = synth.device_offsets(SEED, n, CLUSTER, wl["lmin"], wl["lmax"])
             h_all = torch.empty((int(off_all[-1]), 6), dtype=torch.float64, pin_memory=True)
-            for (sb, se) in shard_bounds(n, world):
+            for (sb, se) in all_bounds:
                 so = (off_all[sb:se + 1] - off_all[sb]).astype(np.uint64)
                 part = synth.device_histories(SEED, se - sb, CLUSTER, wl_amp(wl), pert, so, first=sb, device=dev, **wl_model(wl))
                 h_all[int(off_all[sb]):int(off_all[se])].copy_(part)
@@ -680,6 +693,7 @@ def run_ours(args, wl, wl_name):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": wl_config(wl, wl_name),
             "run": {"variant": eff_variant, "parallelism": f"tile-shard x{world}",
+                    "exchange": (sc.path if (world > 1 and overlapped) else ("plain" if world > 1 else None)),
                     "filter_arithmetic": ("fp16 split operands (centred copies) on tcgen05, fp32 accumulate; every survivor and every "
                                           "emitted distance recomputed in f64 in the reference's operation order")
                     if eff_variant == "tc" else "f64",

@@ -160,6 +160,29 @@ int scema_nearest(scema_ctx *ctx, uint32_t *nearest_id_host, double *nearest_dif
 int scema_cluster(scema_ctx *ctx, const double *steps, const uint64_t *offsets, const uint32_t *ids,
                   uint64_t n, uint32_t spline_points, double threshold, int variant, uint64_t *n_edges);
 
+/* ---- sharded prepare of the tcgen05 filter (one context per GPU, each owning the rows [row0, row1), row0 a multiple of
+ *      128, of a spline matrix whose full-size buffer has been installed with scema_set_spline): every GPU builds the fp16
+ *      operand image of its own rows only and the caller all-gathers the images (128 bytes per row and 64-column chunk)
+ *      instead of waiting for the FP64 rows of everybody (8 K bytes per row), which only the exact recompute needs:
+ *        scema_tc_shard_begin   -> *centre_dev: K doubles on the device (centre candidate of the own rows); all-gather them
+ *                                  and pass ONE of them (the same on every GPU) to
+ *        scema_tc_shard_stats   -> *packet_dev: *packet_words 8-byte words (norm statistics and the survivor-density sample
+ *                                  of the own rows); all-gather the packets of all n_shards GPUs and pass them to
+ *        scema_tc_shard_finish  -> *choice: 1 = one fp16 slice with centred copies: the own rows' image now sits at
+ *                                  *image_dev + row0 * *image_bytes_per_row (hi-only layout); all-gather the images in
+ *                                  place, then scema_tc_shard_commit. Any other value (2: two slices, 3: raw copies,
+ *                                  0: SCEMA_PAIRS_DMMA, -1: SCEMA_PAIRS_EXACT): nothing was built, take the ordinary
+ *                                  scema_compare (every GPU gets the same value).
+ *        scema_tc_shard_commit  derives the second operand flavour; rows_ready_event (a cudaEvent_t as void*, may be NULL)
+ *                                  is what the exact recompute of the following scema_compare(threshold, SCEMA_PAIRS_TC,
+ *                                  shard, n_shards) waits for — record it behind the all-gather of the FP64 rows, which may
+ *                                  then overlap the filter. scema_b200/distributed.py drives this with torch.distributed. */
+int scema_tc_shard_begin(scema_ctx *ctx, double threshold, uint64_t row0, uint64_t row1, const double **centre_dev);
+int scema_tc_shard_stats(scema_ctx *ctx, const double *centre_dev, const uint64_t **packet_dev, uint64_t *packet_words);
+int scema_tc_shard_finish(scema_ctx *ctx, const uint64_t *packets_dev, uint32_t n_shards, uint64_t pairs, int *choice,
+                          const void **image_dev, uint64_t *image_bytes_per_row);
+int scema_tc_shard_commit(scema_ctx *ctx, void *rows_ready_event);
+
 /* ---- several GPUs of one box behind the same boundary: replaces the collective of compare_histories_with_all_ranks
  *      (strain2spline.h:546-614: R - 1 ring steps of blocking messages per history, called at FE_problem.h:1229) with a
  *      tile-sharded all-pairs driven from ONE process. scema_multi_create(devices[n_devices]; NULL = 0..n-1) makes one

@@ -488,6 +488,38 @@ int scema_tc_centre(scema_ctx *c, double *centre_host)
     return SCEMA_OK;
 }
 
+int scema_tc_shard_begin(scema_ctx *c, double threshold, uint64_t row0, uint64_t row1, const double **centre_dev)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    return tc_shard_begin(c, threshold, row0, row1, centre_dev);
+}
+
+int scema_tc_shard_stats(scema_ctx *c, const double *centre_dev, const uint64_t **packet_dev, uint64_t *packet_words)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    const unsigned long long *p = nullptr;
+    rc = tc_shard_stats(c, centre_dev, &p, packet_words);
+    if (packet_dev) *packet_dev = reinterpret_cast<const uint64_t *>(p);
+    return rc;
+}
+
+int scema_tc_shard_finish(scema_ctx *c, const uint64_t *packets_dev, uint32_t n_shards, uint64_t pairs, int *choice,
+                          const void **image_dev, uint64_t *image_bytes_per_row)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    return tc_shard_finish(c, reinterpret_cast<const unsigned long long *>(packets_dev), n_shards, pairs, choice, image_dev, image_bytes_per_row);
+}
+
+int scema_tc_shard_commit(scema_ctx *c, void *rows_ready_event)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    return tc_shard_commit(c, rows_ready_event);
+}
+
 int scema_tc_debug(scema_ctx *c, double threshold, uint32_t slices, float *acc_host, uint64_t ld, void *operand_a_host,
                    void *operand_b_host)
 {

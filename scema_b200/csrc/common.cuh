@@ -122,6 +122,9 @@ struct scema_ctx {
     uint32_t tc_mode = 0;  // 1: the filter was chosen automatically and compare_panels may change it on overflow; 0: SCEMA_TC_SLICES pins it
     double tc_thr = 0.0, tc_T0 = 0.0, tc_cguard = 0.0;
     bool tc_valid = false;
+    bool tc_compact = false;             // hi-only operand copies (sharded prepare)
+    uint64_t shard_r0 = 0, shard_r1 = 0; // own rows of a sharded prepare
+    void *rows_ready_event = nullptr;    // cudaEvent_t the exact recompute of the next compare waits for (FP64 rows still arriving)
 
     // ---- candidate queue + edges
     scema::DevBuf d_cand, d_counters;  // counters: [0] candidates, [1] edges, [2] flags
@@ -182,6 +185,7 @@ int store_resample(scema_ctx *ctx, uint32_t P);
 int select_rows(scema_ctx *ctx, const uint32_t *rows, uint64_t m);
 // pairs.cu
 int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards);
+int wait_rows(scema_ctx *ctx);
 int compare_stream_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards, uint32_t panels_per_chunk,
                        scema_edge_sink sink, void *user, uint64_t *n_total);
 int fp64_peak_run(scema_ctx *ctx, double out[2]);
@@ -203,6 +207,11 @@ void tc_choose(uint64_t pairs, uint32_t K, const uint64_t counts[5], uint64_t sa
 int tc_centre_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1);
 int tc_plan_rows(scema_ctx *ctx, uint64_t r1, uint64_t counts[5]);
 uint32_t tc_plan_sample_size();
+int tc_shard_begin(scema_ctx *ctx, double thr, uint64_t r0, uint64_t r1, const double **centre_dev);
+int tc_shard_stats(scema_ctx *ctx, const double *centre_dev, const unsigned long long **packet_dev, uint64_t *packet_words);
+int tc_shard_finish(scema_ctx *ctx, const unsigned long long *packets_dev, uint32_t G, uint64_t pairs, int *choice, const void **image_dev,
+                    uint64_t *image_bytes_per_row);
+int tc_shard_commit(scema_ctx *ctx, void *rows_ready_event);
 int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices);
 int tc_stats_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1, bool into_scale);
 int tc_fix_scale(scema_ctx *ctx, int headroom);

@@ -763,6 +763,7 @@ int nearest_run(scema_ctx *ctx, uint32_t *nearest_id_host, double *nearest_diff_
     if (!ctx->have_spline) return fail(ctx, SCEMA_ERR_STATE, "Spline is not up to date.");
     const uint64_t n = ctx->n;
     if (n == 0) return SCEMA_OK;
+    { const int rcw = wait_rows(ctx); if (rcw) return rcw; }
     DevBuf d_ids, d_bits, d_minid;
     std::vector<unsigned long long> bits(n, 0x7ff0000000000000ull);  // +inf: also what the reference starts from (:256)
     int rc = SCEMA_OK;
@@ -933,6 +934,17 @@ static uint32_t bits_for(uint64_t n)
     return b;
 }
 
+// A sharded prepare lets the filter start before the FP64 rows of the other GPUs have arrived (tc_shard_commit):
+// everything that reads the rows themselves waits for that event first.
+int wait_rows(scema_ctx *ctx)
+{
+    if (ctx->rows_ready_event) {
+        SCEMA_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, (cudaEvent_t)ctx->rows_ready_event, 0));
+        ctx->rows_ready_event = nullptr;
+    }
+    return SCEMA_OK;
+}
+
 static int prepare_filter(scema_ctx *ctx, int variant)
 {
     FilterLayout &fl = ctx->fl;
@@ -941,6 +953,7 @@ static int prepare_filter(scema_ctx *ctx, int variant)
         return SCEMA_OK;
     fl.K = ctx->K;
     fl.n = ctx->n;
+    { const int rcw = wait_rows(ctx); if (rcw) return rcw; }
     static const char *k2_env = getenv("SCEMA_K2");
     const bool ws = variant == SCEMA_PAIRS_DMMA && !(k2_env && strcmp(k2_env, "v1") == 0);
     if (ws) choose_chunks_tail(fl.K, &fl.kc, &fl.kt, &fl.n_chunks);
@@ -1033,6 +1046,8 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
         if (passes > 8) return fail(ctx, SCEMA_ERR_NOMEM, "compare: buffers kept overflowing");
         SCEMA_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 8 * sizeof(uint64_t), ctx->stream));
         if (*variant == SCEMA_PAIRS_EXACT) {
+            rc = wait_rows(ctx);
+            if (rc) return rc;
             const uint32_t nbx = (uint32_t)((n + XT - 1) / XT);
             const uint32_t per_panel = PANEL_ROWBLOCKS * (TILE / XT);
             const uint32_t i_first = (uint32_t)std::min<uint64_t>((uint64_t)p0 * per_panel, nbx);
@@ -1055,6 +1070,8 @@ static int compare_panels(scema_ctx *ctx, double thr, int *variant, uint32_t sha
                            d_cnt + 0, nullptr, 0);
             if (rc) return rc;
             t_end(ctx, SCEMA_T_FILTER);
+            rc = wait_rows(ctx);  // sharded prepare: the filter ran on the gathered fp16 images; the rows themselves are needed from here on
+            if (rc) return rc;
             t_begin(ctx, SCEMA_T_EXACT);
             k_exact_queue<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->d_spline, K, ctx->d_cand.as<uint64_t>(), d_cnt + 0,
                                                                       ctx->cand_cap, thr, ctx->key_shift, d_cnt + 1,

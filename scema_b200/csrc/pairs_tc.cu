@@ -237,6 +237,8 @@ struct Args {
     uint32_t shard, n_shards;
     uint32_t slices;   // 2: a_hi.b_hi + a_lo.b_hi + a_hi.b_lo; 1: a_hi.b_hi only (coarser guard band, a third of the MMAs)
     uint32_t nc;       // 64-column chunks per row (K <= 60: 1); a 128-row block holds nc x [hi | lo]
+    uint32_t compact;  // 1: hi-only operand copies (a 128-row block holds nc x hi, 16 KB each): the layout a sharded
+                       // compare all-gathers between the GPUs (one slice only)
     // shared-memory plan (tc_launch): A buffers of a_bytes each, then a ring of 2^lg_nst B stages
     uint32_t a_bytes, n_abuf, lg_nst, stage_bytes, data_bytes;
     // norm-band mode (rows sorted by norm): band schedule + map from sorted position to row index
@@ -294,7 +296,8 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
     // twice the stages in the same memory); A: all chunks of the row tile, double-buffered over items when it fits
     const uint32_t lg_nst = a.lg_nst, nst_mask = (1u << lg_nst) - 1u, stage_bytes = a.stage_bytes;
     const uint32_t a_chunk = a.slices == 1 ? SLICE_BYTES : BLOCK_BYTES;  // bytes of one chunk of an A tile in shared memory
-    const uint64_t gblk = (uint64_t)k_nc * BLOCK_BYTES;                  // bytes of a 128-row block in global memory
+    const uint32_t g_chunk = a.compact ? SLICE_BYTES : BLOCK_BYTES;      // bytes of one chunk of a 128-row block in global memory
+    const uint64_t gblk = (uint64_t)k_nc * g_chunk;                      // bytes of a 128-row block in global memory
     const uint32_t off_tmem = a.data_bytes + SM::n_bars * 8;
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem_raw + (base - raw) + off_tmem);
 
@@ -336,13 +339,13 @@ __global__ void __launch_bounds__(384, 1) k_filter_tc(const Args a)
                         mbar_expect_tx(bar_full(st), (COLT / CG / ROWS) * a_chunk + (first ? nc * a_chunk : 0u));
                         if (first)
                             for (uint32_t ca = 0; ca < nc; ca++)
-                                bulk_g2s(sA + ab * a_bytes + ca * a_chunk, HA + (uint64_t)(I * CG + rank) * gblk + (uint64_t)ca * BLOCK_BYTES,
+                                bulk_g2s(sA + ab * a_bytes + ca * a_chunk, HA + (uint64_t)(I * CG + rank) * gblk + (uint64_t)ca * g_chunk,
                                          a_chunk, bar_full(st));
                         if (CG == 2) {
-                            bulk_g2s(dst, HB + (uint64_t)(J * 2 + rank) * gblk + (uint64_t)c * BLOCK_BYTES, a_chunk, bar_full(st));
+                            bulk_g2s(dst, HB + (uint64_t)(J * 2 + rank) * gblk + (uint64_t)c * g_chunk, a_chunk, bar_full(st));
                         } else {
                             // 256 B rows of one CTA: the hi slices of both 128-row blocks, then both lo slices
-                            const unsigned char *b0 = HB + (uint64_t)(J * 2) * gblk + (uint64_t)c * BLOCK_BYTES;
+                            const unsigned char *b0 = HB + (uint64_t)(J * 2) * gblk + (uint64_t)c * g_chunk;
                             bulk_g2s(dst, b0, SLICE_BYTES, bar_full(st));
                             bulk_g2s(dst + SLICE_BYTES, b0 + gblk, SLICE_BYTES, bar_full(st));
                             if (slices != 1) {
@@ -680,7 +683,7 @@ __device__ __forceinline__ double h16z(double v)
 __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, uint64_t n, uint64_t r0, uint64_t r1, uint32_t K,
                                                  uint32_t nc, uint32_t slices, double vmax, const double *__restrict__ NRM,
                                                  unsigned long long *__restrict__ misc, double T0, double cguard,
-                                                 const uint32_t *__restrict__ perm, const double *__restrict__ centre,
+                                                 const uint32_t *__restrict__ perm, const double *__restrict__ centre, uint32_t compact,
                                                  unsigned char *__restrict__ HA, unsigned char *__restrict__ HB)
 {
     const uint64_t row = r0 + (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);  // position in the operand copies
@@ -723,7 +726,7 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
     const uint64_t blk = row / ROWS;
     const uint32_t r = (uint32_t)(row % ROWS);
     for (uint32_t c = 0; c < nc; c++) {
-        const uint64_t base = (blk * nc + c) * BLOCK_BYTES + (uint64_t)r * 128;
+        const uint64_t base = (blk * nc + c) * (compact ? SLICE_BYTES : BLOCK_BYTES) + (uint64_t)r * 128;
         unsigned char *a_hi = HA + base, *a_lo = a_hi + SLICE_BYTES;
         unsigned char *b_hi = HB + base, *b_lo = b_hi + SLICE_BYTES;
 #pragma unroll
@@ -744,7 +747,7 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
             }
             const uint32_t off = ((((k >> 3) ^ (r & 7u)) << 4) | ((k & 7u) << 1));  // swizzled 16-byte chunk, element in chunk
             *reinterpret_cast<__half *>(a_hi + off) = __double2half(ahi);
-            *reinterpret_cast<__half *>(b_hi + off) = __double2half(bhi);
+            if (!compact) *reinterpret_cast<__half *>(b_hi + off) = __double2half(bhi);  // compact: B is derived from the gathered A image
             if (slices != 1) {  // the one-slice kernel never reads the lo halves
                 *reinterpret_cast<__half *>(a_lo + off) = __double2half(alo);
                 *reinterpret_cast<__half *>(b_lo + off) = __double2half(blo);
@@ -766,13 +769,14 @@ __device__ __forceinline__ uint64_t plan_mix(uint64_t z)
     z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
     return z ^ (z >> 31);
 }
-__global__ void __launch_bounds__(256) k_tc_plan_sample(const double *__restrict__ S, const double *__restrict__ NRM, uint64_t n,
-                                                        uint32_t K, double T0, unsigned long long *__restrict__ misc)
+__global__ void __launch_bounds__(256) k_tc_plan_sample(const double *__restrict__ S, const double *__restrict__ NRM, uint64_t r0,
+                                                        uint64_t n, uint32_t K, double T0, unsigned long long *__restrict__ misc)
 {
     const uint32_t t = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (t >= PLAN_SAMPLE) return;
-    const uint64_t i = plan_mix(0x5ce3a0000ull + 2 * t) % n, j = plan_mix(0x5ce3a0001ull + 2 * t) % n;
+    // pairs among the n rows starting at r0
+    const uint64_t i = r0 + plan_mix(0x5ce3a0000ull + 2 * t) % n, j = r0 + plan_mix(0x5ce3a0001ull + 2 * t) % n;
     if (i == j) return;
     double d2 = 0.0, ua = 0.0, ub = 0.0;
     for (uint32_t k = lane; k < K; k += 32) {
@@ -896,6 +900,7 @@ int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices)
     const uint32_t K = ctx->K;
     const uint64_t n_pad = (n + tc::COLT - 1) / tc::COLT * tc::COLT;
     ctx->tc_valid = false;
+    ctx->tc_compact = false;  // [hi | lo] blocks unless a sharded prepare (tc_shard_*) asks for the hi-only layout
     ctx->tc_band = false;  // row order unless tc_prepare sorts by norm afterwards
     const uint32_t nc = tc_chunks(K);
     if (nc > 1 && slices != 1) return fail(ctx, SCEMA_ERR_INVALID, "tensor-core filter: rows wider than 60 columns run with one slice");
@@ -970,7 +975,7 @@ int tc_prep_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1)
         ctx->d_spline, ctx->n, r0, r1, ctx->K, tc_chunks(ctx->K), ctx->tc_slices, ldexp(1.0, 12 - tc_k_headroom(ctx->K)),
         ctx->d_tc_nrm.as<double>(),
         ctx->d_tc_misc.as<unsigned long long>(), ctx->tc_T0, ctx->tc_cguard, ctx->tc_band ? ctx->d_tc_perm.as<uint32_t>() : nullptr,
-        ctx->d_tc_centre.as<double>(), ctx->d_tc_a.as<unsigned char>(), ctx->d_tc_b.as<unsigned char>());
+        ctx->d_tc_centre.as<double>(), ctx->tc_compact ? 1u : 0u, ctx->d_tc_a.as<unsigned char>(), ctx->d_tc_b.as<unsigned char>());
     ctx->launches++;
     SCEMA_CUDA(ctx, cudaGetLastError());
     return SCEMA_OK;
@@ -1028,7 +1033,9 @@ int tc_prepare(scema_ctx *ctx, double thr, uint32_t slices, bool want_band, uint
         return SCEMA_OK;
     }
     const bool two_ok = tc_two_slices_possible(ctx);
-    int rc = tc_prepare_begin(ctx, thr, slices ? slices : 1);
+    int rc = wait_rows(ctx);   // a full prepare reads every row
+    if (rc) return rc;
+    rc = tc_prepare_begin(ctx, thr, slices ? slices : 1);
     ctx->tc_band = false;
     ctx->tc_band_wanted = want_band;
     if (!rc) rc = tc_centre_rows(ctx, 0, n);
@@ -1100,7 +1107,7 @@ int tc_plan_rows(scema_ctx *ctx, uint64_t r1, uint64_t counts[5])
     if (r1 < 2) return SCEMA_OK;
     unsigned long long *d_plan = ctx->d_tc_misc.as<unsigned long long>() + tc::PLAN_WORD, plan[8];
     SCEMA_CUDA(ctx, cudaMemsetAsync(d_plan, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    tc::k_tc_plan_sample<<<tc::PLAN_SAMPLE / 8, 256, 0, ctx->stream>>>(ctx->d_spline, ctx->d_tc_nrm.as<double>(), r1, ctx->K, ctx->tc_T0,
+    tc::k_tc_plan_sample<<<tc::PLAN_SAMPLE / 8, 256, 0, ctx->stream>>>(ctx->d_spline, ctx->d_tc_nrm.as<double>(), 0, r1, ctx->K, ctx->tc_T0,
                                                                      ctx->d_tc_misc.as<unsigned long long>());
     ctx->launches++;
     SCEMA_CUDA(ctx, cudaMemcpyAsync(plan, d_plan, sizeof(plan), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1109,6 +1116,126 @@ int tc_plan_rows(scema_ctx *ctx, uint64_t r1, uint64_t counts[5])
     return SCEMA_OK;
 }
 uint32_t tc_plan_sample_size() { return tc::PLAN_SAMPLE; }
+
+// ------------------------------------------------------------------------------------------------
+// Sharded prepare (one context per GPU, rows split between them): every GPU builds the operand copies of ITS OWN rows
+// only and the GPUs all-gather the fp16 images (128 bytes per row and chunk instead of 8 K bytes of FP64 rows), so the
+// filter can start while the FP64 rows — which only the exact recompute needs — are still travelling. Centre and scale
+// must be the same everywhere:
+//   tc_shard_begin   own rows [r0, r1): centre candidate (column medians of the own sample)       -> all-gather, take rank 0's
+//   tc_shard_stats   with the agreed centre: norms, magnitude, exponent histogram, survivor sample -> all-gather the packets
+//   tc_shard_finish  packets of all GPUs reduced (max / sums) -> same scale and same choice of filter on every GPU; if that is
+//                    "one slice, centred copies": hi-only A image of the own rows, in place          -> all-gather the images
+//   tc_shard_commit  B image derived from A (fold columns swapped), operand copies declared valid; the exact recompute of
+//                    the following scema_compare waits for `rows_ready` (the event behind the FP64 all-gather)
+// Any other choice (two slices, raw copies, DMMA, ...) is reported to the caller, which then takes the ordinary path.
+// ------------------------------------------------------------------------------------------------
+namespace tc {
+__global__ void __launch_bounds__(256) k_tc_reduce_packets(const unsigned long long *__restrict__ packets, uint32_t G,
+                                                           unsigned long long *__restrict__ misc)
+{
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < MISC_WORDS; w += gridDim.x * blockDim.x) {
+        unsigned long long acc = 0;
+        for (uint32_t g = 0; g < G; g++) {
+            const unsigned long long v = packets[(uint64_t)g * MISC_WORDS + w];
+            if (w == 0) acc = v > acc ? v : acc;   // largest magnitude: non-negative doubles order as integers
+            else acc += v;
+        }
+        if (w == 1 || w == 2 || w == 3) acc = 0;    // scale (set by k_tc_fix_scale), rows beyond the scale, band tiles
+        misc[w] = acc;
+    }
+}
+// B image from the A image (hi slices, compact layout): same data columns, fold columns [x0 x1 P Q] -> [P Q x0 x1]
+__global__ void __launch_bounds__(256) k_tc_derive_b(const uint4 *__restrict__ HA, uint4 *__restrict__ HB, uint64_t n_chunks16, uint32_t nc)
+{
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // 16-byte chunk index
+    if (q >= n_chunks16) return;
+    uint4 v = HA[q];
+    // chunk q: row = (q / 8) % 128 of slice (q / 1024); stored position p = q % 8 holds logical chunk p ^ (row & 7)
+    const uint32_t row = (uint32_t)((q >> 3) & 127u), logical = (uint32_t)(q & 7u) ^ (row & 7u);
+    const uint32_t c = (uint32_t)((q >> 10) % nc);
+    if (c == nc - 1 && logical == 7u) { const uint32_t t0 = v.z; v.z = v.w; v.w = t0; }  // halves 60,61 <-> 62,63
+    HB[q] = v;
+}
+}  // namespace tc
+
+int tc_shard_begin(scema_ctx *ctx, double thr, uint64_t r0, uint64_t r1, const double **centre_dev)
+{
+    if (!ctx->have_spline) return fail(ctx, SCEMA_ERR_STATE, "Spline is not up to date.");
+    if (!tc_supported(ctx) || r0 > r1 || r1 > ctx->n || (r0 % 128) != 0) return fail(ctx, SCEMA_ERR_INVALID, "tc_shard_begin: bad row range or row width");
+    int rc = tc_prepare_begin(ctx, thr, 1);
+    if (rc) return rc;
+    ctx->tc_band_wanted = false;
+    ctx->tc_compact = true;
+    ctx->shard_r0 = r0;
+    ctx->shard_r1 = r1;
+    rc = tc_centre_rows(ctx, r0, r1);
+    if (rc) return rc;
+    if (centre_dev) *centre_dev = ctx->d_tc_centre.as<double>();
+    return SCEMA_OK;
+}
+
+int tc_shard_stats(scema_ctx *ctx, const double *centre_dev, const unsigned long long **packet_dev, uint64_t *packet_words)
+{
+    if (!ctx->tc_compact) return fail(ctx, SCEMA_ERR_STATE, "tc_shard_stats: no sharded prepare in progress");
+    if (centre_dev && centre_dev != ctx->d_tc_centre.as<double>())
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->d_tc_centre.p, centre_dev, (size_t)ctx->K * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    const uint64_t r0 = ctx->shard_r0, r1 = ctx->shard_r1;
+    int rc = tc_stats_rows(ctx, r0, r1, true);
+    if (!rc) rc = tc_fix_scale(ctx, 0);   // the local scale only feeds the (negligible) e0 term of the sample
+    if (rc) return rc;
+    if (r1 - r0 >= 2) {
+        tc::k_tc_plan_sample<<<tc::PLAN_SAMPLE / 8, 256, 0, ctx->stream>>>(ctx->d_spline, ctx->d_tc_nrm.as<double>(), r0, r1 - r0, ctx->K,
+                                                                         ctx->tc_T0, ctx->d_tc_misc.as<unsigned long long>());
+        ctx->launches++;
+        SCEMA_CUDA(ctx, cudaGetLastError());
+    }
+    if (packet_dev) *packet_dev = ctx->d_tc_misc.as<unsigned long long>();
+    if (packet_words) *packet_words = tc::MISC_WORDS;
+    return SCEMA_OK;
+}
+
+int tc_shard_finish(scema_ctx *ctx, const unsigned long long *packets_dev, uint32_t G, uint64_t pairs, int *choice, const void **image_dev,
+                    uint64_t *image_bytes_per_row)
+{
+    if (!ctx->tc_compact || !packets_dev || G == 0 || !choice) return fail(ctx, SCEMA_ERR_STATE, "tc_shard_finish: no sharded prepare in progress");
+    unsigned long long *misc = ctx->d_tc_misc.as<unsigned long long>(), plan[8];
+    tc::k_tc_reduce_packets<<<(tc::MISC_WORDS + 255) / 256, 256, 0, ctx->stream>>>(packets_dev, G, misc);
+    ctx->launches++;
+    SCEMA_CUDA(ctx, cudaMemcpyAsync(plan, misc + tc::PLAN_WORD, sizeof(plan), cudaMemcpyDeviceToHost, ctx->stream));
+    SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint64_t counts[5];
+    for (int i = 0; i < 5; i++) ctx->tc_plan_counts[i] = counts[i] = plan[i];
+    int ch = 1, centred = 1;
+    uint64_t est = 0;
+    tc_choose(pairs, ctx->K, counts, (uint64_t)tc::PLAN_SAMPLE * G, (uint64_t)ctx->mem_budget, true, &ch, &centred, &est);
+    *choice = (ch == 1 && centred) ? 1 : (ch == 1 ? 3 : ch);   // 3: one slice but raw copies -> ordinary path
+    if (*choice != 1) { ctx->tc_compact = false; return SCEMA_OK; }
+    ctx->tc_slices = 1;
+    ctx->tc_cguard = 0.001953125;
+    ctx->cand_cap = std::max<uint64_t>(ctx->cand_cap, std::max<uint64_t>(std::max<uint64_t>(1ull << 20, 32 * ctx->n), est + est / 4));
+    int rc = tc_fix_scale(ctx, 0);
+    const uint64_t n_pad = (ctx->n + tc::COLT - 1) / tc::COLT * tc::COLT;
+    if (!rc) rc = tc_prep_rows(ctx, ctx->shard_r0, ctx->shard_r1 == ctx->n ? n_pad : ctx->shard_r1);
+    if (rc) return rc;
+    if (image_dev) *image_dev = ctx->d_tc_a.p;
+    if (image_bytes_per_row) *image_bytes_per_row = (uint64_t)tc_chunks(ctx->K) * 128;
+    return SCEMA_OK;
+}
+
+int tc_shard_commit(scema_ctx *ctx, void *rows_ready_event)
+{
+    if (!ctx->tc_compact) return fail(ctx, SCEMA_ERR_STATE, "tc_shard_commit: no sharded prepare in progress");
+    const uint64_t n_pad = (ctx->n + tc::COLT - 1) / tc::COLT * tc::COLT;
+    const uint32_t nc = tc_chunks(ctx->K);
+    const uint64_t chunks16 = n_pad * nc * 8;
+    tc::k_tc_derive_b<<<(unsigned)((chunks16 + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_tc_a.as<uint4>(), ctx->d_tc_b.as<uint4>(), chunks16, nc);
+    ctx->launches++;
+    SCEMA_CUDA(ctx, cudaGetLastError());
+    ctx->rows_ready_event = rows_ready_event;
+    ctx->tc_valid = true;
+    return SCEMA_OK;
+}
 
 template <int CG, bool DBG, bool WIDE, bool BAND>
 static int tc_launch_t(scema_ctx *ctx, const tc::Args &a, uint64_t items)
@@ -1193,6 +1320,7 @@ int tc_launch(scema_ctx *ctx, uint32_t I0, uint32_t I1, uint32_t C0, uint32_t C1
     a.dbg = dbg;
     a.dbg_ld = dbg_ld;
     a.nc = tc_chunks(ctx->K);
+    a.compact = ctx->tc_compact ? 1u : 0u;
     a.band_item_start = a.band_jend = a.perm = nullptr;
     a.band_row_tiles = 0;
     static const char *cg_env = getenv("SCEMA_TC_CG");

@@ -33,10 +33,20 @@ def shard_bounds(n, world):
     return out
 
 
-def gather_rows(local_rows, n, world, group=None):
-    """All-gather row blocks of possibly uneven height into the full [n, K] matrix."""
+def aligned_shard_bounds(n, world, align=2048):
+    """Equal shares of a multiple of `align` rows (the last ranks take what is left): rank r owns
+    [r * per, min(n, (r + 1) * per)). Equal, aligned shares make every exchange of the sharded path an in-place
+    all-gather (row blocks, fp16 operand images). -> (per, list of (begin, end))."""
+    per = (n + world - 1) // world
+    per = (per + align - 1) // align * align
+    return per, [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+
+
+def gather_rows(local_rows, n, world, group=None, bounds=None):
+    """All-gather row blocks of possibly uneven height into the full [n, K] matrix (bounds: the ranks' row ranges,
+    default shard_bounds(n, world))."""
     K = local_rows.shape[1]
-    bounds = shard_bounds(n, world)
+    bounds = bounds or shard_bounds(n, world)
     h_max = max(e - b for b, e in bounds)
     if all(e - b == h_max for b, e in bounds):
         full = torch.empty((n, K), dtype=local_rows.dtype, device=local_rows.device)
@@ -85,11 +95,19 @@ def gather_edges(a, b, d, n, counts, device, group=None):
 class ShardedCluster:
     """Tile-sharded all-pairs over the ranks of a process group (rank == GPU)."""
 
-    def __init__(self, hc, group=None):
+    def __init__(self, hc, group=None, side_group=None, bounds=None):
+        """side_group: a second NCCL group over the same ranks (dist.new_group): the all-gather of the FP64 rows then
+        runs on its own stream and overlaps the tcgen05 filter, which only needs the gathered fp16 operand images
+        (run_overlapped). Without it run() is the plain sequence."""
         self.hc = hc
         self.group = group
+        self.side_group = side_group
+        self.bounds = bounds    # row ranges of the ranks for run() (default: shard_bounds); run_overlapped needs aligned_shard_bounds
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self._full = None
+        self._side_stream = None
+        self.path = "plain"
 
     def stream(self):
         """The context's CUDA stream as a torch stream: the collectives and every torch op of run()
@@ -112,12 +130,69 @@ class ShardedCluster:
             local = torch.as_tensor(CudaView(ptr, (n_local, K)), device="cuda")
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-            full = gather_rows(local, n, self.world, self.group)
+            full = gather_rows(local, n, self.world, self.group, self.bounds)
             ev1.record()
             self.gather_events = (ev0, ev1)  # ev0.elapsed_time(ev1) after a synchronize = the all-gather alone
             hc.set_spline(device_ptr=full.data_ptr(), n=n, k=K)
             ne, counts, offs = self.compare_all_ranks(threshold, variant, sink, full.device)
         return ne, counts, offs, full
+
+    def run_overlapped(self, n, spline_points, threshold, sink=None):
+        """The tcgen05 path with the exchanges taken off the critical path (scema_tc_shard_*, include/scema_hist.h).
+        Shares: aligned_shard_bounds(n, world) — set_histories must have installed exactly that share. Every rank
+        resamples its rows into its slot of the full matrix; the all-gather of the FP64 rows (8 K bytes per row) goes to
+        a side stream; meanwhile the ranks agree on centre and scale (two tiny all-gathers), build the fp16 image of their
+        OWN rows and all-gather the images (128 bytes per row): the filter starts as soon as those are there, and only the
+        exact recompute waits for the FP64 rows. Falls back to the plain sequence when the survivor sample prefers
+        another filter. -> (local_edge_count, counts, offsets, full_rows tensor)."""
+        hc, G = self.hc, self.world
+        per, bounds = aligned_shard_bounds(n, G)
+        b, e = bounds[self.rank]
+        main = self.stream()
+        with torch.cuda.stream(main):
+            hc.resample(spline_points)
+            n_local, K, ptr = hc.spline_info()
+            assert n_local == e - b, "set_histories must hold the rows of aligned_shard_bounds"
+            if self._full is None or self._full.shape != (G * per, K):
+                self._full = torch.empty((G * per, K), dtype=torch.float64, device="cuda")
+                self._side_stream = torch.cuda.Stream()
+            full = self._full
+            if n_local:
+                full[b:e].copy_(torch.as_tensor(CudaView(ptr, (n_local, K)), device="cuda"))
+            k1_done = torch.cuda.Event()
+            k1_done.record(main)
+            hc.set_spline(device_ptr=full.data_ptr(), n=n, k=K)
+            # FP64 rows: in-place all-gather on the side stream
+            with torch.cuda.stream(self._side_stream):
+                self._side_stream.wait_event(k1_done)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                dist.all_gather_into_tensor(full, full[self.rank * per:(self.rank + 1) * per], group=self.side_group)
+                ev1.record()
+                self.gather_events = (ev0, ev1)
+                rows_ready = torch.cuda.Event()
+                rows_ready.record()
+            self._rows_ready = rows_ready
+            # centre: every rank's candidate, rank 0's is taken
+            c_ptr = hc.tc_shard_begin(threshold, b, e)
+            mine = torch.as_tensor(CudaView(c_ptr, (K,)), device="cuda")
+            cents = torch.empty((G, K), dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(cents, mine, group=self.group)
+            p_ptr, words = hc.tc_shard_stats(cents[0].data_ptr())
+            pk = torch.as_tensor(CudaView(p_ptr, (words,), typestr="<i8"), device="cuda")
+            packets = torch.empty((G, words), dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(packets, pk, group=self.group)
+            choice, img_ptr, bpr = hc.tc_shard_finish(packets.data_ptr(), G, n * (n - 1) // 2 // G)
+            if choice == 1:
+                img = torch.as_tensor(CudaView(img_ptr, (G * per * bpr,), typestr="|u1"), device="cuda")
+                dist.all_gather_into_tensor(img, img[self.rank * per * bpr:(self.rank + 1) * per * bpr], group=self.group)
+                hc.tc_shard_commit(rows_ready.cuda_event)
+                self.path = "overlapped"
+            else:
+                main.wait_event(rows_ready)   # another filter: it needs all rows first
+                self.path = "plain (sample chose %d)" % choice
+            ne, counts, offs = self.compare_all_ranks(threshold, 3, sink, full.device)
+        return ne, counts, offs, full[:n]
 
     def compare_all_ranks(self, threshold, variant, sink, device):
         """This rank's share of the pair matrix, then ONE all-gather of (edge count, flag) per rank. The filters split

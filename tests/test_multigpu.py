@@ -20,7 +20,7 @@ def test_two_gpu_sharded_pipeline():
                         "--master-addr", "127.0.0.1", "--master-port", "29611",
                         os.path.join(ROOT, "tools", "multigpu_check.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("multigpu_check ok") == 4   # DMMA, FMA, tcgen05 one-shot, tcgen05 streamed
+    assert r.stdout.count("multigpu_check ok") == 7   # DMMA, FMA, tcgen05 one-shot, tcgen05 streamed; overlapped x2, plain on aligned shares
 
 
 def test_multi_gpu_behind_the_c_abi(oracle):

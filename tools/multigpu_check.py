@@ -10,7 +10,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import scema_b200
 from scema_b200 import synth
-from scema_b200.distributed import ShardedCluster, shard_bounds
+from scema_b200.distributed import ShardedCluster, aligned_shard_bounds, shard_bounds
 
 
 def main():
@@ -58,6 +58,7 @@ def main():
             want_rows = o.splinify_batch(st_all, off_all, P)
             assert np.array_equal(rows.view(np.uint64), want_rows.view(np.uint64)), "gathered spline matrix differs"
             wi, wj, wd, _ = o.all_pairs(want_rows, thr)
+            globals().update(want_rows=want_rows, wi=wi, wj=wj, wd=wd)
             parts = [allb[r * m: r * m + counts[r]].cpu().numpy() for r in range(world)]
             got = np.concatenate(parts, axis=0)
             order = np.lexsort((got[:, 1], got[:, 0]))
@@ -66,6 +67,29 @@ def main():
             assert np.array_equal(got[:, 0].astype(np.uint32), wi) and np.array_equal(got[:, 1].astype(np.uint32), wj)
             assert np.array_equal(np.ascontiguousarray(got[:, 2]).view(np.uint64), wd.view(np.uint64))
             print(f"multigpu_check ok: world={world} variant={variant} streamed={streamed} edges={len(wi)} per-rank={counts}", flush=True)
+    # the overlapped path (scema_tc_shard_*: own-row operand images all-gathered, FP64 rows on a side stream), twice on the
+    # same context, then the plain path again on the same aligned shares
+    per, ab = aligned_shard_bounds(n, world)
+    b, e = ab[rank]
+    off = synth.offsets(6, e - b, 16, 5, 70, first=b)
+    steps = synth.histories(6, e - b, 16, 5e-3, synth.default_pert(thr, P), off, first=b)
+    hc.set_histories(steps, off)
+    sc2 = ShardedCluster(hc, side_group=dist.new_group(backend="nccl"), bounds=ab)
+    for mode in ("overlapped", "overlapped", "plain"):
+        if mode == "overlapped":
+            ne, counts, offs, full = sc2.run_overlapped(n, P, thr)
+            assert sc2.path == "overlapped", sc2.path
+        else:
+            ne, counts, offs, full = sc2.run(n, P, thr, 3)
+        a, bb, d = hc.get_edges()
+        assert ne == counts[rank] and len(a) == ne and hc.counters()["tc_slices"] == 1
+        from scema_b200.distributed import gather_edges
+        A, B, D = gather_edges(a, bb, d, n, counts, dev)
+        if rank == 0:
+            rows = full.cpu().numpy()
+            assert np.array_equal(rows.view(np.uint64), want_rows.view(np.uint64)), "gathered spline matrix differs"
+            assert len(A) == len(wi) and np.array_equal(A, wi) and np.array_equal(B, wj) and np.array_equal(D.view(np.uint64), wd.view(np.uint64))
+            print(f"multigpu_check ok: world={world} tcgen05 {mode} path edges={len(wi)} per-rank={counts}", flush=True)
     hc.close()
     dist.barrier()
     dist.destroy_process_group()
