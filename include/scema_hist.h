@@ -168,7 +168,7 @@ int scema_cluster(scema_ctx *ctx, const double *steps, const uint64_t *offsets, 
  *                                  and pass ONE of them (the same on every GPU) to
  *        scema_tc_shard_stats   -> *packet_dev: *packet_words 8-byte words (norm statistics and the survivor-density sample
  *                                  of the own rows); all-gather the packets of all n_shards GPUs and pass them to
- *        scema_tc_shard_finish  -> *choice: 1 = one fp16 slice with centred copies: the own rows' image now sits at
+ *        scema_tc_shard_finish  (optimistic = 0) -> *choice: 1 = one fp16 slice with centred copies: the own rows' image now sits at
  *                                  *image_dev + row0 * *image_bytes_per_row (hi-only layout); all-gather the images in
  *                                  place, then scema_tc_shard_commit. Any other value (2: two slices, 3: raw copies,
  *                                  0: SCEMA_PAIRS_DMMA, -1: SCEMA_PAIRS_EXACT): nothing was built, take the ordinary
@@ -179,9 +179,15 @@ int scema_cluster(scema_ctx *ctx, const double *steps, const uint64_t *offsets, 
  *                                  then overlap the filter. scema_b200/distributed.py drives this with torch.distributed. */
 int scema_tc_shard_begin(scema_ctx *ctx, double threshold, uint64_t row0, uint64_t row1, const double **centre_dev);
 int scema_tc_shard_stats(scema_ctx *ctx, const double *centre_dev, const uint64_t **packet_dev, uint64_t *packet_words);
-int scema_tc_shard_finish(scema_ctx *ctx, const uint64_t *packets_dev, uint32_t n_shards, uint64_t pairs, int *choice,
+int scema_tc_shard_finish(scema_ctx *ctx, const uint64_t *packets_dev, uint32_t n_shards, uint64_t pairs, int optimistic, int *choice,
                           const void **image_dev, uint64_t *image_bytes_per_row);
 int scema_tc_shard_commit(scema_ctx *ctx, void *rows_ready_event);
+/* optimistic != 0 in scema_tc_shard_finish: no host synchronisation in the middle of the step — the image is built on the
+ * assumption that the sample again says "one slice, centred copies" (*choice = 1), and scema_tc_shard_check, called after
+ * the following scema_compare (which synchronises anyway), returns what the sample really said; anything but 1 means the
+ * step has to be repeated on the ordinary path (the optimistic result is still a correct edge list — every survivor is
+ * recomputed exactly — it may just have cost more than necessary; overflowing queues are handled by the compare). */
+int scema_tc_shard_check(scema_ctx *ctx, int *choice);
 
 /* ---- several GPUs of one box behind the same boundary: replaces the collective of compare_histories_with_all_ranks
  *      (strain2spline.h:546-614: R - 1 ring steps of blocking messages per history, called at FE_problem.h:1229) with a

@@ -70,7 +70,8 @@ def lib():
         "scema_tc_plan": (i32, [u32, u32, u32, vp]),
         "scema_tc_shard_begin": (i32, [vp, dbl, u64, u64, P(vp)]),
         "scema_tc_shard_stats": (i32, [vp, vp, P(vp), P(u64)]),
-        "scema_tc_shard_finish": (i32, [vp, vp, u32, u64, P(i32), P(vp), P(u64)]),
+        "scema_tc_shard_finish": (i32, [vp, vp, u32, u64, i32, P(i32), P(vp), P(u64)]),
+        "scema_tc_shard_check": (i32, [vp, P(i32)]),
         "scema_tc_shard_commit": (i32, [vp, vp]),
         "scema_tc_centre": (i32, [vp, vp]),
         "scema_tc_last_plan": (i32, [vp, vp]),
@@ -117,7 +118,7 @@ EXPORTED = (
     "scema_store_reset scema_store_append scema_store_info scema_store_resample scema_select_rows "
     "scema_set_spline scema_get_spline scema_spline_info scema_compare scema_compare_stream scema_get_edges scema_edges_device "
     "scema_get_degrees scema_cluster scema_nearest scema_write_similar_hist scema_reduce_edges scema_reduce_calls scema_reduce_dir "
-    "scema_last_timings scema_last_counters scema_kernel_launches scema_last_audit scema_fp64_peak scema_tc_debug scema_tc_plan scema_tc_shard_begin scema_tc_shard_stats scema_tc_shard_finish scema_tc_shard_commit scema_tc_centre scema_tc_last_plan scema_tc_choose scema_pipeline_plan scema_synth_offsets "
+    "scema_last_timings scema_last_counters scema_kernel_launches scema_last_audit scema_fp64_peak scema_tc_debug scema_tc_plan scema_tc_shard_begin scema_tc_shard_stats scema_tc_shard_finish scema_tc_shard_check scema_tc_shard_commit scema_tc_centre scema_tc_last_plan scema_tc_choose scema_pipeline_plan scema_synth_offsets "
     "scema_multi_create scema_multi_destroy scema_multi_last_error scema_multi_devices scema_multi_context scema_multi_cluster "
     "scema_multi_compare_rows scema_multi_shard_edges scema_multi_last_ms "
     "scema_synth_histories_device scema_synth_rows_device scema_synth_histories_model_device scema_synth_rows_model_device scema_ingest_last_error scema_batch_read_dir "
@@ -462,11 +463,18 @@ class HistCluster:
         self._ck(self._L.scema_tc_shard_stats(self._h, int(centre_ptr), C.byref(p), C.byref(w)))
         return int(p.value), int(w.value)
 
-    def tc_shard_finish(self, packets_ptr, n_shards, pairs):
+    def tc_shard_finish(self, packets_ptr, n_shards, pairs, optimistic=False):
         """-> (choice, device pointer of the operand image, bytes per row)."""
         ch, p, b = C.c_int(0), C.c_void_p(None), C.c_uint64(0)
-        self._ck(self._L.scema_tc_shard_finish(self._h, int(packets_ptr), int(n_shards), int(pairs), C.byref(ch), C.byref(p), C.byref(b)))
+        self._ck(self._L.scema_tc_shard_finish(self._h, int(packets_ptr), int(n_shards), int(pairs), int(bool(optimistic)), C.byref(ch),
+                                               C.byref(p), C.byref(b)))
         return int(ch.value), int(p.value or 0), int(b.value)
+
+    def tc_shard_check(self):
+        """What the sample of the last optimistic tc_shard_finish really said (1 = the assumption held)."""
+        ch = C.c_int(0)
+        self._ck(self._L.scema_tc_shard_check(self._h, C.byref(ch)))
+        return int(ch.value)
 
     def tc_shard_commit(self, rows_ready_event=None):
         self._ck(self._L.scema_tc_shard_commit(self._h, int(rows_ready_event) if rows_ready_event else None))

@@ -56,6 +56,7 @@ void scema_destroy(scema_ctx *c)
     c->d_tc_a.release(); c->d_tc_b.release(); c->d_tc_nrm.release(); c->d_tc_misc.release(); c->d_tc_centre.release();
     c->d_tc_perm.release(); c->d_tc_iota.release(); c->d_tc_snrm.release(); c->d_tc_band.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_plan) cudaFreeHost(c->h_plan);
     for (int k = 0; k < 2; k++) {
         if (c->h_stage_key[k]) cudaFreeHost(c->h_stage_key[k]);
         if (c->h_stage_val[k]) cudaFreeHost(c->h_stage_val[k]);
@@ -119,7 +120,8 @@ static int set_histories_impl(scema_ctx *c, const double *steps, int steps_mode,
     c->max_len = mx;
     c->min_len = n ? mn : 0;
     c->total_steps = n ? offsets[n] : 0;  // offsets index `steps` absolutely
-    set_ids(c->hist_ids, ids, n);
+    c->hist_ids_lazy = ids == nullptr;
+    if (ids) set_ids(c->hist_ids, ids, n);
     SCEMA_CUDA(c, c->d_offsets.reserve((n + 1) * sizeof(uint64_t)));
     SCEMA_CUDA(c, cudaMemcpyAsync(c->d_offsets.p, c->h_offsets.data(), (n + 1) * sizeof(uint64_t),
                                   cudaMemcpyHostToDevice, c->stream));
@@ -202,7 +204,8 @@ int scema_set_spline(scema_ctx *c, const double *rows, int rows_on_device, uint6
     c->have_edges = false;
     c->n = n;
     c->K = k;
-    set_ids(c->ids, ids, n);
+    c->ids_lazy = ids == nullptr;   // 0 .. n-1: filled on first use (ids_of)
+    if (ids) set_ids(c->ids, ids, n);
     if (rows_on_device) {
         c->d_spline = rows;
     } else {
@@ -393,11 +396,12 @@ int scema_reduce_edges(scema_ctx *c, uint32_t num_gps, uint32_t *mapping_host, u
     for (uint64_t i = 0; i < c->n; i++) start[i + 1] += start[i];
     std::vector<uint64_t> fill(start.begin(), start.begin() + c->n);
     std::vector<uint32_t> eu(2 * m), ev(2 * m);
+    const std::vector<uint32_t> &idv = ids_of(c);
     for (uint64_t e = 0; e < m; e++) {
         if (d[e] == 0.0) return fail(c, SCEMA_ERR_MAPPING, "reduce: dist == 0 (the script raises ZeroDivisionError)");
-        uint64_t q = fill[b[e]]++; eu[q] = c->ids[b[e]]; ev[q] = c->ids[a[e]];
+        uint64_t q = fill[b[e]]++; eu[q] = idv[b[e]]; ev[q] = idv[a[e]];
     }
-    for (uint64_t e = 0; e < m; e++) { uint64_t q = fill[a[e]]++; eu[q] = c->ids[a[e]]; ev[q] = c->ids[b[e]]; }
+    for (uint64_t e = 0; e < m; e++) { uint64_t q = fill[a[e]]++; eu[q] = idv[a[e]]; ev[q] = idv[b[e]]; }
     rc = reduce_graph_calls(eu.data(), ev.data(), 2 * m, num_gps, mapping_host, iterations, neighbours_removed);
     if (rc) return fail(c, rc, "reduce: history ID >= num_gps (the script raises IndexError)");
     return SCEMA_OK;
@@ -505,12 +509,21 @@ int scema_tc_shard_stats(scema_ctx *c, const double *centre_dev, const uint64_t 
     return rc;
 }
 
-int scema_tc_shard_finish(scema_ctx *c, const uint64_t *packets_dev, uint32_t n_shards, uint64_t pairs, int *choice,
+int scema_tc_shard_finish(scema_ctx *c, const uint64_t *packets_dev, uint32_t n_shards, uint64_t pairs, int optimistic, int *choice,
                           const void **image_dev, uint64_t *image_bytes_per_row)
 {
     int rc = enter(c);
     if (rc) return rc;
-    return tc_shard_finish(c, reinterpret_cast<const unsigned long long *>(packets_dev), n_shards, pairs, choice, image_dev, image_bytes_per_row);
+    return tc_shard_finish(c, reinterpret_cast<const unsigned long long *>(packets_dev), n_shards, pairs, optimistic, choice, image_dev,
+                           image_bytes_per_row);
+}
+
+int scema_tc_shard_check(scema_ctx *c, int *choice)
+{
+    int rc = enter(c);
+    if (rc) return rc;
+    if (!choice) return fail(c, SCEMA_ERR_INVALID, "tc_shard_check: null pointer");
+    return tc_shard_check(c, choice, nullptr);
 }
 
 int scema_tc_shard_commit(scema_ctx *c, void *rows_ready_event)

@@ -124,6 +124,12 @@ struct scema_ctx {
     bool tc_valid = false;
     bool tc_compact = false;             // hi-only operand copies (sharded prepare)
     uint64_t shard_r0 = 0, shard_r1 = 0; // own rows of a sharded prepare
+    uint64_t *h_plan = nullptr;          // pinned: survivor-density sample of a sharded prepare (read back asynchronously)
+    bool plan_pending = false;
+    uint32_t plan_shards = 1;
+    uint64_t plan_pairs = 0;
+    bool ids_lazy = false, hist_ids_lazy = false;  // the IDs are 0 .. n-1 and the vector has not been filled (a million-entry
+                                                   // refill per call is a millisecond of host time on the per-timestep path)
     void *rows_ready_event = nullptr;    // cudaEvent_t the exact recompute of the next compare waits for (FP64 rows still arriving)
 
     // ---- candidate queue + edges
@@ -165,6 +171,17 @@ namespace scema {
             return e__ == cudaErrorMemoryAllocation ? SCEMA_ERR_NOMEM : SCEMA_ERR_CUDA;         \
         }                                                                                       \
     } while (0)
+
+// IDs of the current spline rows, filled on first use when they are the default 0 .. n-1
+inline const std::vector<uint32_t> &ids_of(scema_ctx *c)
+{
+    if (c->ids_lazy) {
+        c->ids.resize(c->n);
+        for (uint64_t i = 0; i < c->n; i++) c->ids[i] = (uint32_t)i;
+        c->ids_lazy = false;
+    }
+    return c->ids;
+}
 
 inline int fail(scema_ctx *ctx, int code, const std::string &msg)
 {
@@ -209,8 +226,9 @@ int tc_plan_rows(scema_ctx *ctx, uint64_t r1, uint64_t counts[5]);
 uint32_t tc_plan_sample_size();
 int tc_shard_begin(scema_ctx *ctx, double thr, uint64_t r0, uint64_t r1, const double **centre_dev);
 int tc_shard_stats(scema_ctx *ctx, const double *centre_dev, const unsigned long long **packet_dev, uint64_t *packet_words);
-int tc_shard_finish(scema_ctx *ctx, const unsigned long long *packets_dev, uint32_t G, uint64_t pairs, int *choice, const void **image_dev,
-                    uint64_t *image_bytes_per_row);
+int tc_shard_finish(scema_ctx *ctx, const unsigned long long *packets_dev, uint32_t G, uint64_t pairs, int optimistic, int *choice,
+                    const void **image_dev, uint64_t *image_bytes_per_row);
+int tc_shard_check(scema_ctx *ctx, int *choice, uint64_t *est_survivors);
 int tc_shard_commit(scema_ctx *ctx, void *rows_ready_event);
 int tc_prepare_begin(scema_ctx *ctx, double thr, uint32_t slices);
 int tc_stats_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1, bool into_scale);

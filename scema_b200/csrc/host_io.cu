@@ -47,17 +47,18 @@ int write_similar_hist(scema_ctx *c, const char *pattern)
     std::vector<double> dist(2 * m);
     for (uint64_t e = 0; e < m; e++) { uint64_t q = fill[b[e]]++; other[q] = a[e]; dist[q] = d[e]; }
     for (uint64_t e = 0; e < m; e++) { uint64_t q = fill[a[e]]++; other[q] = b[e]; dist[q] = d[e]; }
+    const std::vector<uint32_t> &idv = ids_of(c);
     char name[4096];
     std::string buf;
     char line[96];
     for (uint64_t k = 0; k < n; k++) {
-        snprintf(name, sizeof name, pattern, c->ids[k]);
+        snprintf(name, sizeof name, pattern, idv[k]);
         FILE *f = fopen(name, "w");
         if (!f) return fail(c, SCEMA_ERR_IO, std::string("Could not open ") + name + " for writing.");
         buf.clear();
         for (uint64_t q = start[k]; q < start[k + 1]; q++) {
             // default ostream formatting of a double == %g (6 significant digits)
-            int len = snprintf(line, sizeof line, "%u %u %g\n", c->ids[k], c->ids[other[q]], dist[q]);
+            int len = snprintf(line, sizeof line, "%u %u %g\n", idv[k], idv[other[q]], dist[q]);
             buf.append(line, len);
         }
         if (!buf.empty() && fwrite(buf.data(), 1, buf.size(), f) != buf.size()) {

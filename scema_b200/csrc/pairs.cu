@@ -771,7 +771,7 @@ int nearest_run(scema_ctx *ctx, uint32_t *nearest_id_host, double *nearest_diff_
         SCEMA_CUDA(ctx, d_ids.reserve(n * sizeof(uint32_t)));
         SCEMA_CUDA(ctx, d_bits.reserve(n * sizeof(unsigned long long)));
         SCEMA_CUDA(ctx, d_minid.reserve(n * sizeof(unsigned int)));
-        SCEMA_CUDA(ctx, cudaMemcpyAsync(d_ids.p, ctx->ids.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        SCEMA_CUDA(ctx, cudaMemcpyAsync(d_ids.p, ids_of(ctx).data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         SCEMA_CUDA(ctx, cudaMemcpyAsync(d_bits.p, bits.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
         SCEMA_CUDA(ctx, cudaMemsetAsync(d_minid.p, 0xff, n * sizeof(unsigned int), ctx->stream));
         const uint32_t nbx = (uint32_t)((n + XT - 1) / XT);

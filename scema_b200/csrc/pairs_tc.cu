@@ -1195,21 +1195,29 @@ int tc_shard_stats(scema_ctx *ctx, const double *centre_dev, const unsigned long
     return SCEMA_OK;
 }
 
-int tc_shard_finish(scema_ctx *ctx, const unsigned long long *packets_dev, uint32_t G, uint64_t pairs, int *choice, const void **image_dev,
-                    uint64_t *image_bytes_per_row)
+// optimistic != 0: do not wait for the sample (no host synchronisation in the middle of the step): the image is built on
+// the assumption that the choice is again "one slice, centred copies"; tc_shard_check, called after the compare has
+// synchronised anyway, says whether that was right (if not, the caller repeats the step on the ordinary path).
+int tc_shard_finish(scema_ctx *ctx, const unsigned long long *packets_dev, uint32_t G, uint64_t pairs, int optimistic, int *choice,
+                    const void **image_dev, uint64_t *image_bytes_per_row)
 {
     if (!ctx->tc_compact || !packets_dev || G == 0 || !choice) return fail(ctx, SCEMA_ERR_STATE, "tc_shard_finish: no sharded prepare in progress");
-    unsigned long long *misc = ctx->d_tc_misc.as<unsigned long long>(), plan[8];
+    unsigned long long *misc = ctx->d_tc_misc.as<unsigned long long>();
+    if (!ctx->h_plan) SCEMA_CUDA(ctx, cudaMallocHost(&ctx->h_plan, 8 * sizeof(uint64_t)));
     tc::k_tc_reduce_packets<<<(tc::MISC_WORDS + 255) / 256, 256, 0, ctx->stream>>>(packets_dev, G, misc);
     ctx->launches++;
-    SCEMA_CUDA(ctx, cudaMemcpyAsync(plan, misc + tc::PLAN_WORD, sizeof(plan), cudaMemcpyDeviceToHost, ctx->stream));
-    SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    uint64_t counts[5];
-    for (int i = 0; i < 5; i++) ctx->tc_plan_counts[i] = counts[i] = plan[i];
-    int ch = 1, centred = 1;
+    SCEMA_CUDA(ctx, cudaMemcpyAsync(ctx->h_plan, misc + tc::PLAN_WORD, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->plan_pending = true;
+    ctx->plan_shards = G;
+    ctx->plan_pairs = pairs;
     uint64_t est = 0;
-    tc_choose(pairs, ctx->K, counts, (uint64_t)tc::PLAN_SAMPLE * G, (uint64_t)ctx->mem_budget, true, &ch, &centred, &est);
-    *choice = (ch == 1 && centred) ? 1 : (ch == 1 ? 3 : ch);   // 3: one slice but raw copies -> ordinary path
+    if (!optimistic) {
+        SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int rc0 = tc_shard_check(ctx, choice, &est);
+        if (rc0) return rc0;
+    } else {
+        *choice = 1;
+    }
     if (*choice != 1) { ctx->tc_compact = false; return SCEMA_OK; }
     ctx->tc_slices = 1;
     ctx->tc_cguard = 0.001953125;
@@ -1220,6 +1228,22 @@ int tc_shard_finish(scema_ctx *ctx, const unsigned long long *packets_dev, uint3
     if (rc) return rc;
     if (image_dev) *image_dev = ctx->d_tc_a.p;
     if (image_bytes_per_row) *image_bytes_per_row = (uint64_t)tc_chunks(ctx->K) * 128;
+    return SCEMA_OK;
+}
+
+// The choice the (by now arrived) sample of the last tc_shard_finish stands for: 1 = one slice with centred copies, anything
+// else = the ordinary path should have been taken. Call after a host synchronisation of the context's stream.
+int tc_shard_check(scema_ctx *ctx, int *choice, uint64_t *est_survivors)
+{
+    if (!ctx->plan_pending || !ctx->h_plan) return fail(ctx, SCEMA_ERR_STATE, "tc_shard_check: no sharded prepare to check");
+    uint64_t counts[5];
+    for (int i = 0; i < 5; i++) ctx->tc_plan_counts[i] = counts[i] = ctx->h_plan[i];
+    ctx->plan_pending = false;
+    int ch = 1, centred = 1;
+    uint64_t est = 0;
+    tc_choose(ctx->plan_pairs, ctx->K, counts, (uint64_t)tc::PLAN_SAMPLE * ctx->plan_shards, (uint64_t)ctx->mem_budget, true, &ch, &centred, &est);
+    *choice = (ch == 1 && centred) ? 1 : (ch == 1 ? 3 : ch);   // 3: one slice but raw copies -> ordinary path
+    if (est_survivors) *est_survivors = est;
     return SCEMA_OK;
 }
 

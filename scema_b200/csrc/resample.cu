@@ -652,7 +652,8 @@ int resample_prepare(scema_ctx *ctx, uint32_t P, const std::vector<uint64_t> &bo
     SCEMA_CUDA(ctx, ctx->spline_own.reserve((size_t)(ctx->hn ? ctx->hn : 1) * K * sizeof(double)));
     ctx->d_spline = ctx->spline_own.as<double>();
     ctx->n = ctx->hn;
-    ctx->ids = ctx->hist_ids;
+    ctx->ids_lazy = ctx->hist_ids_lazy;
+    if (!ctx->hist_ids_lazy) ctx->ids = ctx->hist_ids;
     ctx->K = K;
     ctx->spline_version++;
     ctx->have_spline = true;
@@ -779,6 +780,7 @@ int store_resample(scema_ctx *ctx, uint32_t P)
     ctx->d_spline = ctx->spline_own.as<double>();
     ctx->n = n;
     ctx->ids = ctx->store_ids;
+    ctx->ids_lazy = false;
     ctx->K = K;
     ctx->spline_version++;
     ctx->have_spline = true;
@@ -843,8 +845,10 @@ int select_rows(scema_ctx *ctx, const uint32_t *rows, uint64_t m)
         SCEMA_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `rows` is the caller's buffer
     }
     std::vector<uint32_t> ids(m);
-    for (uint64_t i = 0; i < m; i++) ids[i] = ctx->ids[rows[i]];
+    const std::vector<uint32_t> &cur = ids_of(ctx);
+    for (uint64_t i = 0; i < m; i++) ids[i] = cur[rows[i]];
     ctx->ids.swap(ids);
+    ctx->ids_lazy = false;
     ctx->d_spline = dst.as<double>();
     ctx->n = m;
     ctx->spline_version++;
