@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
                                                  uint32_t nc, uint32_t slices, double vmax, const double *__restrict__ NRM,
                                                  unsigned long long *__restrict__ misc, double T0, double cguard,
                                                  const uint32_t *__restrict__ perm, const double *__restrict__ centre, uint32_t compact,
-                                                 unsigned char *__restrict__ HA, unsigned char *__restrict__ HB)
+                                                 uint32_t vec, unsigned char *__restrict__ HA, unsigned char *__restrict__ HB)
 {
     const uint64_t row = r0 + (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);  // position in the operand copies
     const int lane = threadIdx.x & 31;
@@ -694,16 +694,33 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
     const uint64_t src = real && perm ? perm[row] : row;                     // row of S (norm-band mode: sorted order)
     const bool wild = real && !isfinite(NRM[src]);
     const bool data = real && !wild;
+    // Lane l owns the ADJACENT columns 2l and 2l + 1 of every 64-column chunk (K = 6 P is even, so a pair never straddles
+    // the end of the row): one 16-byte load per pair and pass, one 4-byte store per pair and copy.
     // norm of the scaled row; a row beyond the range the scale was chosen for (possible only when the scale was
     // fixed before every row had been seen) gets no fp16 image and survives against everybody, like a row with
     // a non-finite norm
-    double nrm = 0.0;
+    auto load2 = [&](uint32_t kd, double &v0, double &v1) {   // scaled, centred columns kd, kd + 1 (0 beyond the row)
+        v0 = v1 = 0.0;
+        if (kd + 1 < K) {
+            double2 x, m;
+            if (vec) { x = *reinterpret_cast<const double2 *>(S + src * K + kd); m = *reinterpret_cast<const double2 *>(centre + kd); }
+            else { x = make_double2(S[src * K + kd], S[src * K + kd + 1]); m = make_double2(centre[kd], centre[kd + 1]); }
+            v0 = __dsub_rn(x.x, m.x) * s;
+            v1 = __dsub_rn(x.y, m.y) * s;
+        } else if (kd < K) {
+            v0 = __dsub_rn(S[src * K + kd], centre[kd]) * s;
+        }
+    };
+    double nrm = 0.0, first0 = 0.0, first1 = 0.0;
     bool big = false;
     if (data)
-        for (uint32_t k = lane; k < K; k += 32) {
-            const double v = __dsub_rn(S[src * K + k], centre[k]) * s;
-            nrm = fma(v, v, nrm);
-            big |= fabs(v) >= vmax;
+        for (uint32_t c = 0; c < nc; c++) {
+            double v0, v1;
+            load2(c * 64 + 2 * lane, v0, v1);
+            if (c == 0) { first0 = v0; first1 = v1; }
+            nrm = fma(v0, v0, nrm);
+            nrm = fma(v1, v1, nrm);
+            big |= fabs(v0) >= vmax || fabs(v1) >= vmax;
         }
     const bool too_big = __any_sync(0xffffffffu, big);
     if (too_big && lane == 0) atomicAdd(misc + 2, 1ull);
@@ -725,33 +742,40 @@ __global__ void __launch_bounds__(256) k_tc_prep(const double *__restrict__ S, u
     }
     const uint64_t blk = row / ROWS;
     const uint32_t r = (uint32_t)(row % ROWS);
+    const bool two = slices != 1;  // the one-slice kernel never reads the lo halves: neither computed nor written
     for (uint32_t c = 0; c < nc; c++) {
         const uint64_t base = (blk * nc + c) * (compact ? SLICE_BYTES : BLOCK_BYTES) + (uint64_t)r * 128;
-        unsigned char *a_hi = HA + base, *a_lo = a_hi + SLICE_BYTES;
-        unsigned char *b_hi = HB + base, *b_lo = b_hi + SLICE_BYTES;
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const uint32_t k = lane + 32 * e;  // column 0..63 of the chunk
-            const uint32_t kd = c * 64 + k;    // data column
-            double v = 0.0;
-            if (data && !too_big && kd < K) v = __dsub_rn(S[src * K + kd], centre[kd]) * s;
-            const double hi = h16z(v);
-            const double lo = h16z(v - hi);
-            double ahi = hi, alo = lo, bhi = hi, blo = lo;
-            if (c == nc - 1 && k >= KMAX) {
-                const uint32_t f = k - KMAX;
-                ahi = f == 0 ? x0 : f == 1 ? x1 : f == 2 ? P : Q;
-                alo = f == 1 ? x2 : 0.0;
-                bhi = f == 0 ? P : f == 1 ? Q : f == 2 ? x0 : x1;
-                blo = f == 3 ? x2 : 0.0;
+        const uint32_t k = 2 * lane;       // columns k, k + 1 of the chunk
+        double v0 = 0.0, v1 = 0.0;
+        if (data && !too_big) {
+            if (c == 0) { v0 = first0; v1 = first1; }
+            else load2(c * 64 + k, v0, v1);
+        }
+        const double hi0 = h16z(v0), hi1 = h16z(v1);
+        __half2 ahi = __halves2half2(__double2half(hi0), __double2half(hi1)), bhi = ahi;
+        __half2 alo = __halves2half2(__double2half(0.0), __double2half(0.0)), blo = alo;
+        if (two) alo = blo = __halves2half2(__double2half(h16z(v0 - hi0)), __double2half(h16z(v1 - hi1)));
+        if (c == nc - 1 && k >= KMAX) {
+            // fold columns 60..63:  A hi [x0 x1 | P Q], A lo [0 x2 | 0 0];  B hi [P Q | x0 x1], B lo [0 0 | 0 x2]
+            const __half z = __double2half(0.0);
+            if (k == KMAX) {
+                ahi = __halves2half2(__double2half(x0), __double2half(x1));
+                bhi = __halves2half2(__double2half(P), __double2half(Q));
+                alo = __halves2half2(z, __double2half(x2));
+                blo = __halves2half2(z, z);
+            } else {
+                ahi = __halves2half2(__double2half(P), __double2half(Q));
+                bhi = __halves2half2(__double2half(x0), __double2half(x1));
+                alo = __halves2half2(z, z);
+                blo = __halves2half2(z, __double2half(x2));
             }
-            const uint32_t off = ((((k >> 3) ^ (r & 7u)) << 4) | ((k & 7u) << 1));  // swizzled 16-byte chunk, element in chunk
-            *reinterpret_cast<__half *>(a_hi + off) = __double2half(ahi);
-            if (!compact) *reinterpret_cast<__half *>(b_hi + off) = __double2half(bhi);  // compact: B is derived from the gathered A image
-            if (slices != 1) {  // the one-slice kernel never reads the lo halves
-                *reinterpret_cast<__half *>(a_lo + off) = __double2half(alo);
-                *reinterpret_cast<__half *>(b_lo + off) = __double2half(blo);
-            }
+        }
+        const uint32_t off = ((((k >> 3) ^ (r & 7u)) << 4) | ((k & 7u) << 1));  // swizzled 16-byte chunk, pair inside it
+        *reinterpret_cast<__half2 *>(HA + base + off) = ahi;
+        if (!compact) *reinterpret_cast<__half2 *>(HB + base + off) = bhi;  // compact: B is derived from the gathered A image
+        if (two) {
+            *reinterpret_cast<__half2 *>(HA + base + SLICE_BYTES + off) = alo;
+            *reinterpret_cast<__half2 *>(HB + base + SLICE_BYTES + off) = blo;
         }
     }
 }
@@ -975,7 +999,9 @@ int tc_prep_rows(scema_ctx *ctx, uint64_t r0, uint64_t r1)
         ctx->d_spline, ctx->n, r0, r1, ctx->K, tc_chunks(ctx->K), ctx->tc_slices, ldexp(1.0, 12 - tc_k_headroom(ctx->K)),
         ctx->d_tc_nrm.as<double>(),
         ctx->d_tc_misc.as<unsigned long long>(), ctx->tc_T0, ctx->tc_cguard, ctx->tc_band ? ctx->d_tc_perm.as<uint32_t>() : nullptr,
-        ctx->d_tc_centre.as<double>(), ctx->tc_compact ? 1u : 0u, ctx->d_tc_a.as<unsigned char>(), ctx->d_tc_b.as<unsigned char>());
+        ctx->d_tc_centre.as<double>(), ctx->tc_compact ? 1u : 0u,
+        (reinterpret_cast<uintptr_t>(ctx->d_spline) % 16 == 0 && ctx->K % 2 == 0) ? 1u : 0u,   // 16-byte loads of column pairs
+        ctx->d_tc_a.as<unsigned char>(), ctx->d_tc_b.as<unsigned char>());
     ctx->launches++;
     SCEMA_CUDA(ctx, cudaGetLastError());
     return SCEMA_OK;

@@ -145,6 +145,32 @@ inline bool keep_nearest()
 
 void resolve_splines(std::vector<Strain6D *> &pending);
 
+// ---- device-resident history store behind the in-process call pattern. FE_problem.h appends one sample to EVERY
+// quadrature point per timestep (:1091-1103), calls splinify() on every point (spline_building, :1167-1191) and compares
+// the flagged subset (:1202-1229). The objects that asked for a (deferred) splinify() since the last comparison are
+// remembered here; when they all have the same length and spline point count — the production case — their histories are
+// kept on the GPU (scema_store_*, time-major) and a timestep only uploads the samples added since the last comparison
+// (48 bytes per point and step) instead of every history again. The fit of all points and the selection of the flagged
+// rows then happen on the device (scema_store_resample, scema_select_rows). Anything irregular (different lengths, a
+// history replaced by from_file, points created or destroyed) rebuilds the store once or falls back to the flat upload.
+// SCEMA_B200_STORE=0 switches it off.
+struct StoreState {
+    std::vector<Strain6D *> registry;     // objects with a pending splinify(), in call order (NULL: destroyed since)
+    std::vector<uint32_t> ids;            // IDs of the store's rows
+    std::vector<uint64_t> epochs;         // data epoch of every row's object when it was stored
+    uint32_t steps;                       // samples per point in the store
+    bool valid;
+    uint64_t rebuilds, appended_steps, h2d_bytes, flat_uploads;
+    StoreState() : steps(0), valid(false), rebuilds(0), appended_steps(0), h2d_bytes(0), flat_uploads(0) {}
+};
+inline StoreState &store_state() { static StoreState st; return st; }
+inline bool store_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SCEMA_B200_STORE"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
+}
+
 // Partner order of the reference's ring (strain2spline.h:571-599). `li` lists the partners of one history of rank
 // `my_rank` by batch index, ascending, where the batch is the rank-major concatenation of every rank's local vector
 // and ring_rank[j] is the rank history j lives on. The ring visits the own rank first (the local a < b loop: partners
@@ -178,7 +204,17 @@ public:
         ID_to_get_results_from = std::numeric_limits<uint32_t>::max();
         most_recent_ID_to_get_results_from = std::numeric_limits<uint32_t>::max();
         for (int i = 0; i < 6; i++) stress[i] = 0.0;
+        reg_slot = -1;
+        data_epoch = next_epoch();
     }
+    // a copy is a new object as far as the registry of pending fits is concerned (PointHistory holds a Strain6D by value)
+    Strain6D(const Strain6D &o) { reg_slot = -1; copy_from(o); }
+    Strain6D &operator=(const Strain6D &o)
+    {
+        if (this != &o) { unregister(); copy_from(o); }
+        return *this;
+    }
+    ~Strain6D() { unregister(); }
 
     void set_ID(uint32_t id) { ID = id; ID_is_set = true; }
 
@@ -208,6 +244,7 @@ public:
             fprintf(stderr, "Could not open %s for reading.\n", in_fname);
             exit(1);
         }
+        data_epoch = next_epoch();  // not an append of one sample per timestep: a device copy of this history is stale
         double s[6];
         while (in >> s[0] >> s[1] >> s[2] >> s[3] >> s[4] >> s[5]) {
             steps.insert(steps.end(), s, s + 6);
@@ -231,6 +268,11 @@ public:
         spline.clear();
         pending = true;
         up_to_date = true;
+        if (reg_slot < 0 && b200::store_enabled()) {  // remembered until the next comparison (b200::StoreState)
+            b200::StoreState &st = b200::store_state();
+            reg_slot = (long)st.registry.size();
+            st.registry.push_back(this);
+        }
     }
 
     void print()
@@ -334,6 +376,8 @@ public:
     uint32_t get_most_recent_ID_to_get_results_from() { return most_recent_ID_to_get_results_from; }
 
     // ---- batch plumbing used by this header's free functions (not part of the reference API)
+    uint64_t b200_epoch() const { return data_epoch; }
+    void b200_left_registry() { reg_slot = -1; }
     bool b200_pending() const { return pending; }
     bool b200_up_to_date() const { return up_to_date; }
     uint32_t b200_num_steps() const { return num_steps_added; }
@@ -367,6 +411,25 @@ public:
     const std::vector<HISTORY_ID_DIFF_PAIR> &b200_all_similar() const { return all_similar_histories; }
 
 private:
+    static uint64_t next_epoch() { static uint64_t e = 0; return ++e; }
+    void unregister()
+    {
+        if (reg_slot >= 0) {
+            b200::StoreState &st = b200::store_state();
+            if ((size_t)reg_slot < st.registry.size() && st.registry[reg_slot] == this) st.registry[reg_slot] = NULL;
+            reg_slot = -1;
+        }
+    }
+    void copy_from(const Strain6D &o)
+    {
+        up_to_date = o.up_to_date; pending = o.pending; num_steps_added = o.num_steps_added; steps = o.steps;
+        for (int i = 0; i < 6; i++) stress[i] = o.stress[i];
+        ID = o.ID; ID_is_set = o.ID_is_set; num_spline_points_per_component = o.num_spline_points_per_component;
+        spline = o.spline; most_similar_history = o.most_similar_history; most_similar_histories = o.most_similar_histories;
+        all_similar_histories = o.all_similar_histories; ID_to_get_results_from = o.ID_to_get_results_from;
+        most_recent_ID_to_get_results_from = o.most_recent_ID_to_get_results_from;
+        data_epoch = next_epoch();
+    }
     void materialise()
     {
         if (!pending) return;
@@ -394,6 +457,8 @@ private:
         for (size_t i = 0; i < list.size(); i++) out << ID << " " << list[i].ID << " " << list[i].diff << "\n";
     }
 
+    long reg_slot;         // position in b200::StoreState::registry while a deferred splinify() is pending there, else -1
+    uint64_t data_epoch;   // changes whenever the history is anything but appended to
     bool up_to_date, pending;
     uint32_t num_steps_added;
     std::vector<double> steps;  // [num_steps_added][6]: xx yy zz xy xz yz
@@ -447,6 +512,73 @@ inline void resolve_splines(std::vector<Strain6D *> &pending)
     }
 }
 
+// The store path of compare_batch (see StoreState). True when the comparison ran from the device-resident store; false
+// when this batch does not fit the pattern (the caller then uploads the flat batch as before).
+inline bool store_compare(std::vector<Strain6D *> &hist, const std::vector<uint32_t> &ids, uint32_t P0, double threshold)
+{
+    if (!store_enabled()) return false;
+    StoreState &st = store_state();
+    // the points that asked for a fit since the last comparison, still alive and still waiting for it
+    std::vector<Strain6D *> all;
+    all.reserve(st.registry.size());
+    for (size_t i = 0; i < st.registry.size(); i++) {
+        Strain6D *h = st.registry[i];
+        if (!h) continue;
+        h->b200_left_registry();
+        if (h->b200_pending()) all.push_back(h);
+    }
+    st.registry.clear();
+    const size_t N = all.size();
+    // the in-process pattern is "fit every point, compare the flagged subset"; a one-off batch in which every fitted point
+    // is also compared (the command lines, the proxies of the multi-rank branch) is cheaper as one flat upload
+    if (N <= hist.size() || N == 0) return false;
+    const uint32_t L = all[0]->b200_num_steps();
+    if (L < 3) return false;
+    for (size_t i = 0; i < N; i++)
+        if (all[i]->b200_num_steps() != L || all[i]->get_num_spline_points_per_component() != P0) return false;
+    // rows of the flagged points: position in `all` by address (both lists are in the caller's order in production)
+    std::vector<uint32_t> rows(hist.size());
+    {
+        size_t cursor = 0;
+        for (size_t i = 0; i < hist.size(); i++) {
+            size_t tries = 0;
+            while (tries < N && all[cursor] != hist[i]) { cursor = cursor + 1 == N ? 0 : cursor + 1; tries++; }
+            if (all[cursor] != hist[i]) return false;   // a flagged point that never asked for a fit through splinify()
+            rows[i] = (uint32_t)cursor;
+        }
+    }
+    scema_ctx *ctx = context();
+    bool same = st.valid && st.ids.size() == N && L >= st.steps;
+    for (size_t i = 0; same && i < N; i++) same = st.ids[i] == all[i]->get_ID() && st.epochs[i] == all[i]->b200_epoch();
+    if ((same ? L - st.steps : L) > 4096) return false;   // that many single-step uploads: the flat copy is the better catch-up
+    if (!same) {
+        st.ids.resize(N);
+        st.epochs.resize(N);
+        for (size_t i = 0; i < N; i++) { st.ids[i] = all[i]->get_ID(); st.epochs[i] = all[i]->b200_epoch(); }
+        check(scema_store_reset(ctx, N, st.ids.data(), L + 64), "add_current_strain");
+        st.steps = 0;
+        st.valid = true;
+        st.rebuilds++;
+    }
+    std::vector<double> sample(N * 6);
+    for (uint32_t s = st.steps; s < L; s++) {   // one 48 N-byte upload per new timestep
+        for (size_t i = 0; i < N; i++) {
+            const double *src = all[i]->b200_steps().data() + (size_t)s * 6;
+            for (int c = 0; c < 6; c++) sample[i * 6 + c] = src[c];
+        }
+        check(scema_store_append(ctx, sample.data(), 0), "add_current_strain");
+        st.appended_steps++;
+        st.h2d_bytes += N * 48;
+    }
+    st.steps = L;
+    check(scema_store_resample(ctx, P0), "splinify");
+    check(scema_select_rows(ctx, rows.data(), rows.size()), "compare_histories_with_all_ranks");
+    uint64_t m = 0;
+    check(scema_compare(ctx, threshold, SCEMA_PAIRS_TC, 0, 1, &m), "compare_histories_with_all_ranks");
+    (void)ids;
+    return true;
+}
+
 // All-pairs on the GPU for one (already rank-merged) batch; fills every object's result lists.
 // ring_rank[i] / n_ranks describe which MPI rank history i lives on, to reproduce the partner
 // order of the reference's ring when more than one rank takes part.
@@ -471,7 +603,10 @@ inline void compare_batch(std::vector<Strain6D *> &hist, double threshold, const
     bool direct = true, clustered = false;
     const uint32_t P0 = hist[0]->get_num_spline_points_per_component();
     for (size_t i = 0; i < n; i++) direct = direct && hist[i]->b200_pending() && hist[i]->get_num_spline_points_per_component() == P0;
-    if (direct && P0 > 0) {
+    if (direct && P0 > 0 && !keep_all_similar() && !multi() && store_compare(hist, ids, P0, threshold)) {
+        clustered = true;   // histories kept on the device, only the new samples uploaded
+    } else if (direct && P0 > 0) {
+        store_state().flat_uploads++;
         std::vector<uint64_t> offsets(1, 0);
         std::vector<double> flat;
         for (size_t i = 0; i < n; i++) {

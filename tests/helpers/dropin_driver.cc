@@ -116,5 +116,12 @@ int main(int argc, char **argv)
     }
     std::cout << "run_new_md: " << new_md << " of " << n_qp << ", point 1 takes results from "
               << qp[1].get_ID_to_get_results_from() << " (was " << qp[1].get_most_recent_ID_to_get_results_from() << ")\n";
+#ifndef DROPIN_REFERENCE
+    if (getenv("DROPIN_STATS")) {  // how the histories reached the GPU (stderr: not part of the compared output)
+        const MatHistPredict::b200::StoreState &st = MatHistPredict::b200::store_state();
+        fprintf(stderr, "store: rebuilds=%llu appended_steps=%llu h2d_bytes=%llu flat_uploads=%llu\n", (unsigned long long)st.rebuilds,
+                (unsigned long long)st.appended_steps, (unsigned long long)st.h2d_bytes, (unsigned long long)st.flat_uploads);
+    }
+#endif
     return 0;
 }

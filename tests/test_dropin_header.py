@@ -44,6 +44,36 @@ def test_same_caller_same_bytes(tmp_path, n_qp, n_steps, P, thr, seed):
     assert any(os.path.getsize(tmp_path / "ref" / f) > 0 for f in files if f.endswith("similar_hist"))
 
 
+def test_in_process_pattern_uploads_only_the_new_samples(tmp_path):
+    """FE_problem.h's pattern (append a sample to every point, fit every point, compare the flagged subset) keeps the
+    histories on the GPU: one store build, then 48 bytes per point and NEW timestep — same bytes out as the reference,
+    and as the flat-upload path (SCEMA_B200_STORE=0)."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref not built")
+    ours_exe = build_ours(tmp_path)
+    n_qp, n_steps = 300, 21
+    args = [str(n_qp), str(n_steps), "10", "4e-7", "9"]
+    outs, errs = {}, {}
+    for name, exe, env in (("ref", REF_BIN, {}), ("store", ours_exe, {"DROPIN_STATS": "1"}),
+                           ("flat", ours_exe, {"DROPIN_STATS": "1", "SCEMA_B200_STORE": "0"})):
+        d = tmp_path / name
+        d.mkdir()
+        r = subprocess.run([exe, str(d)] + args, capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr
+        outs[name], errs[name] = r.stdout, r.stderr
+    assert outs["store"] == outs["ref"] == outs["flat"]
+    files = sorted(os.listdir(tmp_path / "ref"))
+    for other in ("store", "flat"):
+        match, mismatch, errors = filecmp.cmpfiles(tmp_path / "ref", tmp_path / other, files, shallow=False)
+        assert not mismatch and not errors, other
+    stats = dict(kv.split("=") for kv in errs["store"].split("store:")[1].split())
+    # comparisons at t = 3, 5, 10, 15, 20, 21: one build (3 samples), then exactly the samples added since: 21 in total
+    assert int(stats["rebuilds"]) == 1 and int(stats["appended_steps"]) == n_steps and int(stats["flat_uploads"]) == 0, stats
+    assert int(stats["h2d_bytes"]) == 48 * n_qp * n_steps, stats
+    flat = dict(kv.split("=") for kv in errs["flat"].split("store:")[1].split())
+    assert int(flat["appended_steps"]) == 0 and int(flat["rebuilds"]) == 0
+
+
 @pytest.mark.parametrize("legacy,env", [("1", {"SCEMA_B200_ALL_SIMILAR": "1"}), ("2", {"SCEMA_B200_NEAREST": "1"})])
 def test_legacy_outputs_on_request(tmp_path, legacy, env):
     """The reference's "theory-checking" outputs: all_similar_histories_to_file (every comparison of every history,
