@@ -163,7 +163,9 @@ struct StoreState {
     uint64_t rebuilds, appended_steps, h2d_bytes, flat_uploads;
     StoreState() : steps(0), valid(false), rebuilds(0), appended_steps(0), h2d_bytes(0), flat_uploads(0) {}
 };
-inline StoreState &store_state() { static StoreState st; return st; }
+// per thread: SCEMa drives this header from one thread per process; a test that runs several "ranks" as threads of one
+// process (tests/helpers/mpi_threads) must not share the registry between them
+inline StoreState &store_state() { static thread_local StoreState st; return st; }
 inline bool store_enabled()
 {
     static int v = -1;
