@@ -600,7 +600,7 @@ def run_ours(args, wl, wl_name):
             except Exception:
                 mp = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
             peak = float(mp.get("bf16_tflops", 1590.0))
-            tc_slices = hc.counters().get("tc_slices", 2) or 2
+            tc_slices = (acc.get("plan") or {}).get("slices") or 1   # of the timed steps (the verification ran other filters since)
             n_products = 1 if tc_slices == 1 else 3
             n_chunks = (K + 4 + 63) // 64
             executed = ((NT * (NT + 1) / 2) / world * 256 * 256 * n_products * 64 * n_chunks * 2 / (filt_ms * 1e-3) / 1e12
