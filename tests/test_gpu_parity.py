@@ -508,3 +508,26 @@ def test_config5_shape_properties(hc, oracle):
     hc.compare(THR, PAIRS_EXACT)
     assert edges_equal(hc.get_edges(), (a, b, d))
     del d_rows
+
+
+def test_select_rows_twice_and_with_duplicates(hc, oracle):
+    """scema_select_rows on an already selected matrix (the gather must not run in place nor free its own
+    source), with duplicates that make the second selection larger than the first."""
+    rng = np.random.default_rng(5)
+    rows = synth.rows(9, 3000, 16, 10, 5e-3, synth.default_pert(THR, 10))
+    hc.set_spline(rows, ids=np.arange(3000, dtype=np.uint32) + 100)
+    first = rng.choice(3000, size=700, replace=False).astype(np.uint32)
+    hc.select_rows(first)
+    assert same_bits(hc.get_spline(), rows[first])
+    second = rng.integers(0, 700, size=2500).astype(np.uint32)      # duplicates, more rows than before
+    hc.select_rows(second)
+    want = rows[first][second]
+    assert same_bits(hc.get_spline(), want)
+    third = np.arange(0, 2500, 3, dtype=np.uint32)
+    hc.select_rows(third)
+    want = want[third]
+    assert same_bits(hc.get_spline(), want)
+    # distinct rows only for the compare (exact duplicates are at distance 0, still a valid edge)
+    wi, wj, wd, _ = oracle.all_pairs(want, THR)
+    assert hc.compare(THR, PAIRS_TC) == len(wi)
+    assert edges_equal(hc.get_edges(), (wi, wj, wd))
