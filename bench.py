@@ -386,8 +386,8 @@ def run_ours(args, wl, wl_name):
     pert = synth.default_pert(THR, P)
     # N > 1: the plain sequence (all-gather of the FP64 rows, then every rank prepares and filters) is the default.
     # SCEMA_SHARD_OVERLAP=1 selects the overlapped exchange (ShardedCluster.run_overlapped: own-row operand images
-    # all-gathered, FP64 rows on a side stream) — measured on 2 GPUs it gains nothing yet: NCCL's all-gather kernel and the
-    # persistent filter (one CTA per SM, static schedule) compete for SMs (filter 16.8 -> 18.1 ms), DESIGN.md section 4
+    # all-gathered, FP64 rows pulled by copy engines on a side stream) — measured on 2 GPUs it gains nothing: the filter is
+    # power-capped and clocks lower by what the overlap saves (filter 16.8 -> 18.1 ms), DESIGN.md section 4
     overlapped = (world > 1 and args.variant == "tc" and K <= 636 and not args.stream and n >= 4096 * world and
                   os.environ.get("SCEMA_SHARD_OVERLAP", "0") == "1" and not args.norm_band)
     all_bounds = aligned_shard_bounds(n, world)[1] if overlapped else shard_bounds(n, world)

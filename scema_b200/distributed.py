@@ -110,6 +110,8 @@ class ShardedCluster:
         self._main = None
         self._packets = None
         self._views = {}
+        self._peers = None
+        self._flag = None
         self._last_choice = None
         self.path = "plain"
 
@@ -165,17 +167,29 @@ class ShardedCluster:
                 self._full = torch.empty((G * per, K), dtype=torch.float64, device="cuda")
                 self._cents = torch.empty((G, K), dtype=torch.float64, device="cuda")
                 self._views = {}
+                self._peers = self._map_peers(self._full)
             full = self._full
             if n_local:
                 full[b:e].copy_(self._view(ptr, (n_local, K), "<f8"))
             ev0, ev1, k1_done, rows_ready = self._events
             k1_done.record(main)
             hc.set_spline(device_ptr=full.data_ptr(), n=n, k=K)
-            # FP64 rows: in-place all-gather on the side stream
+            # FP64 rows on the side stream. An NCCL all-gather is an SM kernel and competes with the persistent filter
+            # (one CTA per SM, static schedule) for SMs; COPY ENGINES do not: every rank maps its peers' buffers (CUDA IPC,
+            # exchanged once) and PULLS their row blocks with peer-to-peer copies over NVLink, after a one-element
+            # all-reduce on the side stream has established that every rank's K1 is done. (SCEMA_SHARD_PULL=0: NCCL.)
             with torch.cuda.stream(self._side_stream):
                 self._side_stream.wait_event(k1_done)
                 ev0.record()
-                dist.all_gather_into_tensor(full, full[self.rank * per:(self.rank + 1) * per], group=self.side_group)
+                if self._peers is not None:
+                    dist.all_reduce(self._flag, group=self.side_group)
+                    for step in range(1, G):
+                        q = (self.rank + step) % G
+                        qb, qe = bounds[q]
+                        if qe > qb:
+                            full[qb:qe].copy_(self._peers[q][qb:qe], non_blocking=True)
+                else:
+                    dist.all_gather_into_tensor(full, full[self.rank * per:(self.rank + 1) * per], group=self.side_group)
                 ev1.record()
                 self.gather_events = (ev0, ev1)
                 rows_ready.record()
@@ -206,6 +220,25 @@ class ShardedCluster:
             else:
                 self._last_choice = choice
         return ne, counts, offs, full[:n]
+
+    def _map_peers(self, full):
+        """CUDA IPC: every rank's full-size row buffer mapped into every other rank (once per buffer). None when the
+        environment asks for the NCCL all-gather or the mapping fails (then the all-gather is used)."""
+        import os
+        if os.environ.get("SCEMA_SHARD_PULL", "1") == "0":
+            return None
+        try:
+            from torch.multiprocessing.reductions import reduce_tensor
+            fn, args = reduce_tensor(full)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (fn, args), group=self.group)
+            peers = [None if q == self.rank else handles[q][0](*handles[q][1]) for q in range(self.world)]
+            self._flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+            ok = torch.ones(1, dtype=torch.int32, device="cuda")
+        except Exception:  # noqa: BLE001 - no IPC (e.g. a container without it): every rank must take the same decision
+            peers, ok = None, torch.zeros(1, dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        return peers if int(ok.item()) == 1 else None
 
     def _view(self, ptr, shape, typestr):
         """Cached zero-copy tensor over library-owned device memory (the library keeps these buffers between steps)."""
