@@ -531,3 +531,16 @@ def test_select_rows_twice_and_with_duplicates(hc, oracle):
     wi, wj, wd, _ = oracle.all_pairs(want, THR)
     assert hc.compare(THR, PAIRS_TC) == len(wi)
     assert edges_equal(hc.get_edges(), (wi, wj, wd))
+
+
+def test_result_file_pattern_is_validated(hc, tmp_path):
+    """The file name pattern of scema_write_similar_hist goes to snprintf: exactly one %u, nothing else."""
+    rows = synth.rows(2, 300, 16, 10, 5e-3, synth.default_pert(THR, 10))
+    hc.set_spline(rows)
+    hc.compare(THR, PAIRS_TC)
+    for bad in ("%s", "a_%u_%u", "plain", "%u%n", "%d"):
+        with pytest.raises(scema_b200.ScemaError) as e:
+            hc.write_similar_hist(str(tmp_path / bad))
+        assert e.value.code == 1
+    hc.write_similar_hist(str(tmp_path / "100%%_ID_%u.txt"))
+    assert len([f for f in os.listdir(tmp_path) if f.startswith("100%_ID_")]) == 300
