@@ -81,10 +81,10 @@ def gather_edges(a, b, d, n, counts, device, group=None):
     if mine:
         buf[0, :mine] = torch.from_numpy(a.astype(np.int64) * int(n) + b.astype(np.int64))
         buf[1, :mine] = torch.from_numpy(np.ascontiguousarray(d, dtype=np.float64).view(np.int64).copy())
-    buf = buf.to(device)
-    allb = torch.empty((world, 2, m), dtype=torch.int64, device=device)
+    buf = buf.to(device).reshape(-1)
+    allb = torch.empty(world * 2 * m, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(allb, buf, group=group)
-    allb = allb.cpu().numpy()
+    allb = allb.cpu().numpy().reshape(world, 2, m)
     keys = np.concatenate([allb[r, 0, :counts[r]] for r in range(world)])
     bits = np.concatenate([allb[r, 1, :counts[r]] for r in range(world)])
     order = np.argsort(keys, kind="stable")
@@ -213,10 +213,10 @@ class ShardedCluster:
                 self.path = "plain (sample chose %d)" % choice
             ne, counts, offs = self.compare_all_ranks(threshold, 3, sink, full.device)
             if choice == 1 and optimistic:
+                # what the sample really said; the edge list of this step is correct either way (every survivor is
+                # recomputed exactly, an overflowing queue is handled inside the compare) — a different answer only means
+                # the NEXT step waits for its sample again and takes the filter it names
                 self._last_choice = hc.tc_shard_check()
-                if self._last_choice != 1:   # the data changed character: this step again, the ordinary way (same on every rank)
-                    self.path = "plain (sample chose %d after an optimistic step)" % self._last_choice
-                    ne, counts, offs = self.compare_all_ranks(threshold, 3, sink, full.device)
             else:
                 self._last_choice = choice
         return ne, counts, offs, full[:n]

@@ -90,3 +90,47 @@ def test_tile_shards_partition_the_groups():
                 local = (groups - s + w - 1) // w if groups > s else 0
                 owned += [lg * w + s for lg in range(local)]
             assert sorted(owned) == list(range(groups))
+
+
+def test_aligned_shard_bounds():
+    """Equal shares of whole 2048-row panels (what the overlapped exchange all-gathers in place): contiguous, cover
+    [0, n), every inner boundary a multiple of 2048, every share but the last ones full."""
+    from scema_b200.distributed import aligned_shard_bounds
+    for n in (1, 2047, 2048, 20011, 1000000, 4000000):
+        for w in (1, 2, 3, 4, 8):
+            per, b = aligned_shard_bounds(n, w)
+            assert per % 2048 == 0 and per * w >= n
+            assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert all(s % 2048 == 0 for s, _ in b if s < n)
+            assert all(e - s == per for s, e in b if e < n)
+    assert aligned_shard_bounds(1000000, 8)[1][0] == (0, 126976) and aligned_shard_bounds(1000000, 8)[1][-1] == (888832, 1000000)
+
+
+def _edges_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        from scema_b200.distributed import gather_edges
+        n = 1000
+        rng = np.random.default_rng(7)
+        a_all = rng.integers(0, n - 1, size=300).astype(np.uint32)
+        b_all = (a_all + 1 + rng.integers(0, 5, size=300)).clip(max=n - 1).astype(np.uint32)
+        keys = np.unique(a_all.astype(np.int64) * n + b_all)
+        a_all, b_all = (keys // n).astype(np.uint32), (keys % n).astype(np.uint32)
+        d_all = (a_all * 1e-9 + b_all * 1e-12).astype(np.float64)
+        mine = np.arange(len(keys)) % world == rank             # interleaved shards, like the tile items
+        counts = [int((np.arange(len(keys)) % world == r).sum()) for r in range(world)]
+        A, B, D = gather_edges(a_all[mine], b_all[mine], d_all[mine], n, counts, torch.device("cpu"))
+        assert np.array_equal(A, a_all) and np.array_equal(B, b_all) and np.array_equal(D.view(np.uint64), d_all.view(np.uint64))
+        open(os.path.join(out_dir, f"edges_ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_edges_world3(tmp_path):
+    """The union of the ranks' (interleaved) edge lists, gathered and put back in canonical order (what bench.py verifies)."""
+    port = _free_port()
+    mp.spawn(_edges_worker, args=(3, port, str(tmp_path)), nprocs=3, join=True)
+    assert all(os.path.exists(tmp_path / f"edges_ok{r}") for r in range(3))
