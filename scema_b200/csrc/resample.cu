@@ -121,6 +121,25 @@ __device__ __forceinline__ double div_tab(double a, double b, double rb)
     return __ddiv_rn(a, b);
 }
 
+// The same quotient WITHOUT a branch, for the streamed kernel: the guard only ACCUMULATES (`ok` goes false when a numerator
+// is outside the range the two corrections are proven for: subnormal, huge, inf, NaN), and a chain whose flag is false at
+// the end is redone by resample_chain_slow with IEEE divisions. ncu (profiles/r02_ncu_resample_c3.txt): with a fast / slow
+// branch at each of the 36 division sites, control flow (BRA, BSSY, BSYNC, ISETP) was 20 % of the executed instructions —
+// as much as the FP64 arithmetic — and the inlined IEEE sequences doubled the size of the hot loops. A zero numerator is
+// exact in the first product (a * rb = +-0 with the sign of a / b) and stays in range.
+__device__ __forceinline__ double div_fast(double a, double b, double rb, bool &ok)
+{
+    const uint32_t e = ((uint32_t)__double2hiint(a) >> 20) & 0x7ffu;
+    const double q0 = __dmul_rn(a, rb);
+    double r = __fma_rn(-b, q0, a);
+    double q = __fma_rn(r, rb, q0);
+    r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, rb, q);
+    const bool zero = a == 0.0;
+    ok = ok && (zero || e - 128u < 1792u);
+    return zero ? q0 : q;
+}
+
 constexpr int RS_WARPS = 4;    // warps per CTA
 constexpr int RING = 8;        // steps per unrolled block
 constexpr int DEPTH = 16;      // slots of the per-lane shared-memory prefetch ring (y, then z)
@@ -184,7 +203,7 @@ __device__ __forceinline__ double2 tab_f64x2(const double2 *p) { return STAB ? *
         z_prev = __dsub_rn(r, sum);                                                                 \
         __stcg(zb + (size_t)(U) * 32, z_prev);                                                      \
         s_prev = s_cur;                                                                             \
-        if (i + 1 < L - 1) s_cur = div_tab(__dsub_rn(y_nx, y_hi), E0.y, E0.x);                      \
+        if (i + 1 < L - 1) s_cur = div_fast(__dsub_rn(y_nx, y_hi), E0.y, E0.x, ok);                 \
         y_hi = y_nx;                                                                                \
     }
 
@@ -202,13 +221,13 @@ __device__ __forceinline__ double2 tab_f64x2(const double2 *p) { return STAB ? *
         if (i + 1 - DEPTH >= 0) cp_async8(rz + ((i + 1) & (DEPTH - 1)) * 32, zb - (size_t)((U) - 1 + DEPTH) * 32); \
         cp_async_commit();                                                                          \
         const double sum = __dadd_rn(0.0, __dmul_rn(W0.x, b_next));                                 \
-        const double b_i = div_tab(__dsub_rn(zi, sum), W0.y, W1.x);                                 \
+        const double b_i = div_fast(__dsub_rn(zi, sum), W0.y, W1.x, ok);                            \
         if (i == nxt) {                                                                             \
             const double2 f0 = tab_f64x2<STAB>(FW + 2 * i);                                         \
             const double hdv = f0.y;                                                                \
-            const double a_i = div_tab(__dmul_rn(third, __dsub_rn(b_next, b_i)), hdv, f0.x);        \
+            const double a_i = div_fast(__dmul_rn(third, __dsub_rn(b_next, b_i)), hdv, f0.x, ok);   \
             const double c_i =                                                                      \
-                __dsub_rn(div_tab(__dsub_rn(y_b, y_a), hdv, f0.x),                                  \
+                __dsub_rn(div_fast(__dsub_rn(y_b, y_a), hdv, f0.x, ok),                             \
                           __dmul_rn(__dmul_rn(third, __dadd_rn(__dmul_rn(2.0, b_i), b_next)), hdv)); \
             do {                                                                                    \
                 const double hstep = tab_f64<STAB>(ht + p);                                         \
@@ -223,6 +242,56 @@ __device__ __forceinline__ double2 tab_f64x2(const double2 *p) { return STAB ? *
         }                                                                                           \
         b_next = b_i;                                                                               \
     }
+
+// One chain (history, component) with IEEE divisions throughout — the arithmetic of k_resample_global — for the chains
+// whose numerators left the range of div_fast. z, then b, live in the warp-private scratch column zs[i * 32].
+__device__ __noinline__ void resample_chain_slow(const double *__restrict__ y, uint64_t ys, int L, const double *__restrict__ tab, uint32_t P,
+                                                 double *__restrict__ zs, double *__restrict__ orow)
+{
+    const uint32_t Lp = pad2((uint32_t)L);
+    const double *hd = tab + Lp, *sd = hd + Lp, *lo = sd + Lp, *up = lo + Lp, *di = up + Lp;
+    const double *ht = tab + 6ull * Lp, *ix = ht + pad2(P);
+    const double third = 1.0 / 3.0;
+    double y1 = __ldg(y), y2 = __ldg(y + ys);
+    double s_prev = __ddiv_rn(__dsub_rn(y2, y1), __ldg(hd));
+    double z_prev = __dsub_rn(__dmul_rn(0.0, __ldg(sd)), 0.0);
+    zs[0] = z_prev;
+    y1 = y2;
+    for (int i = 1; i < L - 1; i++) {
+        y2 = __ldg(y + (size_t)(i + 1) * ys);
+        const double s_cur = __ddiv_rn(__dsub_rn(y2, y1), __ldg(hd + i));
+        const double r = __dmul_rn(__dsub_rn(s_cur, s_prev), __ldg(sd + i));
+        const double sum = __dadd_rn(0.0, __dmul_rn(__ldg(lo + i), z_prev));
+        z_prev = __dsub_rn(r, sum);
+        zs[(size_t)i * 32] = z_prev;
+        s_prev = s_cur;
+        y1 = y2;
+    }
+    {
+        const double r = __dmul_rn(0.0, __ldg(sd + L - 1));
+        const double sum = __dadd_rn(0.0, __dmul_rn(__ldg(lo + L - 1), z_prev));
+        z_prev = __dsub_rn(r, sum);
+    }
+    double b_next = __ddiv_rn(__dsub_rn(z_prev, 0.0), __ldg(di + L - 1));
+    zs[(size_t)(L - 1) * 32] = b_next;
+    for (int i = L - 2; i >= 0; i--) {
+        const double sum = __dadd_rn(0.0, __dmul_rn(__ldg(up + i), b_next));
+        b_next = __ddiv_rn(__dsub_rn(zs[(size_t)i * 32], sum), __ldg(di + i));
+        zs[(size_t)i * 32] = b_next;
+    }
+    for (uint32_t p = 0; p < P; p++) {
+        const int idx = (int)__ldg(ix + p);
+        const double hstep = __ldg(ht + p), hdv = __ldg(hd + idx);
+        const double ya = __ldg(y + (size_t)idx * ys), yb = __ldg(y + (size_t)(idx + 1) * ys);
+        const double b0 = zs[(size_t)idx * 32], b1 = zs[(size_t)(idx + 1) * 32];
+        const double a_i = __ddiv_rn(__dmul_rn(third, __dsub_rn(b1, b0)), hdv);
+        const double c_i = __dsub_rn(__ddiv_rn(__dsub_rn(yb, ya), hdv), __dmul_rn(__dmul_rn(third, __dadd_rn(__dmul_rn(2.0, b0), b1)), hdv));
+        double v = __dadd_rn(__dmul_rn(a_i, hstep), b0);
+        v = __dadd_rn(__dmul_rn(v, hstep), c_i);
+        v = __dadd_rn(__dmul_rn(v, hstep), ya);
+        orow[(size_t)p * 6] = v;
+    }
+}
 
 // ys = distance (in doubles) between consecutive steps of one history: 6 for the ragged batch
 // ([L][6] blocks, history h starts at offsets[h]; `order` lists the histories group by group, five
@@ -308,14 +377,15 @@ __global__ void __launch_bounds__(32 * RS_WARPS, 6) k_resample_stream(const doub
                 cp_async_commit();
             }
             double s_prev, s_cur, z_prev, y_hi;
+            bool ok = true;          // every numerator of this chain stayed in the range of the branch-free division
             double2 a1, a0, b1, b0;  // ping-pong: {sd, lo} of the coming step and {1/hd, hd} of the one after
             {
                 const double y_0 = __ldg(y), y_1 = __ldg(y + ys), y_2 = __ldg(y + 2 * ys);  // L >= 3
                 const double2 f00 = tab_f64x2<STAB>(FW), f01 = tab_f64x2<STAB>(FW + 1), f10 = tab_f64x2<STAB>(FW + 2);
                 ld_tab<STAB>(a1, FW + 3);  // {sd_1, lo_1}
                 ld_tab<STAB>(a0, FW + 4);  // {1/hd_2, hd_2}
-                s_prev = div_tab(__dsub_rn(y_1, y_0), f00.y, f00.x);  // s_0
-                s_cur = div_tab(__dsub_rn(y_2, y_1), f10.y, f10.x);   // s_1
+                s_prev = div_fast(__dsub_rn(y_1, y_0), f00.y, f00.x, ok);  // s_0
+                s_cur = div_fast(__dsub_rn(y_2, y_1), f10.y, f10.x, ok);   // s_1
                 z_prev = __dsub_rn(__dmul_rn(0.0, f01.x), 0.0);       // row 0: rhs = 0, empty sum
                 __stcg(zs, z_prev);
                 y_hi = y_2;
@@ -352,7 +422,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS, 6) k_resample_stream(const doub
             double b_next;
             {
                 const double2 w0 = tab_f64x2<STAB>(BW + 2 * (L - 1)), w1 = tab_f64x2<STAB>(BW + 2 * (L - 1) + 1);
-                b_next = div_tab(__dsub_rn(z_prev, 0.0), w0.y, w1.x);
+                b_next = div_fast(__dsub_rn(z_prev, 0.0), w0.y, w1.x, ok);
             }
             int p = (int)P - 1;
             int nxt = (int)tab_f64<STAB>(ix + p);
@@ -373,6 +443,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS, 6) k_resample_stream(const doub
                 K1_BWD_STEP(7, b0, b1, a0, a1)
             }
             cp_async_wait<0>();  // nothing of this group may land in the ring after the next group starts
+            if (!ok) resample_chain_slow(y, ys, L, tab, P, zs, out + h * K + c);  // rare: subnormal / huge / non-finite numerators
         }
     }
 }
