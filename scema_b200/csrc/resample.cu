@@ -21,79 +21,10 @@
 //  * k_resample_global: fallback for histories longer than 131072 steps.
 #include "common.cuh"
 #include <algorithm>
+#include "resample_pair.cuh"
 
 namespace scema {
 
-// table for one L, every array padded to an even length Lp (so each starts 16-byte aligned and the
-// five arrays the sweeps need are one contiguous block for a bulk copy):
-//   x[Lp] | hd[Lp] sd[Lp] lo[Lp] up[Lp] di[Lp] | ht[Pp] idx[Pp] | FW[Lp][4] | BW[Lp][4]
-// FW[i] = {1/hd_i, hd_i, sd_i, lo_i} and BW[i] = {up_i, di_i, 1/di_i, 0} are what one forward / one
-// backward step of k_resample_stream needs, packed so that each step is two 16-byte loads; the
-// correctly rounded reciprocals feed the exact division div_tab() below.
-__host__ __device__ inline uint32_t pad2(uint32_t v) { return v + (v & 1u); }
-__host__ __device__ inline uint64_t table_fw_offset(uint32_t L, uint32_t P) { return 6ull * pad2(L) + 2ull * pad2(P); }
-__host__ __device__ inline uint64_t table_doubles(uint32_t L, uint32_t P) { return table_fw_offset(L, P) + 8ull * pad2(L); }
-
-__global__ void k_build_tables(const uint32_t *__restrict__ lens, const uint64_t *__restrict__ offs,
-                               uint32_t n_tables, uint32_t P, double *__restrict__ tables)
-{
-    uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ti >= n_tables) return;
-    const uint32_t L = lens[ti];
-    const int n = (int)L;
-    const uint32_t Lp = pad2(L);
-    double *x = tables + offs[ti], *hd = x + Lp, *sd = hd + Lp, *lo = sd + Lp, *up = lo + Lp, *di = up + Lp,
-           *ht = di + Lp, *ix = ht + pad2(P);
-    if (Lp != L) x[L] = hd[L] = sd[L] = lo[L] = up[L] = di[L] = 0.0;
-    const double third = 1.0 / 3.0, twothird = 2.0 / 3.0;  // spline.h:303-305
-    for (int i = 0; i < n; i++) x[i] = __ddiv_rn((double)i, (double)(L - 1));  // strain2spline.h:157
-    for (int i = 0; i < n; i++) hd[i] = i < n - 1 ? __dsub_rn(x[i + 1], x[i]) : 0.0;
-    // rows, spline.h:302-305 and natural boundary rows :309-313, :323-327
-    for (int i = 1; i < n - 1; i++) {
-        lo[i] = __dmul_rn(third, __dsub_rn(x[i], x[i - 1]));
-        di[i] = __dmul_rn(twothird, __dsub_rn(x[i + 1], x[i - 1]));
-        up[i] = __dmul_rn(third, __dsub_rn(x[i + 1], x[i]));
-    }
-    di[0] = 2.0; up[0] = 0.0; lo[0] = 0.0;
-    di[n - 1] = 2.0; lo[n - 1] = 0.0; up[n - 1] = 0.0;
-    // preconditioning, spline.h:195-204
-    for (int i = 0; i < n; i++) {
-        sd[i] = __ddiv_rn(1.0, di[i]);
-        if (i > 0) lo[i] = __dmul_rn(lo[i], sd[i]);
-        if (i < n - 1) up[i] = __dmul_rn(up[i], sd[i]);
-        di[i] = 1.0;
-    }
-    // elimination, spline.h:207-219
-    for (int k = 0; k < n - 1; k++) {
-        double xx = __ddiv_rn(-lo[k + 1], di[k]);
-        lo[k + 1] = -xx;
-        di[k + 1] = __dadd_rn(di[k + 1], __dmul_rn(xx, up[k]));
-    }
-    // sample -> interval map, strain2spline.h:171 and spline.h:380-383
-    for (uint32_t p = 0; p < P; p++) {
-        double t = __ddiv_rn((double)p, (double)(P - 1));
-        int it = 0;
-        while (it < n && x[it] < t) it++;  // std::lower_bound on the rounded knots
-        int idx = it - 1 > 0 ? it - 1 : 0;
-        if (idx > n - 2) idx = n - 2;      // t <= x[n-1] always, so this never binds
-        ht[p] = __dsub_rn(t, x[idx]);
-        ix[p] = (double)idx;
-    }
-    double *fw = tables + offs[ti] + table_fw_offset(L, P), *bw = fw + 4ull * Lp;
-    for (uint32_t i = 0; i < Lp; i++) {
-        const bool in = i < L;
-        fw[4 * i + 0] = in && i < L - 1 ? __ddiv_rn(1.0, hd[i]) : 0.0;
-        fw[4 * i + 1] = in ? hd[i] : 0.0;
-        fw[4 * i + 2] = in ? sd[i] : 0.0;
-        fw[4 * i + 3] = in ? lo[i] : 0.0;
-        bw[4 * i + 0] = in ? up[i] : 0.0;
-        bw[4 * i + 1] = in ? di[i] : 1.0;
-        bw[4 * i + 2] = in ? __ddiv_rn(1.0, di[i]) : 1.0;
-        bw[4 * i + 3] = 0.0;
-    }
-}
-
-constexpr int GROUP = 5;  // histories per warp (5*6 = 30 chain lanes)
 
 // ---- streamed kernel. One warp per group of five histories of the SAME length, lane = (history,
 // component) chain; 30 of 32 lanes busy. Nothing is staged in bulk, so the number of resident chains
@@ -140,17 +71,10 @@ __device__ __forceinline__ double div_fast(double a, double b, double rb, bool &
     return zero ? q0 : q;
 }
 
-constexpr int RS_WARPS = 4;    // warps per CTA
 constexpr int RING = 8;        // steps per unrolled block
 constexpr int DEPTH = 16;      // slots of the per-lane shared-memory prefetch ring (y, then z)
-constexpr int CHUNK_GROUPS = 16;  // groups (of one length) handed to a CTA at a time
-constexpr uint32_t SMEM_TAB_MAX_L = 256;  // longer histories read the factor table from global memory
 constexpr size_t RS_RING_BYTES = (size_t)RS_WARPS * DEPTH * 32 * sizeof(double);
-__host__ __device__ inline size_t rs_table_doubles(uint32_t L, uint32_t P) { return 8ull * pad2(L) + 2ull * pad2(P); }
 
-struct K1Chunk {
-    uint32_t first_group, n_groups, L, pad;
-};
 
 // The two long-latency streams of a chain — y on the way up, z on the way down — are prefetched
 // DEPTH-2 steps ahead with 8-byte cp.async copies into a per-lane shared-memory ring (one commit
@@ -242,56 +166,6 @@ __device__ __forceinline__ double2 tab_f64x2(const double2 *p) { return STAB ? *
         }                                                                                           \
         b_next = b_i;                                                                               \
     }
-
-// One chain (history, component) with IEEE divisions throughout — the arithmetic of k_resample_global — for the chains
-// whose numerators left the range of div_fast. z, then b, live in the warp-private scratch column zs[i * 32].
-__device__ __noinline__ void resample_chain_slow(const double *__restrict__ y, uint64_t ys, int L, const double *__restrict__ tab, uint32_t P,
-                                                 double *__restrict__ zs, double *__restrict__ orow)
-{
-    const uint32_t Lp = pad2((uint32_t)L);
-    const double *hd = tab + Lp, *sd = hd + Lp, *lo = sd + Lp, *up = lo + Lp, *di = up + Lp;
-    const double *ht = tab + 6ull * Lp, *ix = ht + pad2(P);
-    const double third = 1.0 / 3.0;
-    double y1 = __ldg(y), y2 = __ldg(y + ys);
-    double s_prev = __ddiv_rn(__dsub_rn(y2, y1), __ldg(hd));
-    double z_prev = __dsub_rn(__dmul_rn(0.0, __ldg(sd)), 0.0);
-    zs[0] = z_prev;
-    y1 = y2;
-    for (int i = 1; i < L - 1; i++) {
-        y2 = __ldg(y + (size_t)(i + 1) * ys);
-        const double s_cur = __ddiv_rn(__dsub_rn(y2, y1), __ldg(hd + i));
-        const double r = __dmul_rn(__dsub_rn(s_cur, s_prev), __ldg(sd + i));
-        const double sum = __dadd_rn(0.0, __dmul_rn(__ldg(lo + i), z_prev));
-        z_prev = __dsub_rn(r, sum);
-        zs[(size_t)i * 32] = z_prev;
-        s_prev = s_cur;
-        y1 = y2;
-    }
-    {
-        const double r = __dmul_rn(0.0, __ldg(sd + L - 1));
-        const double sum = __dadd_rn(0.0, __dmul_rn(__ldg(lo + L - 1), z_prev));
-        z_prev = __dsub_rn(r, sum);
-    }
-    double b_next = __ddiv_rn(__dsub_rn(z_prev, 0.0), __ldg(di + L - 1));
-    zs[(size_t)(L - 1) * 32] = b_next;
-    for (int i = L - 2; i >= 0; i--) {
-        const double sum = __dadd_rn(0.0, __dmul_rn(__ldg(up + i), b_next));
-        b_next = __ddiv_rn(__dsub_rn(zs[(size_t)i * 32], sum), __ldg(di + i));
-        zs[(size_t)i * 32] = b_next;
-    }
-    for (uint32_t p = 0; p < P; p++) {
-        const int idx = (int)__ldg(ix + p);
-        const double hstep = __ldg(ht + p), hdv = __ldg(hd + idx);
-        const double ya = __ldg(y + (size_t)idx * ys), yb = __ldg(y + (size_t)(idx + 1) * ys);
-        const double b0 = zs[(size_t)idx * 32], b1 = zs[(size_t)(idx + 1) * 32];
-        const double a_i = __ddiv_rn(__dmul_rn(third, __dsub_rn(b1, b0)), hdv);
-        const double c_i = __dsub_rn(__ddiv_rn(__dsub_rn(yb, ya), hdv), __dmul_rn(__dmul_rn(third, __dadd_rn(__dmul_rn(2.0, b0), b1)), hdv));
-        double v = __dadd_rn(__dmul_rn(a_i, hstep), b0);
-        v = __dadd_rn(__dmul_rn(v, hstep), c_i);
-        v = __dadd_rn(__dmul_rn(v, hstep), ya);
-        orow[(size_t)p * 6] = v;
-    }
-}
 
 // ys = distance (in doubles) between consecutive steps of one history: 6 for the ragged batch
 // ([L][6] blocks, history h starts at offsets[h]; `order` lists the histories group by group, five
@@ -443,7 +317,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS, 6) k_resample_stream(const doub
                 K1_BWD_STEP(7, b0, b1, a0, a1)
             }
             cp_async_wait<0>();  // nothing of this group may land in the ring after the next group starts
-            if (!ok) resample_chain_slow(y, ys, L, tab, P, zs, out + h * K + c);  // rare: subnormal / huge / non-finite numerators
+            if (!ok) resample_chain_slow(y, ys, L, tab, P, zs, 32, out + h * K + c);  // rare: subnormal / huge / non-finite numerators
         }
     }
 }
@@ -684,13 +558,24 @@ static int build_plan(scema_ctx *ctx, const std::vector<uint64_t> &bounds)
     return SCEMA_OK;
 }
 
+// Which streamed kernel runs: the first-generation k_resample_stream (one chain per lane) or, with SCEMA_K1_KERNEL=pair,
+// k_resample_pair (two chains per lane, resample_pair.cuh). Both take the same plan, tables and arguments; a warp's z
+// scratch is cap rows of 32 (stream) or 64 (pair) doubles.
+static bool k1_pair()
+{
+    static const char *env = getenv("SCEMA_K1_KERNEL");
+    return env && !strcmp(env, "pair");
+}
+static size_t k1_row_bytes() { return k1_pair() ? PR_ROW * sizeof(double) : 32 * sizeof(double); }
+
 // resident warps for a launch over n_groups groups of at most cap steps, and the z scratch they need
 static uint64_t stream_warps_for(const scema_ctx *ctx, uint64_t n_groups, uint32_t cap)
 {
     static const char *wps_env = getenv("SCEMA_K1_WPS");
-    const int wps = wps_env && atoi(wps_env) > 0 ? atoi(wps_env) : 24;
-    uint64_t w = std::min<uint64_t>((uint64_t)ctx->sm_count * wps, n_groups);
-    w = std::min<uint64_t>(w, std::max<uint64_t>(RS_WARPS, (1ull << 30) / ((uint64_t)cap * 256)));
+    const int wps = wps_env && atoi(wps_env) > 0 ? atoi(wps_env) : (k1_pair() ? RS_WARPS * PR_MIN_CTAS : 24);
+    const uint64_t units = k1_pair() ? (n_groups + 1) / 2 : n_groups;  // what one warp takes at a time
+    uint64_t w = std::min<uint64_t>((uint64_t)ctx->sm_count * wps, units);
+    w = std::min<uint64_t>(w, std::max<uint64_t>(RS_WARPS, (1ull << 30) / ((uint64_t)cap * k1_row_bytes())));
     return (w + RS_WARPS - 1) / RS_WARPS * RS_WARPS;
 }
 
@@ -699,9 +584,10 @@ static int launch_stream(scema_ctx *ctx, const double *steps, const uint64_t *of
                          uint64_t ys, uint32_t uniform_L)
 {
     const bool stab = cap <= SMEM_TAB_MAX_L;
-    const size_t smem = RS_RING_BYTES + (stab ? rs_table_doubles(cap, P) * sizeof(double) : 0);
+    const bool pair = k1_pair();
+    const size_t smem = (pair ? PR_RING_BYTES : RS_RING_BYTES) + (stab ? rs_table_doubles(cap, P) * sizeof(double) : 0);
     if (smem > ctx->smem_optin) return fail(ctx, SCEMA_ERR_INVALID, "resample: spline_points too large for the shared-memory table");
-    auto kern = stab ? k_resample_stream<true> : k_resample_stream<false>;
+    auto kern = pair ? (stab ? k_resample_pair<true> : k_resample_pair<false>) : (stab ? k_resample_stream<true> : k_resample_stream<false>);
     SCEMA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)(warps / RS_WARPS), 32 * RS_WARPS, smem, ctx->stream>>>(
         steps, offsets, order, n_hist, chunks, n_chunks, counter, ctx->d_table_index.as<int64_t>(), ctx->d_tables.as<double>(), P,
@@ -742,7 +628,7 @@ int resample_prepare(scema_ctx *ctx, uint32_t P, const std::vector<uint64_t> &bo
             if (!ctx->plan_groups[r * K1_NCLS + k]) continue;
             if (k == K1_NCLS - 1) { scratch_need = std::max<uint64_t>(scratch_need, (uint64_t)ctx->total_steps * 6 * sizeof(double)); continue; }
             const uint32_t cap = std::min<uint32_t>(K1_CAPS[k], ctx->plan_max_len[r]);
-            scratch_need = std::max<uint64_t>(scratch_need, stream_warps_for(ctx, ctx->plan_groups[r * K1_NCLS + k], cap) * cap * 256);
+            scratch_need = std::max<uint64_t>(scratch_need, stream_warps_for(ctx, ctx->plan_groups[r * K1_NCLS + k], cap) * cap * k1_row_bytes());
         }
     if (scratch_need) SCEMA_CUDA(ctx, ctx->zscratch.reserve(scratch_need));
     SCEMA_CUDA(ctx, ctx->d_chunk_counters.reserve(n_ranges * K1_NCLS * sizeof(unsigned int)));
@@ -865,7 +751,7 @@ int store_resample(scema_ctx *ctx, uint32_t P)
     if (L > K1_CAPS[K1_NCLS - 2]) return fail(ctx, SCEMA_ERR_INVALID, "store_resample: more than 131072 steps per history");
     const uint64_t n_groups = (n + GROUP - 1) / GROUP;
     const uint64_t w = stream_warps_for(ctx, n_groups, L);
-    SCEMA_CUDA(ctx, ctx->zscratch.reserve(w * L * 256));
+    SCEMA_CUDA(ctx, ctx->zscratch.reserve(w * L * k1_row_bytes()));
     SCEMA_CUDA(ctx, ctx->d_chunk_counters.reserve(K1_NCLS * sizeof(unsigned int)));
     SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_chunk_counters.p, 0, sizeof(unsigned int), ctx->stream));
     t_begin(ctx, SCEMA_T_RESAMPLE);
