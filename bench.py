@@ -652,7 +652,7 @@ def run_ours(args, wl, wl_name):
         k1_bytes = steps_bytes + n_local * K * 8
         roofline_resample = {"bound": "hbm", "achieved": k1_bytes / (res_ms * 1e-3) / 1e9 if res_ms > 0 else None, "peak": hbm_peak,
                              "unit": "GB/s", "frac": (k1_bytes / (res_ms * 1e-3) / 1e9 / hbm_peak) if res_ms > 0 else None,
-                             "launch_ms": res_ms, "kernel": "k_resample_stream (K1), launches per length class summed",
+                             "launch_ms": res_ms, "kernel": "k_resample_pair (K1; SCEMA_K1_KERNEL=stream selects the first-generation kernel), launches per length class summed",
                              "peak_source": "of %s: MEASURED_PEAKS.json hbm_gbs" % hbm_src,
                              "note": "instruction-bound, not bandwidth-bound: bit-exact division sequences in two dependent sweeps per history"}
         # BASELINE's metric is quoted as a fraction of the FP64 peak: the true FP64 contraction (DMMA filter) on a bounded

@@ -289,6 +289,13 @@ int scema_pipeline_plan(uint64_t n, uint64_t *bounds, uint32_t cap, uint32_t *n_
  * plan = {chunks of 64 columns, bytes per A buffer, A buffers, log2(B stages), bytes per B stage, bytes used}.
  * SCEMA_ERR_INVALID when the variant does not take such rows (more than 10 chunks, or two slices on wide rows). */
 int scema_tc_plan(uint32_t k, uint32_t slices, uint32_t cta_group, uint32_t plan[6]);
+/* Measurement hook of K1 (process-wide, no device needed; the results never depend on it): which streamed resample kernel
+ * runs (1 = two chains per lane, the default; 0 = one), the resident warps per SM its launches are sized for (ragged batch /
+ * history store; 0 = the library's default) and the memory-behaviour flags of the two-chain kernel (y prefetch whole history /
+ * none / windows = 0 / 1 / 2, +4 = evict_first on the y copies, +8 = evict_last on the z stores; -2 = chosen per launch, the
+ * default). A negative argument (-1) leaves that setting as it is. The same settings come from SCEMA_K1_KERNEL=pair|stream,
+ * SCEMA_K1_WPS and SCEMA_K1_FLAGS when the library is loaded. */
+int scema_k1_tune(int kernel, int warps_per_sm_ragged, int warps_per_sm_store, int flags);
 /* Measured FP64 issue rates on the context's device (TFLOP/s): out[0] DFMA, out[1] DMMA m8n8k4. */
 int scema_fp64_peak(scema_ctx *ctx, double out[2]);
 

@@ -66,6 +66,7 @@ def lib():
         "scema_kernel_launches": (u64, [vp]),
         "scema_last_audit": (i32, [vp, vp]),
         "scema_fp64_peak": (i32, [vp, P(dbl)]),
+        "scema_k1_tune": (i32, [C.c_int, C.c_int, C.c_int, C.c_int]),
         "scema_tc_debug": (i32, [vp, dbl, u32, vp, u64, vp, vp]),
         "scema_tc_plan": (i32, [u32, u32, u32, vp]),
         "scema_tc_shard_begin": (i32, [vp, dbl, u64, u64, P(vp)]),
@@ -118,7 +119,7 @@ EXPORTED = (
     "scema_store_reset scema_store_append scema_store_info scema_store_resample scema_select_rows "
     "scema_set_spline scema_get_spline scema_spline_info scema_compare scema_compare_stream scema_get_edges scema_edges_device "
     "scema_get_degrees scema_cluster scema_nearest scema_write_similar_hist scema_reduce_edges scema_reduce_calls scema_reduce_dir "
-    "scema_last_timings scema_last_counters scema_kernel_launches scema_last_audit scema_fp64_peak scema_tc_debug scema_tc_plan scema_tc_shard_begin scema_tc_shard_stats scema_tc_shard_finish scema_tc_shard_check scema_tc_shard_commit scema_tc_centre scema_tc_last_plan scema_tc_choose scema_pipeline_plan scema_synth_offsets "
+    "scema_last_timings scema_last_counters scema_kernel_launches scema_last_audit scema_fp64_peak scema_k1_tune scema_tc_debug scema_tc_plan scema_tc_shard_begin scema_tc_shard_stats scema_tc_shard_finish scema_tc_shard_check scema_tc_shard_commit scema_tc_centre scema_tc_last_plan scema_tc_choose scema_pipeline_plan scema_synth_offsets "
     "scema_multi_create scema_multi_destroy scema_multi_last_error scema_multi_devices scema_multi_context scema_multi_cluster "
     "scema_multi_compare_rows scema_multi_shard_edges scema_multi_last_ms "
     "scema_synth_histories_device scema_synth_rows_device scema_synth_histories_model_device scema_synth_rows_model_device scema_ingest_last_error scema_batch_read_dir "
@@ -492,6 +493,10 @@ class HistCluster:
         self._ck(self._L.scema_tc_last_plan(self._h, p))
         return {"one_slice": int(p[0]), "two_slices": int(p[1]), "one_slice_raw": int(p[2]), "two_slices_raw": int(p[3]),
                 "dmma": int(p[4]), "sample": int(p[5])}
+
+    def k1_tune(self, kernel=-1, wps_ragged=-1, wps_store=-1, flags=-1):
+        """Measurement hook of K1 (process-wide): kernel 1 = two chains per lane / 0 = one, resident warps per SM, memory flags."""
+        self._ck(self._L.scema_k1_tune(kernel, wps_ragged, wps_store, flags))
 
     def fp64_peak(self):
         out = (C.c_double * 2)()

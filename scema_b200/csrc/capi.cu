@@ -447,6 +447,11 @@ int scema_fp64_peak(scema_ctx *c, double out[2])
     return fp64_peak_run(c, out);
 }
 
+int scema_k1_tune(int kernel, int warps_per_sm_ragged, int warps_per_sm_store, int flags)
+{
+    return k1_tune(kernel, warps_per_sm_ragged, warps_per_sm_store, flags);
+}
+
 int scema_pipeline_plan(uint64_t n, uint64_t *bounds, uint32_t cap, uint32_t *n_ranges)
 {
     if (!bounds || !n_ranges || n < 2) return SCEMA_ERR_INVALID;

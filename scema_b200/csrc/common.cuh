@@ -199,6 +199,7 @@ int resample_launch_range(scema_ctx *ctx, uint32_t P, size_t r);
 int store_reset(scema_ctx *ctx, uint64_t n, const uint32_t *ids, uint32_t capacity_steps);
 int store_append(scema_ctx *ctx, const double *strain, int on_device);
 int store_resample(scema_ctx *ctx, uint32_t P);
+int k1_tune(int kernel, int wps_ragged, int wps_store, int flags);
 int select_rows(scema_ctx *ctx, const uint32_t *rows, uint64_t m);
 // pairs.cu
 int compare_run(scema_ctx *ctx, double thr, int variant, uint32_t shard, uint32_t n_shards);

@@ -23,6 +23,21 @@
 #include <algorithm>
 #include "resample_pair.cuh"
 
+// Defaults of the K1 tuning (k1_tuning below), from the grid of tools/k1_probe.py --scan on one B200
+// (profiles/r02_k1_scan.txt): the two-chain kernel; 12 resident warps per SM for the ragged batch (more chains in flight
+// push the z rows out of L2 before they are read back: 20 warps cost 8-12 %), 20 for the time-major store; whole-history
+// L2 prefetch for histories of at most 64 steps, windowed prefetch above; evict_last on the store's z rows.
+#ifndef K1_DEFAULT_KERNEL
+#define K1_DEFAULT_KERNEL 1
+#endif
+#ifndef K1_PAIR_WPS_RAGGED
+#define K1_PAIR_WPS_RAGGED 12
+#endif
+#ifndef K1_PAIR_WPS_STORE
+#define K1_PAIR_WPS_STORE 20
+#endif
+constexpr uint32_t K1_FLAGS_AUTO = 0xffffffffu;  // per launch: by layout and length class (k1_flags_for)
+
 namespace scema {
 
 
@@ -558,21 +573,56 @@ static int build_plan(scema_ctx *ctx, const std::vector<uint64_t> &bounds)
     return SCEMA_OK;
 }
 
-// Which streamed kernel runs: the first-generation k_resample_stream (one chain per lane) or, with SCEMA_K1_KERNEL=pair,
-// k_resample_pair (two chains per lane, resample_pair.cuh). Both take the same plan, tables and arguments; a warp's z
-// scratch is cap rows of 32 (stream) or 64 (pair) doubles.
-static bool k1_pair()
+// Which streamed kernel runs and how: process-wide settings, read once from the environment and adjustable through
+// scema_k1_tune (a measurement hook: tools/k1_probe.py scans them in one process).
+//   kernel  1 = k_resample_pair (two chains per lane, resample_pair.cuh), 0 = the first-generation k_resample_stream;
+//           SCEMA_K1_KERNEL=pair|stream
+//   wps     resident warps per SM a launch is sized for, for the ragged batch and for the history store
+//           (0 = the kernel's default); SCEMA_K1_WPS (both)
+//   flags   memory-system behaviour of k_resample_pair (PR_* in resample_pair.cuh); SCEMA_K1_FLAGS; unset = per launch
+//           (k1_flags_for)
+// Both kernels take the same plan, tables and arguments; a warp's z scratch is cap rows of 32 (stream) or 64 (pair) doubles.
+struct K1Tuning {
+    int kernel, wps_ragged, wps_store;
+    uint32_t flags;
+};
+static K1Tuning &k1_tuning()
 {
-    static const char *env = getenv("SCEMA_K1_KERNEL");
-    return env && !strcmp(env, "pair");
+    static K1Tuning t = [] {
+        K1Tuning v{K1_DEFAULT_KERNEL, 0, 0, K1_FLAGS_AUTO};
+        if (const char *e = getenv("SCEMA_K1_KERNEL")) v.kernel = !strcmp(e, "pair") ? 1 : !strcmp(e, "stream") ? 0 : v.kernel;
+        if (const char *e = getenv("SCEMA_K1_WPS")) v.wps_ragged = v.wps_store = atoi(e) > 0 ? atoi(e) : 0;
+        if (const char *e = getenv("SCEMA_K1_FLAGS")) v.flags = (uint32_t)strtoul(e, nullptr, 0);
+        return v;
+    }();
+    return t;
+}
+int k1_tune(int kernel, int wps_ragged, int wps_store, int flags)
+{
+    K1Tuning &t = k1_tuning();
+    if (kernel == 0 || kernel == 1) t.kernel = kernel;
+    if (wps_ragged >= 0) t.wps_ragged = wps_ragged;
+    if (wps_store >= 0) t.wps_store = wps_store;
+    if (flags >= 0) t.flags = (uint32_t)flags;
+    if (flags == -2) t.flags = K1_FLAGS_AUTO;
+    return SCEMA_OK;
+}
+static bool k1_pair() { return k1_tuning().kernel == 1; }
+static uint32_t k1_flags_for(uint32_t cap, bool store)
+{
+    const uint32_t f = k1_tuning().flags;
+    if (f != K1_FLAGS_AUTO) return f;
+    if (store) return PR_Z_EVICT_LAST;
+    return cap <= 64 ? PR_PF_WHOLE : PR_PF_WINDOWS;
 }
 static size_t k1_row_bytes() { return k1_pair() ? PR_ROW * sizeof(double) : 32 * sizeof(double); }
 
 // resident warps for a launch over n_groups groups of at most cap steps, and the z scratch they need
-static uint64_t stream_warps_for(const scema_ctx *ctx, uint64_t n_groups, uint32_t cap)
+static uint64_t stream_warps_for(const scema_ctx *ctx, uint64_t n_groups, uint32_t cap, bool store)
 {
-    static const char *wps_env = getenv("SCEMA_K1_WPS");
-    const int wps = wps_env && atoi(wps_env) > 0 ? atoi(wps_env) : (k1_pair() ? RS_WARPS * PR_MIN_CTAS : 24);
+    const K1Tuning &t = k1_tuning();
+    int wps = store ? t.wps_store : t.wps_ragged;
+    if (wps <= 0) wps = k1_pair() ? (store ? K1_PAIR_WPS_STORE : K1_PAIR_WPS_RAGGED) : 24;
     const uint64_t units = k1_pair() ? (n_groups + 1) / 2 : n_groups;  // what one warp takes at a time
     uint64_t w = std::min<uint64_t>((uint64_t)ctx->sm_count * wps, units);
     w = std::min<uint64_t>(w, std::max<uint64_t>(RS_WARPS, (1ull << 30) / ((uint64_t)cap * k1_row_bytes())));
@@ -587,11 +637,21 @@ static int launch_stream(scema_ctx *ctx, const double *steps, const uint64_t *of
     const bool pair = k1_pair();
     const size_t smem = (pair ? PR_RING_BYTES : RS_RING_BYTES) + (stab ? rs_table_doubles(cap, P) * sizeof(double) : 0);
     if (smem > ctx->smem_optin) return fail(ctx, SCEMA_ERR_INVALID, "resample: spline_points too large for the shared-memory table");
-    auto kern = pair ? (stab ? k_resample_pair<true> : k_resample_pair<false>) : (stab ? k_resample_stream<true> : k_resample_stream<false>);
-    SCEMA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)(warps / RS_WARPS), 32 * RS_WARPS, smem, ctx->stream>>>(
-        steps, offsets, order, n_hist, chunks, n_chunks, counter, ctx->d_table_index.as<int64_t>(), ctx->d_tables.as<double>(), P,
-        ctx->spline_own.as<double>(), ctx->zscratch.as<double>(), cap, ys, uniform_L);
+    const unsigned grid = (unsigned)(warps / RS_WARPS);
+    if (pair) {
+        auto kern = stab ? k_resample_pair<true> : k_resample_pair<false>;
+        SCEMA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 32 * RS_WARPS, smem, ctx->stream>>>(steps, offsets, order, n_hist, chunks, n_chunks, counter,
+                                                        ctx->d_table_index.as<int64_t>(), ctx->d_tables.as<double>(), P,
+                                                        ctx->spline_own.as<double>(), ctx->zscratch.as<double>(), cap, ys, uniform_L,
+                                                        k1_flags_for(cap, uniform_L != 0));
+    } else {
+        auto kern = stab ? k_resample_stream<true> : k_resample_stream<false>;
+        SCEMA_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 32 * RS_WARPS, smem, ctx->stream>>>(steps, offsets, order, n_hist, chunks, n_chunks, counter,
+                                                        ctx->d_table_index.as<int64_t>(), ctx->d_tables.as<double>(), P,
+                                                        ctx->spline_own.as<double>(), ctx->zscratch.as<double>(), cap, ys, uniform_L);
+    }
     ctx->launches++;
     return SCEMA_OK;
 }
@@ -628,7 +688,7 @@ int resample_prepare(scema_ctx *ctx, uint32_t P, const std::vector<uint64_t> &bo
             if (!ctx->plan_groups[r * K1_NCLS + k]) continue;
             if (k == K1_NCLS - 1) { scratch_need = std::max<uint64_t>(scratch_need, (uint64_t)ctx->total_steps * 6 * sizeof(double)); continue; }
             const uint32_t cap = std::min<uint32_t>(K1_CAPS[k], ctx->plan_max_len[r]);
-            scratch_need = std::max<uint64_t>(scratch_need, stream_warps_for(ctx, ctx->plan_groups[r * K1_NCLS + k], cap) * cap * k1_row_bytes());
+            scratch_need = std::max<uint64_t>(scratch_need, stream_warps_for(ctx, ctx->plan_groups[r * K1_NCLS + k], cap, false) * cap * k1_row_bytes());
         }
     if (scratch_need) SCEMA_CUDA(ctx, ctx->zscratch.reserve(scratch_need));
     SCEMA_CUDA(ctx, ctx->d_chunk_counters.reserve(n_ranges * K1_NCLS * sizeof(unsigned int)));
@@ -648,7 +708,7 @@ int resample_launch_range(scema_ctx *ctx, uint32_t P, size_t r)
             const uint32_t cb = ctx->plan_chunk_begin[r * (K1_NCLS + 1) + k], ce = ctx->plan_chunk_begin[r * (K1_NCLS + 1) + k + 1];
             rc = launch_stream(ctx, ctx->d_steps, ctx->d_offsets.as<uint64_t>(), ctx->d_order.as<uint32_t>(), ctx->hn,
                                ctx->d_chunks.as<K1Chunk>() + cb, ce - cb, ctx->d_chunk_counters.as<unsigned int>() + r * K1_NCLS + k, P,
-                               stream_warps_for(ctx, n_groups, cap), cap, 6, 0);
+                               stream_warps_for(ctx, n_groups, cap, false), cap, 6, 0);
             if (rc) return rc;
         } else {
             // histories longer than the last class: sweeps through a global scratch of the input's shape
@@ -750,7 +810,7 @@ int store_resample(scema_ctx *ctx, uint32_t P)
     if (rc) return rc;
     if (L > K1_CAPS[K1_NCLS - 2]) return fail(ctx, SCEMA_ERR_INVALID, "store_resample: more than 131072 steps per history");
     const uint64_t n_groups = (n + GROUP - 1) / GROUP;
-    const uint64_t w = stream_warps_for(ctx, n_groups, L);
+    const uint64_t w = stream_warps_for(ctx, n_groups, L, true);
     SCEMA_CUDA(ctx, ctx->zscratch.reserve(w * L * k1_row_bytes()));
     SCEMA_CUDA(ctx, ctx->d_chunk_counters.reserve(K1_NCLS * sizeof(unsigned int)));
     SCEMA_CUDA(ctx, cudaMemsetAsync(ctx->d_chunk_counters.p, 0, sizeof(unsigned int), ctx->stream));

@@ -182,6 +182,32 @@ K1_DEV void pr_cp_async8(uint32_t dst, const double *src)
 {
     asm volatile("cp.async.ca.shared.global [%0+%1], [%2], 8;" ::"r"(dst), "n"(OFF), "l"(src) : "memory");
 }
+// the same with an L2 eviction policy (pr_policy) for the source line
+template <int OFF>
+K1_DEV void pr_cp_async8_hint(uint32_t dst, const double *src, uint64_t policy)
+{
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0+%1], [%2], 8, %3;" ::"r"(dst), "n"(OFF), "l"(src), "l"(policy) : "memory");
+}
+// L2 eviction policy of the y stream: evict_first (read once: it should not displace the z rows that come back) or normal
+K1_DEV uint64_t pr_policy(bool evict_first)
+{
+    uint64_t pf, pn;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pf));
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pn));
+    return evict_first ? pf : pn;
+}
+// L2 eviction policy of the z stores: evict_last (written once, read back once, soon: keep it in L2 over the y stream) or normal
+K1_DEV uint64_t pr_policy_z(bool evict_last)
+{
+    uint64_t pl, pn;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pl));
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pn));
+    return evict_last ? pl : pn;
+}
+K1_DEV void pr_store_z(double *p, double v, uint64_t policy)
+{
+    asm volatile("st.global.cg.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy) : "memory");
+}
 K1_DEV void pr_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 K1_DEV void pr_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -264,7 +290,7 @@ K1_DEV double div_acc(double a, double b, double rb, uint32_t &acc)
 // s_{i+1} = (y_{i+2} - y_{i+1}) / hd_{i+1}. On entry E1 = {sd_i, lo_i}, E0 = {1/hd_{i+1}, hd_{i+1}}; the same two entries of
 // step i+1 are loaded into N1/N0. y_{i+2} comes from ring slot (i+2) % PR_DEPTH (its copy is the oldest of the PR_DEPTH-1
 // groups in flight); the slot read one step earlier is refilled with y_{i+1+PR_DEPTH}.
-#define PR_FWD_STEP(E1, E0, N1, N0)                                                                   \
+#define PR_FWD_STEP(E1, E0, N1, N0, PF)                                                               \
     {                                                                                                 \
         fwc.template ld<3>(N1);                                                                       \
         fwc.template ld<4>(N0);                                                                       \
@@ -273,17 +299,23 @@ K1_DEV double div_acc(double a, double b, double rb, uint32_t &acc)
         const double ynA = pr_ring_read<0>(rd), ynB = pr_ring_read<256>(rd);                          \
         if (i + 1 + PR_DEPTH < L) {                                                                   \
             const uint32_t wr = ring + (uint32_t)((i + 1) & (PR_DEPTH - 1)) * (PR_ROW * 8);           \
-            pr_cp_async8<0>(wr, ypA);                                                                 \
-            pr_cp_async8<256>(wr, ypB);                                                               \
+            pr_cp_async8_hint<0>(wr, ypA, ypol);                                                      \
+            pr_cp_async8_hint<256>(wr, ypB, ypol);                                                    \
         }                                                                                             \
         pr_cp_async_commit();                                                                         \
         ypA += ys;                                                                                    \
         ypB += ys;                                                                                    \
+        if (PF && pf_windows && (i & (PR_PF_WINDOW - 1)) == 0 && i + PR_PF_WINDOW < L) {              \
+            /* steps [i+W, i+2W) of both histories -> L2, by the lane of component 0 */               \
+            const int w0 = i + PR_PF_WINDOW, wn = L - w0 < PR_PF_WINDOW ? L - w0 : PR_PF_WINDOW;      \
+            pr_prefetch_l2(yA + (size_t)w0 * 6, 48u * (uint32_t)wn);                                  \
+            if (two) pr_prefetch_l2(yB + (size_t)w0 * 6, 48u * (uint32_t)wn);                         \
+        }                                                                                             \
         {                                                                                             \
             const double r = __dmul_rn(__dsub_rn(sA_cur, sA_prev), E1.x);                             \
             const double sum = __dadd_rn(0.0, __dmul_rn(E1.y, zA));                                   \
             zA = __dsub_rn(r, sum);                                                                   \
-            __stcg(zp, zA);                                                                           \
+            pr_store_z(zp, zA, zpol);                                                                 \
             sA_prev = sA_cur;                                                                         \
             sA_cur = div_acc(__dsub_rn(ynA, yA_hi), E0.y, E0.x, accA);                                \
             yA_hi = ynA;                                                                              \
@@ -292,7 +324,7 @@ K1_DEV double div_acc(double a, double b, double rb, uint32_t &acc)
             const double r = __dmul_rn(__dsub_rn(sB_cur, sB_prev), E1.x);                             \
             const double sum = __dadd_rn(0.0, __dmul_rn(E1.y, zB));                                   \
             zB = __dsub_rn(r, sum);                                                                   \
-            __stcg(zp + 32, zB);                                                                      \
+            pr_store_z(zp + 32, zB, zpol);                                                            \
             sB_prev = sB_cur;                                                                         \
             sB_cur = div_acc(__dsub_rn(ynB, yB_hi), E0.y, E0.x, accB);                                \
             yB_hi = ynB;                                                                              \
@@ -361,6 +393,16 @@ K1_DEV double div_acc(double a, double b, double rb, uint32_t &acc)
 #define PR_MIN_CTAS 5
 #endif
 
+// `flags` of k_resample_pair (memory-system behaviour only; the arithmetic never depends on them):
+//   bits 0-1  how y reaches L2 in the ragged layout: 0 = one bulk prefetch of the whole history when its chains start,
+//             1 = nothing ahead of the ring copies, 2 = windows of PR_PF_WINDOW steps, one window ahead of the ring
+//   bit 2     the ring copies of y carry the L2 evict_first policy
+//   bit 3     the z stores carry the L2 evict_last policy
+// (discard.global.L2 of the z rows after their read-back was tried in round 1 — DRAM writes fell, the time did not — and is
+// not here: one lane would drop a line that holds sixteen lanes' values, which needs the warp to be in lockstep.)
+constexpr uint32_t PR_PF_MASK = 3u, PR_PF_WHOLE = 0u, PR_PF_NONE = 1u, PR_PF_WINDOWS = 2u, PR_Y_EVICT_FIRST = 4u, PR_Z_EVICT_LAST = 8u;
+constexpr int PR_PF_WINDOW = 16;  // steps per prefetch window (768 bytes of one history)
+
 // ys = distance (in doubles) between consecutive steps of one history: 6 for the ragged batch ([L][6] blocks, history h
 // starts at offsets[h]; `order` lists the histories group by group, five slots per group, 0xffffffff = empty slot), n*6
 // for the time-major history store ([step][n][6], history h starts at h, every history uniform_L steps long, order ==
@@ -374,7 +416,7 @@ __launch_bounds__(32 * RS_WARPS, PR_MIN_CTAS)
 k_resample_pair(const double *K1_RESTRICT steps, const uint64_t *K1_RESTRICT offsets, const uint32_t *K1_RESTRICT order, uint64_t n_hist,
                 const K1Chunk *K1_RESTRICT chunks, uint32_t n_chunks, unsigned int *K1_RESTRICT chunk_counter,
                 const int64_t *K1_RESTRICT table_index, const double *K1_RESTRICT tables, uint32_t P, double *K1_RESTRICT out,
-                double *K1_RESTRICT zscratch, uint32_t cap, uint64_t ys, uint32_t uniform_L)
+                double *K1_RESTRICT zscratch, uint32_t cap, uint64_t ys, uint32_t uniform_L, uint32_t flags)
 {
     K1_SHARED_DECL(rs_smem, s_chunk)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -386,6 +428,7 @@ k_resample_pair(const double *K1_RESTRICT steps, const uint64_t *K1_RESTRICT off
     const uint32_t K = 6 * P, Pp = pad2(P);
     const double third = 1.0 / 3.0;
     const int hh = lane / 6, c = lane - hh * 6;
+    const uint64_t ypol = pr_policy((flags & PR_Y_EVICT_FIRST) != 0), zpol = pr_policy_z((flags & PR_Z_EVICT_LAST) != 0);
     int loaded_L = -1;
 
     while (true) {
@@ -441,10 +484,14 @@ k_resample_pair(const double *K1_RESTRICT steps, const uint64_t *K1_RESTRICT off
             const uint64_t offA = uniform_L ? hA : offsets[hA], offB = uniform_L ? hB : offsets[hB];
             const double *yA = steps + offA * 6 + c, *yB = steps + offB * 6 + c;
 
-            // whole history -> L2 now (one bulk prefetch per history); the ring copies then hit L2
-            if (c == 0 && !uniform_L) {
-                pr_prefetch_l2(steps + offA * 6, 48u * (uint32_t)L);
-                if (twoA && twoB) pr_prefetch_l2(steps + offB * 6, 48u * (uint32_t)L);
+            // ragged layout: the history (or its first two windows) -> L2 now, one bulk prefetch per history by the lane
+            // of component 0; the ring copies then hit L2
+            const bool two = twoA && twoB;
+            const bool pf_windows = c == 0 && !uniform_L && (flags & PR_PF_MASK) == PR_PF_WINDOWS;
+            if (c == 0 && !uniform_L && (flags & PR_PF_MASK) != PR_PF_NONE) {
+                const uint32_t nb = 48u * (uint32_t)(pf_windows && L > 2 * PR_PF_WINDOW ? 2 * PR_PF_WINDOW : L);
+                pr_prefetch_l2(steps + offA * 6, nb);
+                if (two) pr_prefetch_l2(steps + offB * 6, nb);
             }
 
             // ---- forward substitution fused with the right-hand side. Software pipeline: the slope s_{i+1} and the
@@ -453,8 +500,8 @@ k_resample_pair(const double *K1_RESTRICT steps, const uint64_t *K1_RESTRICT off
             for (int m = 3; m <= PR_DEPTH + 1; m++) {  // y_3 .. y_{PR_DEPTH+1}: PR_DEPTH-1 groups
                 if (m < L) {
                     const uint32_t wr = ring + (uint32_t)(m & (PR_DEPTH - 1)) * (PR_ROW * 8);
-                    pr_cp_async8<0>(wr, yA + (size_t)m * ys);
-                    pr_cp_async8<256>(wr, yB + (size_t)m * ys);
+                    pr_cp_async8_hint<0>(wr, yA + (size_t)m * ys, ypol);
+                    pr_cp_async8_hint<256>(wr, yB + (size_t)m * ys, ypol);
                 }
                 pr_cp_async_commit();
             }
@@ -474,8 +521,8 @@ k_resample_pair(const double *K1_RESTRICT steps, const uint64_t *K1_RESTRICT off
                 sA_cur = div_acc(__dsub_rn(yA2, yA1), f10.y, f10.x, accA);   // s_1
                 sB_cur = div_acc(__dsub_rn(yB2, yB1), f10.y, f10.x, accB);
                 zA = zB = __dsub_rn(__dmul_rn(0.0, f01.x), 0.0);             // row 0: rhs = 0, empty sum
-                __stcg(zs, zA);
-                __stcg(zs + 32, zB);
+                pr_store_z(zs, zA, zpol);
+                pr_store_z(zs + 32, zB, zpol);
                 yA_hi = yA2;
                 yB_hi = yB2;
             }
@@ -484,18 +531,18 @@ k_resample_pair(const double *K1_RESTRICT steps, const uint64_t *K1_RESTRICT off
                 const double *ypA = yA + (size_t)(2 + PR_DEPTH) * ys, *ypB = yB + (size_t)(2 + PR_DEPTH) * ys;  // y_{i+1+PR_DEPTH}
                 double *zp = zs + PR_ROW;                                                                       // row i
                 // full steps i = 1 .. L-3 (each also produces s_{i+1}), two per trip
-                while (i + 1 <= L - 3) {
-                    PR_FWD_STEP(a1, a0, b1, b0)
-                    PR_FWD_STEP(b1, b0, a1, a0)
+                while (i + 1 <= L - 3) {  // i odd in the first step, even in the second: windows start on even steps
+                    PR_FWD_STEP(a1, a0, b1, b0, false)
+                    PR_FWD_STEP(b1, b0, a1, a0, true)
                 }
-                if (i <= L - 3) PR_FWD_STEP(a1, a0, b1, b0)
+                if (i <= L - 3) PR_FWD_STEP(a1, a0, b1, b0, false)
                 // i == L-2: the last interior row has no next slope
                 {
                     const double2 e = pr_tab_f64x2<STAB>(FW + 2 * i + 1);  // {sd_{L-2}, lo_{L-2}}
                     zA = __dsub_rn(__dmul_rn(__dsub_rn(sA_cur, sA_prev), e.x), __dadd_rn(0.0, __dmul_rn(e.y, zA)));
                     zB = __dsub_rn(__dmul_rn(__dsub_rn(sB_cur, sB_prev), e.x), __dadd_rn(0.0, __dmul_rn(e.y, zB)));
-                    __stcg(zp, zA);
-                    __stcg(zp + 32, zB);
+                    pr_store_z(zp, zA, zpol);
+                    pr_store_z(zp + 32, zB, zpol);
                 }
             }
             {
@@ -545,7 +592,7 @@ k_resample_pair(const double *K1_RESTRICT steps, const uint64_t *K1_RESTRICT off
             pr_cp_async_wait<0>();  // nothing of this pair may land in the ring after the next pair starts
             // rare: subnormal / huge / non-finite numerators
             if (accA >= PR_ACC_LIMIT) resample_chain_slow(yA, ys, L, tab, P, zs, PR_ROW, orowA);
-            if (accB >= PR_ACC_LIMIT && twoA && twoB) resample_chain_slow(yB, ys, L, tab, P, zs + 32, PR_ROW, orowB);
+            if (accB >= PR_ACC_LIMIT && two) resample_chain_slow(yB, ys, L, tab, P, zs + 32, PR_ROW, orowB);
         }
     }
 }

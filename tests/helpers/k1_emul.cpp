@@ -121,6 +121,11 @@ static inline void pr_cp_async8(uint32_t dst, const double *src)
     if (emu.mode == 0 || (emu.mode == 2 && emu_coin())) emu_land(EmuCopy{dst + (uint32_t)OFF, src});
     else emu.open.push_back(EmuCopy{dst + (uint32_t)OFF, src});
 }
+template <int OFF>
+static inline void pr_cp_async8_hint(uint32_t dst, const double *src, uint64_t) { pr_cp_async8<OFF>(dst, src); }
+static inline uint64_t pr_policy(bool) { return 0; }
+static inline uint64_t pr_policy_z(bool) { return 0; }
+static inline void pr_store_z(double *p, double v, uint64_t) { emu_check_global(p, 8); *p = v; }
 static inline void pr_cp_async_commit()
 {
     emu.groups.push_back(std::move(emu.open));
@@ -197,6 +202,7 @@ struct Launch {
     uint32_t cap;
     uint64_t ys;
     uint32_t uniform_L;
+    uint32_t flags;
 };
 
 // one launch: n_ctas CTAs of 128 threads, all resident at once
@@ -204,9 +210,12 @@ void run_launch(const Launch &a, int n_ctas, int mode, uint64_t *stats)
 {
     unsigned counter = 0;
     const size_t smem = PR_RING_BYTES + (a.stab ? rs_table_doubles(a.cap, a.P) * sizeof(double) : 0);
-    std::vector<double> zscratch((size_t)n_ctas * RS_WARPS * a.cap * PR_ROW);
-    for (double &v : zscratch) v = std::nan("");
-    g_ranges.push_back(EmuRange{(const unsigned char *)zscratch.data(), (const unsigned char *)(zscratch.data() + zscratch.size())});
+    const size_t zn = (size_t)n_ctas * RS_WARPS * a.cap * PR_ROW;
+    std::vector<double> zraw(zn + 16);
+    double *zscratch = zraw.data();
+    while ((uintptr_t)zscratch % 128) zscratch++;  // cudaMalloc alignment: a scratch row is four whole 128-byte lines
+    for (size_t q = 0; q < zn; q++) zscratch[q] = std::nan("");
+    g_ranges.push_back(EmuRange{(const unsigned char *)zscratch, (const unsigned char *)(zscratch + zn)});
     std::vector<std::unique_ptr<EmuCta>> ctas;
     std::vector<std::unique_ptr<std::barrier<>>> bars;
     for (int b = 0; b < n_ctas; b++) {
@@ -229,10 +238,10 @@ void run_launch(const Launch &a, int n_ctas, int mode, uint64_t *stats)
                 emu.rng ^= (uint64_t)(b * 131 + t + 1) * 0xD1B54A32D192ED03ull;
                 if (a.stab)
                     k_resample_pair<true>(a.steps, a.offsets, a.order, a.n_hist, a.chunks, a.n_chunks, &counter, a.table_index, a.tables, a.P,
-                                          a.out, zscratch.data(), a.cap, a.ys, a.uniform_L);
+                                          a.out, zscratch, a.cap, a.ys, a.uniform_L, a.flags);
                 else
                     k_resample_pair<false>(a.steps, a.offsets, a.order, a.n_hist, a.chunks, a.n_chunks, &counter, a.table_index, a.tables, a.P,
-                                           a.out, zscratch.data(), a.cap, a.ys, a.uniform_L);
+                                           a.out, zscratch, a.cap, a.ys, a.uniform_L, a.flags);
                 copies += emu.copies;
                 late += emu.late;
             });
@@ -267,7 +276,7 @@ void build_tables(const std::vector<uint32_t> &lens, uint32_t P, std::vector<dou
 // stats[0] = cp.async copies issued, stats[1] = copies that landed only because a wait_group forced them,
 // stats[2] = accesses outside the launch's buffers / the lane's own ring (must be 0).
 extern "C" int k1_emul_ragged(const double *steps, const uint64_t *offsets, uint64_t n, uint32_t P, double *out, int mode, int n_ctas,
-                              int force_global_table, uint64_t *stats)
+                              int force_global_table, uint32_t flags, uint64_t *stats)
 {
     static const uint32_t caps[] = {64, SMEM_TAB_MAX_L, 2048, 16384, 131072};
     std::map<uint32_t, std::vector<uint32_t>> by_len;
@@ -308,14 +317,15 @@ extern "C" int k1_emul_ragged(const double *steps, const uint64_t *offsets, uint
         if (chunks.empty()) continue;
         const uint32_t cap = std::min(cap_k, max_len);
         Launch a{!force_global_table && cap <= SMEM_TAB_MAX_L, steps, offsets, order.data(), n, chunks.data(), (uint32_t)chunks.size(),
-                 index.data(), tables.data(), P, out, cap, 6, 0};
+                 index.data(), tables.data(), P, out, cap, 6, 0, flags};
         run_launch(a, n_ctas, mode, stats);
     }
     return 0;
 }
 
 // History store: steps time-major [L][n][6], every history L steps long; out [n][6P].
-extern "C" int k1_emul_store(const double *steps, uint64_t n, uint32_t L, uint32_t P, double *out, int mode, int n_ctas, uint64_t *stats)
+extern "C" int k1_emul_store(const double *steps, uint64_t n, uint32_t L, uint32_t P, double *out, int mode, int n_ctas, uint32_t flags,
+                             uint64_t *stats)
 {
     if (L < 3) return 1;
     std::vector<double> tables;
@@ -327,7 +337,7 @@ extern "C" int k1_emul_store(const double *steps, uint64_t n, uint32_t L, uint32
     g_ranges.push_back(EmuRange{(const unsigned char *)tables.data(), (const unsigned char *)(tables.data() + tables.size())});
     const uint64_t n_groups = (n + GROUP - 1) / GROUP;
     Launch a{L <= SMEM_TAB_MAX_L, steps, nullptr, nullptr, n, nullptr, (uint32_t)((n_groups + CHUNK_GROUPS - 1) / CHUNK_GROUPS),
-             index.data(), tables.data(), P, out, L, n * 6, L};
+             index.data(), tables.data(), P, out, L, n * 6, L, flags};
     run_launch(a, n_ctas, mode, stats);
     return 0;
 }

@@ -24,8 +24,8 @@ def emul(tmp_path_factory):
                            "-Wno-unknown-pragmas", "-o", so, os.path.join(HERE, "helpers", "k1_emul.cpp")])
     lib = ctypes.CDLL(so)
     dp, u64p = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)
-    lib.k1_emul_ragged.argtypes = [dp, u64p, ctypes.c_uint64, ctypes.c_uint32, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, u64p]
-    lib.k1_emul_store.argtypes = [dp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, dp, ctypes.c_int, ctypes.c_int, u64p]
+    lib.k1_emul_ragged.argtypes = [dp, u64p, ctypes.c_uint64, ctypes.c_uint32, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, u64p]
+    lib.k1_emul_store.argtypes = [dp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, dp, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, u64p]
     return lib
 
 
@@ -33,14 +33,14 @@ def _ptr(a, t):
     return a.ctypes.data_as(ctypes.POINTER(t))
 
 
-def run_ragged(lib, steps, off, P, mode, n_ctas=2, global_table=False):
+def run_ragged(lib, steps, off, P, mode, n_ctas=2, global_table=False, flags=0):
     steps = np.ascontiguousarray(steps, dtype=np.float64)
     off = np.ascontiguousarray(off, dtype=np.uint64)
     n = len(off) - 1
     out = np.full((n, 6 * P), np.nan)
     stats = np.zeros(3, dtype=np.uint64)
     rc = lib.k1_emul_ragged(_ptr(steps, ctypes.c_double), _ptr(off, ctypes.c_uint64), n, P, _ptr(out, ctypes.c_double), MODES[mode], n_ctas,
-                            int(global_table), _ptr(stats, ctypes.c_uint64))
+                            int(global_table), flags, _ptr(stats, ctypes.c_uint64))
     assert rc == 0
     assert stats[2] == 0, "the kernel touched memory outside its buffers / its own ring"
     return out, stats
@@ -76,8 +76,14 @@ def test_every_short_length_and_partial_groups(emul, oracle, mode):
             assert stats[1] == stats[0]  # every copy landed only when a wait forced it
 
 
+# memory-behaviour flags of the kernel (resample_pair.cuh): y prefetch whole / none / windows, evict_first on the y copies —
+# the result may not depend on any of them
+FLAGS = [0, 1, 2, 2 | 4]
+
+
+@pytest.mark.parametrize("flags", FLAGS)
 @pytest.mark.parametrize("mode", list(MODES))
-def test_longer_lengths_both_table_paths(emul, oracle, mode):
+def test_longer_lengths_both_table_paths(emul, oracle, mode, flags):
     """Lengths across the class boundaries (64 | 65, 256 | 257: table in shared memory / read from global memory), odd and
     even, and the same batch with the shared-memory table switched off."""
     rng = np.random.default_rng(12)
@@ -86,14 +92,15 @@ def test_longer_lengths_both_table_paths(emul, oracle, mode):
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
     steps = rng.standard_normal((int(off[-1]), 6)) * 1e-2
     want = oracle.splinify_batch(steps, off, 10)
-    got, _ = run_ragged(emul, steps, off, 10, mode)
+    got, stats = run_ragged(emul, steps, off, 10, mode, flags=flags)
     assert same_bits(got, want)
-    got, _ = run_ragged(emul, steps, off, 10, mode, global_table=True)
+    got, _ = run_ragged(emul, steps, off, 10, mode, global_table=True, flags=flags)
     assert same_bits(got, want)
 
 
+@pytest.mark.parametrize("flags", [0, 2])
 @pytest.mark.parametrize("mode", ["eager", "lazy"])
-def test_special_magnitudes_take_the_slow_path(emul, oracle, mode):
+def test_special_magnitudes_take_the_slow_path(emul, oracle, mode, flags):
     """The data of test_gpu_parity.py::test_k1_special_magnitudes: zeros and -0 stay on the fast path (sign of a zero
     quotient), subnormal / huge / inf / NaN numerators hand the chain to the IEEE-division path, chain A and chain B of a
     lane independently."""
@@ -114,21 +121,22 @@ def test_special_magnitudes_take_the_slow_path(emul, oracle, mode):
     steps[21 * L:(22 * L)] = -0.0
     steps[22 * L:(23 * L), 2] *= -1.0
     for P in (10, 50):  # P > L puts several samples into one interval
-        got, _ = run_ragged(emul, steps, off, P, mode)
+        got, _ = run_ragged(emul, steps, off, P, mode, flags=flags)
         with np.errstate(all="ignore"):
             want = oracle.splinify_batch(steps, off, P)
         assert same_bits(got, want), P
 
 
+@pytest.mark.parametrize("flags", [0, 2])
 @pytest.mark.parametrize("mode", list(MODES))
-def test_history_store_layout(emul, oracle, mode):
+def test_history_store_layout(emul, oracle, mode, flags):
     """Time-major store [step][n][6] (implicit chunks, groups in index order, n not a multiple of 5 or 10)."""
     rng = np.random.default_rng(13)
     for n, L in ((1, 3), (7, 9), (83, 20), (161, 12), (10, 70)):
         tm = rng.standard_normal((L, n, 6)) * 1e-4
         out = np.full((n, 60), np.nan)
         stats = np.zeros(3, dtype=np.uint64)
-        rc = emul.k1_emul_store(_ptr(tm, ctypes.c_double), n, L, 10, _ptr(out, ctypes.c_double), MODES[mode], 2, _ptr(stats, ctypes.c_uint64))
+        rc = emul.k1_emul_store(_ptr(tm, ctypes.c_double), n, L, 10, _ptr(out, ctypes.c_double), MODES[mode], 2, flags, _ptr(stats, ctypes.c_uint64))
         assert rc == 0 and stats[2] == 0
         ragged = np.ascontiguousarray(tm.transpose(1, 0, 2)).reshape(n * L, 6)
         off = (np.arange(n + 1, dtype=np.uint64) * L)
