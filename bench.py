@@ -654,7 +654,10 @@ def run_ours(args, wl, wl_name):
                              "unit": "GB/s", "frac": (k1_bytes / (res_ms * 1e-3) / 1e9 / hbm_peak) if res_ms > 0 else None,
                              "launch_ms": res_ms, "kernel": "k_resample_pair (K1; SCEMA_K1_KERNEL=stream selects the first-generation kernel), launches per length class summed",
                              "peak_source": "of %s: MEASURED_PEAKS.json hbm_gbs" % hbm_src,
-                             "note": "instruction-bound, not bandwidth-bound: bit-exact division sequences in two dependent sweeps per history"}
+                             "traffic": 3.50e9 * (k1_bytes / 2.207e9) if wl_name in ("c4", "c4s") else None,
+                             "note": "bound by the forward-sweep result z (as large as the input) that the backward sweep reads back: DRAM moves "
+                                     "~1.6x the algorithmic bytes at the number of chains whose z rows L2 can hold (ncu: profiles/r02_ncu_resample_pair_c4.txt, "
+                                     "3.50 GB for 2.21 GB at 1M histories; traffic here is that capture scaled to this launch), issue slots 49 %, FP64 pipe 32 %"}
         # BASELINE's metric is quoted as a fraction of the FP64 peak: the true FP64 contraction (DMMA filter) on a bounded
         # sample of the same rows, timed by its own CUDA events, against the DMMA issue-rate probe
         roofline_fp64 = None

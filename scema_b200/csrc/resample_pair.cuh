@@ -170,7 +170,10 @@ void resample_chain_slow(const double *K1_RESTRICT y, uint64_t ys, int L, const 
 }
 
 // ---- primitives of the pair kernel (the emulation provides its own under K1_EMULATE)
-constexpr int PR_DEPTH = 8;        // ring slots per chain: y (then z) of step m sits in slot m % PR_DEPTH
+#ifndef PR_DEPTH_SLOTS
+#define PR_DEPTH_SLOTS 8
+#endif
+constexpr int PR_DEPTH = PR_DEPTH_SLOTS;  // ring slots per chain (a power of two): y (then z) of step m sits in slot m % PR_DEPTH
 constexpr int PR_ROW = 64;         // doubles per ring slot and per scratch row of a warp: [chain A: 32 lanes | chain B: 32 lanes]
 constexpr uint32_t PR_ACC_LIMIT = 0xE0000000u;  // div_acc: every numerator in range <=> running maximum below this
 constexpr size_t PR_RING_BYTES = (size_t)RS_WARPS * PR_DEPTH * PR_ROW * sizeof(double);
@@ -421,7 +424,7 @@ k_resample_pair(const double *K1_RESTRICT steps, const uint64_t *K1_RESTRICT off
     K1_SHARED_DECL(rs_smem, s_chunk)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // this lane's ring: slot s of chain A at ring + s * 512 bytes, of chain B 256 bytes further; y on the way up, then (all y
-    // copies have landed by then) z on the way down; 4 KB per warp
+    // copies have landed by then) z on the way down; PR_DEPTH * 512 bytes per warp
     const uint32_t ring = pr_smem_addr(rs_smem + (size_t)warp * (PR_DEPTH * PR_ROW) + lane);
     double *stab = rs_smem + (size_t)RS_WARPS * PR_DEPTH * PR_ROW;  // [ht | ix | FW | BW] of the current length
     double *K1_RESTRICT zs = zscratch + ((uint64_t)blockIdx.x * RS_WARPS + warp) * cap * PR_ROW + lane;

@@ -73,10 +73,11 @@ static inline void emu_check_global(const void *p, size_t bytes)
         if (q >= r.b && q + bytes <= r.e) return;
     g_oob++;
 }
+static uint32_t g_ring_bytes_per_warp = 4096;  // PR_DEPTH * PR_ROW * 8, set before a launch
 static inline void emu_check_ring(uint32_t a)
 {
     const uint32_t warp = threadIdx.x >> 5;
-    if (a < warp * 4096u || a + 8 > (warp + 1) * 4096u) g_oob++;
+    if (a < warp * g_ring_bytes_per_warp || a + 8 > (warp + 1) * g_ring_bytes_per_warp) g_oob++;
 }
 
 static inline void __syncthreads() { emu.cta->bar->arrive_and_wait(); }
@@ -163,7 +164,7 @@ struct TabCursor {
     {
         if (STAB) {
             const unsigned char *q = (const unsigned char *)(p + E), *b = emu.cta->smem.data();
-            if (q < b + 4 * 4096 || q + 16 > b + emu.cta->smem.size()) g_oob++;
+            if (q < b + 4 * g_ring_bytes_per_warp || q + 16 > b + emu.cta->smem.size()) g_oob++;
         } else
             emu_check_global(p + E, 16);
         d = p[E];
@@ -209,6 +210,7 @@ struct Launch {
 void run_launch(const Launch &a, int n_ctas, int mode, uint64_t *stats)
 {
     unsigned counter = 0;
+    g_ring_bytes_per_warp = PR_DEPTH * PR_ROW * 8;
     const size_t smem = PR_RING_BYTES + (a.stab ? rs_table_doubles(a.cap, a.P) * sizeof(double) : 0);
     const size_t zn = (size_t)n_ctas * RS_WARPS * a.cap * PR_ROW;
     std::vector<double> zraw(zn + 16);

@@ -15,13 +15,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 MODES = {"eager": 0, "lazy": 1, "mixed": 2}
 
 
-@pytest.fixture(scope="module")
-def emul(tmp_path_factory):
+@pytest.fixture(scope="module", params=[0, 8, 16], ids=["depth-default", "depth-8", "depth-16"])
+def emul(tmp_path_factory, request):
+    """The emulation library, built with the kernel's own ring depth and with 8 / 16 slots per chain (PR_DEPTH_SLOTS)."""
     if "fma" not in open("/proc/cpuinfo").read():
         pytest.skip("host CPU has no FMA instruction")
     so = str(tmp_path_factory.mktemp("k1emul") / "libk1emul.so")
+    depth = ["-DPR_DEPTH_SLOTS=%d" % request.param] if request.param else []
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-mfma", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
-                           "-Wno-unknown-pragmas", "-o", so, os.path.join(HERE, "helpers", "k1_emul.cpp")])
+                           "-Wno-unknown-pragmas"] + depth + ["-o", so, os.path.join(HERE, "helpers", "k1_emul.cpp")])
     lib = ctypes.CDLL(so)
     dp, u64p = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)
     lib.k1_emul_ragged.argtypes = [dp, u64p, ctypes.c_uint64, ctypes.c_uint32, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, u64p]
