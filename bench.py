@@ -522,6 +522,7 @@ def run_ours(args, wl, wl_name):
     ev1.record(stream)
     barrier()
     ms_e2e = ev0.elapsed_time(ev1)
+    e2e_pipeline_ranges = hc.counters().get("pipeline_ranges", 0) if world == 1 else 0   # of the last e2e step, before later calls reset the counters
     if world > 1:
         t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -708,7 +709,7 @@ def run_ours(args, wl, wl_name):
             "clocks": clocks,
             "e2e": ({"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                      "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                     "pipeline_ranges": hc.counters().get("pipeline_ranges", 0) if world == 1 else 0,
+                     "pipeline_ranges": e2e_pipeline_ranges,
                      "api": "scema_cluster + scema_get_edges (C ABI)" if world == 1 and not args.stream else
                             "scema_set_histories + resample + NCCL all-gather (torch.distributed) + sharded compare, one process per GPU"}
                     if e2e_lib is None else e2e_lib),

@@ -44,3 +44,15 @@ def test_product_never_touches_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in src and "liboracle" not in src and "oracle/" not in src.replace("oracle/_ref binaries", ""), f
+
+
+def test_k1_tune_hook_needs_no_device():
+    """scema_k1_tune is process-wide host state (which spline kernel, warps per SM, memory hints): callable without a
+    GPU, negative arguments leave a setting as it is, -2 returns the flags to the per-launch default."""
+    import scema_b200
+    lib = ctypes.CDLL(scema_b200.lib_path())
+    lib.scema_k1_tune.argtypes = [ctypes.c_int] * 4
+    lib.scema_k1_tune.restype = ctypes.c_int
+    assert lib.scema_k1_tune(1, 12, 20, 2) == 0
+    assert lib.scema_k1_tune(-1, -1, -1, -1) == 0
+    assert lib.scema_k1_tune(1, 0, 0, -2) == 0   # back to the shipped defaults
