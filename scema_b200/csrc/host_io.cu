@@ -6,8 +6,10 @@
 //  * reduce_graph_calls / scema_reduce_dir: clustering/coarsegrain_dependency_network.py:24-94 —
 //    greedy removal of the maximum-degree node with its neighbours; ties go to the node that
 //    entered the networkx node dict last (stable sort + [-1], :20-21). The script re-sorts all
-//    nodes every iteration (O(V^2 log V)); here a lazy max-heap keyed by (degree, insertion
-//    position) gives O(E log E) with the identical choice sequence.
+//    nodes every iteration (O(V^2 log V)); here the graph is a counting-sorted CSR adjacency and
+//    the greedy choice runs connected component by connected component (a removal only changes
+//    degrees inside its own component, so the mapping is the same): a scan per pick for the usual
+//    small clusters, degree buckets of lazy max-heaps for large components.
 #include "common.cuh"
 #include <algorithm>
 #include <dirent.h>
@@ -84,43 +86,53 @@ int reduce_graph_calls(const uint32_t *eu, const uint32_t *ev, uint64_t n_calls,
         if (pos[eu[e]] < 0) { pos[eu[e]] = (int64_t)order.size(); order.push_back(eu[e]); }
         if (pos[ev[e]] < 0) { pos[ev[e]] = (int64_t)order.size(); order.push_back(ev[e]); }
     }
-    // deduplicated adjacency (both directions)
-    std::vector<uint64_t> arcs;
-    arcs.reserve(2 * n_calls);
-    for (uint64_t e = 0; e < n_calls; e++) {
-        arcs.push_back(((uint64_t)eu[e] << 32) | ev[e]);
-        arcs.push_back(((uint64_t)ev[e] << 32) | eu[e]);
-    }
-    std::sort(arcs.begin(), arcs.end());
-    arcs.erase(std::unique(arcs.begin(), arcs.end()), arcs.end());
+    // deduplicated adjacency (both directions) in CSR form: counting sort by source node, then sort + unique inside each
+    // (short) list. The similarity files list every edge from both endpoints, so most arcs arrive twice.
     std::vector<uint64_t> start((size_t)num_gps + 1, 0);
-    for (uint64_t x : arcs) start[(x >> 32) + 1]++;
+    for (uint64_t e = 0; e < n_calls; e++) { start[(size_t)eu[e] + 1]++; start[(size_t)ev[e] + 1]++; }
     for (uint32_t i = 0; i < num_gps; i++) start[i + 1] += start[i];
-    std::vector<int64_t> deg(num_gps, 0);
-    for (uint32_t i = 0; i < num_gps; i++) {
-        deg[i] = (int64_t)(start[i + 1] - start[i]);
-        for (uint64_t q = start[i]; q < start[i + 1]; q++)
-            if ((uint32_t)arcs[q] == i) deg[i]++;  // a self loop counts twice in networkx
+    std::vector<uint32_t> arcs(2 * n_calls);
+    {
+        std::vector<uint64_t> fill(start.begin(), start.end() - 1);
+        for (uint64_t e = 0; e < n_calls; e++) { arcs[fill[eu[e]]++] = ev[e]; arcs[fill[ev[e]]++] = eu[e]; }
     }
-    std::vector<uint8_t> alive(num_gps, 0);
-    typedef std::pair<int64_t, int64_t> Key;  // (degree, insertion position): max = script's choice
-    std::priority_queue<std::pair<Key, uint32_t>> heap;
-    for (uint32_t v : order) { alive[v] = 1; heap.push({{deg[v], pos[v]}, v}); }
-    uint64_t remaining = order.size(), iters = 0, removed = 0;
-    std::vector<uint32_t> batch;
-    while (remaining > 0) {
-        uint32_t best;
-        while (true) {
-            auto top = heap.top();
-            heap.pop();
-            best = top.second;
-            if (alive[best] && top.first.first == deg[best]) break;
+    std::vector<int64_t> deg(num_gps, 0);
+    {
+        uint64_t w = 0;
+        for (uint32_t i = 0; i < num_gps; i++) {
+            const uint64_t b0 = start[i], b1 = start[i + 1];
+            std::sort(arcs.begin() + b0, arcs.begin() + b1);
+            const uint64_t n_u = (uint64_t)(std::unique(arcs.begin() + b0, arcs.begin() + b1) - (arcs.begin() + b0));
+            start[i] = w;
+            bool self = false;
+            for (uint64_t q = 0; q < n_u; q++) { arcs[w + q] = arcs[b0 + q]; self |= arcs[b0 + q] == i; }  // w <= b0: compaction in place
+            w += n_u;
+            deg[i] = (int64_t)n_u + (self ? 1 : 0);  // a self loop counts twice in networkx
         }
+        start[num_gps] = w;
+    }
+    // The script's choice = the alive node with the largest (degree, insertion position); it maps itself and its alive
+    // neighbours to itself and removes them. A removal only changes degrees inside the connected component it happens in,
+    // so the picks inside one component — and with them the mapping — are the same whether the components are worked on
+    // interleaved (the script's global order) or one after the other. Component by component:
+    //  * up to SMALL nodes (the usual case: one cluster of similar histories): every pick is a scan of the component's
+    //    node list for the largest (degree, position) — no priority structure at all, everything cache-resident;
+    //  * larger: one bucket per degree (degrees only fall, so the largest degree present never rises), each a max-heap
+    //    of insertion positions with lazy deletion (a node enters the bucket of a degree exactly once, when its degree
+    //    becomes that value; an entry is stale when the node is gone or its degree has moved on).
+    constexpr size_t SMALL = 96;
+    std::vector<uint8_t> alive(num_gps, 0), seen(num_gps, 0);
+    for (uint32_t v : order) alive[v] = 1;
+    uint64_t iters = 0, removed = 0;
+    std::vector<uint32_t> comp, batch;
+    std::vector<std::vector<uint32_t>> bucket;
+    // removes `best` with its alive neighbours; on_drop(w) is called for every alive node whose degree fell
+    auto take = [&](uint32_t best, auto &&on_drop) {
         mapping[best] = best;
         batch.clear();
         batch.push_back(best);
         for (uint64_t q = start[best]; q < start[best + 1]; q++) {
-            uint32_t w = (uint32_t)arcs[q];
+            const uint32_t w = arcs[q];
             if (!alive[w]) continue;
             mapping[w] = best;
             removed++;
@@ -129,11 +141,56 @@ int reduce_graph_calls(const uint32_t *eu, const uint32_t *ev, uint64_t n_calls,
         for (uint32_t rnode : batch) alive[rnode] = 0;
         for (uint32_t rnode : batch)
             for (uint64_t q = start[rnode]; q < start[rnode + 1]; q++) {
-                uint32_t w = (uint32_t)arcs[q];
-                if (alive[w]) { deg[w]--; heap.push({{deg[w], pos[w]}, w}); }
+                const uint32_t w = arcs[q];
+                if (alive[w]) { deg[w]--; on_drop(w); }
             }
-        remaining -= batch.size();
         iters++;
+        return batch.size();
+    };
+    for (uint32_t root : order) {
+        if (seen[root]) continue;
+        // the component of `root` (depth-first over the adjacency)
+        comp.clear();
+        comp.push_back(root);
+        seen[root] = 1;
+        for (size_t h = 0; h < comp.size(); h++)
+            for (uint64_t q = start[comp[h]]; q < start[comp[h] + 1]; q++) {
+                const uint32_t w = arcs[q];
+                if (!seen[w]) { seen[w] = 1; comp.push_back(w); }
+            }
+        size_t remaining = comp.size();
+        if (comp.size() <= SMALL) {
+            while (remaining > 0) {
+                uint32_t best = 0;
+                int64_t bd = -1, bp = -1;
+                for (uint32_t v : comp)
+                    if (alive[v] && (deg[v] > bd || (deg[v] == bd && pos[v] > bp))) { best = v; bd = deg[v]; bp = pos[v]; }
+                remaining -= take(best, [](uint32_t) {});
+            }
+            continue;
+        }
+        int64_t max_deg = 0;
+        for (uint32_t v : comp) max_deg = std::max(max_deg, deg[v]);
+        if (bucket.size() < (size_t)max_deg + 1) bucket.resize((size_t)max_deg + 1);
+        for (int64_t d = 0; d <= max_deg; d++) bucket[d].clear();
+        for (uint32_t v : comp) bucket[deg[v]].push_back((uint32_t)pos[v]);
+        for (int64_t d = 0; d <= max_deg; d++) std::make_heap(bucket[d].begin(), bucket[d].end());
+        int64_t d = max_deg;
+        while (remaining > 0) {
+            uint32_t best;
+            while (true) {
+                while (bucket[d].empty()) d--;  // some alive node of the component always sits in a bucket <= d
+                std::pop_heap(bucket[d].begin(), bucket[d].end());
+                best = order[bucket[d].back()];
+                bucket[d].pop_back();
+                if (alive[best] && deg[best] == d) break;
+            }
+            remaining -= take(best, [&](uint32_t w) {
+                std::vector<uint32_t> &bk = bucket[deg[w]];
+                bk.push_back((uint32_t)pos[w]);
+                std::push_heap(bk.begin(), bk.end());
+            });
+        }
     }
     if (iterations) *iterations = iters;
     if (neighbours_removed) *neighbours_removed = removed;

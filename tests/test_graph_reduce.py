@@ -97,3 +97,52 @@ def test_reduce_dir_vs_script_live(tmp_path):
     assert f"Converged in {it} iterations" in py.stdout
     assert f"udpated:  {nf}" in py.stdout
     assert f"required:  {nf - nr}" in py.stdout
+
+
+def _random_calls(rng, kind, n):
+    """add_edge call sequences of several shapes: (eu, ev) with duplicates, both directions, self loops."""
+    if kind == "clusters":          # the usual case: small cliques-with-holes, every edge listed from both endpoints
+        cs = int(rng.integers(2, 24))
+        eu, ev = [], []
+        for b in range(0, n - cs, cs):
+            for i in range(cs):
+                for j in range(i + 1, cs):
+                    if rng.random() < 0.5:
+                        eu += [b + i, b + j]
+                        ev += [b + j, b + i]
+        o = rng.permutation(len(eu))
+        return np.array(eu)[o], np.array(ev)[o]
+    if kind == "giant":             # one big sparse component (> 96 nodes: the bucket path) plus debris
+        m = int(n * rng.uniform(1.0, 3.0))
+        return rng.integers(0, n, m), rng.integers(0, n, m)
+    if kind == "hubs":              # a few nodes of very high degree, many ties among the rest
+        hubs = rng.integers(0, n, 5)
+        eu = rng.choice(hubs, 3 * n)
+        ev = rng.integers(0, n, 3 * n)
+        return np.concatenate([eu, ev[: n // 2]]), np.concatenate([ev, (ev[: n // 2] + 1) % n])
+    if kind == "chains":            # paths and rings: all degrees 1 or 2, the tie-break decides everything
+        a = np.arange(n - 1)
+        keep = rng.random(n - 1) < 0.9
+        eu, ev = a[keep], a[keep] + 1
+        o = rng.permutation(len(eu))
+        return eu[o], ev[o]
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["clusters", "giant", "hubs", "chains"])
+def test_reduce_random_graphs_match_the_restated_script(oracle, kind):
+    """The native reducer works connected component by connected component (a scan per pick up to 96 nodes, degree
+    buckets above); the oracle restates the script literally (all nodes re-sorted every iteration,
+    coarsegrain_dependency_network.py:6-21,59-94). Same mapping, iteration count and removed-neighbour count."""
+    rng = np.random.default_rng({"clusters": 1, "giant": 2, "hubs": 3, "chains": 4}[kind])
+    for trial in range(12):
+        n = int(rng.integers(5, 1200))
+        eu, ev = _random_calls(rng, kind, n)
+        if trial % 3 == 0 and len(eu):   # self loops (networkx counts them twice in the degree) and repeated calls
+            k = rng.integers(0, len(eu), max(1, len(eu) // 20))
+            eu = np.concatenate([eu, eu[k], eu[k]])
+            ev = np.concatenate([ev, eu[-len(k):], ev[k]])
+        want = oracle.reduce_graph(eu, ev, n)
+        got = native_calls(eu, ev, n)
+        assert got[0].tolist() == want[0].tolist(), (kind, trial, n)
+        assert (got[1], got[2]) == (want[1], want[2]), (kind, trial, n)
