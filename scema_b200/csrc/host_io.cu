@@ -86,8 +86,9 @@ int reduce_graph_calls(const uint32_t *eu, const uint32_t *ev, uint64_t n_calls,
         if (pos[eu[e]] < 0) { pos[eu[e]] = (int64_t)order.size(); order.push_back(eu[e]); }
         if (pos[ev[e]] < 0) { pos[ev[e]] = (int64_t)order.size(); order.push_back(ev[e]); }
     }
-    // deduplicated adjacency (both directions) in CSR form: counting sort by source node, then sort + unique inside each
-    // (short) list. The similarity files list every edge from both endpoints, so most arcs arrive twice.
+    // deduplicated adjacency (both directions) in CSR form: counting sort by source node, then every list is compacted
+    // in place with a last-seen marker (the similarity files list every edge from both endpoints, so most arcs arrive
+    // twice). The order inside a list does not matter below.
     std::vector<uint64_t> start((size_t)num_gps + 1, 0);
     for (uint64_t e = 0; e < n_calls; e++) { start[(size_t)eu[e] + 1]++; start[(size_t)ev[e] + 1]++; }
     for (uint32_t i = 0; i < num_gps; i++) start[i + 1] += start[i];
@@ -98,16 +99,20 @@ int reduce_graph_calls(const uint32_t *eu, const uint32_t *ev, uint64_t n_calls,
     }
     std::vector<int64_t> deg(num_gps, 0);
     {
+        std::vector<uint32_t> last_seen(num_gps, 0xffffffffu);  // node i marks its neighbours with i (IDs are < num_gps <= 2^32 - 1)
         uint64_t w = 0;
         for (uint32_t i = 0; i < num_gps; i++) {
             const uint64_t b0 = start[i], b1 = start[i + 1];
-            std::sort(arcs.begin() + b0, arcs.begin() + b1);
-            const uint64_t n_u = (uint64_t)(std::unique(arcs.begin() + b0, arcs.begin() + b1) - (arcs.begin() + b0));
-            start[i] = w;
+            start[i] = w;  // w <= b0: compaction in place
             bool self = false;
-            for (uint64_t q = 0; q < n_u; q++) { arcs[w + q] = arcs[b0 + q]; self |= arcs[b0 + q] == i; }  // w <= b0: compaction in place
-            w += n_u;
-            deg[i] = (int64_t)n_u + (self ? 1 : 0);  // a self loop counts twice in networkx
+            for (uint64_t q = b0; q < b1; q++) {
+                const uint32_t v = arcs[q];
+                if (last_seen[v] == i) continue;
+                last_seen[v] = i;
+                arcs[w++] = v;
+                self |= v == i;
+            }
+            deg[i] = (int64_t)(w - start[i]) + (self ? 1 : 0);  // a self loop counts twice in networkx
         }
         start[num_gps] = w;
     }
