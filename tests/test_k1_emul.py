@@ -15,9 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 MODES = {"eager": 0, "lazy": 1, "mixed": 2}
 
 
-@pytest.fixture(scope="module", params=[0, 8, 16], ids=["depth-default", "depth-8", "depth-16"])
+@pytest.fixture(scope="module", params=[0, 16], ids=["depth-default", "depth-16"])
 def emul(tmp_path_factory, request):
-    """The emulation library, built with the kernel's own ring depth and with 8 / 16 slots per chain (PR_DEPTH_SLOTS)."""
+    """The emulation library, built with the kernel's own ring depth (8 slots per chain) and with 16 (PR_DEPTH_SLOTS)."""
     if "fma" not in open("/proc/cpuinfo").read():
         pytest.skip("host CPU has no FMA instruction")
     so = str(tmp_path_factory.mktemp("k1emul") / "libk1emul.so")
