@@ -19,6 +19,12 @@
 //    a shifted exponent per chain, zero numerators exempt, the sign of a zero quotient restored by
 //    one LOP3 (see div_acc).
 //
+// What the measurement showed (profiles/r02_k1_experiments.txt, r02_k1_scan.txt): 1.7x fewer executed
+// instructions than k_resample_stream and, at the same number of chains in flight, the same time —
+// K1 is bound by the round trip of z (as large as the input) through L2 / HBM and by memory latency,
+// not by issue. The launch is therefore sized for the chains whose z rows L2 can hold (12 warps per SM
+// for the ragged batch) and told per length class how y should reach L2 (`flags` below).
+//
 // This header is also compiled for the HOST by tests/helpers/k1_emul.cpp (K1_EMULATE): the kernel
 // source below runs there thread by thread, with cp.async modelled in its two extreme legal timings
 // (every copy lands at once / only when a wait_group forces it), against the CPU oracle — the
